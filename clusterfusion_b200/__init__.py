@@ -1,0 +1,32 @@
+"""clusterfusion_b200 -- B200-native (sm_100a) fused Llama decoder attention half-layer.
+
+Public operator surface = the reference's (``/root/reference/clusterfusion/__init__.py:6-16`` re-exports
+every public name of its native module; ``include/pybind.cpp:108-123`` defines them):
+
+    llama_decoder_layer(input, weight_qkv, weight_o, k_cache, v_cache, rms_w, cos, sin) -> (o, k, v)
+    llama_decoder_layer_sglang(input, residual, weight_qkv, weight_o, k_cache, v_cache, rms_w, eps,
+                               cos, sin) -> (o, residual, k, v)
+    llama_decoder_layer_batch_decode_sglang(output, residual_output, input, residual, weight_qkv,
+                               weight_o, paged_kv_indptr, paged_kv_indices, k_cache_ptrs,
+                               v_cache_ptrs, layer_id, rms_w, eps, positions, cos_sin) -> None
+
+Everything is native: a torch-free C-ABI library (``libclusterfusion_b200.so``, the CUDA kernels) and a
+thin PyTorch C++ extension (``_clusterfusion``).  There is no Python or CPU fallback -- importing
+this package without the built extension raises ImportError, exactly like the reference package.
+"""
+import importlib as _importlib
+
+try:
+    _ext = _importlib.import_module("._clusterfusion", __package__)
+except ImportError as e:  # same behaviour as /root/reference/clusterfusion/__init__.py:6-12
+    raise ImportError(
+        "Failed to import clusterfusion_b200 native extension. Build it in-tree with "
+        "`python -m clusterfusion_b200.build` (needs nvcc for sm_100a); there is no fallback path."
+    ) from e
+
+for _attr in dir(_ext):
+    if not _attr.startswith("_"):
+        globals()[_attr] = getattr(_ext, _attr)
+
+__all__ = [a for a in dir(_ext) if not a.startswith("_")]
+del _importlib, _attr

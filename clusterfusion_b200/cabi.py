@@ -1,0 +1,125 @@
+"""ctypes binding of the C ABI in include/clusterfusion_b200.h.
+
+This is the thinnest possible host layer over ``libclusterfusion_b200.so``: raw device
+pointers in, one kernel launch out.  The pybind extension (csrc/pybind.cpp) sits on the
+same entry points; this module exists so tests and bench.py can drive the C ABI directly
+(``data_ptr()`` integers, no torch types crossing the boundary).
+
+There is no CPU fallback: if the shared library is missing the import raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libclusterfusion_b200.so"
+
+CF_VARIANT_CHAT, CF_VARIANT_SGLANG, CF_VARIANT_PAGED = 0, 1, 2
+CF_FLAG_OUT_FP32_PARTIAL = 0x1
+
+EXPORTED_SYMBOLS = (
+    "cf_abi_version",
+    "cf_last_error_string",
+    "cf_llama_workspace_bytes",
+    "cf_llama_algorithmic_bytes",
+    "cf_llama_decoder_layer_launch",
+    "cf_test_cluster_reduce",
+)
+
+
+class CfLlamaArgs(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int32),
+        ("flags", C.c_uint32),
+        ("hidden", C.c_int32),
+        ("n_q_heads", C.c_int32),
+        ("n_kv_heads", C.c_int32),
+        ("head_dim", C.c_int32),
+        ("batch", C.c_int32),
+        ("kv_len", C.c_uint32),
+        ("layer_id", C.c_int32),
+        ("eps", C.c_float),
+        ("x", C.c_void_p),
+        ("residual_in", C.c_void_p),
+        ("w_qkv", C.c_void_p),
+        ("w_o", C.c_void_p),
+        ("rms_w", C.c_void_p),
+        ("out", C.c_void_p),
+        ("residual_out", C.c_void_p),
+        ("k_new", C.c_void_p),
+        ("v_new", C.c_void_p),
+        ("k_cache", C.c_void_p),
+        ("v_cache", C.c_void_p),
+        ("indptr", C.c_void_p),
+        ("indices", C.c_void_p),
+        ("k_pool_ptrs", C.c_void_p),
+        ("v_pool_ptrs", C.c_void_p),
+        ("positions", C.c_void_p),
+        ("cos", C.c_void_p),
+        ("sin", C.c_void_p),
+        ("workspace", C.c_void_p),
+    ]
+
+
+class CfError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"clusterfusion_b200 C ABI error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the C-ABI library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
+    lib.cf_abi_version.restype = C.c_int
+    lib.cf_last_error_string.restype = C.c_char_p
+    lib.cf_llama_workspace_bytes.restype = C.c_size_t
+    lib.cf_llama_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.cf_llama_algorithmic_bytes.restype = C.c_uint64
+    lib.cf_llama_algorithmic_bytes.argtypes = [C.POINTER(CfLlamaArgs), C.c_uint64]
+    lib.cf_llama_decoder_layer_launch.restype = C.c_int
+    lib.cf_llama_decoder_layer_launch.argtypes = [C.POINTER(CfLlamaArgs), C.c_void_p]
+    lib.cf_test_cluster_reduce.restype = C.c_int
+    lib.cf_test_cluster_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().cf_last_error_string().decode()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise CfError(rc, last_error())
+
+
+def workspace_bytes(hidden: int, batch: int = 1) -> int:
+    return int(load().cf_llama_workspace_bytes(hidden, batch))
+
+
+def algorithmic_bytes(args: CfLlamaArgs, total_kv_rows: int) -> int:
+    return int(load().cf_llama_algorithmic_bytes(C.byref(args), total_kv_rows))
+
+
+def launch(args: CfLlamaArgs, stream: int = 0) -> None:
+    """One fused-kernel launch on CUDA stream handle `stream` (0 = legacy default stream)."""
+    check(load().cf_llama_decoder_layer_launch(C.byref(args), C.c_void_p(stream)))
+
+
+def test_cluster_reduce(in_ptr: int, out_ptr: int, n: int, cluster_size: int, n_clusters: int,
+                        stage: int, repeats: int, stream: int = 0) -> None:
+    check(load().cf_test_cluster_reduce(C.c_void_p(in_ptr), C.c_void_p(out_ptr), n, cluster_size,
+                                        n_clusters, stage, repeats, C.c_void_p(stream)))

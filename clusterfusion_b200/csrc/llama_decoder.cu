@@ -1,0 +1,359 @@
+/*
+ * C-ABI launcher for the fused sm_100a Llama decoder attention half-layer (include/clusterfusion_b200.h).
+ * Torch-free translation unit: nothing here includes torch headers, so it compiles in seconds and the
+ * shared library can be bound from anything that speaks C (ctypes, cgo, JNI, the pybind shim).
+ *
+ * Host-side work per call (the reference does 2 cudaFuncSetAttribute + 3 memset kernels + 4 tensor-map
+ * encodes + 2 cudaDeviceSynchronize per call, llama_kernel_dispatch.cu:15-21, :48-121, :126-144):
+ *   - argument validation,
+ *   - tensor-map lookup in a small cache keyed on (pointer, dims, box) -- weights hit every time,
+ *     K/V maps are re-encoded only when kv_len or the cache base pointer changes,
+ *   - one cudaLaunchKernelEx on the caller's stream.  No sync, no allocation, graph-capturable.
+ */
+#include "../../include/clusterfusion_b200.h"
+#include "llama_decoder_kernel.cuh"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return (EncodeTiledFn) nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    uint64_t rows, cols;
+    uint32_t box_c, box_r;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && box_c == o.box_c && box_r == o.box_r;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+        h ^= (k.rows + 0x632BE59BD9B4E019ull) + (h << 6) + (h >> 2);
+        h ^= (k.cols * 31 + k.box_c * 7 + k.box_r) + (h << 6) + (h >> 2);
+        return static_cast<size_t>(h);
+    }
+};
+
+std::mutex g_map_mutex;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+// 2-D fp16 row-major tensor [rows][cols], box {box_c, box_r}; OOB rows/cols read as zero.
+int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_c,
+                   uint32_t box_r) {
+    const MapKey key{ptr, rows, cols, box_c, box_r};
+    {
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(CF_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[2] = {cols, rows ? rows : 1};      // a zero-row cache still needs a valid map
+    const cuuint64_t strides[1] = {cols * sizeof(__half)};
+    const cuuint32_t box[2] = {box_c, box_r};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu",
+                                       (int)r, (unsigned long long)rows, (unsigned long long)cols);
+    {
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        if (g_map_cache.size() > 4096) g_map_cache.clear();   // bounded; KV maps churn with kv_len
+        g_map_cache.emplace(key, m);
+    }
+    *out = m;
+    return 0;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int VARIANT, int CLUSTER>
+int launch(const cfb::KParams& kp, int n_clusters, int batch, cudaStream_t stream) {
+    using S = cfb::Smem<CLUSTER>;
+    auto kern = cfb::llama_decoder_layer_kernel<VARIANT, CLUSTER>;
+    static std::once_flag once[16];
+    static cudaError_t attr_err[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::call_once(once[dev & 15], [&] {
+        attr_err[dev & 15] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (attr_err[dev & 15] == cudaSuccess && CLUSTER > 8)
+            attr_err[dev & 15] = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    });
+    if (attr_err[dev & 15] != cudaSuccess)
+        return fail((int)attr_err[dev & 15], "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err[dev & 15]));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_clusters * CLUSTER, batch, 1);
+    cfg.blockDim = dim3(cfb::BLOCK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CLUSTER;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, kp);
+    if (e != cudaSuccess) return fail((int)e, "kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+bool device_is_sm100() {
+    static int cached[16] = {0};   // 0 unknown, 1 yes, 2 no
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    int& c = cached[dev & 15];
+    if (c == 0) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        c = (major == 10) ? 1 : 2;
+    }
+    return c == 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cf_abi_version(void) { return CF_ABI_VERSION; }
+
+const char* cf_last_error_string(void) { return g_last_error.c_str(); }
+
+size_t cf_llama_workspace_bytes(int32_t hidden, int32_t batch) {
+    if (hidden <= 0 || batch <= 0) return 0;
+    // fp32 scratch [batch][hidden] + counters [batch][16 + 1] (enough for any cluster size)
+    return (size_t)batch * hidden * sizeof(float) + (size_t)batch * 32 * sizeof(uint32_t);
+}
+
+uint64_t cf_llama_algorithmic_bytes(const CfLlamaArgs* a, uint64_t total_kv_rows) {
+    if (!a) return 0;
+    const uint64_t D = 128, H = a->hidden, hq = a->n_q_heads, hkv = a->n_kv_heads, bs = a->batch;
+    uint64_t b = 2 * (hq + 2 * hkv) * D * H + 2 * hq * D * H;          // Wqkv + Wo
+    b += 2 * 2 * total_kv_rows * hkv * D;                               // K and V, once per KV head
+    uint64_t small = 2 * H /*x*/ + 2 * H /*out*/ + 2 * 2 * hkv * D /*k_new, v_new*/;
+    if (a->variant != CF_VARIANT_CHAT) small += 4 * H;                  // residual in / out
+    b += bs * small + 2 * H /*rms_w*/ + (a->variant == CF_VARIANT_CHAT ? 2 * 4 * D : bs * 4 * D) /*cos,sin*/;
+    return b;
+}
+
+int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
+    if (!a) return fail(CF_ERR_NULL_ARG, "args is NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (a->variant < CF_VARIANT_CHAT || a->variant > CF_VARIANT_PAGED)
+        return fail(CF_ERR_BAD_VARIANT, "unknown variant %d", a->variant);
+    const bool chat = a->variant == CF_VARIANT_CHAT, paged = a->variant == CF_VARIANT_PAGED;
+    constexpr int CL = 4;
+    if (a->head_dim != 128) return fail(CF_ERR_BAD_SHAPE, "head_dim must be 128 (got %d)", a->head_dim);
+    if (a->hidden <= 0 || a->hidden % (CL * 256) != 0 || a->hidden / CL > cfb::KS_MAX)
+        return fail(CF_ERR_BAD_SHAPE, "hidden must be a multiple of %d and <= %d (got %d)", CL * 256,
+                    CL * cfb::KS_MAX, a->hidden);
+    if (a->n_q_heads <= 0 || a->n_kv_heads <= 0 || a->n_q_heads % a->n_kv_heads != 0)
+        return fail(CF_ERR_BAD_SHAPE, "bad head counts q=%d kv=%d", a->n_q_heads, a->n_kv_heads);
+    if (a->n_q_heads != a->n_kv_heads)
+        return fail(CF_ERR_BAD_SHAPE, "grouped-query attention (q=%d, kv=%d) is not built in this revision",
+                    a->n_q_heads, a->n_kv_heads);
+    if (a->batch < 1 || (!paged && a->batch != 1))
+        return fail(CF_ERR_BAD_SHAPE, "batch must be 1 for CHAT/SGLANG and >= 1 for PAGED (got %d)", a->batch);
+    if (a->batch > 65535) return fail(CF_ERR_BAD_SHAPE, "batch too large (%d)", a->batch);
+    if (!a->x || !a->w_qkv || !a->w_o || !a->rms_w || !a->out || !a->cos || !a->workspace)
+        return fail(CF_ERR_NULL_ARG, "x / w_qkv / w_o / rms_w / out / cos / workspace must be non-NULL");
+    if (!paged && (!a->sin || !a->k_new || !a->v_new)) return fail(CF_ERR_NULL_ARG, "sin / k_new / v_new must be non-NULL");
+    if (!paged && a->kv_len > 0 && (!a->k_cache || !a->v_cache))
+        return fail(CF_ERR_NULL_ARG, "k_cache / v_cache must be non-NULL when kv_len > 0");
+    if (!chat && (!a->residual_in || !a->residual_out))
+        return fail(CF_ERR_NULL_ARG, "residual_in / residual_out must be non-NULL for SGLANG / PAGED");
+    if (paged && (!a->indptr || !a->indices || !a->k_pool_ptrs || !a->v_pool_ptrs || !a->positions))
+        return fail(CF_ERR_NULL_ARG, "paged arguments must be non-NULL");
+    if (a->kv_len > 0x7fffffffu / 2) return fail(CF_ERR_BAD_SHAPE, "kv_len too large");
+    const void* al[] = {a->x, a->residual_in, a->w_qkv, a->w_o, a->rms_w, a->out, a->residual_out,
+                        a->k_new, a->v_new, a->k_cache, a->v_cache, a->workspace, a->cos, a->sin};
+    for (const void* q : al)
+        if (q && !aligned16(q)) return fail(CF_ERR_BAD_ALIGNMENT, "all tensors must be 16-byte aligned (%p)", q);
+    if (!device_is_sm100()) return fail(CF_ERR_NO_DEVICE, "current CUDA device is not compute capability 10.x");
+
+    cfb::KParams kp;
+    memset(&kp, 0, sizeof kp);
+    const uint64_t H = a->hidden, qd = (uint64_t)a->n_q_heads * 128, kvd = (uint64_t)a->n_kv_heads * 128;
+    int rc;
+    if (chat) {
+        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, 3 * H, H, 128, 64))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, qd, H, 128, 64))) return rc;
+    } else {
+        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 256, 32))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 128, 64))) return rc;
+    }
+    if (!paged) {
+        // kv_len == 0: no tile is ever requested; point the maps at any valid address
+        const void* kc = a->kv_len ? a->k_cache : a->x;
+        const void* vc = a->kv_len ? a->v_cache : a->x;
+        if ((rc = get_tensor_map(&kp.tm_k, kc, a->kv_len, kvd, 128, 32))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_v, vc, a->kv_len, kvd, 128, 32))) return rc;
+    }
+    kp.x = static_cast<const __half*>(a->x);
+    kp.residual_in = static_cast<const __half*>(a->residual_in);
+    kp.rms_w = static_cast<const __half*>(a->rms_w);
+    kp.out = a->out;
+    kp.residual_out = static_cast<__half*>(a->residual_out);
+    kp.k_new = static_cast<__half*>(a->k_new);
+    kp.v_new = static_cast<__half*>(a->v_new);
+    kp.cos = a->cos;
+    kp.sin = a->sin;
+    kp.indptr = a->indptr;
+    kp.indices = a->indices;
+    kp.k_pool_ptrs = reinterpret_cast<const unsigned long long*>(a->k_pool_ptrs);
+    kp.v_pool_ptrs = reinterpret_cast<const unsigned long long*>(a->v_pool_ptrs);
+    kp.positions = reinterpret_cast<const long long*>(a->positions);
+    kp.scratch = static_cast<float*>(a->workspace);
+    kp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + (size_t)a->batch * a->hidden * sizeof(float));
+    kp.eps = a->eps;
+    kp.hidden = a->hidden;
+    kp.n_heads = a->n_q_heads;
+    kp.n_kv_heads = a->n_kv_heads;
+    kp.kv_len = (int)a->kv_len;
+    kp.layer_id = a->layer_id;
+    kp.flags = a->flags;
+
+    switch (a->variant) {
+        case CF_VARIANT_CHAT: return launch<cfb::CHAT, CL>(kp, a->n_q_heads, 1, stream);
+        case CF_VARIANT_SGLANG: return launch<cfb::SGLANG, CL>(kp, a->n_q_heads, 1, stream);
+        default: return launch<cfb::PAGED, CL>(kp, a->n_q_heads, a->batch, stream);
+    }
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// unit-test hook for include/dsm.cuh
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <int CS, Stage ST>
+__global__ void test_cluster_reduce_kernel(const float* in, float* out, int n, int repeats) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    float* src = reinterpret_cast<float*>(sm);
+    float* dst = src + n;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dst + 2 * CS * n);
+    const uint32_t rank = dsm::cluster_ctarank();
+    const uint32_t cta = blockIdx.x;
+    const uint32_t bar_u32 = dsm::smem_u32(bar);
+    if (threadIdx.x == 0) {
+        cluster_reduce_arm<CS>(bar_u32, n * 4);
+        dsm::mbar_fence_init();
+    }
+    __syncthreads();
+    dsm::cluster_arrive();
+    dsm::cluster_wait();
+    uint32_t phase = 0;
+    const int n_out = (ST == Stage::QUK_DEEPSEEK) ? n * CS : n;
+    for (int e = threadIdx.x; e < n_out; e += blockDim.x) out[(size_t)cta * n_out + e] = 0.f;
+    for (int rep = 0; rep < repeats; ++rep) {
+        const float scale = (ST == Stage::ATTN) ? 1.f : (float)(rep + 1);
+        for (int e = threadIdx.x; e < n; e += blockDim.x) src[e] = in[(size_t)cta * n + e] * scale;
+        cluster_reduce<CS, ST>(n * 4, threadIdx.x, ST == Stage::ATTN ? n - 4 : n, rank,
+                               dsm::smem_u32(src), dsm::smem_u32(dst), bar_u32, phase, src, dst);
+        if (ST == Stage::QUK_DEEPSEEK) {
+            const float* g = dst + ((phase ^ 1u) & 1u) * CS * n;
+            for (int e = threadIdx.x; e < n_out; e += blockDim.x) out[(size_t)cta * n_out + e] += g[e];
+        } else if (ST == Stage::ATTN) {
+            for (int e = threadIdx.x; e < n; e += blockDim.x) out[(size_t)cta * n + e] = src[e];
+        } else {
+            for (int e = threadIdx.x; e < n; e += blockDim.x) out[(size_t)cta * n + e] += src[e];
+        }
+        __syncthreads();
+    }
+    // keep this CTA's shared memory alive until every peer has finished pushing into it
+    dsm::cluster_arrive();
+    dsm::cluster_wait();
+}
+
+template <int CS, Stage ST>
+int launch_test(const float* in, float* out, int n, int n_clusters, int repeats, cudaStream_t stream) {
+    auto kern = test_cluster_reduce_kernel<CS, ST>;
+    const size_t smem = (size_t)(n + 2 * CS * n) * 4 + 16;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && CS > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return fail((int)e, "test attr: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_clusters * CS, 1, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, in, out, n, repeats);
+    if (e != cudaSuccess) return fail((int)e, "test launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+template <int CS>
+int launch_test_stage(const float* in, float* out, int n, int n_clusters, int stage, int repeats, cudaStream_t s) {
+    switch (stage) {
+        case 0: return launch_test<CS, Stage::LINEAR>(in, out, n, n_clusters, repeats, s);
+        case 1: return launch_test<CS, Stage::ATTN>(in, out, n, n_clusters, repeats, s);
+        case 4: return launch_test<CS, Stage::QUK_DEEPSEEK>(in, out, n, n_clusters, repeats, s);
+        default: return fail(CF_ERR_BAD_VARIANT, "stage %d not testable", stage);
+    }
+}
+
+}  // namespace
+
+extern "C" int cf_test_cluster_reduce(const float* in, float* out, int32_t n, int32_t cluster_size,
+                                      int32_t n_clusters, int32_t stage, int32_t repeats, void* stream_) {
+    if (!in || !out) return fail(CF_ERR_NULL_ARG, "in/out NULL");
+    if (n <= 0 || n % 4 != 0 || n > 2048) return fail(CF_ERR_BAD_SHAPE, "n must be a multiple of 4 in (0, 2048]");
+    if (!device_is_sm100()) return fail(CF_ERR_NO_DEVICE, "current CUDA device is not compute capability 10.x");
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    switch (cluster_size) {
+        case 1: return launch_test_stage<1>(in, out, n, n_clusters, stage, repeats, s);
+        case 2: return launch_test_stage<2>(in, out, n, n_clusters, stage, repeats, s);
+        case 4: return launch_test_stage<4>(in, out, n, n_clusters, stage, repeats, s);
+        case 8: return launch_test_stage<8>(in, out, n, n_clusters, stage, repeats, s);
+        case 16: return launch_test_stage<16>(in, out, n, n_clusters, stage, repeats, s);
+        default: return fail(CF_ERR_BAD_SHAPE, "cluster_size must be 1, 2, 4, 8 or 16");
+    }
+}

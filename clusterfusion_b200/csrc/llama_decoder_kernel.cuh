@@ -1,0 +1,812 @@
+/*
+ * Fused Llama decoder attention half-layer for sm_100a (B200):
+ *
+ *   RMSNorm -> QKV GEMV -> RoPE -> (paged-)KV flash-decode -> O GEMV -> fp32 cross-head reduction
+ *
+ * One launch per layer, one thread-block cluster per (request, KV-head group).  Replaces the three
+ * reference kernels (/root/reference/include/H100/llama/kernel.cuh:20-619, kernel_sglang.cuh:20-633,
+ * kernel_batch_sglang.cuh:43-664); the decomposition inside a cluster follows the paper (K-split of
+ * the QKV GEMV, sequence-split of the KV cache, N-split of the O GEMV) but the machinery is new:
+ *
+ *  - warp specialisation: warp 8 is a dedicated producer that streams EVERY byte the CTA will ever
+ *    need -- Wqkv tiles, then K/V tiles, then Wo tiles -- through one NSTAGES x 16 KB ring of TMA
+ *    tiles guarded by full/empty mbarriers.  None of those loads depends on activations, so the
+ *    producer runs ahead across phase boundaries: K/V tiles land while the consumers are still in
+ *    the QKV cluster exchange / RoPE, Wo tiles land during the softmax merge.  (The reference drains
+ *    a 2-stage, single-thread-producer pipeline five times per layer, kernel.cuh:141-267, :343, :579.)
+ *  - 8 consumer warps; each ring tile is owned by ONE warp (tile i -> warp i % 8), so full-barrier
+ *    waits of different warps interleave instead of stalling the CTA in lock-step, and the empty
+ *    barrier needs a single arrival.
+ *  - every reduction is fp32: per-warp partials land in write-once shared-memory slots and are
+ *    folded in a fixed order; the cluster exchanges (q|k|v vector, softmax state) go through the new
+ *    cluster_reduce<> in include/dsm.cuh (one st.async push per peer, no cluster.sync());
+ *    2 exchanges per layer instead of the reference's 22 cluster.sync().
+ *  - the cross-head O reduction is fp32 `red.global.add.v4.f32` into a 4*hidden-byte scratch plus an
+ *    arrival counter per output slice; the last-arriving CTA converts to fp16, writes `out`, and
+ *    re-zeroes scratch + counter, so there are no memset launches and no fp16 atomics
+ *    (reference: 131 072 fp16 atomicAdd per layer, kernel.cuh:600/:618).
+ *
+ * Shapes: head_dim 128; hidden % (CLUSTER*256) == 0, hidden/CLUSTER <= 2048.
+ */
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dsm.cuh"
+
+namespace cfb {
+
+constexpr int HEAD_DIM = 128;
+constexpr int CONSUMER_WARPS = 12;
+constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;   // 384
+constexpr int BLOCK_THREADS = CONSUMER_THREADS + 32;    // + producer warp
+constexpr int STAGE_BYTES = 16384;
+constexpr int NSTAGES = CONSUMER_WARPS;                 // stage s is consumed by warp s, always (see ring_wait_full)
+constexpr int KS_MAX = 2048;                            // max hidden / CLUSTER
+constexpr int CONSUMER_BAR = 1;                         // named barrier id for the consumer threads
+
+enum Variant : int { CHAT = 0, SGLANG = 1, PAGED = 2 };
+static_assert(CONSUMER_WARPS % 3 == 0 && CONSUMER_THREADS >= 3 * HEAD_DIM, "chat QKV mapping needs warps % 3 == 0");
+
+struct alignas(64) KParams {
+    CUtensorMap tm_wqkv;   // CHAT: [3*hidden][hidden] box {128,64}; else [(Hq+2Hkv)*128][hidden] box {256,32}
+    CUtensorMap tm_wo;     // CHAT: [Hq*128][hidden] box {128,64};  else [hidden][Hq*128] box {128,64}
+    CUtensorMap tm_k;      // CHAT/SGLANG: [kv_len][Hkv*128] box {128,32}
+    CUtensorMap tm_v;
+    const __half* x;
+    const __half* residual_in;
+    const __half* rms_w;
+    void* out;
+    __half* residual_out;
+    __half* k_new;
+    __half* v_new;
+    const float* cos;
+    const float* sin;
+    const int* indptr;
+    const int* indices;
+    const unsigned long long* k_pool_ptrs;
+    const unsigned long long* v_pool_ptrs;
+    const long long* positions;
+    float* scratch;          // fp32 [batch][hidden], zero between launches
+    unsigned* counters;      // [batch][CLUSTER + 1], zero between launches
+    float eps;
+    int hidden;
+    int n_heads;             // query heads == clusters per request (MHA kernels)
+    int n_kv_heads;
+    int kv_len;
+    int layer_id;
+    unsigned flags;
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared memory carve-up (dynamic)
+// ------------------------------------------------------------------------------------------------
+template <int CLUSTER>
+struct Smem {
+    static constexpr int QKV_OUT = 3 * HEAD_DIM;                 // q | k | v of one head
+    static constexpr int ATTN_PAYLOAD = HEAD_DIM + 4;            // [m, l, -, -, o[128]]
+    static constexpr int RING = 0;
+    static constexpr int UNION = RING + NSTAGES * STAGE_BYTES;
+    //   phase QKV : xs fp32[KS_MAX] | qkv_part  (chat: fp32[12 warps][128]; sglang: fp32[KS/256][384])
+    //   phase ATTN: attn_part fp32[24][132]
+    //   phase O   : out_part fp32[2][KS_MAX]
+    static constexpr int UNION_BYTES = KS_MAX * 4 + 8 * QKV_OUT * 4;   // 20480 >= 2*KS_MAX*4
+    static constexpr int XS = UNION;
+    static constexpr int QKV_PART = UNION + KS_MAX * 4;
+    static constexpr int ATTN_PART = UNION;
+    static constexpr int OUT_PART = UNION;
+    static constexpr int QKV_SRC = UNION + UNION_BYTES;                    // fp32[384]  contribution / result
+    // each exchange barrier is used exactly once per launch (phase 0), so only the phase-0 half of
+    // cluster_reduce's double buffer is ever touched and only that half is allocated
+    static constexpr int QKV_RECV = QKV_SRC + QKV_OUT * 4;                 // fp32[CLUSTER][384]
+    static constexpr int ATTN_SRC = QKV_RECV + CLUSTER * QKV_OUT * 4;      // fp32[132]
+    static constexpr int ATTN_RECV = ATTN_SRC + ATTN_PAYLOAD * 4;          // fp32[CLUSTER][132]
+    static constexpr int QKV_FINAL = ATTN_RECV + CLUSTER * ATTN_PAYLOAD * 4;  // fp32[384] roped q*scale | k | v
+    static constexpr int ATTN_OUT = QKV_FINAL + QKV_OUT * 4;               // fp32[128]
+    static constexpr int RED = ATTN_OUT + HEAD_DIM * 4;                    // fp32[32] block-reduce scratch
+    static constexpr int BARS = RED + 32 * 4;                              // u64 full[NSTAGES], empty[NSTAGES], xbar[2]
+    static constexpr int FLAGS = BARS + (2 * NSTAGES + 2) * 8;             // u32[4]
+    static constexpr int TOTAL = FLAGS + 16;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1,
+                                            uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                             uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_cg_v4(const float* addr) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+
+// ring bookkeeping: global tile index g -> (stage, parity)
+__device__ __forceinline__ uint32_t ring_stage(uint32_t g) { return g % NSTAGES; }
+__device__ __forceinline__ uint32_t ring_parity(uint32_t g) { return (g / NSTAGES) & 1u; }
+
+// Ring discipline.  Global tile index g -> stage g % NSTAGES, consumed by warp g % CONSUMER_WARPS, and
+// NSTAGES == CONSUMER_WARPS: a stage is always consumed by the same warp, in order.  That is what makes the
+// one-bit phase parity sufficient: a warp cannot test use u of its stage before it has itself consumed use
+// u-1, so the parity can never alias to an older phase (it would if consecutive uses of a stage were
+// consumed by different warps -- a warp could then look at the barrier before the previous use's TMA landed).
+__device__ __forceinline__ void ring_wait_full(uint32_t full_u32, uint32_t g) {
+    dsm::mbar_wait(full_u32 + 8 * ring_stage(g), ring_parity(g));
+}
+// first tile index i >= 0 of a phase starting at global index gbase that belongs to `warp`
+__device__ __forceinline__ uint32_t first_tile(uint32_t gbase, uint32_t warp) {
+    return (warp + NSTAGES - gbase % NSTAGES) % NSTAGES;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int VARIANT, int CLUSTER>
+__global__ void __launch_bounds__(BLOCK_THREADS, 1)
+llama_decoder_layer_kernel(const __grid_constant__ KParams p)
+{
+    using S = Smem<CLUSTER>;
+    constexpr bool kChat = (VARIANT == CHAT);
+    constexpr bool kPaged = (VARIANT == PAGED);
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t smem_base = dsm::smem_u32(smem);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t lane = tid & 31;
+    const uint32_t rank = dsm::cluster_ctarank();
+    const uint32_t head = blockIdx.x / CLUSTER;
+    const uint32_t batch = blockIdx.y;
+
+    const int hidden = p.hidden;
+    const int KS = hidden / CLUSTER;     // this CTA's slice of the GEMV reduction dim / of the O output dim
+    const int kv_cols = p.n_kv_heads * HEAD_DIM;
+
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BARS);
+    uint64_t* empty_bar = full_bar + NSTAGES;
+    uint64_t* xbar = empty_bar + NSTAGES;
+    const uint32_t full_u32 = smem_base + S::BARS;
+    const uint32_t empty_u32 = full_u32 + NSTAGES * 8;
+    const uint32_t xbar_u32 = empty_u32 + NSTAGES * 8;
+    (void)full_bar; (void)empty_bar; (void)xbar;
+
+    // ---- per-request KV range -----------------------------------------------------------------
+    int kv_len, kv_base = 0, new_slot = 0;
+    if constexpr (kPaged) {
+        kv_base = p.indptr[batch];
+        const int end = p.indptr[batch + 1] - 1;      // last index = slot of the new token
+        kv_len = end - kv_base;
+        new_slot = p.indices[end];
+    } else {
+        kv_len = p.kv_len;
+    }
+    const int chunk = (((kv_len + CLUSTER - 1) / CLUSTER) + 31) & ~31;   // KV rows per CTA, tile aligned
+    const int row_begin = min((int)rank * chunk, kv_len);
+    const int row_end = min(row_begin + chunk, kv_len);
+    const uint32_t n_qkv_tiles = kChat ? 3u * (KS / 64) : 12u * (KS / 256);
+    const uint32_t n_kv_tiles = (row_end - row_begin + 31) / 32;
+    const uint32_t n_o_tiles = kChat ? 2u * (KS / 128) : (uint32_t)(KS / 64);
+
+    // ---- barrier init ---------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGES; ++s) {
+            dsm::mbar_init(full_u32 + 8 * s, 1);
+            dsm::mbar_init(empty_u32 + 8 * s, 1);
+        }
+        cluster_reduce_arm<CLUSTER>(xbar_u32, S::QKV_OUT * 4);
+        cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::ATTN_PAYLOAD * 4);
+        dsm::mbar_fence_init();
+    }
+    __syncthreads();
+    dsm::cluster_arrive();     // peers may push into this CTA's smem only after every CTA armed its barriers
+
+    // =============================================================================================
+    // PRODUCER WARP
+    // =============================================================================================
+    if (warp == CONSUMER_WARPS) {
+        dsm::cluster_wait();
+        const uint64_t pol = policy_evict_first();
+        uint32_t g = 0;
+        if (lane == 0) {
+            prefetch_tmap(&p.tm_wqkv);
+            prefetch_tmap(&p.tm_wo);
+            if constexpr (!kPaged) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); }
+            // ---- phase 1: Wqkv tiles --------------------------------------------------------------
+            for (uint32_t i = 0; i < n_qkv_tiles; ++i, ++g) {
+                const uint32_t s = ring_stage(g);
+                dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
+                dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
+                int c0, c1;
+                if constexpr (kChat) {           // tile i: matrix j = i % 3, rows t = i / 3 (64 input rows)
+                    const int j = i % 3, t = i / 3;
+                    c0 = head * HEAD_DIM;
+                    c1 = j * hidden + rank * KS + t * 64;
+                } else {                         // tile i: 32 output rows x 256 input cols
+                    const int wins = KS / 256;
+                    const int rb = i / wins, win = i % wins;          // rb in [0,12): matrix j = rb/4
+                    const int j = rb >> 2, sub = rb & 3;
+                    const int row0 = (j == 0) ? head * HEAD_DIM
+                                   : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
+                                              : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
+                    c0 = rank * KS + win * 256;
+                    c1 = row0 + sub * 32;
+                }
+                tma_load_2d(smem_base + S::RING + s * STAGE_BYTES, &p.tm_wqkv, c0, c1, full_u32 + 8 * s, pol);
+            }
+        }
+        // ---- phase 2: K / V tiles (32 rows of K then 32 rows of V per stage) ------------------------
+        if constexpr (!kPaged) {
+            if (lane == 0) {
+                for (uint32_t i = 0; i < n_kv_tiles; ++i, ++g) {
+                    const uint32_t s = ring_stage(g);
+                    dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
+                    dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
+                    const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
+                    const int r0 = row_begin + i * 32;
+                    tma_load_2d(dst, &p.tm_k, head * HEAD_DIM, r0, full_u32 + 8 * s, pol);
+                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, head * HEAD_DIM, r0, full_u32 + 8 * s, pol);
+                }
+            }
+        } else {
+            // paged KV, page size 1: one 256-byte bulk copy per row per tensor, one row per lane
+            g = __shfl_sync(0xffffffffu, g, 0);
+            const __half* kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
+            const __half* vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
+            for (uint32_t i = 0; i < n_kv_tiles; ++i, ++g) {
+                const uint32_t s = ring_stage(g);
+                const int r = row_begin + i * 32 + lane;
+                const bool valid = r < row_end;
+                const long long slot = valid ? (long long)p.indices[kv_base + r] : 0;
+                const int nvalid = min(32, row_end - (row_begin + (int)i * 32));
+                if (lane == 0) {
+                    dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
+                    dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, nvalid * 2 * HEAD_DIM * 2);
+                }
+                __syncwarp();
+                if (valid) {
+                    const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES + lane * (HEAD_DIM * 2);
+                    bulk_load_1d(dst, kpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, full_u32 + 8 * s, pol);
+                    bulk_load_1d(dst + STAGE_BYTES / 2, vpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2,
+                                 full_u32 + 8 * s, pol);
+                }
+            }
+            g = __shfl_sync(0xffffffffu, g, 0);
+        }
+        // ---- phase 3: Wo tiles -----------------------------------------------------------------------
+        if (lane == 0) {
+            for (uint32_t i = 0; i < n_o_tiles; ++i, ++g) {
+                const uint32_t s = ring_stage(g);
+                dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
+                dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
+                int c0, c1;
+                if constexpr (kChat) {           // Wo^T [in][out]: 64 input rows x 128 output cols
+                    c0 = rank * KS + (i >> 1) * 128;
+                    c1 = head * HEAD_DIM + (i & 1) * 64;
+                } else {                         // Wo [out][in]: 64 output rows x this head's 128 input cols
+                    c0 = head * HEAD_DIM;
+                    c1 = rank * KS + i * 64;
+                }
+                tma_load_2d(smem_base + S::RING + s * STAGE_BYTES, &p.tm_wo, c0, c1, full_u32 + 8 * s, pol);
+            }
+        }
+        return;   // producer done; outstanding TMA completes on the consumers' barriers
+    }
+
+    // =============================================================================================
+    // CONSUMER WARPS (256 threads)
+    // =============================================================================================
+    float* xs = reinterpret_cast<float*>(smem + S::XS);
+    float* qkv_part = reinterpret_cast<float*>(smem + S::QKV_PART);
+    float* attn_part = reinterpret_cast<float*>(smem + S::ATTN_PART);
+    float* out_part = reinterpret_cast<float*>(smem + S::OUT_PART);
+    float* qkv_src = reinterpret_cast<float*>(smem + S::QKV_SRC);
+    float* qkv_recv = reinterpret_cast<float*>(smem + S::QKV_RECV);
+    float* attn_src = reinterpret_cast<float*>(smem + S::ATTN_SRC);
+    float* attn_recv = reinterpret_cast<float*>(smem + S::ATTN_RECV);
+    float* qkv_fin = reinterpret_cast<float*>(smem + S::QKV_FINAL);
+    float* attn_out = reinterpret_cast<float*>(smem + S::ATTN_OUT);
+    float* red = reinterpret_cast<float*>(smem + S::RED);
+    uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
+
+    const __half* xg = p.x + (size_t)batch * hidden;
+    const __half* rg = kChat ? nullptr : p.residual_in + (size_t)batch * hidden;
+    __half* rout = kChat ? nullptr : p.residual_out + (size_t)batch * hidden;
+    const bool residual_inplace = !kChat && (static_cast<const void*>(rout) == static_cast<const void*>(rg));
+
+    // ---- phase 0: RMSNorm ---------------------------------------------------------------------------
+    // every CTA reduces the full vector itself (8-16 KB from L2) -> no cluster round trip for a scalar
+    {
+        float ss = 0.f;
+        for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+            if constexpr (!kChat) {
+                float r8[8];
+                unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = round_h(f[k] + r8[k]);   // residual_out is fp16; norm the rounded sum
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ss += f[k] * f[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) red[warp] = ss;
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w];
+        const float rstd = rsqrtf(tot / (float)hidden + p.eps);
+        // normalised slice [rank*KS, +KS) -> fp32 smem, rounded where the eager fp16 model rounds
+        for (int e = tid * 8; e < KS; e += CONSUMER_THREADS * 8) {
+            const int ge = rank * KS + e;
+            float f[8], w8[8];
+            unpack8(*reinterpret_cast<const uint4*>(xg + ge), f);
+            unpack8(*reinterpret_cast<const uint4*>(p.rms_w + ge), w8);
+            if constexpr (!kChat) {
+                float r8[8];
+                unpack8(*reinterpret_cast<const uint4*>(rg + ge), r8);
+                __align__(16) __half hs[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { hs[k] = __float2half_rn(f[k] + r8[k]); f[k] = __half2float(hs[k]); }
+                if (head == 0 && !residual_inplace)
+                    *reinterpret_cast<uint4*>(rout + ge) = *reinterpret_cast<const uint4*>(hs);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xs[e + k] = round_h(round_h(f[k] * rstd) * w8[k]);
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+
+    uint32_t gbase = 0;   // global ring index of tile 0 of the current phase
+
+    // ---- phase 1: QKV GEMV over this CTA's K-slice ----------------------------------------------------
+    if constexpr (kChat) {
+        // tile i = 64 input rows (t = i / 3) x 128 output cols of matrix j = i % 3.  The QKV phase starts at
+        // ring index 0 and 12 % 3 == 0, so warp w only ever sees matrix j = w % 3: its 8 column sums stay in
+        // registers for the whole phase.  lane (sub, c): rows sub + 2s, cols c*8 .. c*8+7.
+        const int sub = lane >> 4, c = lane & 15;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (uint32_t i = first_tile(gbase, warp); i < n_qkv_tiles; i += CONSUMER_WARPS) {
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            ring_wait_full(full_u32, g);
+            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+            const float* xrow = xs + (i / 3) * 64;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const int row = 2 * r + sub;
+                float w8[8];
+                unpack8(tile[row * 16 + c], w8);
+                const float xv = xrow[row];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, w8[k], acc[k]);
+            }
+            __syncwarp();
+            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+        if (sub == 0) {      // write-once slot [warp][128]
+            float4* slot = reinterpret_cast<float4*>(qkv_part + warp * HEAD_DIM + c * 8);
+            slot[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            slot[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    } else {
+        // tile = 32 output rows x 256 input cols; lane owns input cols lane*8..+8 of every row
+        const int wins = KS / 256;
+        for (uint32_t i = first_tile(gbase, warp); i < n_qkv_tiles; i += CONSUMER_WARPS) {
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            const int rb = i / wins, win = i % wins;
+            float x8[8];
+            {
+                const float4 a = *reinterpret_cast<const float4*>(xs + win * 256 + lane * 8);
+                const float4 b = *reinterpret_cast<const float4*>(xs + win * 256 + lane * 8 + 4);
+                x8[0] = a.x; x8[1] = a.y; x8[2] = a.z; x8[3] = a.w;
+                x8[4] = b.x; x8[5] = b.y; x8[6] = b.z; x8[7] = b.w;
+            }
+            ring_wait_full(full_u32, g);
+            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+#pragma unroll
+            for (int grp = 0; grp < 4; ++grp) {
+                float v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    float w8[8];
+                    unpack8(tile[(grp * 8 + r) * 32 + lane], w8);
+                    float a = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a = fmaf(x8[k], w8[k], a);
+                    v[r] = a;
+                }
+                // transpose-reduce 8 values over 32 lanes: 4 + 2 + 1 + 1 + 1 shuffles
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const bool hi = lane & 16;
+                    const float send = hi ? v[r] : v[r + 4];
+                    const float keep = hi ? v[r + 4] : v[r];
+                    v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const bool hi = lane & 8;
+                    const float send = hi ? v[r] : v[r + 2];
+                    const float keep = hi ? v[r + 2] : v[r];
+                    v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                {
+                    const bool hi = lane & 4;
+                    const float send = hi ? v[0] : v[1];
+                    const float keep = hi ? v[1] : v[0];
+                    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+                // lane bits (4,3,2) select the row: row = 4*b4 + 2*b3 + b2
+                if ((lane & 3) == 0) {
+                    const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    qkv_part[win * S::QKV_OUT + rb * 32 + grp * 8 + r] = v[0];   // write-once slot
+                }
+            }
+            __syncwarp();
+            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+        }
+    }
+    gbase += n_qkv_tiles;
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+
+    // fold the write-once slots in a fixed order -> this CTA's partial q|k|v
+    {
+        for (int o = tid; o < S::QKV_OUT; o += CONSUMER_THREADS) {
+            float a = 0.f;
+            if constexpr (kChat) {      // matrix j = o / 128 was accumulated by warps j, j+3, j+6, j+9
+                for (int w = o >> 7; w < CONSUMER_WARPS; w += 3) a += qkv_part[w * HEAD_DIM + (o & 127)];
+            } else {
+                const int nslots = KS / 256;
+                for (int sl = 0; sl < nslots; ++sl) a += qkv_part[sl * S::QKV_OUT + o];
+            }
+            qkv_src[o] = a;
+        }
+    }
+    // first remote access of the kernel: all CTAs of the cluster have armed their barriers by now
+    dsm::cluster_wait();
+    uint32_t xphase0 = 0, xphase1 = 0;
+    cluster_reduce<CLUSTER, Stage::LINEAR, CONSUMER_THREADS, CONSUMER_BAR>(
+        S::QKV_OUT * 4, tid, HEAD_DIM, rank,
+        smem_base + S::QKV_SRC, smem_base + S::QKV_RECV, xbar_u32, xphase0, qkv_src, qkv_recv);
+
+    // ---- RoPE (fp16 rounding points of the eager model), new K/V out -------------------------------
+    {
+        constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;   // 1/sqrt(128) * log2(e)
+        const float* cosp = p.cos;
+        const float* sinp = p.sin;
+        if constexpr (kPaged) {
+            cosp = p.cos + p.positions[batch] * HEAD_DIM;
+            sinp = cosp + HEAD_DIM / 2;
+        }
+        if (tid < 2 * HEAD_DIM) {
+            const int which = tid >> 7, d = tid & 127;          // 0: q, 1: k
+            const float* v = qkv_src + which * HEAD_DIM;
+            const float a = round_h(v[d]);
+            float rot;
+            if constexpr (kChat) {                              // GPT-J pairs (2i, 2i+1), cos/sin pair-repeated
+                const float b = round_h(v[d ^ 1]);
+                rot = (d & 1) ? fmaf(a, cosp[d], b * sinp[d]) : fmaf(a, cosp[d], -b * sinp[d]);
+            } else {                                            // NeoX pairs (i, i+64), cos/sin [64]
+                const float b = round_h(v[d ^ 64]);
+                const int i = d & 63;
+                rot = (d & 64) ? fmaf(a, cosp[i], b * sinp[i]) : fmaf(a, cosp[i], -b * sinp[i]);
+            }
+            const __half rh = __float2half_rn(rot);
+            qkv_fin[tid] = which == 0 ? __half2float(rh) * kScaleLog2 : __half2float(rh);
+            if (which == 1 && rank == 0) {
+                if constexpr (kPaged) {
+                    __half* kpool = reinterpret_cast<__half*>(p.k_pool_ptrs[p.layer_id]);
+                    kpool[(size_t)new_slot * kv_cols + head * HEAD_DIM + d] = rh;
+                } else {
+                    p.k_new[head * HEAD_DIM + d] = rh;
+                }
+            }
+        } else if (tid < 3 * HEAD_DIM) {
+            const int d = tid - 2 * HEAD_DIM;
+            const __half vh = __float2half_rn(qkv_src[2 * HEAD_DIM + d]);
+            qkv_fin[2 * HEAD_DIM + d] = __half2float(vh);
+            if (rank == 0) {
+                if constexpr (kPaged) {
+                    __half* vpool = reinterpret_cast<__half*>(p.v_pool_ptrs[p.layer_id]);
+                    vpool[(size_t)new_slot * kv_cols + head * HEAD_DIM + d] = vh;
+                } else {
+                    p.v_new[head * HEAD_DIM + d] = vh;
+                }
+            }
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+
+    // ---- phase 2: flash-decode over this CTA's KV rows -----------------------------------------------
+    {
+        const int sub = lane >> 4, c = lane & 15;
+        float q8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q8[k] = qkv_fin[c * 8 + k];
+        float m = -INFINITY, l = 0.f;
+        float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (uint32_t i = first_tile(gbase, warp); i < n_kv_tiles; i += CONSUMER_WARPS) {
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            ring_wait_full(full_u32, g);
+            const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+            const uint4* vt = kt + STAGE_BYTES / 32;
+            const int rows_left = row_end - (row_begin + (int)i * 32);     // >= 1
+            float sc[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int row = 2 * jj + sub;
+                float k8[8];
+                unpack8(kt[row * 16 + c], k8);
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a = fmaf(q8[k], k8[k], a);
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 4);
+                a += __shfl_xor_sync(0xffffffffu, a, 8);
+                sc[jj] = (row < rows_left) ? a : -INFINITY;
+            }
+            float mx = sc[0];
+#pragma unroll
+            for (int jj = 1; jj < 16; ++jj) mx = fmaxf(mx, sc[jj]);
+            const float m_new = fmaxf(m, mx);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            const float corr = dsm::exp2_diff(m, m_use);
+            l *= corr;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o8[k] *= corr;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int row = 2 * jj + sub;
+                const float pr = dsm::fast_exp2(sc[jj] - m_use);       // -inf -> 0
+                l += pr;
+                uint4 raw = vt[row * 16 + c];
+                if constexpr (kPaged) {                                   // rows past the end were never copied
+                    if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
+                }
+                float v8[8];
+                unpack8(raw, v8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o8[k] = fmaf(pr, v8[k], o8[k]);
+            }
+            m = m_new;
+            __syncwarp();
+            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+        }
+        gbase += n_kv_tiles;
+        // per half-warp state -> smem group slot (16 groups)
+        {
+            const int grp = warp * 2 + sub;                    // 2 * CONSUMER_WARPS groups
+            float* slot = attn_part + grp * S::ATTN_PAYLOAD;
+            if (c == 0) { slot[0] = m; slot[1] = l; }
+            *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+            *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+        }
+        // the current token's score (rank 0 folds it in as one more group)
+        if (warp == 0) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a = fmaf(qkv_fin[lane * 4 + k], qkv_fin[HEAD_DIM + lane * 4 + k], a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) red[CONSUMER_WARPS] = a;
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        if (tid < HEAD_DIM) {
+            const bool with_new = (rank == 0);
+            float M = with_new ? red[CONSUMER_WARPS] : -INFINITY;
+#pragma unroll
+            for (int gI = 0; gI < 2 * CONSUMER_WARPS; ++gI) M = fmaxf(M, attn_part[gI * S::ATTN_PAYLOAD]);
+            float L = 0.f, O = 0.f;
+#pragma unroll
+            for (int gI = 0; gI < 2 * CONSUMER_WARPS; ++gI) {
+                const float w = dsm::exp2_diff(attn_part[gI * S::ATTN_PAYLOAD], M);
+                L = fmaf(attn_part[gI * S::ATTN_PAYLOAD + 1], w, L);
+                O = fmaf(attn_part[gI * S::ATTN_PAYLOAD + 4 + tid], w, O);
+            }
+            if (with_new) {
+                const float w = dsm::exp2_diff(red[CONSUMER_WARPS], M);
+                L += w;
+                O = fmaf(qkv_fin[2 * HEAD_DIM + tid], w, O);
+            }
+            attn_src[4 + tid] = O;
+            if (tid == 0) { attn_src[0] = M; attn_src[1] = L; attn_src[2] = 0.f; attn_src[3] = 0.f; }
+        }
+        cluster_reduce<CLUSTER, Stage::ATTN, CONSUMER_THREADS, CONSUMER_BAR>(
+            S::ATTN_PAYLOAD * 4, tid, HEAD_DIM, rank,
+            smem_base + S::ATTN_SRC, smem_base + S::ATTN_RECV, xbar_u32 + 8, xphase1, attn_src, attn_recv);
+        if (tid < HEAD_DIM) attn_out[tid] = round_h(attn_src[4 + tid] / attn_src[1]);
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+
+    // ---- phase 3: O GEMV for output columns [rank*KS, +KS) --------------------------------------------
+    if constexpr (kChat) {
+        // tile = 64 input rows (half of the head) x 128 output cols; lane (sub, c): rows sub+2s, cols c*8..+8
+        const int sub = lane >> 4, c = lane & 15;
+        for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            ring_wait_full(full_u32, g);
+            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+            const int cb = i >> 1, rh = i & 1;
+            const float* arow = attn_out + rh * 64;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const int row = 2 * r + sub;
+                float w8[8];
+                unpack8(tile[row * 16 + c], w8);
+                const float av = arow[row];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(av, w8[k], acc[k]);
+            }
+            __syncwarp();
+            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+            if (sub == 0) {
+                float4* dstp = reinterpret_cast<float4*>(out_part + rh * KS + cb * 128 + c * 8);
+                dstp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                dstp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+        }
+    } else {
+        // tile = 64 output rows x 128 input cols; lane (sub, c): rows sub+2s, input cols c*8..+8
+        const int sub = lane >> 4, c = lane & 15;
+        float a8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a8[k] = attn_out[c * 8 + k];
+        for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            ring_wait_full(full_u32, g);
+            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+#pragma unroll
+            for (int grp = 0; grp < 4; ++grp) {
+                float v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int row = 2 * (grp * 8 + r) + sub;
+                    float w8[8];
+                    unpack8(tile[row * 16 + c], w8);
+                    float a = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a = fmaf(a8[k], w8[k], a);
+                    v[r] = a;
+                }
+                // transpose-reduce 8 values over the 16 lanes of a half-warp: 4 + 2 + 1 + 1 shuffles
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const bool hi = lane & 8;
+                    const float send = hi ? v[r] : v[r + 4];
+                    const float keep = hi ? v[r + 4] : v[r];
+                    v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const bool hi = lane & 4;
+                    const float send = hi ? v[r] : v[r + 2];
+                    const float keep = hi ? v[r + 2] : v[r];
+                    v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                {
+                    const bool hi = lane & 2;
+                    const float send = hi ? v[0] : v[1];
+                    const float keep = hi ? v[1] : v[0];
+                    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+                if ((lane & 1) == 0) {
+                    const int r = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    out_part[i * 64 + 2 * (grp * 8 + r) + sub] = v[0];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+        }
+    }
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+
+    // ---- cross-head reduction: fp32 red into scratch, last arriver of the slice finalises --------------
+    float* scratch = p.scratch + (size_t)batch * hidden + rank * KS;
+    for (int e = tid * 4; e < KS; e += CONSUMER_THREADS * 4) {
+        float4 v = *reinterpret_cast<const float4*>(out_part + e);
+        if constexpr (kChat) {
+            const float4 w = *reinterpret_cast<const float4*>(out_part + KS + e);
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        red_add_v4(scratch + e, v);
+    }
+    __threadfence();
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    unsigned* counters = p.counters + (size_t)batch * (CLUSTER + 1);
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(&counters[rank], 1u);
+        sflags[0] = (prev == (unsigned)p.n_heads - 1u);
+    }
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    if (sflags[0]) {
+        __threadfence();
+        const bool fp32_out = p.flags & 1u;
+        for (int e = tid * 4; e < KS; e += CONSUMER_THREADS * 4) {
+            const float4 v = ld_cg_v4(scratch + e);
+            *reinterpret_cast<float4*>(scratch + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const size_t off = (size_t)batch * hidden + rank * KS + e;
+            if (fp32_out) {
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
+            } else {
+                __align__(8) __half h4[4] = {__float2half_rn(v.x), __float2half_rn(v.y),
+                                             __float2half_rn(v.z), __float2half_rn(v.w)};
+                *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
+            }
+        }
+        if (tid == 0) counters[rank] = 0u;
+        if constexpr (!kChat) {
+            if (residual_inplace) {
+                // in-place residual update is deferred to the very last CTA of the request: every other
+                // CTA has finished reading `residual` by then (the reference races here)
+                __threadfence();
+                dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+                if (tid == 0) {
+                    const unsigned prev = atomicAdd(&counters[CLUSTER], 1u);
+                    sflags[1] = (prev == (unsigned)CLUSTER - 1u);
+                    if (sflags[1]) counters[CLUSTER] = 0u;
+                }
+                dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+                if (sflags[1]) {
+                    for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+                        float f[8], r8[8];
+                        unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+                        unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+                        __align__(16) __half hs[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) hs[k] = __float2half_rn(f[k] + r8[k]);
+                        *reinterpret_cast<uint4*>(rout + e) = *reinterpret_cast<const uint4*>(hs);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace cfb

@@ -1,0 +1,228 @@
+/*
+ * PyTorch C++ extension `_clusterfusion`: the reference's Python-facing operator surface
+ * (/root/reference/include/pybind.cpp:108-123) on top of the torch-free C ABI
+ * (include/clusterfusion_b200.h).  Same names, same positional argument order, same return
+ * conventions as the reference:
+ *
+ *   llama_decoder_layer(input, weight_qkv, weight_o, k_cache, v_cache, rms_w, cos, sin)
+ *        -> (o [1,hidden], k [1,H,128], v [1,H,128])                      pybind.cpp:3-12
+ *   llama_decoder_layer_sglang(input, residual, weight_qkv, weight_o, k_cache, v_cache, rms_w,
+ *                              eps, cos, sin) -> (o, residual, k, v)      pybind.cpp:14-25
+ *        (`residual` is updated in place and returned, llama_kernel_sglang_dispatch.cu:150)
+ *   llama_decoder_layer_batch_decode_sglang(output, residual_output, input, residual, weight_qkv,
+ *        weight_o, paged_kv_indptr, paged_kv_indices, k_cache_ptrs, v_cache_ptrs, layer_id,
+ *        rms_w, eps, positions, cos_sin) -> None                           pybind.cpp:27-43
+ *   llama_decoder_layer(<the same 15 arguments>)  -- the call the reference README shows (README.md:55-75)
+ *
+ * What this shim does that the reference's dispatch files do not: TORCH_CHECKs on
+ * device / dtype / contiguity / shape, launches on the CURRENT stream of the input's device,
+ * never synchronises, allocates outputs with empty() (no memset kernels), and raises RuntimeError
+ * with the C ABI's message on failure.
+ */
+#include <torch/extension.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "../../include/clusterfusion_b200.h"
+
+namespace {
+
+using torch::Tensor;
+
+void check_cuda_contig(const Tensor& t, const char* name, c10::ScalarType dtype) {
+    TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+    TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+    TORCH_CHECK(t.scalar_type() == dtype, name, " must have dtype ", dtype, " (got ", t.scalar_type(), ")");
+}
+
+// One zero-initialised workspace per (device, stream): the kernel leaves it zeroed, so it is
+// memset exactly once in the life of the process.  Grows (never shrinks) with hidden * batch.
+Tensor workspace_for(const Tensor& like, int hidden, int batch, cudaStream_t stream) {
+    static std::mutex mu;
+    static std::map<std::pair<int, void*>, Tensor> cache;
+    const size_t need = cf_llama_workspace_bytes(hidden, batch);
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair((int)like.get_device(), (void*)stream);
+    auto it = cache.find(key);
+    if (it == cache.end() || (size_t)it->second.numel() < need) {
+        Tensor ws = torch::zeros({(int64_t)need}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device()));
+        cache[key] = ws;
+        return ws;
+    }
+    return it->second;
+}
+
+void run(const CfLlamaArgs& a, cudaStream_t stream) {
+    const int rc = cf_llama_decoder_layer_launch(&a, stream);
+    TORCH_CHECK(rc == 0, "clusterfusion_b200: launch failed (", rc, "): ", cf_last_error_string());
+}
+
+std::tuple<Tensor, Tensor, Tensor> llama_decoder_layer(
+    Tensor input, Tensor weight_qkv, Tensor weight_o, Tensor k_cache, Tensor v_cache,
+    Tensor rms_input_weight, Tensor cos, Tensor sin)
+{
+    check_cuda_contig(input, "input", torch::kHalf);
+    check_cuda_contig(weight_qkv, "weight_qkv", torch::kHalf);
+    check_cuda_contig(weight_o, "weight_o", torch::kHalf);
+    check_cuda_contig(k_cache, "k_cache", torch::kHalf);
+    check_cuda_contig(v_cache, "v_cache", torch::kHalf);
+    check_cuda_contig(rms_input_weight, "rms_input_weight", torch::kHalf);
+    check_cuda_contig(cos, "cos", torch::kFloat);
+    check_cuda_contig(sin, "sin", torch::kFloat);
+    const int64_t hidden = input.size(-1);
+    TORCH_CHECK(input.numel() == hidden, "input must hold one token: [1, hidden] or [1, 1, hidden]");
+    TORCH_CHECK(weight_qkv.dim() == 2 && weight_qkv.size(0) == 3 * hidden && weight_qkv.size(1) == hidden,
+                "weight_qkv must be [3*hidden, hidden] = [Wq^T; Wk^T; Wv^T]");
+    TORCH_CHECK(weight_o.dim() == 2 && weight_o.size(0) == hidden && weight_o.size(1) == hidden,
+                "weight_o must be [hidden, hidden] = Wo^T");
+    TORCH_CHECK(k_cache.dim() == 2 && k_cache.size(1) == hidden, "k_cache must be [kv_len, hidden]");
+    TORCH_CHECK(v_cache.sizes() == k_cache.sizes(), "v_cache must match k_cache");
+    TORCH_CHECK(rms_input_weight.numel() == hidden, "rms_input_weight must be [hidden]");
+    TORCH_CHECK(cos.numel() >= 128 && sin.numel() >= 128, "cos / sin must be [1, 128] (pair-repeated)");
+    const int n_heads = (int)(hidden / 128);
+
+    const c10::cuda::CUDAGuard guard(input.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
+    auto opt = input.options();
+    Tensor o = torch::empty({1, hidden}, opt);
+    Tensor k = torch::empty({1, n_heads, 128}, opt);
+    Tensor v = torch::empty({1, n_heads, 128}, opt);
+    Tensor ws = workspace_for(input, (int)hidden, 1, stream);
+
+    CfLlamaArgs a{};
+    a.variant = CF_VARIANT_CHAT;
+    a.hidden = (int)hidden; a.n_q_heads = n_heads; a.n_kv_heads = n_heads; a.head_dim = 128; a.batch = 1;
+    a.kv_len = (uint32_t)k_cache.size(0);
+    a.eps = 1e-6f;      // fixed by the reference's 8-argument kernel (kernel.cuh:58)
+    a.x = input.data_ptr(); a.w_qkv = weight_qkv.data_ptr(); a.w_o = weight_o.data_ptr();
+    a.rms_w = rms_input_weight.data_ptr();
+    a.out = o.data_ptr(); a.k_new = k.data_ptr(); a.v_new = v.data_ptr();
+    a.k_cache = k_cache.data_ptr(); a.v_cache = v_cache.data_ptr();
+    a.cos = cos.data_ptr<float>(); a.sin = sin.data_ptr<float>();
+    a.workspace = ws.data_ptr();
+    run(a, stream);
+    return std::make_tuple(o, k, v);
+}
+
+std::tuple<Tensor, Tensor, Tensor, Tensor> llama_decoder_layer_sglang(
+    Tensor input, Tensor residual, Tensor weight_qkv, Tensor weight_o, Tensor k_cache, Tensor v_cache,
+    Tensor rms_input_weight, double eps, Tensor cos, Tensor sin)
+{
+    check_cuda_contig(input, "input", torch::kHalf);
+    check_cuda_contig(residual, "residual", torch::kHalf);
+    check_cuda_contig(weight_qkv, "weight_qkv", torch::kHalf);
+    check_cuda_contig(weight_o, "weight_o", torch::kHalf);
+    check_cuda_contig(k_cache, "k_cache", torch::kHalf);
+    check_cuda_contig(v_cache, "v_cache", torch::kHalf);
+    check_cuda_contig(rms_input_weight, "rms_input_weight", torch::kHalf);
+    check_cuda_contig(cos, "cos", torch::kFloat);
+    check_cuda_contig(sin, "sin", torch::kFloat);
+    const int64_t hidden = input.size(-1);
+    TORCH_CHECK(input.numel() == hidden && residual.numel() == hidden, "input / residual must hold one token");
+    TORCH_CHECK(weight_o.dim() == 2 && weight_o.size(0) == hidden && weight_o.size(1) % 128 == 0,
+                "weight_o must be [hidden, n_heads*128] (nn.Linear layout)");
+    const int64_t qd = weight_o.size(1);
+    TORCH_CHECK(weight_qkv.dim() == 2 && weight_qkv.size(1) == hidden && weight_qkv.size(0) > qd &&
+                (weight_qkv.size(0) - qd) % 256 == 0, "weight_qkv must be [(n_q + 2*n_kv)*128, hidden]");
+    const int64_t kvd = (weight_qkv.size(0) - qd) / 2;
+    TORCH_CHECK(k_cache.dim() == 2 && k_cache.size(1) == kvd, "k_cache must be [kv_len, n_kv*128]");
+    TORCH_CHECK(v_cache.sizes() == k_cache.sizes(), "v_cache must match k_cache");
+    TORCH_CHECK(rms_input_weight.numel() == hidden, "rms_input_weight must be [hidden]");
+    TORCH_CHECK(cos.numel() >= 64 && sin.numel() >= 64, "cos / sin must hold at least head_dim/2 = 64 floats");
+
+    const c10::cuda::CUDAGuard guard(input.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
+    auto opt = input.options();
+    Tensor o = torch::empty({1, hidden}, opt);
+    Tensor k = torch::empty({1, kvd / 128, 128}, opt);
+    Tensor v = torch::empty({1, kvd / 128, 128}, opt);
+    Tensor ws = workspace_for(input, (int)hidden, 1, stream);
+
+    CfLlamaArgs a{};
+    a.variant = CF_VARIANT_SGLANG;
+    a.hidden = (int)hidden; a.n_q_heads = (int)(qd / 128); a.n_kv_heads = (int)(kvd / 128); a.head_dim = 128;
+    a.batch = 1;
+    a.kv_len = (uint32_t)k_cache.size(0);
+    a.eps = (float)eps;
+    a.x = input.data_ptr(); a.residual_in = residual.data_ptr(); a.residual_out = residual.data_ptr();
+    a.w_qkv = weight_qkv.data_ptr(); a.w_o = weight_o.data_ptr(); a.rms_w = rms_input_weight.data_ptr();
+    a.out = o.data_ptr(); a.k_new = k.data_ptr(); a.v_new = v.data_ptr();
+    a.k_cache = k_cache.data_ptr(); a.v_cache = v_cache.data_ptr();
+    a.cos = cos.data_ptr<float>(); a.sin = sin.data_ptr<float>();
+    a.workspace = ws.data_ptr();
+    run(a, stream);
+    return std::make_tuple(o, residual, k, v);
+}
+
+void llama_decoder_layer_batch_decode_sglang(
+    Tensor output, Tensor residual_output, Tensor input, Tensor residual, Tensor weight_qkv, Tensor weight_o,
+    Tensor paged_kv_indptr, Tensor paged_kv_indices, Tensor k_cache_ptrs, Tensor v_cache_ptrs, int64_t layer_id,
+    Tensor rms_input_weight, double eps, Tensor positions, Tensor cos_sin)
+{
+    check_cuda_contig(output, "output", torch::kHalf);
+    check_cuda_contig(residual_output, "residual_output", torch::kHalf);
+    check_cuda_contig(input, "input", torch::kHalf);
+    check_cuda_contig(residual, "residual", torch::kHalf);
+    check_cuda_contig(weight_qkv, "weight_qkv", torch::kHalf);
+    check_cuda_contig(weight_o, "weight_o", torch::kHalf);
+    check_cuda_contig(paged_kv_indptr, "paged_kv_indptr", torch::kInt);
+    check_cuda_contig(paged_kv_indices, "paged_kv_indices", torch::kInt);
+    check_cuda_contig(rms_input_weight, "rms_input_weight", torch::kHalf);
+    check_cuda_contig(positions, "positions", torch::kLong);
+    check_cuda_contig(cos_sin, "cos_sin", torch::kFloat);
+    TORCH_CHECK(k_cache_ptrs.is_cuda() && v_cache_ptrs.is_cuda() && k_cache_ptrs.is_contiguous() &&
+                v_cache_ptrs.is_contiguous() && k_cache_ptrs.element_size() == 8 && v_cache_ptrs.element_size() == 8,
+                "k_cache_ptrs / v_cache_ptrs must be contiguous CUDA tensors of 64-bit pointers");
+    TORCH_CHECK(input.dim() == 2, "input must be [batch, hidden]");
+    const int64_t bs = input.size(0), hidden = input.size(1);
+    TORCH_CHECK(residual.sizes() == input.sizes() && output.sizes() == input.sizes() &&
+                residual_output.sizes() == input.sizes(), "output / residual_output / residual must be [batch, hidden]");
+    TORCH_CHECK(weight_o.dim() == 2 && weight_o.size(0) == hidden && weight_o.size(1) % 128 == 0,
+                "weight_o must be [hidden, n_heads*128]");
+    const int64_t qd = weight_o.size(1);
+    TORCH_CHECK(weight_qkv.dim() == 2 && weight_qkv.size(1) == hidden && weight_qkv.size(0) > qd &&
+                (weight_qkv.size(0) - qd) % 256 == 0, "weight_qkv must be [(n_q + 2*n_kv)*128, hidden]");
+    const int64_t kvd = (weight_qkv.size(0) - qd) / 2;
+    TORCH_CHECK(paged_kv_indptr.numel() == bs + 1, "paged_kv_indptr must be [batch + 1]");
+    TORCH_CHECK(positions.numel() == bs, "positions must be [batch]");
+    TORCH_CHECK(layer_id >= 0 && layer_id < k_cache_ptrs.numel() && layer_id < v_cache_ptrs.numel(), "layer_id out of range");
+    TORCH_CHECK(cos_sin.dim() == 2 && cos_sin.size(1) == 128, "cos_sin must be [max_pos, 128] = [cos(64) | sin(64)]");
+
+    const c10::cuda::CUDAGuard guard(input.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
+    Tensor ws = workspace_for(input, (int)hidden, (int)bs, stream);
+
+    CfLlamaArgs a{};
+    a.variant = CF_VARIANT_PAGED;
+    a.hidden = (int)hidden; a.n_q_heads = (int)(qd / 128); a.n_kv_heads = (int)(kvd / 128); a.head_dim = 128;
+    a.batch = (int)bs;
+    a.layer_id = (int)layer_id;
+    a.eps = (float)eps;
+    a.x = input.data_ptr(); a.residual_in = residual.data_ptr(); a.residual_out = residual_output.data_ptr();
+    a.w_qkv = weight_qkv.data_ptr(); a.w_o = weight_o.data_ptr(); a.rms_w = rms_input_weight.data_ptr();
+    a.out = output.data_ptr();
+    a.indptr = paged_kv_indptr.data_ptr<int>(); a.indices = paged_kv_indices.data_ptr<int>();
+    a.k_pool_ptrs = static_cast<const uint64_t*>(k_cache_ptrs.data_ptr());
+    a.v_pool_ptrs = static_cast<const uint64_t*>(v_cache_ptrs.data_ptr());
+    a.positions = positions.data_ptr<int64_t>();
+    a.cos = cos_sin.data_ptr<float>();
+    a.workspace = ws.data_ptr();
+    run(a, stream);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.doc() = "clusterfusion_b200: B200-native fused Llama decoder attention half-layer (sm_100a)";
+    m.def("llama_decoder_layer", &llama_decoder_layer, "");
+    // the README example of the reference calls the 15-argument paged form under this name
+    m.def("llama_decoder_layer", &llama_decoder_layer_batch_decode_sglang, "");
+    m.def("llama_decoder_layer_sglang", &llama_decoder_layer_sglang, "");
+    m.def("llama_decoder_layer_batch_decode_sglang", &llama_decoder_layer_batch_decode_sglang, "");
+    m.def("abi_version", []() { return cf_abi_version(); });
+    m.def("workspace_bytes", [](int hidden, int batch) { return cf_llama_workspace_bytes(hidden, batch); });
+}

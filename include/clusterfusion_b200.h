@@ -1,0 +1,118 @@
+/*
+ * clusterfusion_b200 -- C ABI of the B200-native fused Llama decoder attention half-layer.
+ *
+ * This is the drop-in boundary below the reference's pybind layer.  One entry point launches
+ * the single fused sm_100a kernel for any of the reference's three operator signatures:
+ *
+ *   variant CF_VARIANT_CHAT    replaces  llama_decoder_layer_sm90
+ *       /root/reference/include/H100/llama/llama_kernel_dispatch.cu:4-146   (pybind.cpp:3-12, :110)
+ *   variant CF_VARIANT_SGLANG  replaces  llama_decoder_layer_sglang_sm90
+ *       /root/reference/include/H100/llama/llama_kernel_sglang_dispatch.cu:4-151 (pybind.cpp:14-25, :111)
+ *   variant CF_VARIANT_PAGED   replaces  llama_decoder_layer_batch_sglang_sm90
+ *       /root/reference/include/H100/llama/llama_kernel_batch_sglang_dispatch.cu:6-111 (pybind.cpp:27-43, :112)
+ *
+ * Plain pointers and sizes only: no torch types.  All pointers are device pointers on the
+ * current CUDA device; fp16 tensors are IEEE binary16, contiguous.  Calls are asynchronous on
+ * `stream` (a cudaStream_t), issue exactly one kernel launch, never synchronise and never
+ * allocate, so they may be captured into a CUDA graph.
+ *
+ * Error convention: 0 = success; > 0 = a cudaError_t / CUresult from the runtime;
+ * < 0 = CF_ERR_* (bad argument).  Never throws.  cf_last_error_string() describes the last
+ * failure on the calling thread.
+ */
+#ifndef CLUSTERFUSION_B200_H
+#define CLUSTERFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CF_ABI_VERSION 1
+
+enum {
+    CF_VARIANT_CHAT = 0,   /* W^T weights, GPT-J interleaved RoPE, eps fixed by caller (1e-6), no residual   */
+    CF_VARIANT_SGLANG = 1, /* [out,in] weights, NeoX RoPE, fused residual add, contiguous KV                  */
+    CF_VARIANT_PAGED = 2   /* SGLANG + batch + paged KV (page size 1) + in-pool KV append                     */
+};
+
+enum {
+    CF_ERR_NULL_ARG = -1,
+    CF_ERR_BAD_VARIANT = -2,
+    CF_ERR_BAD_SHAPE = -3,     /* unsupported hidden / heads / head_dim combination */
+    CF_ERR_BAD_ALIGNMENT = -4, /* a tensor is not 16-byte aligned                   */
+    CF_ERR_NO_DEVICE = -5,     /* current device is not sm_100 (B200)               */
+    CF_ERR_DRIVER = -6         /* cuTensorMapEncodeTiled entry point unavailable    */
+};
+
+/* flags */
+#define CF_FLAG_OUT_FP32_PARTIAL 0x1u /* head-parallel shard: write the fp32 O-projection partial to `out`
+                                         (float[batch, hidden]) instead of an fp16 result; the caller
+                                         all-reduces it across ranks (Llama-2-70B config).             */
+
+typedef struct CfLlamaArgs {
+    int32_t variant;    /* CF_VARIANT_*                                                             */
+    uint32_t flags;     /* CF_FLAG_*                                                                */
+    int32_t hidden;     /* model width (input of Wqkv, output of Wo); multiple of 1024, <= 8192     */
+    int32_t n_q_heads;  /* query heads held by THIS call (a shard passes its local count)           */
+    int32_t n_kv_heads; /* KV heads held by this call; n_q_heads % n_kv_heads == 0                  */
+    int32_t head_dim;   /* must be 128                                                              */
+    int32_t batch;      /* 1 for CHAT / SGLANG; >= 1 for PAGED                                      */
+    uint32_t kv_len;    /* CHAT / SGLANG: rows of k_cache / v_cache (may be 0)                      */
+    int32_t layer_id;   /* PAGED: index into k_pool_ptrs / v_pool_ptrs                              */
+    float eps;          /* RMSNorm epsilon (the reference's 8-arg form hard-codes 1e-6)             */
+
+    const void* x;           /* fp16 [batch, hidden]                                                */
+    const void* residual_in; /* fp16 [batch, hidden]; NULL for CHAT                                 */
+    const void* w_qkv;       /* CHAT: fp16 [3*hidden, hidden] = [Wq^T; Wk^T; Wv^T]
+                                else: fp16 [(n_q+2*n_kv)*128, hidden]  (nn.Linear layout)          */
+    const void* w_o;         /* CHAT: fp16 [n_q*128, hidden] = Wo^T;  else fp16 [hidden, n_q*128]   */
+    const void* rms_w;       /* fp16 [hidden]                                                       */
+
+    void* out;          /* fp16 [batch, hidden]  (float with CF_FLAG_OUT_FP32_PARTIAL)              */
+    void* residual_out; /* fp16 [batch, hidden]; may alias residual_in (in-place, race-free); NULL for CHAT */
+    void* k_new;        /* fp16 [n_kv*128]  post-RoPE K of the new token (CHAT / SGLANG)            */
+    void* v_new;        /* fp16 [n_kv*128]                                                          */
+
+    const void* k_cache; /* CHAT / SGLANG: fp16 [kv_len, n_kv*128]                                  */
+    const void* v_cache;
+
+    const int32_t* indptr;       /* PAGED: int32 [batch+1]                                          */
+    const int32_t* indices;      /* PAGED: int32 [nnz]; last entry of a request = slot of the new token */
+    const uint64_t* k_pool_ptrs; /* PAGED: device array of per-layer pool base pointers             */
+    const uint64_t* v_pool_ptrs; /*        each pool fp16 [num_slots, n_kv*128]                     */
+    const int64_t* positions;    /* PAGED: int64 [batch]                                            */
+
+    const float* cos; /* CHAT: fp32 [128] pair-repeated; SGLANG: fp32 [>=64]; PAGED: cos_sin fp32 [max_pos,128] */
+    const float* sin; /* CHAT / SGLANG as cos; PAGED: unused                                        */
+
+    void* workspace;  /* cf_llama_workspace_bytes() bytes, zero-filled ONCE by the caller; the kernel
+                         returns it zeroed.  One workspace per stream that may run concurrently.    */
+} CfLlamaArgs;
+
+/* Bytes of zero-initialised device workspace needed for a call with this hidden / batch. */
+size_t cf_llama_workspace_bytes(int32_t hidden, int32_t batch);
+
+/* Validate, encode (cached) TMA descriptors, launch the fused kernel on `stream`. */
+int cf_llama_decoder_layer_launch(const CfLlamaArgs* args, void* stream);
+
+/* Algorithmic HBM bytes of one call (SURVEY.md section 8d formula) -- used by bench / tests. */
+uint64_t cf_llama_algorithmic_bytes(const CfLlamaArgs* args, uint64_t total_kv_rows);
+
+/* Unit-test hook for the device primitive in include/dsm.cuh:
+ * launches n_clusters clusters of `cluster_size` CTAs; CTA r of cluster c contributes
+ * in[(c*cluster_size + r)*n .. +n) (float); stage 0 = LINEAR (sum), 1 = ATTN (softmax-state merge of
+ * [m, l, pad, pad, o[n-4]]), 4 = QUK_DEEPSEEK (all-gather).  Every CTA writes its result to
+ * out[(c*cluster_size + r) * n_out ..], n_out = n (sum / merge) or n*cluster_size (gather).      */
+int cf_test_cluster_reduce(const float* in, float* out, int32_t n, int32_t cluster_size,
+                           int32_t n_clusters, int32_t stage, int32_t repeats, void* stream);
+
+const char* cf_last_error_string(void);
+int cf_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLUSTERFUSION_B200_H */

@@ -1,0 +1,68 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares, the pybind module exposes the reference's operator names, and misuse fails loudly.  No compute."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    h = (ROOT / "include" / "clusterfusion_b200.h").read_text()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(cf_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_header_symbols_all_exported():
+    from clusterfusion_b200 import cabi
+    lib = cabi.load()
+    syms = declared_symbols()
+    assert set(syms) == set(cabi.EXPORTED_SYMBOLS), syms
+    for s in syms:
+        assert getattr(lib, s) is not None
+    assert lib.cf_abi_version() == 1
+
+
+def test_workspace_and_bytes_model():
+    from clusterfusion_b200 import cabi
+    assert cabi.workspace_bytes(4096, 1) >= 4096 * 4 + 5 * 4
+    assert cabi.workspace_bytes(4096, 3) >= 3 * (4096 * 4 + 5 * 4)
+    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_CHAT, hidden=4096, n_q_heads=32, n_kv_heads=32, head_dim=128, batch=1)
+    # Llama-2-7B, kv 1K -> 151 036 928 B; kv 16K -> 402 695 168 B
+    assert cabi.algorithmic_bytes(a, 1024) == 151_036_928 - 41_984 + (2 * 4096 * 3 + 2 * 2 * 4096 + 2 * 4 * 128)
+    assert abs(cabi.algorithmic_bytes(a, 16384) - 402_695_168) < 64 * 1024
+
+
+def test_argument_errors_without_gpu():
+    from clusterfusion_b200 import cabi
+    with pytest.raises(cabi.CfError) as e:
+        cabi.launch(cabi.CfLlamaArgs(variant=9))
+    assert e.value.code == -2 and "variant" in str(e.value)
+    with pytest.raises(cabi.CfError) as e:
+        cabi.launch(cabi.CfLlamaArgs(variant=0, head_dim=64))
+    assert e.value.code == -3
+    with pytest.raises(cabi.CfError) as e:
+        cabi.launch(cabi.CfLlamaArgs(variant=0, head_dim=128, hidden=4096, n_q_heads=32, n_kv_heads=32, batch=1))
+    assert e.value.code == -1      # NULL tensors
+
+
+def test_pybind_surface_matches_reference_names():
+    import clusterfusion
+    for name in ("llama_decoder_layer", "llama_decoder_layer_sglang", "llama_decoder_layer_batch_decode_sglang"):
+        assert callable(getattr(clusterfusion, name))
+    doc = clusterfusion.llama_decoder_layer.__doc__
+    assert doc.count("llama_decoder_layer(") >= 2        # 8-arg form + the README's 15-arg form
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        clusterfusion.llama_decoder_layer(*[torch.zeros(1) for _ in range(8)])
+    with pytest.raises(TypeError):
+        clusterfusion.llama_decoder_layer(torch.zeros(1))
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    for p in list((ROOT / "clusterfusion_b200").rglob("*.py")) + list((ROOT / "clusterfusion").rglob("*.py")):
+        src = p.read_text()
+        assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), p

@@ -1,0 +1,308 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the pybind
+operators and through the raw C ABI, against the CPU oracle on the same seeded inputs and against
+the committed golden fixtures.  Tolerance: rtol = atol = 1e-3 in fp16 (BASELINE.json north_star)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import llama_oracle as O
+from oracle.gen_golden import inputs_digest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+RTOL = ATOL = 1e-3
+S7 = O.LayerShape(4096, 32, 32)
+
+
+def cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a, b = a.float().cpu().reshape(-1), b.float().cpu().reshape(-1)
+    ok = torch.allclose(a, b, rtol=rtol, atol=atol)
+    if not ok:
+        diff = (a - b).abs()
+        i = int(diff.argmax())
+        print(f"max diff {diff.max():.3e} at {i}: got {a[i]:.6f} want {b[i]:.6f}; nbad={(diff > atol + rtol * b.abs()).sum()}")
+    return ok
+
+
+# ---------------------------------------------------------------------------------------------------
+# device primitive (include/dsm.cuh) in isolation
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("repeats", [1, 5])
+def test_cluster_reduce_sum(cluster, repeats):
+    from clusterfusion_b200 import cabi
+    n, ncl = 384, 3
+    g = torch.Generator().manual_seed(cluster * 10 + repeats)
+    x = torch.randn(ncl * cluster, n, generator=g)
+    xin = x.cuda()
+    out = torch.full((ncl * cluster, n), float("nan"), device="cuda")
+    cabi.test_cluster_reduce(xin.data_ptr(), out.data_ptr(), n, cluster, ncl, 0, repeats)
+    torch.cuda.synchronize()
+    scale = sum(range(1, repeats + 1))
+    want = x.view(ncl, cluster, n).sum(1, keepdim=True).expand(ncl, cluster, n).reshape(-1, n) * scale
+    assert torch.allclose(out.cpu(), want, rtol=1e-5, atol=1e-5)
+    # rank-ordered fold: every CTA of a cluster holds the bit-identical result
+    o = out.view(ncl, cluster, n)
+    assert torch.equal(o, o[:, :1].expand_as(o))
+
+
+@pytest.mark.parametrize("cluster", [2, 4, 8])
+def test_cluster_reduce_gather(cluster):
+    from clusterfusion_b200 import cabi
+    n, ncl = 128, 2
+    x = torch.randn(ncl * cluster, n)
+    out = torch.zeros(ncl * cluster, n * cluster, device="cuda")
+    cabi.test_cluster_reduce(x.cuda().data_ptr(), out.data_ptr(), n, cluster, ncl, 4, 1)
+    torch.cuda.synchronize()
+    want = x.view(ncl, 1, cluster * n).expand(ncl, cluster, cluster * n).reshape(-1, cluster * n)
+    assert torch.equal(out.cpu(), want)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_cluster_reduce_attn_merge(cluster):
+    from clusterfusion_b200 import cabi
+    D, ncl = 128, 2
+    n = D + 4
+    g = torch.Generator().manual_seed(cluster)
+    st = torch.zeros(ncl * cluster, n)
+    st[:, 0] = torch.randn(ncl * cluster, generator=g) * 4           # m (log2 domain)
+    st[:, 1] = torch.rand(ncl * cluster, generator=g) + 0.5          # l
+    st[:, 4:] = torch.randn(ncl * cluster, D, generator=g)           # o (unnormalised)
+    if cluster > 1:
+        st[1, 0] = float("-inf"); st[1, 1] = 0; st[1, 4:] = 0        # an empty partial state
+    out = torch.zeros(ncl * cluster, n, device="cuda")
+    cabi.test_cluster_reduce(st.cuda().data_ptr(), out.data_ptr(), n, cluster, ncl, 1, 2)
+    torch.cuda.synchronize()
+    s = st.view(ncl, cluster, n).double()
+    M = s[:, :, 0].max(1, keepdim=True).values
+    w = torch.exp2(s[:, :, 0] - M)
+    L = (s[:, :, 1] * w).sum(1)
+    Ov = (s[:, :, 4:] * w[:, :, None]).sum(1)
+    got = out.cpu().view(ncl, cluster, n).double()
+    for r in range(cluster):
+        assert torch.allclose(got[:, r, 0], M[:, 0], rtol=1e-6)
+        assert torch.allclose(got[:, r, 1], L, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(got[:, r, 4:], Ov, rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------
+# 8-arg chat operator (pybind) vs oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kv_len", [0, 1, 31, 37, 128, 256, 1024, 4096])
+def test_chat_operator_vs_oracle(kv_len):
+    import clusterfusion
+    d = O.make_inputs(S7, kv_len, seed=42 + kv_len, layout="chat")
+    want_o, want_k, want_v = O.chat_layer(d["x"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                                          d["rms_w"], d["cos"], d["sin"], n_heads=32, eps=1e-6, mode="eager")
+    c = cuda(d)
+    o, k, v = clusterfusion.llama_decoder_layer(c["x"].view(1, 1, 4096), c["weight_qkv"], c["weight_o"], c["k_cache"],
+                                                c["v_cache"], c["rms_w"], c["cos"], c["sin"])
+    torch.cuda.synchronize()
+    assert o.shape == (1, 4096) and k.shape == (1, 32, 128) and v.shape == (1, 32, 128)
+    assert o.dtype == k.dtype == v.dtype == torch.float16
+    assert close(v, want_v)
+    assert close(k, want_k, atol=4e-3)          # |k| ~ 4 after RoPE: 1 fp16 ulp = 3.9e-3
+    assert close(o, want_o)
+
+
+@pytest.mark.parametrize("kv_len", [0, 1, 37, 256, 1024, 4096, 16384])
+def test_sglang_cabi_vs_oracle(kv_len):
+    import cabi_torch as ct
+    d = O.make_inputs(S7, kv_len, seed=7 + kv_len, layout="sglang")
+    eps = 1e-5
+    want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                          d["rms_w"], eps, d["cos"], d["sin"], n_heads=32, mode="eager")
+    c = cuda(d)
+    o, r, k, v = ct.sglang(c["x"], c["residual"], c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"],
+                           c["rms_w"], eps, c["cos"], c["sin"], n_heads=32)
+    torch.cuda.synchronize()
+    assert torch.equal(r.cpu(), want[1])
+    assert close(v, want[3])
+    assert close(k, want[2], atol=4e-3)
+    assert close(o, want[0])
+    assert torch.equal(c["residual"].cpu(), d["residual"])     # out-of-place form leaves the input alone
+
+
+def test_sglang_operator_updates_residual_in_place():
+    import clusterfusion
+    d = O.make_inputs(S7, 300, seed=3, layout="sglang")
+    want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                          d["rms_w"], 1e-6, d["cos"], d["sin"], n_heads=32, mode="eager")
+    c = cuda(d)
+    res = c["residual"].clone()
+    for _ in range(3):      # exercise scratch / counter reset between launches
+        res.copy_(c["residual"])
+        o, r, k, v = clusterfusion.llama_decoder_layer_sglang(c["x"], res, c["weight_qkv"], c["weight_o"],
+                                                              c["k_cache"], c["v_cache"], c["rms_w"], 1e-6,
+                                                              c["cos"], c["sin"])
+        torch.cuda.synchronize()
+        assert r.data_ptr() == res.data_ptr()
+        assert torch.equal(res.cpu(), want[1])
+        assert close(o, want[0]) and close(k, want[2], atol=4e-3) and close(v, want[3])
+
+
+@pytest.mark.parametrize("name", sorted(p.name for p in GOLDEN.glob("sglang_*w0.02.npz")))
+def test_sglang_operator_vs_reference_golden(name):
+    """CUDA kernel against the fixture the reference's own pure-torch reference() produced."""
+    import clusterfusion
+    z = np.load(GOLDEN / name)
+    d = O.make_inputs(S7, int(z["kv_len"]), seed=int(z["seed"]), w_scale=float(z["w_scale"]), layout="sglang")
+    assert inputs_digest(d) == str(z["digest"])
+    c = cuda(d)
+    o, r, k, v = clusterfusion.llama_decoder_layer_sglang(c["x"], c["residual"], c["weight_qkv"], c["weight_o"],
+                                                          c["k_cache"], c["v_cache"], c["rms_w"], float(z["eps"]),
+                                                          c["cos"], c["sin"])
+    torch.cuda.synchronize()
+    # reference() keeps everything in fp32 (no fp16 rounding of q/k/v); the reference's own bar for this
+    # comparison is output < 5e-2, residual < 1e-3, k/v < 1e-2 (tests/test_llama_tilelang.py:100).
+    # We hold the north-star tolerance wherever there are enough keys to average the q/k/v rounding.
+    tol = 1e-3 if int(z["kv_len"]) >= 37 else 2.5e-3
+    assert close(o, torch.from_numpy(z["out"]), rtol=tol, atol=tol)
+    assert torch.equal(r.cpu(), torch.from_numpy(z["residual_out"]))
+    assert close(k, torch.from_numpy(z["k"]), atol=4e-3)
+    assert close(v, torch.from_numpy(z["v"]))
+
+
+@pytest.mark.parametrize("name", sorted(p.name for p in GOLDEN.glob("chat_fp*_kv*.npz") if "gqa" not in p.name and "70b" not in p.name))
+def test_chat_operator_vs_reference_golden(name):
+    """CUDA kernel against what the reference's eager Attention module produced on CPU."""
+    import clusterfusion
+    z = np.load(GOLDEN / name)
+    kv = int(z["kv_len"])
+    d = O.make_inputs(S7, kv, seed=int(z["seed"]), w_scale=float(z["w_scale"]), layout="sglang")
+    assert inputs_digest(d) == str(z["digest"])
+    wq, wk, wv = d["weight_qkv"].split([4096, 4096, 4096], 0)
+    wqkv_T = torch.cat([wq.t(), wk.t(), wv.t()], 0).contiguous().cuda()
+    wo_T = d["weight_o"].t().contiguous().cuda()
+    cos, sin = torch.from_numpy(z["cos"]).cuda(), torch.from_numpy(z["sin"]).cuda()
+    o, k, v = clusterfusion.llama_decoder_layer(d["x"].cuda(), wqkv_T, wo_T, d["k_cache"].cuda(), d["v_cache"].cuda(),
+                                                d["rms_w"].cuda(), cos, sin)
+    torch.cuda.synchronize()
+    tol = 1e-3 if kv >= 37 else 2.5e-3
+    assert close(o, torch.from_numpy(z["out"]), rtol=tol, atol=tol)
+    assert close(k, torch.from_numpy(z["k"]), atol=4e-3)
+    assert close(v, torch.from_numpy(z["v"]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# 15-arg paged batch operator
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lens", [[5], [0, 33, 1], [700, 64, 0, 129]])
+def test_paged_operator_vs_oracle(lens):
+    import clusterfusion
+    bs = len(lens)
+    nslots = sum(lens) + bs + 17
+    d = O.make_inputs(S7, nslots, seed=100 + bs, layout="sglang", bs=bs)
+    g = torch.Generator().manual_seed(1)
+    slots = torch.randperm(nslots, generator=g)
+    indptr, indices, off = [0], [], 0
+    for L in lens:
+        indices += slots[off:off + L + 1].tolist()
+        off += L + 1
+        indptr.append(len(indices))
+    indptr = torch.tensor(indptr, dtype=torch.int32)
+    indices = torch.tensor(indices, dtype=torch.int32)
+    positions = torch.tensor(lens, dtype=torch.int64)
+    maxpos = max(lens) + 1
+    cos_sin = torch.stack([torch.cat([O.rope_angles(p).cos(), O.rope_angles(p).sin()]) for p in range(maxpos)])
+    kp, vp = d["k_cache"].clone(), d["v_cache"].clone()
+    want_o, want_r = O.paged_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], indptr, indices, kp, vp,
+                                   d["rms_w"], 1e-5, positions, cos_sin, n_heads=32, mode="eager")
+    c = cuda(d)
+    n_layers, layer_id = 3, 1
+    kpools = [torch.zeros_like(c["k_cache"]) for _ in range(n_layers)]
+    vpools = [torch.zeros_like(c["v_cache"]) for _ in range(n_layers)]
+    kpools[layer_id].copy_(c["k_cache"]); vpools[layer_id].copy_(c["v_cache"])
+    kptrs = torch.tensor([t.data_ptr() for t in kpools], dtype=torch.uint64).cuda()
+    vptrs = torch.tensor([t.data_ptr() for t in vpools], dtype=torch.uint64).cuda()
+    out = torch.full((bs, 4096), float("nan"), dtype=torch.float16, device="cuda")
+    rout = torch.full((bs, 4096), float("nan"), dtype=torch.float16, device="cuda")
+    clusterfusion.llama_decoder_layer_batch_decode_sglang(
+        out, rout, c["x"], c["residual"], c["weight_qkv"], c["weight_o"], indptr.cuda(), indices.cuda(),
+        kptrs, vptrs, layer_id, c["rms_w"], 1e-5, positions.cuda(), cos_sin.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(rout.cpu(), want_r)
+    assert close(out, want_o)
+    assert close(kpools[layer_id], kp, atol=4e-3)       # appended K rows (post-RoPE), everything else untouched
+    assert close(vpools[layer_id], vp)
+    touched = {int(indices[indptr[b + 1] - 1]) for b in range(bs)}
+    keep = [i for i in range(nslots) if i not in touched]
+    assert torch.equal(kpools[layer_id].cpu()[keep], d["k_cache"][keep])
+    assert torch.equal(kpools[0].cpu(), torch.zeros_like(d["k_cache"]))
+    # the README spelling of the same call (reference README.md:55-75)
+    out2 = torch.empty_like(out); rout2 = torch.empty_like(rout)
+    kpools[layer_id].copy_(c["k_cache"]); vpools[layer_id].copy_(c["v_cache"])
+    clusterfusion.llama_decoder_layer(out2, rout2, c["x"], c["residual"], c["weight_qkv"], c["weight_o"],
+                                      indptr.cuda(), indices.cuda(), kptrs, vptrs, layer_id, c["rms_w"], 1e-5,
+                                      positions.cuda(), cos_sin.cuda())
+    torch.cuda.synchronize()
+    assert close(out2, want_o)
+
+
+# ---------------------------------------------------------------------------------------------------
+# properties at full BASELINE sizes (no oracle needed) + repeatability
+# ---------------------------------------------------------------------------------------------------
+def test_repeatability_and_workspace_reset():
+    """The reference watches 10 000 runs for atomic-order noise (tests/test_llama.py:22).  Here the only
+    order-dependent step is the fp32 cross-head red: repeats must agree to within 1 fp16 ulp."""
+    import clusterfusion
+    d = cuda(O.make_inputs(S7, 1024, seed=1, layout="chat"))
+    outs = []
+    for _ in range(300):
+        o, k, v = clusterfusion.llama_decoder_layer(d["x"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                                                    d["rms_w"], d["cos"], d["sin"])
+        outs.append(o)
+    torch.cuda.synchronize()
+    ref = outs[0].float()
+    ulp = torch.maximum(ref.abs() * 2 ** -10, torch.full_like(ref, 2 ** -24))
+    for o in outs[1:]:
+        assert bool(((o.float() - ref).abs() <= ulp).all())
+    assert bool(torch.equal(k, k)) and not torch.isnan(outs[-1]).any()
+
+
+def test_softmax_shift_invariance_16k():
+    """Size-independent property at the headline size: attention over a cache whose V rows are all the same
+    vector u must return exactly Wo.u regardless of K (softmax weights sum to 1)."""
+    import clusterfusion
+    kv = 16384
+    d = O.make_inputs(S7, 8, seed=5, layout="chat")
+    c = cuda(d)
+    u = torch.randn(1, 4096, generator=torch.Generator().manual_seed(0)).half().cuda()
+    kc = torch.randn(kv, 4096, device="cuda", dtype=torch.float16)
+    vc = u.expand(kv, 4096).contiguous()
+    # make the new token negligible: its score is finite, but 16K keys dominate only if it is not huge; use
+    # the general identity instead: o = Wo^T-proj of (sum_s p_s u + p_new v_new)
+    o, k, v = clusterfusion.llama_decoder_layer(c["x"], c["weight_qkv"], c["weight_o"], kc, vc, c["rms_w"], c["cos"], c["sin"])
+    # oracle on the collapsed problem: all 16K cache rows share V=u, so the result equals attention over the
+    # true K with that V; compare with the oracle run on a strided subsample is not exact -> run the oracle in full
+    want_o, _, _ = O.chat_layer(d["x"], d["weight_qkv"], d["weight_o"], kc.cpu(), vc.cpu(), d["rms_w"], d["cos"], d["sin"],
+                                n_heads=32, eps=1e-6, mode="eager")
+    torch.cuda.synchronize()
+    assert close(o, want_o)
+
+
+def test_errors_are_loud():
+    import clusterfusion
+    d = cuda(O.make_inputs(S7, 4, seed=1, layout="chat"))
+    with pytest.raises(RuntimeError):
+        clusterfusion.llama_decoder_layer(d["x"].float(), d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                                          d["rms_w"], d["cos"], d["sin"])
+    with pytest.raises(RuntimeError):
+        clusterfusion.llama_decoder_layer(d["x"], d["weight_qkv"][:100], d["weight_o"], d["k_cache"], d["v_cache"],
+                                          d["rms_w"], d["cos"], d["sin"])
+    with pytest.raises(RuntimeError):
+        clusterfusion.llama_decoder_layer(d["x"].cpu(), d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                                          d["rms_w"], d["cos"], d["sin"])
+    from clusterfusion_b200 import cabi
+    a = cabi.CfLlamaArgs(variant=7)
+    with pytest.raises(cabi.CfError) as e:
+        cabi.launch(a)
+    assert e.value.code == -2
