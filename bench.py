@@ -199,7 +199,8 @@ def run_ours(args, rank, world, local_rank):
     ws = torch.zeros(cabi.workspace_bytes(HIDDEN, 1), dtype=torch.uint8, device=dev)
 
     def launch_layer(x, lay, kv_len, cos, sin, stream):
-        a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_CHAT, hidden=HIDDEN, n_q_heads=HEADS, n_kv_heads=HEADS,
+        a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_CHAT, flags=(0 if args.no_pdl else cabi.CF_FLAG_PDL),
+                             hidden=HIDDEN, n_q_heads=HEADS, n_kv_heads=HEADS,
                              head_dim=D, batch=1, kv_len=kv_len, eps=1e-6, x=x.data_ptr(),
                              w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(),
                              out=lay["o"].data_ptr(), k_new=lay["kn"].data_ptr(), v_new=lay["vn"].data_ptr(),
@@ -361,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
                                "(RMSNorm+QKV+RoPE+flash-decode+O fused; FFN / lm_head are outside the hot-path scope)",
                    "hidden": HIDDEN, "heads": HEADS, "head_dim": D, "kv_len": kv, "layers_per_token": LAYERS,
                    "weights": "random N(0, 0.02^2) fp16, 32 distinct layers", "l2": "inputs larger than L2: 4.8 GB touched per step",
-                   "replicas": world, "launch": "CUDA graph of 32 C-ABI launches per step"},
+                   "replicas": world, "launch": "CUDA graph of 32 C-ABI launches per step" + ("" if args.no_pdl else ", programmatic dependent launch between layers (CF_FLAG_PDL)")},
         "per_layer_us": us_layer,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "cfb::llama_decoder_layer_kernel<CHAT,4>",
@@ -392,6 +393,7 @@ def main():
     ap.add_argument("--kv-len", type=int, default=1024)
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="value arm: plain stream-serialised launches instead of programmatic dependent launch")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -14,10 +14,12 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libclusterfusion_b200.so"
+# CF_LIB_PATH: explicit override for kernel experiments (tools/); the product always loads the in-tree library
+LIB_PATH = Path(os.environ["CF_LIB_PATH"]) if os.environ.get("CF_LIB_PATH") else _HERE / "libclusterfusion_b200.so"
 
 CF_VARIANT_CHAT, CF_VARIANT_SGLANG, CF_VARIANT_PAGED = 0, 1, 2
 CF_FLAG_OUT_FP32_PARTIAL = 0x1
+CF_FLAG_PDL = 0x2
 
 EXPORTED_SYMBOLS = (
     "cf_abi_version",

@@ -107,7 +107,7 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int VARIANT, int CLUSTER>
-int launch(const cfb::KParams& kp, int n_clusters, int batch, cudaStream_t stream) {
+int launch(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cudaStream_t stream) {
     using S = cfb::Smem<CLUSTER>;
     auto kern = cfb::llama_decoder_layer_kernel<VARIANT, CLUSTER>;
     static std::once_flag once[16];
@@ -126,13 +126,15 @@ int launch(const cfb::KParams& kp, int n_clusters, int batch, cudaStream_t strea
     cfg.blockDim = dim3(cfb::BLOCK_THREADS, 1, 1);
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CLUSTER;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 2 : 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, kp);
     if (e != cudaSuccess) return fail((int)e, "kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
@@ -253,14 +255,21 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     kp.layer_id = a->layer_id;
     kp.flags = a->flags;
 
+    const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
     switch (a->variant) {
-        case CF_VARIANT_CHAT: return launch<cfb::CHAT, CL>(kp, a->n_q_heads, 1, stream);
-        case CF_VARIANT_SGLANG: return launch<cfb::SGLANG, CL>(kp, a->n_q_heads, 1, stream);
-        default: return launch<cfb::PAGED, CL>(kp, a->n_q_heads, a->batch, stream);
+        case CF_VARIANT_CHAT: return launch<cfb::CHAT, CL>(kp, a->n_q_heads, 1, pdl, stream);
+        case CF_VARIANT_SGLANG: return launch<cfb::SGLANG, CL>(kp, a->n_q_heads, 1, pdl, stream);
+        default: return launch<cfb::PAGED, CL>(kp, a->n_q_heads, a->batch, pdl, stream);
     }
 }
 
 }  // extern "C"
+
+#ifdef CF_TRACE
+extern "C" int cf_debug_set_trace(void* dev_ptr) {
+    return (int)cudaMemcpyToSymbol(cfb::g_cf_trace, &dev_ptr, sizeof(void*));
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // unit-test hook for include/dsm.cuh

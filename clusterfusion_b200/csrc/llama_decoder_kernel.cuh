@@ -46,6 +46,7 @@ constexpr int BLOCK_THREADS = CONSUMER_THREADS + 32;    // + producer warp
 constexpr int STAGE_BYTES = 16384;
 constexpr int NSTAGES = CONSUMER_WARPS;                 // stage s is consumed by warp s, always (see ring_wait_full)
 constexpr int KS_MAX = 2048;                            // max hidden / CLUSTER
+constexpr int INIT_BAR = 2;                             // producer arrives / consumers sync, once
 constexpr int CONSUMER_BAR = 1;                         // named barrier id for the consumer threads
 
 enum Variant : int { CHAT = 0, SGLANG = 1, PAGED = 2 };
@@ -158,6 +159,21 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 }
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
 
+// Optional phase timeline (build with -DCF_TRACE; tools/trace_timeline.py).  Never compiled into the product.
+#ifdef CF_TRACE
+__device__ unsigned long long* g_cf_trace = nullptr;     // [grid][16] globaltimer ns, set by cf_debug_set_trace
+__device__ __forceinline__ void trace_mark(int slot, int launch_id) {
+    if (g_cf_trace && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == (slot >= 12 ? CONSUMER_WARPS : 0)) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_cf_trace[((size_t)launch_id * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
+    }
+}
+#define CF_MARK(slot) trace_mark(slot, p.layer_id)   /* chat/sglang: layer_id is free to carry a launch index */
+#else
+#define CF_MARK(slot) ((void)0)
+#endif
+
 // ring bookkeeping: global tile index g -> (stage, parity)
 __device__ __forceinline__ uint32_t ring_stage(uint32_t g) { return g % NSTAGES; }
 __device__ __forceinline__ uint32_t ring_parity(uint32_t g) { return (g / NSTAGES) & 1u; }
@@ -224,25 +240,66 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     const uint32_t n_kv_tiles = (row_end - row_begin + 31) / 32;
     const uint32_t n_o_tiles = kChat ? 2u * (KS / 128) : (uint32_t)(KS / 64);
 
+    CF_MARK(0);   // kernel entry
     // ---- barrier init ---------------------------------------------------------------------------
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGES; ++s) {
-            dsm::mbar_init(full_u32 + 8 * s, 1);
-            dsm::mbar_init(empty_u32 + 8 * s, 1);
+    // The producer warp initialises the ring barriers itself and starts streaming at once: nothing it does
+    // depends on the other warps, on the peer CTAs or (under programmatic dependent launch) on the previous
+    // kernel in the stream.  The consumers learn about the ring through named barrier INIT_BAR (producer
+    // arrives, consumers sync).  The exchange barriers are armed by consumer thread 0 before the cluster-wide
+    // arrive; only the consumers ever wait on that cluster barrier (before their first push to a peer).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // no-op unless the NEXT launch opted into PDL
+    if (warp == CONSUMER_WARPS) {
+        if (lane == 0) {
+            for (int s = 0; s < NSTAGES; ++s) {
+                dsm::mbar_init(full_u32 + 8 * s, 1);
+                dsm::mbar_init(empty_u32 + 8 * s, 1);
+            }
+            dsm::mbar_fence_init();
         }
-        cluster_reduce_arm<CLUSTER>(xbar_u32, S::QKV_OUT * 4);
-        cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::ATTN_PAYLOAD * 4);
-        dsm::mbar_fence_init();
+        __syncwarp();
+        asm volatile("bar.arrive %0, %1;" ::"n"(INIT_BAR), "n"(BLOCK_THREADS) : "memory");
+    } else {
+        if (tid == 0) {
+            cluster_reduce_arm<CLUSTER>(xbar_u32, S::QKV_OUT * 4);
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::ATTN_PAYLOAD * 4);
+            dsm::mbar_fence_init();
+        }
+        dsm::named_bar_sync(INIT_BAR, BLOCK_THREADS);
     }
-    __syncthreads();
     dsm::cluster_arrive();     // peers may push into this CTA's smem only after every CTA armed its barriers
 
     // =============================================================================================
     // PRODUCER WARP
     // =============================================================================================
     if (warp == CONSUMER_WARPS) {
-        dsm::cluster_wait();
+        CF_MARK(12);  // producer: first TMA issue
         const uint64_t pol = policy_evict_first();
+        // tile coordinates
+        auto qkv_coords = [&](uint32_t i, int& c0, int& c1) {
+            if constexpr (kChat) {           // tile i: matrix j = i % 3, rows t = i / 3 (64 input rows)
+                const int j = i % 3, t = i / 3;
+                c0 = head * HEAD_DIM;
+                c1 = j * hidden + rank * KS + t * 64;
+            } else {                         // tile i: 32 output rows x 256 input cols
+                const int wins = KS / 256;
+                const int rb = i / wins, win = i % wins;          // rb in [0,12): matrix j = rb/4
+                const int j = rb >> 2, sub = rb & 3;
+                const int row0 = (j == 0) ? head * HEAD_DIM
+                               : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
+                                          : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
+                c0 = rank * KS + win * 256;
+                c1 = row0 + sub * 32;
+            }
+        };
+        auto wo_coords = [&](uint32_t i, int& c0, int& c1) {
+            if constexpr (kChat) {           // Wo^T [in][out]: 64 input rows x 128 output cols
+                c0 = rank * KS + (i >> 1) * 128;
+                c1 = head * HEAD_DIM + (i & 1) * 64;
+            } else {                         // Wo [out][in]: 64 output rows x this head's 128 input cols
+                c0 = head * HEAD_DIM;
+                c1 = rank * KS + i * 64;
+            }
+        };
         uint32_t g = 0;
         if (lane == 0) {
             prefetch_tmap(&p.tm_wqkv);
@@ -254,20 +311,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                 dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
                 dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
                 int c0, c1;
-                if constexpr (kChat) {           // tile i: matrix j = i % 3, rows t = i / 3 (64 input rows)
-                    const int j = i % 3, t = i / 3;
-                    c0 = head * HEAD_DIM;
-                    c1 = j * hidden + rank * KS + t * 64;
-                } else {                         // tile i: 32 output rows x 256 input cols
-                    const int wins = KS / 256;
-                    const int rb = i / wins, win = i % wins;          // rb in [0,12): matrix j = rb/4
-                    const int j = rb >> 2, sub = rb & 3;
-                    const int row0 = (j == 0) ? head * HEAD_DIM
-                                   : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
-                                              : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
-                    c0 = rank * KS + win * 256;
-                    c1 = row0 + sub * 32;
-                }
+                qkv_coords(i, c0, c1);
                 tma_load_2d(smem_base + S::RING + s * STAGE_BYTES, &p.tm_wqkv, c0, c1, full_u32 + 8 * s, pol);
             }
         }
@@ -276,7 +320,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             if (lane == 0) {
                 for (uint32_t i = 0; i < n_kv_tiles; ++i, ++g) {
                     const uint32_t s = ring_stage(g);
-                    dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
+                        dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
                     dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
                     const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
                     const int r0 = row_begin + i * 32;
@@ -316,16 +360,11 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                 dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
                 dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
                 int c0, c1;
-                if constexpr (kChat) {           // Wo^T [in][out]: 64 input rows x 128 output cols
-                    c0 = rank * KS + (i >> 1) * 128;
-                    c1 = head * HEAD_DIM + (i & 1) * 64;
-                } else {                         // Wo [out][in]: 64 output rows x this head's 128 input cols
-                    c0 = head * HEAD_DIM;
-                    c1 = rank * KS + i * 64;
-                }
+                wo_coords(i, c0, c1);
                 tma_load_2d(smem_base + S::RING + s * STAGE_BYTES, &p.tm_wo, c0, c1, full_u32 + 8 * s, pol);
             }
         }
+        CF_MARK(13);  // producer: last TMA issued
         return;   // producer done; outstanding TMA completes on the consumers' barriers
     }
 
@@ -349,6 +388,10 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     const __half* rg = kChat ? nullptr : p.residual_in + (size_t)batch * hidden;
     __half* rout = kChat ? nullptr : p.residual_out + (size_t)batch * hidden;
     const bool residual_inplace = !kChat && (static_cast<const void*>(rout) == static_cast<const void*>(rg));
+
+    // Programmatic dependent launch: everything above (and the whole producer warp) may run while the previous
+    // kernel in the stream is still finishing; activations, outputs and the workspace may only be touched after it.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---- phase 0: RMSNorm ---------------------------------------------------------------------------
     // every CTA reduces the full vector itself (8-16 KB from L2) -> no cluster round trip for a scalar
@@ -395,6 +438,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
 
+    CF_MARK(1);   // RMSNorm done
     uint32_t gbase = 0;   // global ring index of tile 0 of the current phase
 
     // ---- phase 1: QKV GEMV over this CTA's K-slice ----------------------------------------------------
@@ -490,6 +534,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     }
     gbase += n_qkv_tiles;
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    CF_MARK(2);   // QKV tiles consumed (this warp)
 
     // fold the write-once slots in a fixed order -> this CTA's partial q|k|v
     {
@@ -511,6 +556,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         S::QKV_OUT * 4, tid, HEAD_DIM, rank,
         smem_base + S::QKV_SRC, smem_base + S::QKV_RECV, xbar_u32, xphase0, qkv_src, qkv_recv);
 
+    CF_MARK(3);   // QKV cluster exchange done
     // ---- RoPE (fp16 rounding points of the eager model), new K/V out -------------------------------
     {
         constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;   // 1/sqrt(128) * log2(e)
@@ -559,6 +605,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
 
+    CF_MARK(4);   // RoPE done
     // ---- phase 2: flash-decode over this CTA's KV rows -----------------------------------------------
     {
         const int sub = lane >> 4, c = lane & 15;
@@ -616,6 +663,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
         }
         gbase += n_kv_tiles;
+        CF_MARK(5);   // KV tiles consumed (this warp)
         // per half-warp state -> smem group slot (16 groups)
         {
             const int grp = warp * 2 + sub;                    // 2 * CONSUMER_WARPS groups
@@ -661,6 +709,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
 
+    CF_MARK(6);   // softmax merge + exchange done
     // ---- phase 3: O GEMV for output columns [rank*KS, +KS) --------------------------------------------
     if constexpr (kChat) {
         // tile = 64 input rows (half of the head) x 128 output cols; lane (sub, c): rows sub+2s, cols c*8..+8
@@ -747,6 +796,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     }
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
 
+    CF_MARK(7);   // O tiles consumed, block-reduced
     // ---- cross-head reduction: fp32 red into scratch, last arriver of the slice finalises --------------
     float* scratch = p.scratch + (size_t)batch * hidden + rank * KS;
     for (int e = tid * 4; e < KS; e += CONSUMER_THREADS * 4) {
@@ -765,6 +815,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         sflags[0] = (prev == (unsigned)p.n_heads - 1u);
     }
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    CF_MARK(8);   // reds issued, counter bumped
     if (sflags[0]) {
         __threadfence();
         const bool fp32_out = p.flags & 1u;
@@ -807,6 +858,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             }
         }
     }
+    CF_MARK(9);   // CTA done
 }
 
 }  // namespace cfb

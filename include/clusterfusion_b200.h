@@ -52,6 +52,13 @@ enum {
                                          (float[batch, hidden]) instead of an fp16 result; the caller
                                          all-reduces it across ranks (Llama-2-70B config).             */
 
+#define CF_FLAG_PDL 0x2u /* programmatic dependent launch: the kernel may START (stream its weight / KV tiles)
+                            while the previous kernel in `stream` is still running; it touches x, residual,
+                            outputs and workspace only after that kernel completed.  Contract: w_qkv, w_o, the KV
+                            cache / pools and indptr / indices of THIS call are not being written by kernels still
+                            in flight in the stream (true for a decoder stack: layer l+1's weights and cache are
+                            not produced by layer l).                                                           */
+
 typedef struct CfLlamaArgs {
     int32_t variant;    /* CF_VARIANT_*                                                             */
     uint32_t flags;     /* CF_FLAG_*                                                                */

@@ -296,6 +296,50 @@ def test_softmax_shift_invariance_16k():
     assert close(o, want_o)
 
 
+def test_pdl_chain_matches_plain_chain():
+    """CF_FLAG_PDL lets layer l+1 start streaming its weights while layer l finishes; results must not change.
+    The chain is the real decoder data flow (sglang form: x_{l+1} = o_l, residual_{l+1} = x_l + residual_l), so every
+    launch consumes what the previous launch produced -- reading x before the previous kernel completed would show."""
+    from clusterfusion_b200 import cabi
+    import cabi_torch as ct
+    nl, kv = 6, 700
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device="cuda") * sc).half()
+    layers = [dict(w_qkv=r(3 * 4096, 4096, sc=0.02), w_o=r(4096, 4096, sc=0.02), k=r(kv, 4096), v=r(kv, 4096),
+                   rms=(1 + 0.1 * r(4096).float()).half()) for _ in range(nl)]
+    x0, res0 = r(1, 4096), r(1, 4096)
+    cos = torch.rand(64, device="cuda"); sin = torch.rand(64, device="cuda")
+    ws = ct.workspace(4096, 1, x0.device)
+
+    def chain(flags):
+        outs, h, res = [], x0, res0
+        for lay in layers:
+            o = torch.empty(1, 4096, dtype=torch.float16, device="cuda")
+            ro = torch.empty(1, 4096, dtype=torch.float16, device="cuda")
+            kn = torch.empty(4096, dtype=torch.float16, device="cuda"); vn = torch.empty_like(kn)
+            a = cabi.CfLlamaArgs(variant=1, flags=flags, hidden=4096, n_q_heads=32, n_kv_heads=32, head_dim=128, batch=1,
+                                 kv_len=kv, eps=1e-5, x=h.data_ptr(), residual_in=res.data_ptr(), residual_out=ro.data_ptr(),
+                                 w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(),
+                                 out=o.data_ptr(), k_new=kn.data_ptr(), v_new=vn.data_ptr(), k_cache=lay["k"].data_ptr(),
+                                 v_cache=lay["v"].data_ptr(), cos=cos.data_ptr(), sin=sin.data_ptr(), workspace=ws.data_ptr())
+            cabi.launch(a, ct.stream_handle())
+            outs += [o, ro, kn, vn]
+            h, res = o, ro
+        torch.cuda.synchronize()
+        return outs
+
+    plain = chain(0)
+    side = torch.cuda.Stream()
+    for it in range(6):
+        if it < 3:
+            pdl = chain(cabi.CF_FLAG_PDL)
+        else:
+            with torch.cuda.stream(side):
+                pdl = chain(cabi.CF_FLAG_PDL)
+        for a, b in zip(plain, pdl):
+            assert close(b, a, rtol=2e-3, atol=4e-3)
+
+
 def test_errors_are_loud():
     import clusterfusion
     d = cuda(O.make_inputs(S7, 4, seed=1, layout="chat"))

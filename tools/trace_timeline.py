@@ -1,0 +1,57 @@
+"""Phase timeline of the fused kernel (debug build with -DCF_TRACE, NOT the product library).
+Builds a separate libclusterfusion_b200_trace.so, runs N back-to-back launches, prints per-phase statistics."""
+import ctypes as C, subprocess, sys, os
+from pathlib import Path
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+lib_path = ROOT / "gpurun_out" / "libcf_trace.so"
+lib_path.parent.mkdir(exist_ok=True)
+extra = os.environ.get("CF_EXTRA_FLAGS", "").split()
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DCF_TRACE", *extra,
+                       "-Xcompiler", "-fPIC", "-shared", "-o", str(lib_path),
+                       str(ROOT / "clusterfusion_b200/csrc/llama_decoder.cu"), "-lcudart"])
+from clusterfusion_b200 import cabi
+lib = C.CDLL(str(lib_path))
+lib.cf_llama_decoder_layer_launch.argtypes = [C.POINTER(cabi.CfLlamaArgs), C.c_void_p]
+kv = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+H, NH, D = 4096, 32, 128
+dev = "cuda"
+nl = 8
+def r(*s, sc=1.0): return (torch.randn(*s, device=dev) * sc).half()
+layers = [dict(w_qkv=r(3 * H, H, sc=0.02), w_o=r(H, H, sc=0.02), k=r(kv + 1, H), v=r(kv + 1, H), rms=r(H) * 0.1 + 1,
+               o=torch.empty(1, H, dtype=torch.float16, device=dev), kn=torch.empty(NH * D, dtype=torch.float16, device=dev),
+               vn=torch.empty(NH * D, dtype=torch.float16, device=dev)) for _ in range(nl)]
+x = r(1, H); cos = torch.rand(1, D, device=dev); sin = torch.rand(1, D, device=dev)
+ws = torch.zeros(cabi.workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
+trace = torch.zeros(nl, 128, 16, dtype=torch.int64, device=dev)
+def launch(i, h):
+    lay = layers[i]
+    a = cabi.CfLlamaArgs(variant=0, flags=flags, layer_id=i, hidden=H, n_q_heads=NH, n_kv_heads=NH, head_dim=D, batch=1, kv_len=kv, eps=1e-6,
+                         x=h.data_ptr(), w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(),
+                         out=lay["o"].data_ptr(), k_new=lay["kn"].data_ptr(), v_new=lay["vn"].data_ptr(),
+                         k_cache=lay["k"].data_ptr(), v_cache=lay["v"].data_ptr(), cos=cos.data_ptr(), sin=sin.data_ptr(),
+                         workspace=ws.data_ptr())
+    rc = lib.cf_llama_decoder_layer_launch(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, rc
+lib.cf_debug_set_trace(C.c_void_p(trace.data_ptr()))
+for rep in range(3):          # back-to-back launches; the last repetition's marks survive
+    h = x
+    for i in range(nl):
+        launch(i, h); h = layers[i]["o"]
+torch.cuda.synchronize()
+t = trace.cpu().numpy().astype("int64")
+names = {0: "entry", 12: "prod first TMA", 1: "rms done", 2: "qkv tiles done", 3: "xchg1 done", 4: "rope done", 5: "kv tiles done",
+         6: "xchg2 done", 7: "o tiles done", 13: "prod last TMA", 8: "reds+counter", 9: "cta done"}
+starts = [t[i][:, 0].min() for i in range(nl)]
+ends = [t[i][:, 9].max() for i in range(nl)]
+print("launch-to-launch (first CTA entry) us:", [round((starts[i + 1] - starts[i]) / 1e3, 2) for i in range(nl - 1)])
+print("gap prev last CTA done -> next first entry us:", [round((starts[i + 1] - ends[i]) / 1e3, 2) for i in range(nl - 1)])
+for li in (nl - 2,):
+    T = t[li]
+    t0 = T[:, 0].min()
+    print(f"layer {li}: kernel span {(T[:, 9].max() - t0) / 1e3:.2f} us (kv={kv})")
+    for k in (0, 12, 1, 2, 3, 4, 5, 6, 7, 13, 8, 9):
+        v = (T[:, k] - t0) / 1e3
+        print(f"  {names[k]:16s} min {v.min():7.2f}  med {sorted(v)[len(v)//2]:7.2f}  max {v.max():7.2f} us")
