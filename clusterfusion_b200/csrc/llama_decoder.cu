@@ -12,6 +12,7 @@
  */
 #include "../../include/clusterfusion_b200.h"
 #include "llama_decoder_kernel.cuh"
+#include "llama_decoder_gqa_kernel.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -106,25 +107,25 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int VARIANT, int CLUSTER>
-int launch(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cudaStream_t stream) {
-    using S = cfb::Smem<CLUSTER>;
-    auto kern = cfb::llama_decoder_layer_kernel<VARIANT, CLUSTER>;
-    static std::once_flag once[16];
-    static cudaError_t attr_err[16];
+template <int CLUSTER, typename Kern>
+int launch_kernel(Kern kern, int smem_bytes, int slot, const cfb::KParams& kp, int n_clusters, int batch, bool pdl,
+                  cudaStream_t stream) {
+    static std::once_flag once[8][16];
+    static cudaError_t attr_err[8][16];
     int dev = 0;
     cudaGetDevice(&dev);
-    std::call_once(once[dev & 15], [&] {
-        attr_err[dev & 15] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-        if (attr_err[dev & 15] == cudaSuccess && CLUSTER > 8)
-            attr_err[dev & 15] = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    std::call_once(once[slot][dev & 15], [&] {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess && CLUSTER > 8)
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        attr_err[slot][dev & 15] = e;
     });
-    if (attr_err[dev & 15] != cudaSuccess)
-        return fail((int)attr_err[dev & 15], "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err[dev & 15]));
+    const cudaError_t ae = attr_err[slot][dev & 15];
+    if (ae != cudaSuccess) return fail((int)ae, "cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_clusters * CLUSTER, batch, 1);
     cfg.blockDim = dim3(cfb::BLOCK_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -138,6 +139,18 @@ int launch(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cudaStre
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, kp);
     if (e != cudaSuccess) return fail((int)e, "kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+template <int VARIANT, int CLUSTER>
+int launch(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cudaStream_t stream) {
+    return launch_kernel<CLUSTER>(cfb::llama_decoder_layer_kernel<VARIANT, CLUSTER>, cfb::Smem<CLUSTER>::TOTAL, VARIANT,
+                                  kp, n_clusters, batch, pdl, stream);
+}
+
+template <int VARIANT>
+int launch_gqa(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cudaStream_t stream) {
+    return launch_kernel<16>(cfb::llama_decoder_layer_gqa_kernel<VARIANT, 16, 4>, cfb::SmemGqa<16, 4>::TOTAL, 4 + VARIANT,
+                             kp, n_clusters, batch, pdl, stream);
 }
 
 bool device_is_sm100() {
@@ -186,14 +199,22 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     const bool chat = a->variant == CF_VARIANT_CHAT, paged = a->variant == CF_VARIANT_PAGED;
     constexpr int CL = 4;
     if (a->head_dim != 128) return fail(CF_ERR_BAD_SHAPE, "head_dim must be 128 (got %d)", a->head_dim);
-    if (a->hidden <= 0 || a->hidden % (CL * 256) != 0 || a->hidden / CL > cfb::KS_MAX)
-        return fail(CF_ERR_BAD_SHAPE, "hidden must be a multiple of %d and <= %d (got %d)", CL * 256,
-                    CL * cfb::KS_MAX, a->hidden);
     if (a->n_q_heads <= 0 || a->n_kv_heads <= 0 || a->n_q_heads % a->n_kv_heads != 0)
         return fail(CF_ERR_BAD_SHAPE, "bad head counts q=%d kv=%d", a->n_q_heads, a->n_kv_heads);
-    if (a->n_q_heads != a->n_kv_heads)
-        return fail(CF_ERR_BAD_SHAPE, "grouped-query attention (q=%d, kv=%d) is not built in this revision",
-                    a->n_q_heads, a->n_kv_heads);
+    const bool gqa = a->n_q_heads != a->n_kv_heads;
+    if (!gqa) {
+        if (a->hidden <= 0 || a->hidden % (CL * 256) != 0 || a->hidden / CL > cfb::KS_MAX)
+            return fail(CF_ERR_BAD_SHAPE, "hidden must be a multiple of %d and <= %d (got %d)", CL * 256,
+                        CL * cfb::KS_MAX, a->hidden);
+    } else {
+        // grouped-query path: 16-CTA clusters, 4 query heads per cluster, nn.Linear weight layout
+        if (chat) return fail(CF_ERR_BAD_SHAPE, "grouped-query attention needs the nn.Linear layout (SGLANG / PAGED)");
+        if ((a->n_q_heads / a->n_kv_heads) % 4 != 0)
+            return fail(CF_ERR_BAD_SHAPE, "grouped-query attention needs a multiple of 4 query heads per KV head (q=%d, kv=%d)",
+                        a->n_q_heads, a->n_kv_heads);
+        if (a->hidden <= 0 || a->hidden % (16 * 256) != 0 || a->hidden / 16 > cfb::GQA_KS_MAX)
+            return fail(CF_ERR_BAD_SHAPE, "GQA: hidden must be a multiple of 4096 and <= %d (got %d)", 16 * cfb::GQA_KS_MAX, a->hidden);
+    }
     if (a->batch < 1 || (!paged && a->batch != 1))
         return fail(CF_ERR_BAD_SHAPE, "batch must be 1 for CHAT/SGLANG and >= 1 for PAGED (got %d)", a->batch);
     if (a->batch > 65535) return fail(CF_ERR_BAD_SHAPE, "batch too large (%d)", a->batch);
@@ -222,7 +243,8 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, qd, H, 128, 64))) return rc;
     } else {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 256, 32))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 128, 64))) return rc;
+        if (gqa) { if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 256, 32))) return rc; }
+        else     { if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 128, 64))) return rc; }
     }
     if (!paged) {
         // kv_len == 0: no tile is ever requested; point the maps at any valid address
@@ -256,6 +278,11 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     kp.flags = a->flags;
 
     const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
+    if (gqa) {
+        const int n_clusters = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
+        return paged ? launch_gqa<cfb::PAGED>(kp, n_clusters, a->batch, pdl, stream)
+                     : launch_gqa<cfb::SGLANG>(kp, n_clusters, 1, pdl, stream);
+    }
     switch (a->variant) {
         case CF_VARIANT_CHAT: return launch<cfb::CHAT, CL>(kp, a->n_q_heads, 1, pdl, stream);
         case CF_VARIANT_SGLANG: return launch<cfb::SGLANG, CL>(kp, a->n_q_heads, 1, pdl, stream);

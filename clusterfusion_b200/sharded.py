@@ -1,0 +1,82 @@
+"""Head-parallel shard of the fused attention half-layer (Llama-2-70B config).
+
+GPU g of N owns query heads [g*Hq/N, (g+1)*Hq/N) and KV heads [g*Hkv/N, (g+1)*Hkv/N): Wqkv is sharded by output
+row, Wo by input column, the KV cache by head -- the Column->Row parallel scheme of the reference's eager model
+(chat/llama/model.py:208-235).  Each rank runs the SAME fused kernel on its shard with
+CF_FLAG_OUT_FP32_PARTIAL, which makes it emit the fp32 O-projection partial; exactly one all-reduce(sum) per
+layer over NVLink (torch.distributed, NCCL) completes the layer, and the fp16 rounding happens after the
+reduce so every rank holds the bit-identical result.  No collective is issued for N = 1.
+
+Host-side helpers only (slicing + one collective); all arithmetic is in the CUDA kernel or in NCCL.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import cabi
+
+HEAD_DIM = 128
+
+
+def shard_heads(n_q_heads: int, n_kv_heads: int, rank: int, world: int):
+    if n_kv_heads % world or n_q_heads % world:
+        raise ValueError(f"world size {world} must divide both head counts ({n_q_heads}, {n_kv_heads})")
+    nq, nkv = n_q_heads // world, n_kv_heads // world
+    return (rank * nq, nq), (rank * nkv, nkv)
+
+
+def shard_layer(weight_qkv: torch.Tensor, weight_o: torch.Tensor, n_q_heads: int, n_kv_heads: int,
+                rank: int, world: int) -> Dict[str, torch.Tensor]:
+    """nn.Linear-layout weights -> this rank's contiguous shard.
+
+    weight_qkv [(Hq+2Hkv)*128, hidden] -> [(Hq/N + 2 Hkv/N)*128, hidden]   (rows = this rank's q | k | v heads)
+    weight_o   [hidden, Hq*128]        -> [hidden, Hq/N*128]               (columns = this rank's heads)
+    """
+    (q0, nq), (k0, nkv) = shard_heads(n_q_heads, n_kv_heads, rank, world)
+    qd, kvd = n_q_heads * HEAD_DIM, n_kv_heads * HEAD_DIM
+    wq = weight_qkv[q0 * HEAD_DIM:(q0 + nq) * HEAD_DIM]
+    wk = weight_qkv[qd + k0 * HEAD_DIM: qd + (k0 + nkv) * HEAD_DIM]
+    wv = weight_qkv[qd + kvd + k0 * HEAD_DIM: qd + kvd + (k0 + nkv) * HEAD_DIM]
+    return {"w_qkv": torch.cat([wq, wk, wv], 0).contiguous(),
+            "w_o": weight_o[:, q0 * HEAD_DIM:(q0 + nq) * HEAD_DIM].contiguous(),
+            "n_q_heads": nq, "n_kv_heads": nkv}
+
+
+def shard_kv(cache: torch.Tensor, n_kv_heads: int, rank: int, world: int) -> torch.Tensor:
+    """[kv_len, Hkv*128] -> this rank's heads [kv_len, Hkv/N*128] (contiguous copy)."""
+    nkv = n_kv_heads // world
+    return cache[:, rank * nkv * HEAD_DIM:(rank + 1) * nkv * HEAD_DIM].contiguous()
+
+
+class ShardedDecoderLayer:
+    """One rank's view of a head-parallel layer.  Buffers are allocated once; `forward` is one kernel launch +
+    (world > 1) one all-reduce + one tiny fp32->fp16 conversion, all on the current stream."""
+
+    def __init__(self, weight_qkv_shard, weight_o_shard, rms_w, n_q_local, n_kv_local, hidden, eps,
+                 group: Optional["torch.distributed.ProcessGroup"] = None, world: int = 1):
+        self.wqkv, self.wo, self.rms_w = weight_qkv_shard, weight_o_shard, rms_w
+        self.nq, self.nkv, self.hidden, self.eps = n_q_local, n_kv_local, hidden, eps
+        self.group, self.world = group, world
+        dev = weight_qkv_shard.device
+        self.partial = torch.empty(1, hidden, dtype=torch.float32, device=dev)
+        self.residual_out = torch.empty(1, hidden, dtype=torch.float16, device=dev)
+        self.k_new = torch.empty(1, n_kv_local, HEAD_DIM, dtype=torch.float16, device=dev)
+        self.v_new = torch.empty(1, n_kv_local, HEAD_DIM, dtype=torch.float16, device=dev)
+        self.ws = torch.zeros(cabi.workspace_bytes(hidden, 1), dtype=torch.uint8, device=dev)
+
+    def forward(self, x, residual, k_cache, v_cache, cos, sin, pdl: bool = False):
+        flags = cabi.CF_FLAG_OUT_FP32_PARTIAL | (cabi.CF_FLAG_PDL if pdl else 0)
+        a = cabi.CfLlamaArgs(
+            variant=cabi.CF_VARIANT_SGLANG, flags=flags, hidden=self.hidden, n_q_heads=self.nq, n_kv_heads=self.nkv,
+            head_dim=HEAD_DIM, batch=1, kv_len=k_cache.shape[0], eps=self.eps, x=x.data_ptr(),
+            residual_in=residual.data_ptr(), residual_out=self.residual_out.data_ptr(), w_qkv=self.wqkv.data_ptr(),
+            w_o=self.wo.data_ptr(), rms_w=self.rms_w.data_ptr(), out=self.partial.data_ptr(),
+            k_new=self.k_new.data_ptr(), v_new=self.v_new.data_ptr(), k_cache=k_cache.data_ptr(),
+            v_cache=v_cache.data_ptr(), cos=cos.data_ptr(), sin=sin.data_ptr(), workspace=self.ws.data_ptr())
+        cabi.launch(a, torch.cuda.current_stream().cuda_stream)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.partial, op=dist.ReduceOp.SUM, group=self.group)     # the ONE collective of the layer
+        return self.partial.to(torch.float16), self.residual_out, self.k_new, self.v_new

@@ -230,4 +230,37 @@ __device__ __forceinline__ void cluster_reduce(
     phase ^= 1u;
 }
 
+// ------------------------------------------------------------------------------------------------
+// cluster_scatter: the first half of a bandwidth-optimal all-reduce for large clusters (8, 16 CTAs).
+// `src` holds this CTA's full contribution, CLUSTER_SIZE slices of `slice_bytes`.  Slice r is pushed into slot
+// [my_rank] of CTA r's receive buffer `recv` (CLUSTER_SIZE * slice_bytes); on return recv[0..CLUSTER_SIZE) holds
+// every CTA's contribution to MY slice, in rank order, ready for any fold (sum, softmax-state merge, ...).
+// Follow with cluster_reduce<.., Stage::QUK_DEEPSEEK> (all-gather) to distribute the folded slices.
+// With 16 CTAs an all-to-all of full vectors needs 16x the receive space and 15x the DSMEM traffic of this.
+// Same arming contract as cluster_reduce: cluster_reduce_arm<CLUSTER_SIZE>(barrier, slice_bytes) once.
+// ------------------------------------------------------------------------------------------------
+template <int CLUSTER_SIZE, int NTHREADS = 0, int BAR_ID = 0>
+__device__ __forceinline__ void cluster_scatter(
+    const uint32_t slice_bytes, const uint32_t tid, const uint32_t cluster_block_id,
+    const uint32_t recv_addr, uint32_t barrier, uint32_t& phase, const float* src, float* recv)
+{
+    const uint32_t nthreads = NTHREADS > 0 ? NTHREADS : blockDim.x;
+    const uint32_t vec_per_slice = slice_bytes >> 4;
+    if (NTHREADS > 0) dsm::named_bar_sync(BAR_ID, NTHREADS); else __syncthreads();
+    for (uint32_t i = tid; i < vec_per_slice * CLUSTER_SIZE; i += nthreads) {
+        const uint32_t peer = i / vec_per_slice, v = i - peer * vec_per_slice;
+        const float4 val = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(src) + peer * slice_bytes + (v << 4));
+        const uint32_t off = cluster_block_id * slice_bytes + (v << 4);
+        if (peer == cluster_block_id) *reinterpret_cast<float4*>(reinterpret_cast<char*>(recv) + off) = val;
+        else dsm::st_async_v4(dsm::mapa(recv_addr + off, peer), val, dsm::mapa(barrier, peer));
+    }
+    dsm::mbar_wait_cluster(barrier, phase & 1u);
+    if (NTHREADS > 0) dsm::named_bar_sync(BAR_ID, NTHREADS); else __syncthreads();
+    // re-arm for a next use; the caller must be done folding `recv` before its peers can scatter again,
+    // which the all-gather that follows a scatter guarantees
+    if (tid == 0 && CLUSTER_SIZE > 1) dsm::mbar_arrive_expect_tx(barrier, (CLUSTER_SIZE - 1) * slice_bytes);
+    else if (tid == 0) dsm::mbar_arrive(barrier);
+    phase ^= 1u;
+}
+
 #endif  // CLUSTERFUSION_B200_DSM_CUH

@@ -255,6 +255,135 @@ def test_paged_operator_vs_oracle(lens):
 
 
 # ---------------------------------------------------------------------------------------------------
+# grouped-query attention: Llama-3-8B (32 Q / 8 KV) and the Llama-2-70B head-parallel shards
+# ---------------------------------------------------------------------------------------------------
+S8 = O.LayerShape(4096, 32, 8)
+S70 = O.LayerShape(8192, 64, 8)
+
+
+@pytest.mark.parametrize("kv_len", [0, 1, 100, 1000, 8192])
+def test_gqa_llama3_8b_operator_vs_oracle(kv_len):
+    import clusterfusion
+    d = O.make_inputs(S8, kv_len, seed=80 + kv_len, layout="sglang", theta=500000.0)
+    want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                          d["rms_w"], 1e-5, d["cos"], d["sin"], n_heads=32, n_kv_heads=8, mode="eager")
+    c = cuda(d)
+    res = c["residual"].clone()
+    o, r, k, v = clusterfusion.llama_decoder_layer_sglang(c["x"], res, c["weight_qkv"], c["weight_o"], c["k_cache"],
+                                                          c["v_cache"], c["rms_w"], 1e-5, c["cos"], c["sin"])
+    torch.cuda.synchronize()
+    assert k.shape == (1, 8, 128) and v.shape == (1, 8, 128)
+    assert torch.equal(r.cpu(), want[1])
+    assert close(v, want[3])
+    assert close(k, want[2], atol=4e-3)
+    assert close(o, want[0])
+
+
+def _gptj_to_neox_perm():
+    perm = torch.empty(128, dtype=torch.long)         # neox index j holds gptj index perm[j]
+    perm[:64] = torch.arange(0, 128, 2)
+    perm[64:] = torch.arange(1, 128, 2)
+    return perm
+
+
+@pytest.mark.parametrize("name,shape", [("chat_fp32_gqa8_kv100.npz", S8)])
+def test_gqa_operator_vs_reference_eager_golden(name, shape):
+    """The GQA fixture came from the reference's eager Attention (GPT-J pair RoPE).  q.k is invariant under a common
+    permutation of the head dimension, so permuting Wq / Wk rows and the K cache columns from pair order to
+    rotate-half order lets the NeoX kernel reproduce the same layer output."""
+    import cabi_torch as ct
+    z = np.load(GOLDEN / name)
+    kv = int(z["kv_len"])
+    d = O.make_inputs(shape, kv, seed=int(z["seed"]), w_scale=float(z["w_scale"]), layout="sglang")
+    assert inputs_digest(d) == str(z["digest"])
+    perm = _gptj_to_neox_perm()
+    wq, wk, wv = d["weight_qkv"].split([shape.q_dim, shape.kv_dim, shape.kv_dim], 0)
+    wq_p = wq.view(shape.n_heads, 128, -1)[:, perm].reshape(shape.q_dim, -1)
+    wk_p = wk.view(shape.n_kv_heads, 128, -1)[:, perm].reshape(shape.kv_dim, -1)
+    kc_p = d["k_cache"].view(kv, shape.n_kv_heads, 128)[:, :, perm].reshape(kv, -1)
+    ang = O.rope_angles(kv)
+    zero = torch.zeros_like(d["x"])
+    o, r, k, v = ct.sglang(d["x"].cuda(), zero.cuda(), torch.cat([wq_p, wk_p, wv], 0).contiguous().cuda(),
+                           d["weight_o"].cuda(), kc_p.contiguous().cuda(), d["v_cache"].cuda(), d["rms_w"].cuda(),
+                           float(z["eps"]), ang.cos().cuda(), ang.sin().cuda(), n_heads=shape.n_heads,
+                           n_kv_heads=shape.n_kv_heads)
+    torch.cuda.synchronize()
+    assert close(o, torch.from_numpy(z["out"]))
+    k_ref = torch.from_numpy(z["k"]).view(shape.n_kv_heads, 128)[:, perm]
+    assert close(k.view(shape.n_kv_heads, 128), k_ref, rtol=2e-3, atol=6e-3)
+    assert close(v, torch.from_numpy(z["v"]), rtol=2e-3, atol=3e-3)
+
+
+def test_gqa_paged_operator_vs_oracle():
+    import clusterfusion
+    lens = [300, 0, 45]
+    bs = len(lens)
+    nslots = sum(lens) + bs + 9
+    d = O.make_inputs(S8, nslots, seed=123, layout="sglang", bs=bs)
+    slots = torch.randperm(nslots, generator=torch.Generator().manual_seed(2))
+    indptr, indices, off = [0], [], 0
+    for L in lens:
+        indices += slots[off:off + L + 1].tolist(); off += L + 1; indptr.append(len(indices))
+    indptr = torch.tensor(indptr, dtype=torch.int32); indices = torch.tensor(indices, dtype=torch.int32)
+    positions = torch.tensor(lens, dtype=torch.int64)
+    cos_sin = torch.stack([torch.cat([O.rope_angles(p, theta=500000.0).cos(), O.rope_angles(p, theta=500000.0).sin()])
+                           for p in range(max(lens) + 1)])
+    kp, vp = d["k_cache"].clone(), d["v_cache"].clone()
+    want_o, want_r = O.paged_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], indptr, indices, kp, vp,
+                                   d["rms_w"], 1e-5, positions, cos_sin, n_heads=32, n_kv_heads=8, mode="eager")
+    c = cuda(d)
+    kpool, vpool = c["k_cache"].clone(), c["v_cache"].clone()
+    kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
+    vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
+    out = torch.empty(bs, 4096, dtype=torch.float16, device="cuda"); rout = torch.empty_like(out)
+    clusterfusion.llama_decoder_layer_batch_decode_sglang(out, rout, c["x"], c["residual"], c["weight_qkv"], c["weight_o"],
+                                                          indptr.cuda(), indices.cuda(), kptrs, vptrs, 0, c["rms_w"], 1e-5,
+                                                          positions.cuda(), cos_sin.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(rout.cpu(), want_r)
+    assert close(out, want_o)
+    assert close(kpool, kp, atol=4e-3) and close(vpool, vp)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_llama2_70b_head_parallel_shards_sum_to_full_layer(world):
+    """Every rank's kernel emits its fp32 O-projection partial (CF_FLAG_OUT_FP32_PARTIAL); the sum over ranks
+    (what the one NCCL all-reduce per layer computes) must equal the full 64/8-head layer.  Ranks emulated in turn."""
+    from clusterfusion_b200 import cabi
+    from clusterfusion_b200 import sharded
+    import cabi_torch as ct
+    kv = 777
+    d = O.make_inputs(S70, kv, seed=70, layout="sglang")
+    want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                          d["rms_w"], 1e-5, d["cos"], d["sin"], n_heads=64, n_kv_heads=8, mode="eager")
+    c = cuda(d)
+    total = torch.zeros(1, 8192, dtype=torch.float32, device="cuda")
+    k_all, v_all = [], []
+    ws = ct.workspace(8192, 1, c["x"].device)
+    for rank in range(world):
+        sh = sharded.shard_layer(c["weight_qkv"], c["weight_o"], 64, 8, rank, world)
+        kc = sharded.shard_kv(c["k_cache"], 8, rank, world); vc = sharded.shard_kv(c["v_cache"], 8, rank, world)
+        part = torch.empty(1, 8192, dtype=torch.float32, device="cuda")
+        ro = torch.empty(1, 8192, dtype=torch.float16, device="cuda")
+        nq, nkv = 64 // world, 8 // world
+        kn = torch.empty(nkv * 128, dtype=torch.float16, device="cuda"); vn = torch.empty_like(kn)
+        a = cabi.CfLlamaArgs(variant=1, flags=cabi.CF_FLAG_OUT_FP32_PARTIAL, hidden=8192, n_q_heads=nq, n_kv_heads=nkv,
+                             head_dim=128, batch=1, kv_len=kv, eps=1e-5, x=c["x"].data_ptr(), residual_in=c["residual"].data_ptr(),
+                             residual_out=ro.data_ptr(), w_qkv=sh["w_qkv"].data_ptr(), w_o=sh["w_o"].data_ptr(),
+                             rms_w=c["rms_w"].data_ptr(), out=part.data_ptr(), k_new=kn.data_ptr(), v_new=vn.data_ptr(),
+                             k_cache=kc.data_ptr(), v_cache=vc.data_ptr(), cos=c["cos"].data_ptr(), sin=c["sin"].data_ptr(),
+                             workspace=ws.data_ptr())
+        cabi.launch(a, ct.stream_handle())
+        torch.cuda.synchronize()
+        total += part
+        k_all.append(kn); v_all.append(vn)
+        assert torch.equal(ro.cpu(), want[1])
+    assert close(total.half(), want[0])
+    assert close(torch.cat(k_all), want[2], atol=4e-3)
+    assert close(torch.cat(v_all), want[3])
+
+
+# ---------------------------------------------------------------------------------------------------
 # properties at full BASELINE sizes (no oracle needed) + repeatability
 # ---------------------------------------------------------------------------------------------------
 def test_repeatability_and_workspace_reset():
