@@ -327,8 +327,17 @@ def run_ours(args, rank, world, local_rank):
                           "bytes": Bk, "launches": reps * nsets, "distinct_layer_sets": nsets})
             del Ls, g2
             torch.cuda.empty_cache()
+    # ------------------------------------------------------------------ BASELINE config 4: Llama-3-8B GQA (32 Q / 8 KV), kv 8K
+    gqa = None
+    if not args.no_sweep:
+        gqa = run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
+
+    # ------------------------------------------------------------------ Llama-2-70B head-parallel layer (N > 1 only)
+    shard70 = None
+    if world in (2, 4, 8) and not args.no_sweep:
+        shard70 = run_70b_sharded(torch, dist, dev, rank, world, peak)
 
     if rank != 0:
         if world > 1:
@@ -379,9 +388,117 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "cpu_baseline": cpu,
     }
+    if gqa is not None:
+        line["llama3_8b_gqa"] = gqa
+    if shard70 is not None:
+        line["llama2_70b_head_parallel"] = shard70
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=True, shape=(4096, 32, 8), kvs=(8192,), nl=8, tag="llama3-8b"):
+    """Grouped-query kernel on one GPU (10-arg sglang form through the C ABI, CUDA graph of `nl` distinct layers)."""
+    H, HQ, HKV = shape
+    g = torch.Generator(device=dev).manual_seed(11)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * sc).half()
+    ws = torch.zeros(cabi.workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
+    out = []
+    for kv in kvs:
+        L = [dict(w_qkv=r((HQ + 2 * HKV) * 128, H, sc=0.02), w_o=r(H, HQ * 128, sc=0.02), k=r(kv, HKV * 128), v=r(kv, HKV * 128),
+                  rms=(1 + 0.1 * r(H).float()).half(), o=torch.empty(1, H, dtype=torch.float16, device=dev),
+                  ro=torch.empty(1, H, dtype=torch.float16, device=dev), kn=torch.empty(HKV * 128, dtype=torch.float16, device=dev),
+                  vn=torch.empty(HKV * 128, dtype=torch.float16, device=dev)) for _ in range(nl)]
+        x = r(1, H); res = r(1, H); cos = torch.rand(64, device=dev); sin = torch.rand(64, device=dev)
+
+        def launch(h, rr, lay, stream):
+            a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_SGLANG, flags=(cabi.CF_FLAG_PDL if pdl else 0), hidden=H, n_q_heads=HQ,
+                                 n_kv_heads=HKV, head_dim=128, batch=1, kv_len=kv, eps=1e-5, x=h.data_ptr(), residual_in=rr.data_ptr(),
+                                 residual_out=lay["ro"].data_ptr(), w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(),
+                                 rms_w=lay["rms"].data_ptr(), out=lay["o"].data_ptr(), k_new=lay["kn"].data_ptr(), v_new=lay["vn"].data_ptr(),
+                                 k_cache=lay["k"].data_ptr(), v_cache=lay["v"].data_ptr(), cos=cos.data_ptr(), sin=sin.data_ptr(),
+                                 workspace=ws.data_ptr())
+            cabi.launch(a, stream)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            launch(x, res, L[0], side.cuda_stream)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            st = torch.cuda.current_stream().cuda_stream
+            h, rr = x, res
+            for lay in L:
+                launch(h, rr, lay, st)
+                h, rr = lay["o"], lay["ro"]
+        B = 2 * (HQ + 2 * HKV) * 128 * H + 2 * HQ * 128 * H + 4 * kv * HKV * 128 + 2 * H * 5 + 4 * HKV * 128 + 512
+        reps = max(20, int(0.25 / (nl * B / (peak * 1e9))))
+        ms = timed_replays(gr, reps, 5)
+        us = ms * 1e3 / (reps * nl)
+        a = B / (us * 1e-6) / 1e9
+        out.append({"model": tag, "hidden": H, "q_heads": HQ, "kv_heads": HKV, "kv_len": kv, "us_per_layer": round(us, 3),
+                    "bytes": B, "achieved_gbs": round(a, 1), "frac_of_measured_peak": round(a / peak, 4),
+                    "frac_of_8tbs": round(a / 8000.0, 4), "kernel": "cfb::llama_decoder_layer_gqa_kernel<SGLANG,8|16,4>"})
+        del L, gr
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_70b_sharded(torch, dist, dev, rank, world, peak):
+    """BASELINE config 5: Llama-2-70B attention half-layer (hidden 8192, 64 Q / 8 KV heads) sharded by head over
+    `world` GPUs, ONE NCCL all-reduce on the fp32 O partial per layer (clusterfusion_b200/sharded.py)."""
+    from clusterfusion_b200 import sharded
+    H70, HQ, HKV, nl = 8192, 64, 8, 8
+    nq, nkv = HQ // world, HKV // world
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * sc).half()
+    res = []
+    for kvs in (1024, 16384):
+        layers = [(sharded.ShardedDecoderLayer(r((nq + 2 * nkv) * 128, H70, sc=0.02), r(H70, nq * 128, sc=0.02),
+                                               (1 + 0.1 * r(H70).float()).half(), nq, nkv, H70, 1e-5, None, world),
+                   r(kvs, nkv * 128), r(kvs, nkv * 128)) for _ in range(nl)]
+        torch.manual_seed(3)
+        x = torch.randn(1, H70, device=dev).half(); resid = torch.randn(1, H70, device=dev).half()
+        dist.broadcast(x, 0); dist.broadcast(resid, 0)
+        cos = torch.rand(64, device=dev); sin = torch.rand(64, device=dev)
+
+        def step():
+            h, rr = x, resid
+            for lay, kc, vc in layers:
+                h, rr, _, _ = lay.forward(h, rr, kc, vc, cos, sin)
+            return h
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        gr = None
+        try:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                step()
+            run = gr.replay
+        except Exception:
+            gr, run = None, step
+        for _ in range(5):
+            run()
+        dist.barrier(); torch.cuda.synchronize()
+        reps = 200 if kvs <= 1024 else 60
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record(); torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item()) * 1e3 / (reps * nl)
+        bytes_gpu = (2 * (HQ + 2 * HKV) * 128 * H70 + 2 * HQ * 128 * H70 + 4 * kvs * HKV * 128) // world
+        res.append({"kv_len": kvs, "world": world, "us_per_layer": round(us, 2), "bytes_per_gpu": bytes_gpu,
+                    "achieved_gbs_per_gpu": round(bytes_gpu / (us * 1e-6) / 1e9, 1),
+                    "collective": "1 x NCCL all_reduce(fp32[8192]) per layer", "cuda_graph": gr is not None,
+                    "tokens_per_s_attn_half_80_layers": round(1e6 / (us * 80), 1)})
+        del layers, gr
+        torch.cuda.empty_cache()
+    return res
 
 
 def main():

@@ -46,8 +46,7 @@ def _run(cmd, verbose):
 
 
 def build_cabi(force: bool = False, verbose: bool = True) -> Path:
-    srcs = [CSRC / "llama_decoder.cu", CSRC / "llama_decoder_kernel.cuh", ROOT / "include" / "dsm.cuh",
-            ROOT / "include" / "clusterfusion_b200.h"]
+    srcs = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*"))
     if not force and _newer(LIB, srcs):
         return LIB
     _run([NVCC, *GENCODE, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-shared",

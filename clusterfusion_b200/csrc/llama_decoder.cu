@@ -147,10 +147,10 @@ int launch(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cudaStre
                                   kp, n_clusters, batch, pdl, stream);
 }
 
-template <int VARIANT>
+template <int VARIANT, int CLUSTER>
 int launch_gqa(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cudaStream_t stream) {
-    return launch_kernel<16>(cfb::llama_decoder_layer_gqa_kernel<VARIANT, 16, 4>, cfb::SmemGqa<16, 4>::TOTAL, 4 + VARIANT,
-                             kp, n_clusters, batch, pdl, stream);
+    return launch_kernel<CLUSTER>(cfb::llama_decoder_layer_gqa_kernel<VARIANT, CLUSTER, 4>, cfb::SmemGqa<CLUSTER, 4>::TOTAL,
+                                  (CLUSTER == 16 ? 3 : 5) + VARIANT, kp, n_clusters, batch, pdl, stream);
 }
 
 bool device_is_sm100() {
@@ -203,17 +203,18 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         return fail(CF_ERR_BAD_SHAPE, "bad head counts q=%d kv=%d", a->n_q_heads, a->n_kv_heads);
     const bool gqa = a->n_q_heads != a->n_kv_heads;
     if (!gqa) {
-        if (a->hidden <= 0 || a->hidden % (CL * 256) != 0 || a->hidden / CL > cfb::KS_MAX)
+        const int ks_max = chat ? 1024 : cfb::KS_MAX;      // chat keeps 4 write-once O-projection slots per column
+        if (a->hidden <= 0 || a->hidden % (CL * 256) != 0 || a->hidden / CL > ks_max)
             return fail(CF_ERR_BAD_SHAPE, "hidden must be a multiple of %d and <= %d (got %d)", CL * 256,
-                        CL * cfb::KS_MAX, a->hidden);
+                        CL * ks_max, a->hidden);
     } else {
         // grouped-query path: 16-CTA clusters, 4 query heads per cluster, nn.Linear weight layout
         if (chat) return fail(CF_ERR_BAD_SHAPE, "grouped-query attention needs the nn.Linear layout (SGLANG / PAGED)");
         if ((a->n_q_heads / a->n_kv_heads) % 4 != 0)
             return fail(CF_ERR_BAD_SHAPE, "grouped-query attention needs a multiple of 4 query heads per KV head (q=%d, kv=%d)",
                         a->n_q_heads, a->n_kv_heads);
-        if (a->hidden <= 0 || a->hidden % (16 * 256) != 0 || a->hidden / 16 > cfb::GQA_KS_MAX)
-            return fail(CF_ERR_BAD_SHAPE, "GQA: hidden must be a multiple of 4096 and <= %d (got %d)", 16 * cfb::GQA_KS_MAX, a->hidden);
+        if (a->hidden <= 0 || a->hidden % (16 * 256) != 0 || a->hidden / 8 > cfb::GQA_KS_MAX)
+            return fail(CF_ERR_BAD_SHAPE, "GQA: hidden must be a multiple of 4096 and <= %d (got %d)", 8 * cfb::GQA_KS_MAX, a->hidden);
     }
     if (a->batch < 1 || (!paged && a->batch != 1))
         return fail(CF_ERR_BAD_SHAPE, "batch must be 1 for CHAT/SGLANG and >= 1 for PAGED (got %d)", a->batch);
@@ -239,19 +240,19 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     const uint64_t H = a->hidden, qd = (uint64_t)a->n_q_heads * 128, kvd = (uint64_t)a->n_kv_heads * 128;
     int rc;
     if (chat) {
-        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, 3 * H, H, 128, 64))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, qd, H, 128, 64))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, 3 * H, H, 128, cfb::ROWS256))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, qd, H, 128, cfb::ROWS256))) return rc;
     } else {
-        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 256, 32))) return rc;
-        if (gqa) { if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 256, 32))) return rc; }
-        else     { if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 128, 64))) return rc; }
+        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 256, cfb::ROWS512))) return rc;
+        if (gqa) { if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 256, cfb::ROWS512))) return rc; }
+        else     { if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 128, cfb::ROWS256))) return rc; }
     }
     if (!paged) {
         // kv_len == 0: no tile is ever requested; point the maps at any valid address
         const void* kc = a->kv_len ? a->k_cache : a->x;
         const void* vc = a->kv_len ? a->v_cache : a->x;
-        if ((rc = get_tensor_map(&kp.tm_k, kc, a->kv_len, kvd, 128, 32))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_v, vc, a->kv_len, kvd, 128, 32))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_k, kc, a->kv_len, kvd, 128, cfb::ROWS512))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_v, vc, a->kv_len, kvd, 128, cfb::ROWS512))) return rc;
     }
     kp.x = static_cast<const __half*>(a->x);
     kp.residual_in = static_cast<const __half*>(a->residual_in);
@@ -279,9 +280,14 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
 
     const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
     if (gqa) {
+        // at most four 16-CTA clusters are co-resident (1 CTA / SM, one cluster per GPC-sized slot): use 16 CTAs per
+        // cluster only when that covers the whole grid, otherwise 8 (all clusters resident at once)
         const int n_clusters = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
-        return paged ? launch_gqa<cfb::PAGED>(kp, n_clusters, a->batch, pdl, stream)
-                     : launch_gqa<cfb::SGLANG>(kp, n_clusters, 1, pdl, stream);
+        const bool wide = (long long)n_clusters * a->batch <= 4;
+        if (paged) return wide ? launch_gqa<cfb::PAGED, 16>(kp, n_clusters, a->batch, pdl, stream)
+                               : launch_gqa<cfb::PAGED, 8>(kp, n_clusters, a->batch, pdl, stream);
+        return wide ? launch_gqa<cfb::SGLANG, 16>(kp, n_clusters, 1, pdl, stream)
+                    : launch_gqa<cfb::SGLANG, 8>(kp, n_clusters, 1, pdl, stream);
     }
     switch (a->variant) {
         case CF_VARIANT_CHAT: return launch<cfb::CHAT, CL>(kp, a->n_q_heads, 1, pdl, stream);

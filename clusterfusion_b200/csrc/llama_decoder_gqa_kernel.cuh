@@ -4,7 +4,8 @@
  * kernels hard-code MHA (KV row stride = HIDDEN_DIM, /root/reference/include/H100/llama/llama_kernel_dispatch.cu:63-64;
  * SURVEY.md section 8 row a7).  nn.Linear ("sglang") weight layout only -- that is how GQA checkpoints are stored.
  *
- * Mapping: one 16-CTA cluster per (request, KV head, group of NQ = 4 query heads).  The 4 query heads share
+ * Mapping: one 8- or 16-CTA cluster per (request, KV head, group of NQ = 4 query heads) -- 16 when at most four
+ * clusters exist (only four 16-CTA clusters with 230 KB of shared memory each are co-resident on a B200), else 8.  The 4 query heads share
  * every K/V tile, so K/V are read from HBM once per KV head (SURVEY.md section 8d bytes model); a KV head with 8
  * query heads (70B) gets two clusters, which recompute the small K/V projection and read the cache twice (the
  * second read hits L2).  Inside the cluster: 16-way K-split of the QKV GEMV, 16-way sequence split of the cache,
@@ -21,7 +22,7 @@
 
 namespace cfb {
 
-constexpr int GQA_KS_MAX = 512;        // hidden / 16 <= 512  (hidden <= 8192)
+constexpr int GQA_KS_MAX = 1024;       // hidden / CLUSTER <= 1024  (hidden 8192 with 8-CTA clusters)
 
 template <int CLUSTER, int NQ>
 struct SmemGqa {
@@ -31,13 +32,14 @@ struct SmemGqa {
     static constexpr int PAY2 = SLICE2 + 4;                       // [m, l, -, -, o[32]]
     static constexpr int RING = 0;
     static constexpr int UNION = RING + NSTAGES * STAGE_BYTES;
-    //   phase QKV : xs fp32[512] | qkv_part fp32[2][R]
+    //   phase QKV : xs fp32[GQA_KS_MAX] | qkv_part fp32[GQA_KS_MAX/256][R]
     //   phase ATTN: attn_part fp32[12][132] | cta_state fp32[NQ][132]
-    //   phase O   : out_part fp32[2][512]
+    //   phase O   : out_part fp32[NQ*128/256][GQA_KS_MAX]
     static constexpr int UNION_BYTES = 12 * (HEAD_DIM + 4) * 4 + NQ * (HEAD_DIM + 4) * 4;      // 8448
     static constexpr int XS = UNION;
     static constexpr int QKV_PART = UNION + GQA_KS_MAX * 4;
-    static constexpr int UNION_SIZE = (GQA_KS_MAX * 4 + 2 * R * 4) > UNION_BYTES ? (GQA_KS_MAX * 4 + 2 * R * 4) : UNION_BYTES;
+    static constexpr int QKV_BYTES = GQA_KS_MAX * 4 + (GQA_KS_MAX / 256) * R * 4;
+    static constexpr int UNION_SIZE = QKV_BYTES > UNION_BYTES ? QKV_BYTES : UNION_BYTES;
     static constexpr int ATTN_PART = UNION;
     static constexpr int CTA_STATE = UNION + 12 * (HEAD_DIM + 4) * 4;
     static constexpr int OUT_PART = UNION;
@@ -46,21 +48,25 @@ struct SmemGqa {
     static constexpr int RED1 = RS1 + CLUSTER * SLICE1 * 4;                // fp32[SLICE1]
     static constexpr int AG1 = RED1 + SLICE1 * 4;                          // fp32[CLUSTER][SLICE1] = full q|k|v
     static constexpr int QKV_FIN = AG1 + CLUSTER * SLICE1 * 4;             // fp32[R] roped q*scale | k | v
-    static constexpr int SEND2 = QKV_FIN + R * 4;                          // fp32[CLUSTER][PAY2]
-    static constexpr int RS2 = SEND2 + CLUSTER * PAY2 * 4;                 // fp32[CLUSTER][PAY2]
-    static constexpr int RED2 = RS2 + CLUSTER * PAY2 * 4;                  // fp32[SLICE2]
-    static constexpr int AG2 = RED2 + SLICE2 * 4;                          // fp32[CLUSTER][SLICE2] = attention output
+    // exchange-2 buffers reuse exchange-1 buffers that are dead by then.  Safe against early peers: a peer can only
+    // scatter into RS2 after it finished the exchange-1 all-gather, which needed this CTA's gather contribution,
+    // which this CTA sends after it has folded RS1.
+    static constexpr int SEND2 = QKV_SRC;                                  // fp32[CLUSTER][PAY2]
+    static constexpr int RS2 = RS1;                                        // fp32[CLUSTER][PAY2]
+    static constexpr int RED2 = RED1;                                      // fp32[SLICE2]
+    static_assert(CLUSTER * PAY2 <= R && CLUSTER * PAY2 <= CLUSTER * SLICE1 && SLICE2 <= SLICE1, "exchange-2 buffers must fit");
+    static constexpr int AG2 = QKV_FIN + R * 4;                            // fp32[CLUSTER][SLICE2] = attention output
     static constexpr int RED = AG2 + CLUSTER * SLICE2 * 4;                 // fp32[32]
-    static constexpr int BARS = RED + 32 * 4;                              // full[12], empty[12], xbar[4]
-    static constexpr int FLAGS = BARS + (2 * NSTAGES + 4) * 8;
+    static constexpr int BARS = RED + 32 * 4;                              // full[24], xbar[4]
+    static constexpr int FLAGS = BARS + (NSTAGES + 4) * 8;
     static constexpr int TOTAL = FLAGS + 16;
 };
 
-// 32 output rows x 256 input columns of an [out,in] weight tile against 8 activations per lane;
-// writes the 32 row sums to out[0..32).  Same inner loop as the MHA kernel's sglang QKV phase.
-__device__ __forceinline__ void gemv_tile_32x256(const uint4* tile, const float (&x8)[8], float* out, uint32_t lane) {
+// 16 output rows x 256 input columns of an [out,in] weight tile against 8 activations per lane;
+// writes the 16 row sums to out[0..16).  Same inner loop as the MHA kernel's sglang QKV phase.
+__device__ __forceinline__ void gemv_tile_16x256(const uint4* tile, const float (&x8)[8], float* out, uint32_t lane) {
 #pragma unroll
-    for (int grp = 0; grp < 4; ++grp) {
+    for (int grp = 0; grp < ROWS512 / 8; ++grp) {
         float v[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -127,9 +133,8 @@ llama_decoder_layer_gqa_kernel(const __grid_constant__ KParams p)
     const int KS = hidden / CLUSTER;
     const int kv_cols = Hkv * HEAD_DIM;
 
-    const uint32_t full_u32 = smem_base + S::BARS;
-    const uint32_t empty_u32 = full_u32 + NSTAGES * 8;
-    const uint32_t xbar_u32 = empty_u32 + NSTAGES * 8;
+    const uint32_t full_u32 = smem_base + S::BARS;          // u64 full[NSTAGES]
+    const uint32_t xbar_u32 = full_u32 + NSTAGES * 8;        // u64 xbar[4]
 
     int kv_len, kv_base = 0, new_slot = 0;
     if constexpr (kPaged) {
@@ -140,115 +145,97 @@ llama_decoder_layer_gqa_kernel(const __grid_constant__ KParams p)
     } else {
         kv_len = p.kv_len;
     }
-    const int chunk = (((kv_len + CLUSTER - 1) / CLUSTER) + 31) & ~31;
+    const int chunk = (((kv_len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);
     const int row_begin = min((int)rank * chunk, kv_len);
     const int row_end = min(row_begin + chunk, kv_len);
     const int wins = KS / 256;
-    const uint32_t n_qkv_tiles = (S::R / 32) * wins;
-    const uint32_t n_kv_tiles = (row_end - row_begin + 31) / 32;
-    const uint32_t n_o_tiles = (KS / 32) * (NQ * HEAD_DIM / 256);
+    const uint32_t n_qkv_tiles = (S::R / ROWS512) * wins;
+    const uint32_t n_kv_tiles = (row_end - row_begin + ROWS512 - 1) / ROWS512;
+    const uint32_t n_o_tiles = (KS / ROWS512) * (NQ * HEAD_DIM / 256);
 
     CF_MARK(0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (warp == CONSUMER_WARPS) {
-        if (lane == 0) {
-            for (int s = 0; s < NSTAGES; ++s) {
-                dsm::mbar_init(full_u32 + 8 * s, 1);
-                dsm::mbar_init(empty_u32 + 8 * s, 1);
+
+    // ---- tile stream: every warp requests, consumes and re-requests its own tiles (see llama_decoder_kernel.cuh) ----
+    const uint64_t pol = policy_evict_first();
+    const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
+    const __half* kpool = nullptr;
+    const __half* vpool = nullptr;
+    if constexpr (kPaged) {
+        kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
+        vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
+    }
+    auto issue_tile = [&](uint32_t g) {
+        if (g >= total_tiles) return;
+        const uint32_t s = ring_stage(g);
+        const uint32_t fb = full_u32 + 8 * s;
+        const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
+        if (g < n_qkv_tiles) {
+            if (lane == 0) {
+                constexpr int BPH = HEAD_DIM / ROWS512;          // 16-row blocks per head (8)
+                const int rb = g / wins, win = g % wins;         // rb: 16-row block inside q(NQ*128) | k(128) | v(128)
+                int row0;
+                if (rb < NQ * BPH) row0 = qh0 * HEAD_DIM + rb * ROWS512;
+                else if (rb < NQ * BPH + BPH) row0 = Hq * HEAD_DIM + kvh * HEAD_DIM + (rb - NQ * BPH) * ROWS512;
+                else row0 = (Hq + Hkv) * HEAD_DIM + kvh * HEAD_DIM + (rb - NQ * BPH - BPH) * ROWS512;
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wqkv, rank * KS + win * 256, row0, fb, pol);
             }
-            dsm::mbar_fence_init();
+        } else if (g < n_qkv_tiles + n_kv_tiles) {
+            const uint32_t i = g - n_qkv_tiles;
+            if constexpr (!kPaged) {
+                if (lane == 0) {
+                    const int r0 = row_begin + i * ROWS512;
+                    dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                    tma_load_2d(dst, &p.tm_k, kvh * HEAD_DIM, r0, fb, pol);
+                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, kvh * HEAD_DIM, r0, fb, pol);
+                }
+            } else {
+                const int r = row_begin + i * ROWS512 + (lane & 15);
+                const bool valid = r < row_end;
+                const long long slot = valid ? (long long)p.indices[kv_base + r] : 0;
+                const int nvalid = min(ROWS512, row_end - (row_begin + (int)i * ROWS512));
+                if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
+                __syncwarp();
+                if (valid) {
+                    const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
+                    if (lane < 16) bulk_load_1d(d, kpool + slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                    else bulk_load_1d(d + STAGE_BYTES / 2, vpool + slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                }
+            }
+        } else {
+            if (lane == 0) {
+                constexpr int owins = NQ * HEAD_DIM / 256;
+                const uint32_t i = g - n_qkv_tiles - n_kv_tiles;
+                const int rb = i / owins, win = i % owins;       // Wo [out][in]: 16 output rows x 256 of this cluster's input cols
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wo, qh0 * HEAD_DIM + win * 256, rank * KS + rb * ROWS512, fb, pol);
+            }
         }
-        __syncwarp();
-        asm volatile("bar.arrive %0, %1;" ::"n"(INIT_BAR), "n"(BLOCK_THREADS) : "memory");
-    } else {
+    };
+
+    if (lane == 0) {
+        dsm::mbar_init(full_u32 + 8 * warp, 1);
+        dsm::mbar_init(full_u32 + 8 * (warp + CONSUMER_WARPS), 1);
         if (tid == 0) {
+            prefetch_tmap(&p.tm_wqkv);
+            prefetch_tmap(&p.tm_wo);
+            if constexpr (!kPaged) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); }
             cluster_reduce_arm<CLUSTER>(xbar_u32, S::SLICE1 * 4);
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::SLICE1 * 4);
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 16, S::PAY2 * 4);
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 24, S::SLICE2 * 4);
-            dsm::mbar_fence_init();
         }
-        dsm::named_bar_sync(INIT_BAR, BLOCK_THREADS);
+        dsm::mbar_fence_init();
     }
+    __syncwarp();
+    CF_MARK(12);
+    issue_tile(warp);
+    issue_tile(warp + CONSUMER_WARPS);
     dsm::cluster_arrive();
 
     // =============================================================================================
-    // PRODUCER WARP
-    // =============================================================================================
-    if (warp == CONSUMER_WARPS) {
-        CF_MARK(12);
-        const uint64_t pol = policy_evict_first();
-        uint32_t g = 0;
-        if (lane == 0) {
-            prefetch_tmap(&p.tm_wqkv);
-            prefetch_tmap(&p.tm_wo);
-            if constexpr (!kPaged) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); }
-            for (uint32_t i = 0; i < n_qkv_tiles; ++i, ++g) {
-                const uint32_t s = ring_stage(g);
-                dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
-                dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
-                const int rb = i / wins, win = i % wins;         // rb: 32-row block inside q(NQ*128) | k(128) | v(128)
-                int row0;
-                if (rb < NQ * 4) row0 = qh0 * HEAD_DIM + rb * 32;
-                else if (rb < NQ * 4 + 4) row0 = Hq * HEAD_DIM + kvh * HEAD_DIM + (rb - NQ * 4) * 32;
-                else row0 = (Hq + Hkv) * HEAD_DIM + kvh * HEAD_DIM + (rb - NQ * 4 - 4) * 32;
-                tma_load_2d(smem_base + S::RING + s * STAGE_BYTES, &p.tm_wqkv, rank * KS + win * 256, row0,
-                            full_u32 + 8 * s, pol);
-            }
-        }
-        if constexpr (!kPaged) {
-            if (lane == 0) {
-                for (uint32_t i = 0; i < n_kv_tiles; ++i, ++g) {
-                    const uint32_t s = ring_stage(g);
-                    dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
-                    dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
-                    const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
-                    const int r0 = row_begin + i * 32;
-                    tma_load_2d(dst, &p.tm_k, kvh * HEAD_DIM, r0, full_u32 + 8 * s, pol);
-                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, kvh * HEAD_DIM, r0, full_u32 + 8 * s, pol);
-                }
-            }
-        } else {
-            g = __shfl_sync(0xffffffffu, g, 0);
-            const __half* kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
-            const __half* vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
-            for (uint32_t i = 0; i < n_kv_tiles; ++i, ++g) {
-                const uint32_t s = ring_stage(g);
-                const int r = row_begin + i * 32 + lane;
-                const bool valid = r < row_end;
-                const long long slot = valid ? (long long)p.indices[kv_base + r] : 0;
-                const int nvalid = min(32, row_end - (row_begin + (int)i * 32));
-                if (lane == 0) {
-                    dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
-                    dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, nvalid * 2 * HEAD_DIM * 2);
-                }
-                __syncwarp();
-                if (valid) {
-                    const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES + lane * (HEAD_DIM * 2);
-                    bulk_load_1d(dst, kpool + slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2, full_u32 + 8 * s, pol);
-                    bulk_load_1d(dst + STAGE_BYTES / 2, vpool + slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2,
-                                 full_u32 + 8 * s, pol);
-                }
-            }
-            g = __shfl_sync(0xffffffffu, g, 0);
-        }
-        if (lane == 0) {
-            constexpr int owins = NQ * HEAD_DIM / 256;
-            for (uint32_t i = 0; i < n_o_tiles; ++i, ++g) {
-                const uint32_t s = ring_stage(g);
-                dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
-                dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
-                const int rb = i / owins, win = i % owins;       // Wo [out][in]: 32 output rows x 256 of this cluster's input cols
-                tma_load_2d(smem_base + S::RING + s * STAGE_BYTES, &p.tm_wo, qh0 * HEAD_DIM + win * 256,
-                            rank * KS + rb * 32, full_u32 + 8 * s, pol);
-            }
-        }
-        CF_MARK(13);
-        return;
-    }
-
-    // =============================================================================================
-    // CONSUMER WARPS
+    // ALL WARPS
     // =============================================================================================
     float* xs = reinterpret_cast<float*>(smem + S::XS);
     float* qkv_part = reinterpret_cast<float*>(smem + S::QKV_PART);
@@ -322,10 +309,10 @@ llama_decoder_layer_gqa_kernel(const __grid_constant__ KParams p)
             x8[0] = a.x; x8[1] = a.y; x8[2] = a.z; x8[3] = a.w; x8[4] = b.x; x8[5] = b.y; x8[6] = b.z; x8[7] = b.w;
         }
         ring_wait_full(full_u32, g);
-        gemv_tile_32x256(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), x8,
-                         qkv_part + win * S::R + rb * 32, lane);
+        gemv_tile_16x256(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), x8,
+                         qkv_part + win * S::R + rb * ROWS512, lane);
         __syncwarp();
-        if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+        issue_tile(g + NSTAGES);
     }
     gbase += n_qkv_tiles;
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
@@ -409,9 +396,9 @@ llama_decoder_layer_gqa_kernel(const __grid_constant__ KParams p)
             ring_wait_full(full_u32, g);
             const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
             const uint4* vt = kt + STAGE_BYTES / 32;
-            const int rows_left = row_end - (row_begin + (int)i * 32);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            const int rows_left = row_end - (row_begin + (int)i * ROWS512);
+            {
+                constexpr int half = 0;
                 float sc[NQ][8];
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
@@ -463,7 +450,7 @@ llama_decoder_layer_gqa_kernel(const __grid_constant__ KParams p)
                 }
             }
             __syncwarp();
-            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+            issue_tile(g + NSTAGES);
         }
         gbase += n_kv_tiles;
         CF_MARK(5);
@@ -564,10 +551,10 @@ llama_decoder_layer_gqa_kernel(const __grid_constant__ KParams p)
                 a8[0] = a.x; a8[1] = a.y; a8[2] = a.z; a8[3] = a.w; a8[4] = b.x; a8[5] = b.y; a8[6] = b.z; a8[7] = b.w;
             }
             ring_wait_full(full_u32, g);
-            gemv_tile_32x256(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), a8,
-                             out_part + win * GQA_KS_MAX + rb * 32, lane);
+            gemv_tile_16x256(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), a8,
+                             out_part + win * GQA_KS_MAX + rb * ROWS512, lane);
             __syncwarp();
-            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+            issue_tile(g + NSTAGES);
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }

@@ -8,15 +8,16 @@
  * kernel_batch_sglang.cuh:43-664); the decomposition inside a cluster follows the paper (K-split of
  * the QKV GEMV, sequence-split of the KV cache, N-split of the O GEMV) but the machinery is new:
  *
- *  - warp specialisation: warp 8 is a dedicated producer that streams EVERY byte the CTA will ever
- *    need -- Wqkv tiles, then K/V tiles, then Wo tiles -- through one NSTAGES x 16 KB ring of TMA
- *    tiles guarded by full/empty mbarriers.  None of those loads depends on activations, so the
- *    producer runs ahead across phase boundaries: K/V tiles land while the consumers are still in
- *    the QKV cluster exchange / RoPE, Wo tiles land during the softmax merge.  (The reference drains
- *    a 2-stage, single-thread-producer pipeline five times per layer, kernel.cuh:141-267, :343, :579.)
- *  - 8 consumer warps; each ring tile is owned by ONE warp (tile i -> warp i % 8), so full-barrier
- *    waits of different warps interleave instead of stalling the CTA in lock-step, and the empty
- *    barrier needs a single arrival.
+ *  - one tile stream for EVERY byte the CTA will ever need -- Wqkv tiles, then K/V tiles, then Wo tiles --
+ *    through 24 x 8 KB TMA stages.  None of those loads depends on activations, so the stream runs ahead
+ *    across phase boundaries: K/V tiles land while the warps are still in the QKV cluster exchange / RoPE,
+ *    Wo tiles land during the softmax merge, and under programmatic dependent launch the first 24 tiles are
+ *    requested while the previous layer is still finishing.  (The reference drains a 2-stage,
+ *    single-thread-producer pipeline five times per layer, kernel.cuh:141-267, :343, :579.)
+ *  - 12 warps, each a self-contained double-buffered stream: tile g lives in stage g % 24 and belongs to warp
+ *    g % 12; a warp consumes its tile, then re-issues the TMA load for tile g + 24 into the stage it just freed
+ *    while its other stage is already landing.  No producer warp, no empty barriers, no head-of-line blocking;
+ *    one full mbarrier per stage whose phase parity cannot alias because a stage only ever has one owner.
  *  - every reduction is fp32: per-warp partials land in write-once shared-memory slots and are
  *    folded in a fixed order; the cluster exchanges (q|k|v vector, softmax state) go through the new
  *    cluster_reduce<> in include/dsm.cuh (one st.async push per peer, no cluster.sync());
@@ -42,11 +43,13 @@ namespace cfb {
 constexpr int HEAD_DIM = 128;
 constexpr int CONSUMER_WARPS = 12;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;   // 384
-constexpr int BLOCK_THREADS = CONSUMER_THREADS + 32;    // + producer warp
-constexpr int STAGE_BYTES = 16384;
-constexpr int NSTAGES = CONSUMER_WARPS;                 // stage s is consumed by warp s, always (see ring_wait_full)
+constexpr int BLOCK_THREADS = CONSUMER_THREADS;         // no producer warp: every warp streams its own tiles
+constexpr int STAGE_BYTES = 8192;
+constexpr int STAGES_PER_WARP = 2;
+constexpr int NSTAGES = STAGES_PER_WARP * CONSUMER_WARPS;   // stage s is consumed by warp s % 12, always (see ring_wait_full)
+constexpr int ROWS256 = STAGE_BYTES / 256;              // rows of a {128 halves wide} tile            (32)
+constexpr int ROWS512 = STAGE_BYTES / 512;              // rows of a {256 halves wide} tile / KV rows per stage (16)
 constexpr int KS_MAX = 2048;                            // max hidden / CLUSTER
-constexpr int INIT_BAR = 2;                             // producer arrives / consumers sync, once
 constexpr int CONSUMER_BAR = 1;                         // named barrier id for the consumer threads
 
 enum Variant : int { CHAT = 0, SGLANG = 1, PAGED = 2 };
@@ -93,7 +96,7 @@ struct Smem {
     static constexpr int UNION = RING + NSTAGES * STAGE_BYTES;
     //   phase QKV : xs fp32[KS_MAX] | qkv_part  (chat: fp32[12 warps][128]; sglang: fp32[KS/256][384])
     //   phase ATTN: attn_part fp32[24][132]
-    //   phase O   : out_part fp32[2][KS_MAX]
+    //   phase O   : out_part  (chat: fp32[4][KS <= 1024]; sglang: fp32[KS])
     static constexpr int UNION_BYTES = KS_MAX * 4 + 8 * QKV_OUT * 4;   // 20480 >= 2*KS_MAX*4
     static constexpr int XS = UNION;
     static constexpr int QKV_PART = UNION + KS_MAX * 4;
@@ -108,8 +111,8 @@ struct Smem {
     static constexpr int QKV_FINAL = ATTN_RECV + CLUSTER * ATTN_PAYLOAD * 4;  // fp32[384] roped q*scale | k | v
     static constexpr int ATTN_OUT = QKV_FINAL + QKV_OUT * 4;               // fp32[128]
     static constexpr int RED = ATTN_OUT + HEAD_DIM * 4;                    // fp32[32] block-reduce scratch
-    static constexpr int BARS = RED + 32 * 4;                              // u64 full[NSTAGES], empty[NSTAGES], xbar[2]
-    static constexpr int FLAGS = BARS + (2 * NSTAGES + 2) * 8;             // u32[4]
+    static constexpr int BARS = RED + 32 * 4;                              // u64 full[NSTAGES], xbar[2]
+    static constexpr int FLAGS = BARS + (NSTAGES + 2) * 8;                 // u32[4]
     static constexpr int TOTAL = FLAGS + 16;
 };
 
@@ -163,7 +166,7 @@ __device__ __forceinline__ float round_h(float v) { return __half2float(__float2
 #ifdef CF_TRACE
 __device__ unsigned long long* g_cf_trace = nullptr;     // [grid][16] globaltimer ns, set by cf_debug_set_trace
 __device__ __forceinline__ void trace_mark(int slot, int launch_id) {
-    if (g_cf_trace && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == (slot >= 12 ? CONSUMER_WARPS : 0)) {
+    if (g_cf_trace && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_cf_trace[((size_t)launch_id * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
@@ -178,8 +181,10 @@ __device__ __forceinline__ void trace_mark(int slot, int launch_id) {
 __device__ __forceinline__ uint32_t ring_stage(uint32_t g) { return g % NSTAGES; }
 __device__ __forceinline__ uint32_t ring_parity(uint32_t g) { return (g / NSTAGES) & 1u; }
 
-// Ring discipline.  Global tile index g -> stage g % NSTAGES, consumed by warp g % CONSUMER_WARPS, and
-// NSTAGES == CONSUMER_WARPS: a stage is always consumed by the same warp, in order.  That is what makes the
+// Ring discipline.  Global tile index g -> stage g % NSTAGES, owned by warp g % CONSUMER_WARPS, and
+// NSTAGES == 2 * CONSUMER_WARPS: a stage always belongs to the same warp, which both consumes it and re-fills it
+// (tile g + NSTAGES) -- while it consumes one of its two stages the other is landing, so a warp's cycle is
+// max(consume, consume/2 + memory latency) instead of consume + latency.  The affinity is also what makes the
 // one-bit phase parity sufficient: a warp cannot test use u of its stage before it has itself consumed use
 // u-1, so the parity can never alias to an older phase (it would if consecutive uses of a stage were
 // consumed by different warps -- a warp could then look at the barrier before the previous use's TMA landed).
@@ -188,7 +193,7 @@ __device__ __forceinline__ void ring_wait_full(uint32_t full_u32, uint32_t g) {
 }
 // first tile index i >= 0 of a phase starting at global index gbase that belongs to `warp`
 __device__ __forceinline__ uint32_t first_tile(uint32_t gbase, uint32_t warp) {
-    return (warp + NSTAGES - gbase % NSTAGES) % NSTAGES;
+    return (warp + CONSUMER_WARPS - gbase % CONSUMER_WARPS) % CONSUMER_WARPS;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -215,13 +220,8 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     const int KS = hidden / CLUSTER;     // this CTA's slice of the GEMV reduction dim / of the O output dim
     const int kv_cols = p.n_kv_heads * HEAD_DIM;
 
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BARS);
-    uint64_t* empty_bar = full_bar + NSTAGES;
-    uint64_t* xbar = empty_bar + NSTAGES;
-    const uint32_t full_u32 = smem_base + S::BARS;
-    const uint32_t empty_u32 = full_u32 + NSTAGES * 8;
-    const uint32_t xbar_u32 = empty_u32 + NSTAGES * 8;
-    (void)full_bar; (void)empty_bar; (void)xbar;
+    const uint32_t full_u32 = smem_base + S::BARS;          // u64 full[NSTAGES]
+    const uint32_t xbar_u32 = full_u32 + NSTAGES * 8;        // u64 xbar[2]
 
     // ---- per-request KV range -----------------------------------------------------------------
     int kv_len, kv_base = 0, new_slot = 0;
@@ -233,143 +233,117 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     } else {
         kv_len = p.kv_len;
     }
-    const int chunk = (((kv_len + CLUSTER - 1) / CLUSTER) + 31) & ~31;   // KV rows per CTA, tile aligned
+    const int chunk = (((kv_len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);   // KV rows per CTA, tile aligned
     const int row_begin = min((int)rank * chunk, kv_len);
     const int row_end = min(row_begin + chunk, kv_len);
-    const uint32_t n_qkv_tiles = kChat ? 3u * (KS / 64) : 12u * (KS / 256);
-    const uint32_t n_kv_tiles = (row_end - row_begin + 31) / 32;
-    const uint32_t n_o_tiles = kChat ? 2u * (KS / 128) : (uint32_t)(KS / 64);
+    const uint32_t n_qkv_tiles = kChat ? 3u * (KS / ROWS256) : (uint32_t)(S::QKV_OUT / ROWS512) * (KS / 256);
+    const uint32_t n_kv_tiles = (row_end - row_begin + ROWS512 - 1) / ROWS512;
+    const uint32_t n_o_tiles = kChat ? (uint32_t)(HEAD_DIM / ROWS256) * (KS / 128) : (uint32_t)(KS / ROWS256);
 
     CF_MARK(0);   // kernel entry
-    // ---- barrier init ---------------------------------------------------------------------------
-    // The producer warp initialises the ring barriers itself and starts streaming at once: nothing it does
-    // depends on the other warps, on the peer CTAs or (under programmatic dependent launch) on the previous
-    // kernel in the stream.  The consumers learn about the ring through named barrier INIT_BAR (producer
-    // arrives, consumers sync).  The exchange barriers are armed by consumer thread 0 before the cluster-wide
-    // arrive; only the consumers ever wait on that cluster barrier (before their first push to a peer).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // no-op unless the NEXT launch opted into PDL
-    if (warp == CONSUMER_WARPS) {
-        if (lane == 0) {
-            for (int s = 0; s < NSTAGES; ++s) {
-                dsm::mbar_init(full_u32 + 8 * s, 1);
-                dsm::mbar_init(empty_u32 + 8 * s, 1);
-            }
-            dsm::mbar_fence_init();
-        }
-        __syncwarp();
-        asm volatile("bar.arrive %0, %1;" ::"n"(INIT_BAR), "n"(BLOCK_THREADS) : "memory");
-    } else {
-        if (tid == 0) {
-            cluster_reduce_arm<CLUSTER>(xbar_u32, S::QKV_OUT * 4);
-            cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::ATTN_PAYLOAD * 4);
-            dsm::mbar_fence_init();
-        }
-        dsm::named_bar_sync(INIT_BAR, BLOCK_THREADS);
-    }
-    dsm::cluster_arrive();     // peers may push into this CTA's smem only after every CTA armed its barriers
 
-    // =============================================================================================
-    // PRODUCER WARP
-    // =============================================================================================
-    if (warp == CONSUMER_WARPS) {
-        CF_MARK(12);  // producer: first TMA issue
-        const uint64_t pol = policy_evict_first();
-        // tile coordinates
-        auto qkv_coords = [&](uint32_t i, int& c0, int& c1) {
-            if constexpr (kChat) {           // tile i: matrix j = i % 3, rows t = i / 3 (64 input rows)
-                const int j = i % 3, t = i / 3;
-                c0 = head * HEAD_DIM;
-                c1 = j * hidden + rank * KS + t * 64;
-            } else {                         // tile i: 32 output rows x 256 input cols
-                const int wins = KS / 256;
-                const int rb = i / wins, win = i % wins;          // rb in [0,12): matrix j = rb/4
-                const int j = rb >> 2, sub = rb & 3;
-                const int row0 = (j == 0) ? head * HEAD_DIM
-                               : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
-                                          : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
-                c0 = rank * KS + win * 256;
-                c1 = row0 + sub * 32;
-            }
-        };
-        auto wo_coords = [&](uint32_t i, int& c0, int& c1) {
-            if constexpr (kChat) {           // Wo^T [in][out]: 64 input rows x 128 output cols
-                c0 = rank * KS + (i >> 1) * 128;
-                c1 = head * HEAD_DIM + (i & 1) * 64;
-            } else {                         // Wo [out][in]: 64 output rows x this head's 128 input cols
-                c0 = head * HEAD_DIM;
-                c1 = rank * KS + i * 64;
-            }
-        };
-        uint32_t g = 0;
-        if (lane == 0) {
-            prefetch_tmap(&p.tm_wqkv);
-            prefetch_tmap(&p.tm_wo);
-            if constexpr (!kPaged) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); }
-            // ---- phase 1: Wqkv tiles --------------------------------------------------------------
-            for (uint32_t i = 0; i < n_qkv_tiles; ++i, ++g) {
-                const uint32_t s = ring_stage(g);
-                dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
-                dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
-                int c0, c1;
-                qkv_coords(i, c0, c1);
-                tma_load_2d(smem_base + S::RING + s * STAGE_BYTES, &p.tm_wqkv, c0, c1, full_u32 + 8 * s, pol);
-            }
-        }
-        // ---- phase 2: K / V tiles (32 rows of K then 32 rows of V per stage) ------------------------
-        if constexpr (!kPaged) {
+    // ---- tile stream ----------------------------------------------------------------------------------
+    const uint64_t pol = policy_evict_first();
+    const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
+    const __half* kpool = nullptr;
+    const __half* vpool = nullptr;
+    if constexpr (kPaged) {
+        kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
+        vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
+    }
+    // Request global tile g into its stage.  Called warp-converged by the owner warp (g % 12 == warp), after it has
+    // finished reading the stage (tile g - 24).  Weights and tiled KV: one elected lane; paged KV: one row per lane.
+    auto issue_tile = [&](uint32_t g) {
+        if (g >= total_tiles) return;
+        const uint32_t s = ring_stage(g);
+        const uint32_t fb = full_u32 + 8 * s;
+        const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
+        if (g < n_qkv_tiles) {
             if (lane == 0) {
-                for (uint32_t i = 0; i < n_kv_tiles; ++i, ++g) {
-                    const uint32_t s = ring_stage(g);
-                        dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
-                    dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
-                    const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
-                    const int r0 = row_begin + i * 32;
-                    tma_load_2d(dst, &p.tm_k, head * HEAD_DIM, r0, full_u32 + 8 * s, pol);
-                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, head * HEAD_DIM, r0, full_u32 + 8 * s, pol);
+                const uint32_t i = g;
+                int c0, c1;
+                if constexpr (kChat) {           // tile i: matrix j = i % 3, rows t = i / 3 (32 input rows x 128 output cols)
+                    const int j = i % 3, t = i / 3;
+                    c0 = head * HEAD_DIM;
+                    c1 = j * hidden + rank * KS + t * ROWS256;
+                } else {                         // tile i: 16 output rows x 256 input cols
+                    const int wins = KS / 256;
+                    const int rb = i / wins, win = i % wins;          // rb in [0,24): matrix j = rb / 8
+                    const int j = rb / (HEAD_DIM / ROWS512), sub = rb % (HEAD_DIM / ROWS512);
+                    const int row0 = (j == 0) ? head * HEAD_DIM
+                                   : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
+                                              : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
+                    c0 = rank * KS + win * 256;
+                    c1 = row0 + sub * ROWS512;
+                }
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wqkv, c0, c1, fb, pol);
+            }
+        } else if (g < n_qkv_tiles + n_kv_tiles) {
+            const uint32_t i = g - n_qkv_tiles;                 // 16 KV rows: K in the first 4 KB of the stage, V in the second
+            if constexpr (!kPaged) {
+                if (lane == 0) {
+                    const int r0 = row_begin + i * ROWS512;
+                    dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                    tma_load_2d(dst, &p.tm_k, head * HEAD_DIM, r0, fb, pol);
+                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, head * HEAD_DIM, r0, fb, pol);
+                }
+            } else {
+                // paged KV, page size 1: one 256-byte bulk copy per row per tensor; lanes 0-15 fetch K rows, 16-31 V rows
+                const int r = row_begin + i * ROWS512 + (lane & 15);
+                const bool valid = r < row_end;
+                const long long slot = valid ? (long long)p.indices[kv_base + r] : 0;
+                const int nvalid = min(ROWS512, row_end - (row_begin + (int)i * ROWS512));
+                if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
+                __syncwarp();
+                if (valid) {
+                    const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
+                    if (lane < 16) bulk_load_1d(d, kpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                    else bulk_load_1d(d + STAGE_BYTES / 2, vpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
                 }
             }
         } else {
-            // paged KV, page size 1: one 256-byte bulk copy per row per tensor, one row per lane
-            g = __shfl_sync(0xffffffffu, g, 0);
-            const __half* kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
-            const __half* vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
-            for (uint32_t i = 0; i < n_kv_tiles; ++i, ++g) {
-                const uint32_t s = ring_stage(g);
-                const int r = row_begin + i * 32 + lane;
-                const bool valid = r < row_end;
-                const long long slot = valid ? (long long)p.indices[kv_base + r] : 0;
-                const int nvalid = min(32, row_end - (row_begin + (int)i * 32));
-                if (lane == 0) {
-                    dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
-                    dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, nvalid * 2 * HEAD_DIM * 2);
-                }
-                __syncwarp();
-                if (valid) {
-                    const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES + lane * (HEAD_DIM * 2);
-                    bulk_load_1d(dst, kpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, full_u32 + 8 * s, pol);
-                    bulk_load_1d(dst + STAGE_BYTES / 2, vpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2,
-                                 full_u32 + 8 * s, pol);
-                }
-            }
-            g = __shfl_sync(0xffffffffu, g, 0);
-        }
-        // ---- phase 3: Wo tiles -----------------------------------------------------------------------
-        if (lane == 0) {
-            for (uint32_t i = 0; i < n_o_tiles; ++i, ++g) {
-                const uint32_t s = ring_stage(g);
-                dsm::mbar_wait(empty_u32 + 8 * s, ring_parity(g) ^ 1u);
-                dsm::mbar_arrive_expect_tx(full_u32 + 8 * s, STAGE_BYTES);
+            if (lane == 0) {
+                const uint32_t i = g - n_qkv_tiles - n_kv_tiles;
                 int c0, c1;
-                wo_coords(i, c0, c1);
-                tma_load_2d(smem_base + S::RING + s * STAGE_BYTES, &p.tm_wo, c0, c1, full_u32 + 8 * s, pol);
+                if constexpr (kChat) {           // Wo^T [in][out]: 32 input rows x 128 output cols
+                    c0 = rank * KS + (i >> 2) * 128;
+                    c1 = head * HEAD_DIM + (i & 3) * ROWS256;
+                } else {                         // Wo [out][in]: 32 output rows x this head's 128 input cols
+                    c0 = head * HEAD_DIM;
+                    c1 = rank * KS + i * ROWS256;
+                }
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wo, c0, c1, fb, pol);
             }
         }
-        CF_MARK(13);  // producer: last TMA issued
-        return;   // producer done; outstanding TMA completes on the consumers' barriers
+    };
+
+    // ---- barrier init + first two tiles of every warp ---------------------------------------------------
+    // Each warp initialises the full barriers of its own two stages and requests its first two tiles at once:
+    // nothing here depends on the other warps, on the peer CTAs or (under programmatic dependent launch) on the
+    // previous kernel in the stream.  The exchange barriers are armed by thread 0 before the cluster-wide arrive.
+    if (lane == 0) {
+        dsm::mbar_init(full_u32 + 8 * warp, 1);
+        dsm::mbar_init(full_u32 + 8 * (warp + CONSUMER_WARPS), 1);
+        if (tid == 0) {
+            prefetch_tmap(&p.tm_wqkv);
+            prefetch_tmap(&p.tm_wo);
+            if constexpr (!kPaged) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); }
+            cluster_reduce_arm<CLUSTER>(xbar_u32, S::QKV_OUT * 4);
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::ATTN_PAYLOAD * 4);
+        }
+        dsm::mbar_fence_init();
     }
+    __syncwarp();
+    CF_MARK(12);  // first TMA issue
+    issue_tile(warp);
+    issue_tile(warp + CONSUMER_WARPS);
+    dsm::cluster_arrive();     // peers may push into this CTA's smem only after every CTA armed its barriers
 
     // =============================================================================================
-    // CONSUMER WARPS (256 threads)
+    // ALL WARPS
     // =============================================================================================
     float* xs = reinterpret_cast<float*>(smem + S::XS);
     float* qkv_part = reinterpret_cast<float*>(smem + S::QKV_PART);
@@ -443,7 +417,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
 
     // ---- phase 1: QKV GEMV over this CTA's K-slice ----------------------------------------------------
     if constexpr (kChat) {
-        // tile i = 64 input rows (t = i / 3) x 128 output cols of matrix j = i % 3.  The QKV phase starts at
+        // tile i = 32 input rows (t = i / 3) x 128 output cols of matrix j = i % 3.  The QKV phase starts at
         // ring index 0 and 12 % 3 == 0, so warp w only ever sees matrix j = w % 3: its 8 column sums stay in
         // registers for the whole phase.  lane (sub, c): rows sub + 2s, cols c*8 .. c*8+7.
         const int sub = lane >> 4, c = lane & 15;
@@ -452,9 +426,9 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             const uint32_t g = gbase + i, s = ring_stage(g);
             ring_wait_full(full_u32, g);
             const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
-            const float* xrow = xs + (i / 3) * 64;
+            const float* xrow = xs + (i / 3) * ROWS256;
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
+            for (int r = 0; r < ROWS256 / 2; ++r) {
                 const int row = 2 * r + sub;
                 float w8[8];
                 unpack8(tile[row * 16 + c], w8);
@@ -463,7 +437,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                 for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, w8[k], acc[k]);
             }
             __syncwarp();
-            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+            issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
@@ -473,7 +447,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             slot[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
     } else {
-        // tile = 32 output rows x 256 input cols; lane owns input cols lane*8..+8 of every row
+        // tile = 16 output rows x 256 input cols; lane owns input cols lane*8..+8 of every row
         const int wins = KS / 256;
         for (uint32_t i = first_tile(gbase, warp); i < n_qkv_tiles; i += CONSUMER_WARPS) {
             const uint32_t g = gbase + i, s = ring_stage(g);
@@ -488,7 +462,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             ring_wait_full(full_u32, g);
             const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
 #pragma unroll
-            for (int grp = 0; grp < 4; ++grp) {
+            for (int grp = 0; grp < ROWS512 / 8; ++grp) {
                 float v[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -525,11 +499,11 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                 // lane bits (4,3,2) select the row: row = 4*b4 + 2*b3 + b2
                 if ((lane & 3) == 0) {
                     const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                    qkv_part[win * S::QKV_OUT + rb * 32 + grp * 8 + r] = v[0];   // write-once slot
+                    qkv_part[win * S::QKV_OUT + rb * ROWS512 + grp * 8 + r] = v[0];   // write-once slot
                 }
             }
             __syncwarp();
-            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+            issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
         }
     }
     gbase += n_qkv_tiles;
@@ -619,10 +593,10 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             ring_wait_full(full_u32, g);
             const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
             const uint4* vt = kt + STAGE_BYTES / 32;
-            const int rows_left = row_end - (row_begin + (int)i * 32);     // >= 1
-            float sc[16];
+            const int rows_left = row_end - (row_begin + (int)i * ROWS512);     // >= 1
+            float sc[ROWS512 / 2];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
+            for (int jj = 0; jj < ROWS512 / 2; ++jj) {
                 const int row = 2 * jj + sub;
                 float k8[8];
                 unpack8(kt[row * 16 + c], k8);
@@ -637,7 +611,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             }
             float mx = sc[0];
 #pragma unroll
-            for (int jj = 1; jj < 16; ++jj) mx = fmaxf(mx, sc[jj]);
+            for (int jj = 1; jj < ROWS512 / 2; ++jj) mx = fmaxf(mx, sc[jj]);
             const float m_new = fmaxf(m, mx);
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
             const float corr = dsm::exp2_diff(m, m_use);
@@ -645,7 +619,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
 #pragma unroll
             for (int k = 0; k < 8; ++k) o8[k] *= corr;
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
+            for (int jj = 0; jj < ROWS512 / 2; ++jj) {
                 const int row = 2 * jj + sub;
                 const float pr = dsm::fast_exp2(sc[jj] - m_use);       // -inf -> 0
                 l += pr;
@@ -660,7 +634,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             }
             m = m_new;
             __syncwarp();
-            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+            issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
         }
         gbase += n_kv_tiles;
         CF_MARK(5);   // KV tiles consumed (this warp)
@@ -712,17 +686,17 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     CF_MARK(6);   // softmax merge + exchange done
     // ---- phase 3: O GEMV for output columns [rank*KS, +KS) --------------------------------------------
     if constexpr (kChat) {
-        // tile = 64 input rows (half of the head) x 128 output cols; lane (sub, c): rows sub+2s, cols c*8..+8
+        // tile = 32 input rows (a quarter of the head) x 128 output cols; lane (sub, c): rows sub+2s, cols c*8..+8
         const int sub = lane >> 4, c = lane & 15;
         for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
             const uint32_t g = gbase + i, s = ring_stage(g);
             ring_wait_full(full_u32, g);
             const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
-            const int cb = i >> 1, rh = i & 1;
-            const float* arow = attn_out + rh * 64;
+            const int cb = i >> 2, rh = i & 3;
+            const float* arow = attn_out + rh * ROWS256;
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
+            for (int r = 0; r < ROWS256 / 2; ++r) {
                 const int row = 2 * r + sub;
                 float w8[8];
                 unpack8(tile[row * 16 + c], w8);
@@ -731,7 +705,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                 for (int k = 0; k < 8; ++k) acc[k] = fmaf(av, w8[k], acc[k]);
             }
             __syncwarp();
-            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+            issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
             if (sub == 0) {
@@ -741,7 +715,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             }
         }
     } else {
-        // tile = 64 output rows x 128 input cols; lane (sub, c): rows sub+2s, input cols c*8..+8
+        // tile = 32 output rows x 128 input cols; lane (sub, c): rows sub+2s, input cols c*8..+8
         const int sub = lane >> 4, c = lane & 15;
         float a8[8];
 #pragma unroll
@@ -751,7 +725,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             ring_wait_full(full_u32, g);
             const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
 #pragma unroll
-            for (int grp = 0; grp < 4; ++grp) {
+            for (int grp = 0; grp < ROWS256 / 16; ++grp) {
                 float v[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -787,11 +761,11 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                 v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
                 if ((lane & 1) == 0) {
                     const int r = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    out_part[i * 64 + 2 * (grp * 8 + r) + sub] = v[0];
+                    out_part[i * ROWS256 + 2 * (grp * 8 + r) + sub] = v[0];
                 }
             }
             __syncwarp();
-            if (lane == 0) dsm::mbar_arrive(empty_u32 + 8 * s);
+            issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
         }
     }
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
@@ -802,8 +776,11 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     for (int e = tid * 4; e < KS; e += CONSUMER_THREADS * 4) {
         float4 v = *reinterpret_cast<const float4*>(out_part + e);
         if constexpr (kChat) {
-            const float4 w = *reinterpret_cast<const float4*>(out_part + KS + e);
-            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+#pragma unroll
+            for (int q = 1; q < HEAD_DIM / ROWS256; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(out_part + q * KS + e);
+                v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
         }
         red_add_v4(scratch + e, v);
     }

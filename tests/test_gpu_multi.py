@@ -1,0 +1,71 @@
+"""Two-process GPU test (needs >= 2 GPUs; skipped otherwise): the Llama-2-70B head-parallel layer -- fused kernel per
+rank on its shard + ONE NCCL all-reduce -- against the full-layer oracle.  Run with `gpurun --gpus 2`."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle import llama_oracle as O
+    from clusterfusion_b200 import sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    shape = O.LayerShape(8192, 64, 8)
+    kv = 300
+    d = O.make_inputs(shape, kv, seed=70, layout="sglang")
+    c = {k: v.cuda() for k, v in d.items()}
+    sh = sharded.shard_layer(c["weight_qkv"], c["weight_o"], 64, 8, rank, world)
+    lay = sharded.ShardedDecoderLayer(sh["w_qkv"], sh["w_o"], c["rms_w"], sh["n_q_heads"], sh["n_kv_heads"], 8192, 1e-5,
+                                      None, world)
+    kc = sharded.shard_kv(c["k_cache"], 8, rank, world); vc = sharded.shard_kv(c["v_cache"], 8, rank, world)
+    outs = []
+    for it in range(3):
+        o, r, k, v = lay.forward(c["x"], c["residual"], kc, vc, c["cos"], c["sin"], pdl=(it == 2))
+        torch.cuda.synchronize()
+        outs.append(o.clone())
+    ks = [torch.empty_like(k) for _ in range(world)]; vs = [torch.empty_like(v) for _ in range(world)]
+    dist.all_gather(ks, k.contiguous()); dist.all_gather(vs, v.contiguous())
+    allo = [torch.empty_like(o) for _ in range(world)]
+    dist.all_gather(allo, o.contiguous())
+    if rank == 0:
+        q.put((outs[0].cpu(), outs[2].cpu(), r.cpu(), torch.cat(ks, 1).cpu(), torch.cat(vs, 1).cpu(),
+               all(torch.equal(allo[0], a) for a in allo)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_70b_head_parallel_nccl(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    from oracle import llama_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    o0, o2, r, k, v, same = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    shape = O.LayerShape(8192, 64, 8)
+    d = O.make_inputs(shape, 300, seed=70, layout="sglang")
+    want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"], d["rms_w"],
+                          1e-5, d["cos"], d["sin"], n_heads=64, n_kv_heads=8, mode="eager")
+    assert same, "ranks disagree on the all-reduced output"
+    assert torch.allclose(o0.float(), want[0].float(), rtol=1e-3, atol=1e-3)
+    assert torch.allclose(o2.float(), want[0].float(), rtol=1e-3, atol=1e-3)
+    assert torch.equal(r, want[1])
+    assert torch.allclose(k.view(-1).float(), want[2].view(-1).float(), rtol=1e-3, atol=4e-3)
+    assert torch.allclose(v.view(-1).float(), want[3].view(-1).float(), rtol=1e-3, atol=1e-3)

@@ -16,19 +16,31 @@ lib = C.CDLL(str(lib_path))
 lib.cf_llama_decoder_layer_launch.argtypes = [C.POINTER(cabi.CfLlamaArgs), C.c_void_p]
 kv = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-H, NH, D = 4096, 32, 128
+variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0            # 0 chat, 1 sglang
+H = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
+NH = int(sys.argv[5]) if len(sys.argv) > 5 else 32
+NKV = int(sys.argv[6]) if len(sys.argv) > 6 else NH
+D = 128
 dev = "cuda"
 nl = 8
 def r(*s, sc=1.0): return (torch.randn(*s, device=dev) * sc).half()
-layers = [dict(w_qkv=r(3 * H, H, sc=0.02), w_o=r(H, H, sc=0.02), k=r(kv + 1, H), v=r(kv + 1, H), rms=r(H) * 0.1 + 1,
-               o=torch.empty(1, H, dtype=torch.float16, device=dev), kn=torch.empty(NH * D, dtype=torch.float16, device=dev),
+layers = [dict(w_qkv=r((NH + 2 * NKV) * D, H, sc=0.02), w_o=r(H, NH * D, sc=0.02), k=r(kv + 1, NKV * D), v=r(kv + 1, NKV * D), rms=r(H) * 0.1 + 1,
+               o=torch.empty(1, H, dtype=torch.float16, device=dev), ro=torch.empty(1, H, dtype=torch.float16, device=dev),
+               kn=torch.empty(NH * D, dtype=torch.float16, device=dev),
                vn=torch.empty(NH * D, dtype=torch.float16, device=dev)) for _ in range(nl)]
+res = r(1, H)
 x = r(1, H); cos = torch.rand(1, D, device=dev); sin = torch.rand(1, D, device=dev)
 ws = torch.zeros(cabi.workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
-trace = torch.zeros(nl, 128, 16, dtype=torch.int64, device=dev)
+if NH == NKV:
+    ncta = NH * 4
+else:
+    ncl = NKV * ((NH // NKV) // 4)
+    ncta = ncl * (16 if ncl <= 4 else 8)
+trace = torch.zeros(nl, ncta, 16, dtype=torch.int64, device=dev)
 def launch(i, h):
     lay = layers[i]
-    a = cabi.CfLlamaArgs(variant=0, flags=flags, layer_id=i, hidden=H, n_q_heads=NH, n_kv_heads=NH, head_dim=D, batch=1, kv_len=kv, eps=1e-6,
+    a = cabi.CfLlamaArgs(variant=variant, flags=flags, layer_id=i, hidden=H, n_q_heads=NH, n_kv_heads=NKV, head_dim=D, batch=1, kv_len=kv, eps=1e-6,
+                         residual_in=res.data_ptr(), residual_out=lay["ro"].data_ptr(),
                          x=h.data_ptr(), w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(),
                          out=lay["o"].data_ptr(), k_new=lay["kn"].data_ptr(), v_new=lay["vn"].data_ptr(),
                          k_cache=lay["k"].data_ptr(), v_cache=lay["v"].data_ptr(), cos=cos.data_ptr(), sin=sin.data_ptr(),
@@ -42,7 +54,8 @@ for rep in range(3):          # back-to-back launches; the last repetition's mar
         launch(i, h); h = layers[i]["o"]
 torch.cuda.synchronize()
 t = trace.cpu().numpy().astype("int64")
-names = {0: "entry", 12: "prod first TMA", 1: "rms done", 2: "qkv tiles done", 3: "xchg1 done", 4: "rope done", 5: "kv tiles done",
+print("variant", variant, "H", H, "heads", NH, NKV, "ctas", ncta)
+names = {0: "entry", 12: "first TMA issue", 1: "rms done", 2: "qkv tiles done", 3: "xchg1 done", 4: "rope done", 5: "kv tiles done",
          6: "xchg2 done", 7: "o tiles done", 13: "prod last TMA", 8: "reds+counter", 9: "cta done"}
 starts = [t[i][:, 0].min() for i in range(nl)]
 ends = [t[i][:, 9].max() for i in range(nl)]
@@ -52,6 +65,6 @@ for li in (nl - 2,):
     T = t[li]
     t0 = T[:, 0].min()
     print(f"layer {li}: kernel span {(T[:, 9].max() - t0) / 1e3:.2f} us (kv={kv})")
-    for k in (0, 12, 1, 2, 3, 4, 5, 6, 7, 13, 8, 9):
+    for k in (0, 12, 1, 2, 3, 4, 5, 6, 7, 8, 9):
         v = (T[:, k] - t0) / 1e3
         print(f"  {names[k]:16s} min {v.min():7.2f}  med {sorted(v)[len(v)//2]:7.2f}  max {v.max():7.2f} us")
