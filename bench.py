@@ -331,6 +331,10 @@ def run_ours(args, rank, world, local_rank):
     gqa = None
     if not args.no_sweep:
         gqa = run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
+    # ------------------------------------------------------------------ whole-model decode
+    full = None
+    if not args.no_sweep and not args.no_full_model:
+        full = run_full_model(torch, dist, dev, world, peak)
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
 
@@ -388,6 +392,8 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "cpu_baseline": cpu,
     }
+    if full is not None:
+        line["full_model_decode"] = full
     if gqa is not None:
         line["llama3_8b_gqa"] = gqa
     if shard70 is not None:
@@ -395,6 +401,51 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128):
+    """Llama-2-7B-shaped whole-model decode (random init): fused attention op + torch FFN / lm_head + device-side
+    greedy sampling, one CUDA graph per token (clusterfusion_b200/decode.py).  Also the same loop with eager
+    PyTorch attention (the reference's USE_CLUSTER_FUSION=false path on this GPU)."""
+    from clusterfusion_b200.decode import LlamaDecodeEngine, LLAMA2_7B
+    out = {"model": "llama2-7b shapes, random init, fp16", "kv_len_start": kv0, "tokens": n_tok, "replicas": world}
+    for mode in ("fused", "eager"):
+        eng = LlamaDecodeEngine(LLAMA2_7B, max_seq=kv0 + 3 * n_tok + 16, device=dev, seed=5, attn=mode)
+        eng.set_position(kv0)
+        eng.capture()
+        for _ in range(8):
+            eng.step()
+        eng.set_position(kv0, fill_random=False)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_tok):
+            eng.step()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        tps = world * n_tok * 1e3 / ms
+        btok = eng.bytes_per_token(kv0 + n_tok // 2)
+        out[mode] = {"tokens_per_s": round(tps, 1), "ms_per_token": round(ms / n_tok, 4),
+                     "achieved_gbs_per_gpu": round(btok / (ms / n_tok * 1e-3) / 1e9, 1), "bytes_per_token": btok}
+        if mode == "fused":
+            # user-facing step: token id from the host, next token id back to the host, every token
+            eng.set_position(kv0, fill_random=False)
+            tok = 1
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n_tok):
+                tok = eng.step_host(tok)
+            dt = time.perf_counter() - t0
+            out["fused"]["tokens_per_s_host_step"] = round(n_tok / dt, 1)
+            out["fused"]["h2d_d2h_bytes_per_token"] = 16
+        del eng
+        torch.cuda.empty_cache()
+    out["speedup_fused_vs_eager_attention"] = round(out["fused"]["tokens_per_s"] / out["eager"]["tokens_per_s"], 3)
+    return out
 
 
 def run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=True, shape=(4096, 32, 8), kvs=(8192,), nl=8, tag="llama3-8b"):
@@ -510,6 +561,7 @@ def main():
     ap.add_argument("--kv-len", type=int, default=1024)
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-model", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="value arm: plain stream-serialised launches instead of programmatic dependent launch")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
