@@ -328,9 +328,10 @@ def run_ours(args, rank, world, local_rank):
             del Ls, g2
             torch.cuda.empty_cache()
     # ------------------------------------------------------------------ BASELINE config 4: Llama-3-8B GQA (32 Q / 8 KV), kv 8K
-    gqa = None
+    gqa = ffn_res = None
     if not args.no_sweep:
         gqa = run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
+        ffn_res = run_ffn(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
     # ------------------------------------------------------------------ whole-model decode
     full = None
     if not args.no_sweep and not args.no_full_model:
@@ -394,6 +395,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if full is not None:
         line["full_model_decode"] = full
+    if ffn_res is not None:
+        line["fused_ffn_half_layer"] = ffn_res
     if gqa is not None:
         line["llama3_8b_gqa"] = gqa
     if shard70 is not None:
@@ -403,14 +406,55 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_ffn(torch, cabi, dev, timed_replays, peak, pdl=True, hidden=4096, ffn=11008, nl=8):
+    """Fused FFN half-layer alone: CUDA graph of `nl` distinct layers through the C ABI (row f1)."""
+    g = torch.Generator(device=dev).manual_seed(21)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * sc).half()
+    ws = torch.zeros(cabi.workspace_bytes(hidden, 1), dtype=torch.uint8, device=dev)
+    L = [dict(w13=r(2 * ffn, hidden, sc=0.02), w2t=r(ffn, hidden, sc=0.02), rms=(1 + 0.1 * r(hidden).float()).half(),
+              o=torch.empty(1, hidden, dtype=torch.float16, device=dev), ro=torch.empty(1, hidden, dtype=torch.float16, device=dev))
+         for _ in range(nl)]
+    x, res = r(1, hidden), r(1, hidden)
+
+    def launch(h, rr, lay, st):
+        a = cabi.CfFfnArgs(flags=(cabi.CF_FLAG_PDL if pdl else 0), hidden=hidden, ffn=ffn, eps=1e-5, x=h.data_ptr(),
+                           residual_in=rr.data_ptr(), w_gate_up=lay["w13"].data_ptr(), w_down_t=lay["w2t"].data_ptr(),
+                           rms_w=lay["rms"].data_ptr(), out=lay["o"].data_ptr(), residual_out=lay["ro"].data_ptr(),
+                           workspace=ws.data_ptr())
+        cabi.launch_ffn(a, st)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        launch(x, res, L[0], side.cuda_stream)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        st = torch.cuda.current_stream().cuda_stream
+        h, rr = x, res
+        for lay in L:
+            launch(h, rr, lay, st)
+            h, rr = lay["o"], lay["ro"]
+    B = 2 * 3 * ffn * hidden + 2 * hidden * 5
+    reps = max(20, int(0.25 / (nl * B / (peak * 1e9))))
+    ms = timed_replays(gr, reps, 5)
+    us = ms * 1e3 / (reps * nl)
+    a = B / (us * 1e-6) / 1e9
+    return {"hidden": hidden, "ffn": ffn, "us_per_layer": round(us, 3), "bytes": B, "achieved_gbs": round(a, 1),
+            "frac_of_measured_peak": round(a / peak, 4), "frac_of_8tbs": round(a / 8000.0, 4),
+            "kernel": "cfb::llama_ffn_layer_kernel", "launches": reps * nl}
+
+
 def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128):
     """Llama-2-7B-shaped whole-model decode (random init): fused attention op + torch FFN / lm_head + device-side
     greedy sampling, one CUDA graph per token (clusterfusion_b200/decode.py).  Also the same loop with eager
     PyTorch attention (the reference's USE_CLUSTER_FUSION=false path on this GPU)."""
     from clusterfusion_b200.decode import LlamaDecodeEngine, LLAMA2_7B
     out = {"model": "llama2-7b shapes, random init, fp16", "kv_len_start": kv0, "tokens": n_tok, "replicas": world}
-    for mode in ("fused", "eager"):
-        eng = LlamaDecodeEngine(LLAMA2_7B, max_seq=kv0 + 3 * n_tok + 16, device=dev, seed=5, attn=mode)
+    for mode in ("fused_attn_fused_ffn", "fused", "eager"):
+        eng = LlamaDecodeEngine(LLAMA2_7B, max_seq=kv0 + 3 * n_tok + 16, device=dev, seed=5,
+                                attn="eager" if mode == "eager" else "fused",
+                                ffn="fused" if mode == "fused_attn_fused_ffn" else "torch")
         eng.set_position(kv0)
         eng.capture()
         for _ in range(8):
@@ -431,7 +475,7 @@ def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128):
         btok = eng.bytes_per_token(kv0 + n_tok // 2)
         out[mode] = {"tokens_per_s": round(tps, 1), "ms_per_token": round(ms / n_tok, 4),
                      "achieved_gbs_per_gpu": round(btok / (ms / n_tok * 1e-3) / 1e9, 1), "bytes_per_token": btok}
-        if mode == "fused":
+        if mode == "fused_attn_fused_ffn":
             # user-facing step: token id from the host, next token id back to the host, every token
             eng.set_position(kv0, fill_random=False)
             tok = 1
@@ -440,11 +484,12 @@ def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128):
             for _ in range(n_tok):
                 tok = eng.step_host(tok)
             dt = time.perf_counter() - t0
-            out["fused"]["tokens_per_s_host_step"] = round(n_tok / dt, 1)
-            out["fused"]["h2d_d2h_bytes_per_token"] = 16
+            out[mode]["tokens_per_s_host_step"] = round(n_tok / dt, 1)
+            out[mode]["h2d_d2h_bytes_per_token"] = 16
         del eng
         torch.cuda.empty_cache()
-    out["speedup_fused_vs_eager_attention"] = round(out["fused"]["tokens_per_s"] / out["eager"]["tokens_per_s"], 3)
+    out["speedup_fused_attention_vs_eager"] = round(out["fused"]["tokens_per_s"] / out["eager"]["tokens_per_s"], 3)
+    out["speedup_fused_attention_and_ffn_vs_eager"] = round(out["fused_attn_fused_ffn"]["tokens_per_s"] / out["eager"]["tokens_per_s"], 3)
     return out
 
 

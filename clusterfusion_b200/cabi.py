@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "cf_llama_workspace_bytes",
     "cf_llama_algorithmic_bytes",
     "cf_llama_decoder_layer_launch",
+    "cf_llama_ffn_launch",
     "cf_test_cluster_reduce",
 )
 
@@ -65,6 +66,23 @@ class CfLlamaArgs(C.Structure):
     ]
 
 
+class CfFfnArgs(C.Structure):
+    _fields_ = [
+        ("flags", C.c_uint32),
+        ("hidden", C.c_int32),
+        ("ffn", C.c_int32),
+        ("eps", C.c_float),
+        ("x", C.c_void_p),
+        ("residual_in", C.c_void_p),
+        ("w_gate_up", C.c_void_p),
+        ("w_down_t", C.c_void_p),
+        ("rms_w", C.c_void_p),
+        ("out", C.c_void_p),
+        ("residual_out", C.c_void_p),
+        ("workspace", C.c_void_p),
+    ]
+
+
 class CfError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"clusterfusion_b200 C ABI error {code}: {msg}")
@@ -92,6 +110,8 @@ def load() -> C.CDLL:
     lib.cf_llama_algorithmic_bytes.argtypes = [C.POINTER(CfLlamaArgs), C.c_uint64]
     lib.cf_llama_decoder_layer_launch.restype = C.c_int
     lib.cf_llama_decoder_layer_launch.argtypes = [C.POINTER(CfLlamaArgs), C.c_void_p]
+    lib.cf_llama_ffn_launch.restype = C.c_int
+    lib.cf_llama_ffn_launch.argtypes = [C.POINTER(CfFfnArgs), C.c_void_p]
     lib.cf_test_cluster_reduce.restype = C.c_int
     lib.cf_test_cluster_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_int32, C.c_void_p]
@@ -119,6 +139,11 @@ def algorithmic_bytes(args: CfLlamaArgs, total_kv_rows: int) -> int:
 def launch(args: CfLlamaArgs, stream: int = 0) -> None:
     """One fused-kernel launch on CUDA stream handle `stream` (0 = legacy default stream)."""
     check(load().cf_llama_decoder_layer_launch(C.byref(args), C.c_void_p(stream)))
+
+
+def launch_ffn(args: CfFfnArgs, stream: int = 0) -> None:
+    """One fused FFN half-layer launch on CUDA stream handle `stream`."""
+    check(load().cf_llama_ffn_launch(C.byref(args), C.c_void_p(stream)))
 
 
 def test_cluster_reduce(in_ptr: int, out_ptr: int, n: int, cluster_size: int, n_clusters: int,

@@ -13,6 +13,7 @@
 #include "../../include/clusterfusion_b200.h"
 #include "llama_decoder_kernel.cuh"
 #include "llama_decoder_gqa_kernel.cuh"
+#include "llama_ffn_kernel.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -297,6 +298,68 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
 }
 
 }  // extern "C"
+
+extern "C" int cf_llama_ffn_launch(const CfFfnArgs* a, void* stream_) {
+    if (!a) return fail(CF_ERR_NULL_ARG, "args is NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (a->hidden <= 0 || a->hidden % 256 != 0 || a->hidden > cfb::FFN_HIDDEN_MAX)
+        return fail(CF_ERR_BAD_SHAPE, "ffn: hidden must be a multiple of 256 and <= %d (got %d)", cfb::FFN_HIDDEN_MAX, a->hidden);
+    if (a->ffn <= 0 || a->ffn % cfb::FFN_BLOCK != 0)
+        return fail(CF_ERR_BAD_SHAPE, "ffn: intermediate size must be a multiple of %d (got %d)", cfb::FFN_BLOCK, a->ffn);
+    if (!a->x || !a->residual_in || !a->w_gate_up || !a->w_down_t || !a->rms_w || !a->out || !a->residual_out || !a->workspace)
+        return fail(CF_ERR_NULL_ARG, "ffn: all pointers must be non-NULL");
+    const void* al[] = {a->x, a->residual_in, a->w_gate_up, a->w_down_t, a->rms_w, a->out, a->residual_out, a->workspace};
+    for (const void* q : al)
+        if (!aligned16(q)) return fail(CF_ERR_BAD_ALIGNMENT, "all tensors must be 16-byte aligned (%p)", q);
+    if (!device_is_sm100()) return fail(CF_ERR_NO_DEVICE, "current CUDA device is not compute capability 10.x");
+    static int sm_count[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sm_count[dev & 15] == 0) cudaDeviceGetAttribute(&sm_count[dev & 15], cudaDevAttrMultiProcessorCount, dev);
+    const int n_blocks = a->ffn / cfb::FFN_BLOCK;
+    int grid = sm_count[dev & 15] < n_blocks ? sm_count[dev & 15] : n_blocks;
+    if ((n_blocks + grid - 1) / grid > cfb::FFN_NB_MAX)
+        return fail(CF_ERR_BAD_SHAPE, "ffn: intermediate size %d too large for %d SMs", a->ffn, grid);
+
+    cfb::FfnParams fp;
+    memset(&fp, 0, sizeof fp);
+    int rc;
+    if ((rc = get_tensor_map(&fp.tm_w13, a->w_gate_up, 2ull * a->ffn, a->hidden, 256, cfb::FFN_BLOCK))) return rc;
+    if ((rc = get_tensor_map(&fp.tm_w2t, a->w_down_t, a->ffn, a->hidden, 256, cfb::FFN_BLOCK))) return rc;
+    fp.x = static_cast<const __half*>(a->x);
+    fp.residual_in = static_cast<const __half*>(a->residual_in);
+    fp.rms_w = static_cast<const __half*>(a->rms_w);
+    fp.out = a->out;
+    fp.residual_out = static_cast<__half*>(a->residual_out);
+    fp.scratch = static_cast<float*>(a->workspace);
+    fp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + (size_t)a->hidden * sizeof(float));
+    fp.eps = a->eps;
+    fp.hidden = a->hidden;
+    fp.ffn = a->ffn;
+    fp.flags = a->flags;
+
+    static std::once_flag once[16];
+    static cudaError_t attr_err[16];
+    std::call_once(once[dev & 15], [&] {
+        attr_err[dev & 15] = cudaFuncSetAttribute(cfb::llama_ffn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  cfb::SmemFfn::TOTAL);
+    });
+    if (attr_err[dev & 15] != cudaSuccess)
+        return fail((int)attr_err[dev & 15], "cudaFuncSetAttribute(ffn): %s", cudaGetErrorString(attr_err[dev & 15]));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(cfb::BLOCK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = cfb::SmemFfn::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (a->flags & CF_FLAG_PDL) ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, cfb::llama_ffn_layer_kernel, fp);
+    if (e != cudaSuccess) return fail((int)e, "ffn kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
 
 #ifdef CF_TRACE
 extern "C" int cf_debug_set_trace(void* dev_ptr) {

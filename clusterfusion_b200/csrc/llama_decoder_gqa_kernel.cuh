@@ -60,6 +60,7 @@ struct SmemGqa {
     static constexpr int BARS = RED + 32 * 4;                              // full[24], xbar[4]
     static constexpr int FLAGS = BARS + (NSTAGES + 4) * 8;
     static constexpr int TOTAL = FLAGS + 16;
+    static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
 };
 
 // 16 output rows x 256 input columns of an [out,in] weight tile against 8 activations per lane;

@@ -114,6 +114,7 @@ struct Smem {
     static constexpr int BARS = RED + 32 * 4;                              // u64 full[NSTAGES], xbar[2]
     static constexpr int FLAGS = BARS + (NSTAGES + 2) * 8;                 // u32[4]
     static constexpr int TOTAL = FLAGS + 16;
+    static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -56,6 +56,10 @@ Tensor workspace_for(const Tensor& like, int hidden, int batch, cudaStream_t str
     return it->second;
 }
 
+// Programmatic dependent launch for every op issued through this module (off by default).  Contract: see CF_FLAG_PDL in
+// include/clusterfusion_b200.h -- weights / KV pools / page tables of a call are not written by kernels still in flight.
+bool g_pdl = false;
+
 void run(const CfLlamaArgs& a, cudaStream_t stream) {
     const int rc = cf_llama_decoder_layer_launch(&a, stream);
     TORCH_CHECK(rc == 0, "clusterfusion_b200: launch failed (", rc, "): ", cf_last_error_string());
@@ -104,6 +108,7 @@ std::tuple<Tensor, Tensor, Tensor> llama_decoder_layer(
     a.k_cache = k_cache.data_ptr(); a.v_cache = v_cache.data_ptr();
     a.cos = cos.data_ptr<float>(); a.sin = sin.data_ptr<float>();
     a.workspace = ws.data_ptr();
+    if (g_pdl) a.flags |= CF_FLAG_PDL;
     run(a, stream);
     return std::make_tuple(o, k, v);
 }
@@ -154,6 +159,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> llama_decoder_layer_sglang(
     a.k_cache = k_cache.data_ptr(); a.v_cache = v_cache.data_ptr();
     a.cos = cos.data_ptr<float>(); a.sin = sin.data_ptr<float>();
     a.workspace = ws.data_ptr();
+    if (g_pdl) a.flags |= CF_FLAG_PDL;
     run(a, stream);
     return std::make_tuple(o, residual, k, v);
 }
@@ -211,7 +217,49 @@ void llama_decoder_layer_batch_decode_sglang(
     a.positions = positions.data_ptr<int64_t>();
     a.cos = cos_sin.data_ptr<float>();
     a.workspace = ws.data_ptr();
+    if (g_pdl) a.flags |= CF_FLAG_PDL;
     run(a, stream);
+}
+
+void llama_ffn_layer_out(Tensor output, Tensor residual_output, Tensor input, Tensor residual, Tensor weight_gate_up,
+                         Tensor weight_down_t, Tensor rms_weight, double eps)
+{
+    check_cuda_contig(output, "output", torch::kHalf);
+    check_cuda_contig(residual_output, "residual_output", torch::kHalf);
+    check_cuda_contig(input, "input", torch::kHalf);
+    check_cuda_contig(residual, "residual", torch::kHalf);
+    check_cuda_contig(weight_gate_up, "weight_gate_up", torch::kHalf);
+    check_cuda_contig(weight_down_t, "weight_down_t", torch::kHalf);
+    check_cuda_contig(rms_weight, "rms_weight", torch::kHalf);
+    const int64_t hidden = input.size(-1);
+    TORCH_CHECK(input.numel() == hidden && residual.numel() == hidden && output.numel() == hidden &&
+                residual_output.numel() == hidden, "input / residual / output / residual_output must hold one token");
+    TORCH_CHECK(weight_down_t.dim() == 2 && weight_down_t.size(1) == hidden, "weight_down_t must be [ffn, hidden] (W2 transposed)");
+    const int64_t ffn = weight_down_t.size(0);
+    TORCH_CHECK(weight_gate_up.dim() == 2 && weight_gate_up.size(0) == 2 * ffn && weight_gate_up.size(1) == hidden,
+                "weight_gate_up must be [2*ffn, hidden] = [W1; W3]");
+    TORCH_CHECK(rms_weight.numel() == hidden, "rms_weight must be [hidden]");
+    const c10::cuda::CUDAGuard guard(input.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
+    Tensor ws = workspace_for(input, (int)hidden, 1, stream);
+    CfFfnArgs a{};
+    a.flags = g_pdl ? CF_FLAG_PDL : 0u;
+    a.hidden = (int)hidden; a.ffn = (int)ffn; a.eps = (float)eps;
+    a.x = input.data_ptr(); a.residual_in = residual.data_ptr();
+    a.w_gate_up = weight_gate_up.data_ptr(); a.w_down_t = weight_down_t.data_ptr(); a.rms_w = rms_weight.data_ptr();
+    a.out = output.data_ptr(); a.residual_out = residual_output.data_ptr(); a.workspace = ws.data_ptr();
+    const int rc = cf_llama_ffn_launch(&a, stream);
+    TORCH_CHECK(rc == 0, "clusterfusion_b200: ffn launch failed (", rc, "): ", cf_last_error_string());
+}
+
+std::tuple<Tensor, Tensor> llama_ffn_layer(Tensor input, Tensor residual, Tensor weight_gate_up, Tensor weight_down_t,
+                                           Tensor rms_weight, double eps)
+{
+    TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+    Tensor out = torch::empty({1, input.size(-1)}, input.options());
+    Tensor res_out = torch::empty({1, input.size(-1)}, input.options());
+    llama_ffn_layer_out(out, res_out, input, residual, weight_gate_up, weight_down_t, rms_weight, eps);
+    return std::make_tuple(out, res_out);
 }
 
 }  // namespace
@@ -223,6 +271,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("llama_decoder_layer", &llama_decoder_layer_batch_decode_sglang, "");
     m.def("llama_decoder_layer_sglang", &llama_decoder_layer_sglang, "");
     m.def("llama_decoder_layer_batch_decode_sglang", &llama_decoder_layer_batch_decode_sglang, "");
+    // fused FFN half-layer (new op; the reference's FFN is eager PyTorch): (out, residual_out) = f(input, residual, [W1;W3], W2^T, w, eps)
+    m.def("llama_ffn_layer", &llama_ffn_layer, "");
+    m.def("llama_ffn_layer_out", &llama_ffn_layer_out, "");
+    m.def("set_pdl", [](bool on) { g_pdl = on; }, "enable / disable programmatic dependent launch for all ops of this module");
+    m.def("get_pdl", []() { return g_pdl; });
     m.def("abi_version", []() { return cf_abi_version(); });
     m.def("workspace_bytes", [](int hidden, int batch) { return cf_llama_workspace_bytes(hidden, batch); });
 }

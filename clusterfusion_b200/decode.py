@@ -9,8 +9,10 @@ chat/llama/generation.py:234-271 token loop), arranged so that ONE CUDA graph re
   the same captured graph serves every position -- the 8/10-argument forms bake kv_len into TMA descriptors on
   the host.  K/V of the new token are appended in-pool by the kernel itself (no copy kernels), the residual
   stream follows the fused-add-norm convention (residual_out = x + residual).
-* FFN half-layer, final norm, lm_head: plain PyTorch (cuBLAS GEMV), exactly like the reference, whose FFN stays
-  eager PyTorch (model.py:519).  They are outside the hot-path scope of this repo; row f1 (fused FFN) is next.
+* FFN half-layer: `ffn="torch"` = plain PyTorch (cuBLAS GEMV), exactly like the reference, whose FFN stays eager
+  PyTorch (model.py:519); `ffn="fused"` = `llama_ffn_layer` (csrc/llama_ffn_kernel.cuh), which makes the
+  decode step a chain of our own kernels (attention, FFN, attention, ...) with programmatic dependent launch between
+  them.  Final norm and lm_head stay PyTorch.
 * sampling: greedy argmax on the device; the next token id is fed back through a device tensor, so a replay
   needs no host interaction at all.  `step_host()` is the user-facing variant that takes / returns Python ints
   (one 8-byte H2D + one 8-byte D2H per token, like the reference's `.item()` per token).
@@ -51,10 +53,12 @@ LLAMA3_8B = ModelShape(n_kv_heads=8, ffn=14336, vocab=128256, rope_theta=500000.
 
 class LlamaDecodeEngine:
     def __init__(self, shape: ModelShape = LLAMA2_7B, max_seq: int = 2048, device="cuda", seed: int = 0,
-                 attn: str = "fused", w_scale: float = 0.02):
+                 attn: str = "fused", w_scale: float = 0.02, ffn: str = "torch"):
         import clusterfusion_b200 as cf       # raises ImportError if the native extension is missing: no fallback
         self._op = cf.llama_decoder_layer_batch_decode_sglang
-        self.shape, self.max_seq, self.attn = shape, max_seq, attn
+        self._ffn_op = cf.llama_ffn_layer_out
+        self._cf = cf
+        self.shape, self.max_seq, self.attn, self.ffn_mode = shape, max_seq, attn, ffn
         self.dev = torch.device(device)
         s = shape
         g = torch.Generator(device=self.dev).manual_seed(seed)
@@ -72,6 +76,9 @@ class LlamaDecodeEngine:
                 w13=r(2 * s.ffn, s.hidden), w2=r(s.hidden, s.ffn),
                 k_pool=torch.zeros(max_seq, kvd, dtype=torch.float16, device=self.dev),
                 v_pool=torch.zeros(max_seq, kvd, dtype=torch.float16, device=self.dev)))
+        if ffn == "fused":
+            for l in self.layers:          # one-time re-layout at load, like the reference's _build_cf_weights
+                l["w2t"] = l.pop("w2").t().contiguous()
         self.k_ptrs = torch.tensor([l["k_pool"].data_ptr() for l in self.layers], dtype=torch.uint64).to(self.dev)
         self.v_ptrs = torch.tensor([l["v_pool"].data_ptr() for l in self.layers], dtype=torch.uint64).to(self.dev)
         # RoPE table [max_seq, 128] = [cos(64) | sin(64)]  (kernel_batch_sglang.cuh:322-323 layout)
@@ -88,6 +95,8 @@ class LlamaDecodeEngine:
         self.attn_out = torch.empty(1, H, dtype=torch.float16, device=self.dev)
         self.res_out = torch.empty(1, H, dtype=torch.float16, device=self.dev)
         self.zero_res = torch.zeros(1, H, dtype=torch.float16, device=self.dev)
+        self.ffn_out = torch.empty(1, H, dtype=torch.float16, device=self.dev)
+        self.ffn_res = torch.empty(1, H, dtype=torch.float16, device=self.dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._host_in = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._host_out = torch.zeros(1, dtype=torch.int64).pin_memory()
@@ -145,11 +154,16 @@ class LlamaDecodeEngine:
                 a, h = self.attn_out, self.res_out
             else:
                 a, h = self._eager_attention(lid, x, residual)
-            h2 = h + a                                               # residual after attention (model.py:488-492)
-            n = self._rmsnorm(h2, l["ffn_norm"])
-            gu = F.linear(n, l["w13"])
-            x = F.linear(F.silu(gu[:, :s.ffn]) * gu[:, s.ffn:], l["w2"])      # SwiGLU (model.py:447-448)
-            residual = h2
+            if self.ffn_mode == "fused":
+                # fused FFN half-layer: residual add + norm + SwiGLU + down projection in one launch (row f1)
+                self._ffn_op(self.ffn_out, self.ffn_res, a, h, l["w13"], l["w2t"], l["ffn_norm"], s.norm_eps)
+                x, residual = self.ffn_out, self.ffn_res
+            else:
+                h2 = h + a                                           # residual after attention (model.py:488-492)
+                n = self._rmsnorm(h2, l["ffn_norm"])
+                gu = F.linear(n, l["w13"])
+                x = F.linear(F.silu(gu[:, :s.ffn]) * gu[:, s.ffn:], l["w2"])      # SwiGLU (model.py:447-448)
+                residual = h2
         hf = self._rmsnorm(x + residual, self.final_norm)
         logits = F.linear(hf, self.lm_head)
         self.token.copy_(logits.argmax(dim=-1))
@@ -157,8 +171,18 @@ class LlamaDecodeEngine:
         self.indptr[1:].add_(1)
 
     @torch.no_grad()
-    def capture(self):
-        """Capture one decode step into a CUDA graph (3 eager warm-up steps first, position restored after)."""
+    def capture(self, pdl: bool = True):
+        """Capture one decode step into a CUDA graph (3 eager warm-up steps first, position restored after).
+        With both halves fused, consecutive kernels are all ours and neither writes what the next one streams
+        before its griddepcontrol.wait (layer l+1's weights / KV pool), so PDL is safe inside the step."""
+        use_pdl = pdl and self.attn == "fused" and self.ffn_mode == "fused"
+        self._cf.set_pdl(use_pdl)
+        try:
+            return self._capture()
+        finally:
+            self._cf.set_pdl(False)
+
+    def _capture(self):
         pos0, ind0, tok0 = self.positions.clone(), self.indptr.clone(), self.token.clone()
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())

@@ -108,6 +108,27 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* args, void* stream);
 /* Algorithmic HBM bytes of one call (SURVEY.md section 8d formula) -- used by bench / tests. */
 uint64_t cf_llama_algorithmic_bytes(const CfLlamaArgs* args, uint64_t total_kv_rows);
 
+/* ---- fused FFN half-layer (no counterpart kernel in the reference, whose FFN stays
+ * eager PyTorch, chat/llama/model.py:407-448, :519) --------------------------------------------------------------
+ * h = x + residual; residual_out = fp16(h); out = W2 (silu(W1 n) * (W3 n)), n = rmsnorm(h) * rms_w.              */
+typedef struct CfFfnArgs {
+    uint32_t flags;          /* CF_FLAG_OUT_FP32_PARTIAL, CF_FLAG_PDL                                       */
+    int32_t hidden;          /* multiple of 256, <= 8192                                                    */
+    int32_t ffn;             /* intermediate size, multiple of 16 (11008, 14336, 28672 / N ...)             */
+    float eps;
+    const void* x;           /* fp16 [hidden]                                                               */
+    const void* residual_in; /* fp16 [hidden]                                                               */
+    const void* w_gate_up;   /* fp16 [2*ffn, hidden] = [W1; W3], nn.Linear layout                           */
+    const void* w_down_t;    /* fp16 [ffn, hidden] = W2^T (transpose W2 once at load time)                  */
+    const void* rms_w;       /* fp16 [hidden]                                                               */
+    void* out;               /* fp16 [hidden] (float with CF_FLAG_OUT_FP32_PARTIAL)                         */
+    void* residual_out;      /* fp16 [hidden]; may alias residual_in                                        */
+    void* workspace;         /* cf_llama_workspace_bytes(hidden, 1) bytes, zeroed once; may be shared with the
+                                attention op on the same stream                                            */
+} CfFfnArgs;
+
+int cf_llama_ffn_launch(const CfFfnArgs* args, void* stream);
+
 /* Unit-test hook for the device primitive in include/dsm.cuh:
  * launches n_clusters clusters of `cluster_size` CTAs; CTA r of cluster c contributes
  * in[(c*cluster_size + r)*n .. +n) (float); stage 0 = LINEAR (sum), 1 = ATTN (softmax-state merge of

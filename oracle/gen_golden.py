@@ -181,6 +181,40 @@ def gen_chat(model, shape: LayerShape, kv_len: int, seed: int, w_scale: float, d
                 v=v_new.float().numpy().astype(np.float32)[None], **fused)
 
 
+def gen_ffn(model, seed: int, dtype):
+    """Reference FeedForward (chat/llama/model.py:407-448) + RMSNorm (:36-79) on CPU, Llama-2-7B dims (ffn 11008)."""
+    hidden = 4096
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *sh, sc=1.0: (torch.randn(*sh, generator=g, dtype=torch.float32) * sc).half()
+    torch.set_default_dtype(dtype)
+    try:
+        ff = model.FeedForward(dim=hidden, hidden_dim=4 * hidden, multiple_of=256, ffn_dim_multiplier=None)
+        norm = model.RMSNorm(hidden, eps=1e-5)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    ffn = ff.w1.weight.shape[0]
+    x, residual = rn(1, hidden), rn(1, hidden)
+    w1, w3, w2 = rn(ffn, hidden, sc=0.02), rn(ffn, hidden, sc=0.02), rn(hidden, ffn, sc=0.02)
+    rms = (1.0 + 0.1 * torch.randn(hidden, generator=g)).half()
+    with torch.no_grad():
+        ff.w1.weight.copy_(w1); ff.w3.weight.copy_(w3); ff.w2.weight.copy_(w2); norm.weight.copy_(rms)
+        h = (x.float() + residual.float()).half().to(dtype)            # the stream is an fp16 tensor in the model
+        out = ff(norm(h.view(1, 1, hidden)))
+    d = dict(x=x, residual=residual, w1=w1, w3=w3, w2=w2, rms=rms)
+    return dict(kind="ffn", dtype=str(dtype).split(".")[-1], seed=seed, hidden=hidden, ffn=ffn, eps=1e-5,
+                digest=inputs_digest(d), out=out.reshape(1, -1).float().numpy().astype(np.float32))
+
+
+def ffn_inputs(seed: int, hidden: int = 4096, ffn: int = 11008):
+    """Regenerate the tensors gen_ffn drew (same generator order)."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *sh, sc=1.0: (torch.randn(*sh, generator=g, dtype=torch.float32) * sc).half()
+    x, residual = rn(1, hidden), rn(1, hidden)
+    w1, w3, w2 = rn(ffn, hidden, sc=0.02), rn(ffn, hidden, sc=0.02), rn(hidden, ffn, sc=0.02)
+    rms = (1.0 + 0.1 * torch.randn(hidden, generator=g)).half()
+    return dict(x=x, residual=residual, w1=w1, w3=w3, w2=w2, rms=rms)
+
+
 def main():
     assert REF.exists(), "run in the build container (needs /root/reference)"
     OUT.mkdir(parents=True, exist_ok=True)
@@ -201,6 +235,12 @@ def main():
     # GQA through the reference's eager Attention (repeat_kv, model.py:166-175)
     cases.append(("chat_fp32_gqa8_kv100", lambda: gen_chat(model, LayerShape(4096, 32, 8), 100, 11, 0.02, torch.float32)))
     cases.append(("chat_fp32_70b_kv64", lambda: gen_chat(model, LayerShape(8192, 64, 8), 64, 13, 0.02, torch.float32)))
+
+    cases.append(("ffn_fp32_seed21", lambda: gen_ffn(model, 21, torch.float32)))
+    cases.append(("ffn_fp16_seed21", lambda: gen_ffn(model, 21, torch.float16)))
+    only = os.environ.get("GOLDEN_ONLY")
+    if only:
+        cases = [c for c in cases if only in c[0]]
 
     for name, fn in cases:
         r = fn()

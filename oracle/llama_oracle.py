@@ -290,6 +290,33 @@ def paged_layer(
 
 
 # --------------------------------------------------------------------------------------
+# FFN half-layer (the reference ships no fused FFN kernel, only the eager module)
+# --------------------------------------------------------------------------------------
+def ffn_layer(
+    x: torch.Tensor,            # fp16 [1, hidden]
+    residual: torch.Tensor,     # fp16 [1, hidden]
+    w_gate_up: torch.Tensor,    # fp16 [2*ffn, hidden] = [W1; W3]  (nn.Linear layout; chat/llama/model.py:437-445)
+    w_down_t: torch.Tensor,     # fp16 [ffn, hidden]   = W2^T       (W2 is [hidden, ffn], model.py:440-442)
+    rms_w: torch.Tensor,        # fp16 [hidden]  (ffn_norm weight)
+    eps: float,
+    mode: str = "fp32",
+):
+    """h = x + residual; out = W2 (silu(W1 n) * (W3 n)), n = rmsnorm(h) * w  (model.py:447-448 SwiGLU, :519
+    `h + feed_forward(ffn_norm(h))`; the add of `out` onto the stream is the next op's fused residual add).
+    Returns (out [1, hidden] fp16, residual_out [1, hidden] fp16 = fp16(x + residual))."""
+    ffn = w_down_t.shape[0]
+    h = x.reshape(-1).float() + residual.reshape(-1).float()
+    res_out = h.half()
+    h = res_out.float()          # the residual stream is an fp16 tensor in the model, in either flavour
+    n = rmsnorm(h, rms_w, eps, mode)
+    gu = w_gate_up.float() @ n
+    g, u = _r16(gu[:ffn], mode), _r16(gu[ffn:], mode)
+    a = _r16(_r16(torch.nn.functional.silu(g), mode) * u, mode)
+    out = w_down_t.float().t() @ a
+    return out.half().view(1, -1), res_out.view(1, -1)
+
+
+# --------------------------------------------------------------------------------------
 # the eager fp16 CPU layer, native half tensors -- the timed CPU baseline
 # --------------------------------------------------------------------------------------
 def eager_fp16_cpu_layer(x, wq, wk, wv, wo, cache_k, cache_v, rms_w, freqs_cis, pos, eps=1e-5):

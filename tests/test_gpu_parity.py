@@ -469,14 +469,112 @@ def test_pdl_chain_matches_plain_chain():
             assert close(b, a, rtol=2e-3, atol=4e-3)
 
 
+# ---------------------------------------------------------------------------------------------------
+# fused FFN half-layer
+# ---------------------------------------------------------------------------------------------------
+def _ffn_inputs(hidden, ffn, seed):
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *sh, sc=1.0: (torch.randn(*sh, generator=g, dtype=torch.float32) * sc).half()
+    return dict(x=rn(1, hidden), residual=rn(1, hidden), w13=rn(2 * ffn, hidden, sc=0.02), w2t=rn(ffn, hidden, sc=0.02),
+                rms=(1.0 + 0.1 * torch.randn(hidden, generator=g)).half())
+
+
+@pytest.mark.parametrize("hidden,ffn", [(4096, 11008), (4096, 14336), (8192, 3584), (1024, 16), (2048, 4800)])
+def test_ffn_operator_vs_oracle(hidden, ffn):
+    import clusterfusion
+    d = _ffn_inputs(hidden, ffn, seed=ffn)
+    want_o, want_r = O.ffn_layer(d["x"], d["residual"], d["w13"], d["w2t"], d["rms"], 1e-5, mode="eager")
+    c = cuda(d)
+    for _ in range(3):                                  # workspace must come back zeroed every time
+        o, r = clusterfusion.llama_ffn_layer(c["x"], c["residual"], c["w13"], c["w2t"], c["rms"], 1e-5)
+        torch.cuda.synchronize()
+        assert torch.equal(r.cpu(), want_r)
+        assert close(o, want_o, rtol=2e-3, atol=2e-3)   # |out| ~ 2: 1 fp16 ulp = 2e-3 (the attention bar of 1e-3 is for |out| < 1)
+    # in-place residual stream
+    res = c["residual"].clone()
+    o2 = torch.empty_like(o)
+    clusterfusion.llama_ffn_layer_out(o2, res, c["x"], res, c["w13"], c["w2t"], c["rms"], 1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(res.cpu(), want_r) and close(o2, want_o, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", sorted(p.name for p in GOLDEN.glob("ffn_*.npz")))
+def test_ffn_operator_vs_reference_feedforward_golden(name):
+    """CUDA FFN kernel against the reference's FeedForward + RMSNorm modules run on CPU (model.py:407-448)."""
+    import clusterfusion
+    from oracle.gen_golden import ffn_inputs
+    z = np.load(GOLDEN / name)
+    d = ffn_inputs(int(z["seed"]))
+    assert inputs_digest(d) == str(z["digest"])
+    w13 = torch.cat([d["w1"], d["w3"]], 0).contiguous().cuda()
+    w2t = d["w2"].t().contiguous().cuda()
+    o, r = clusterfusion.llama_ffn_layer(d["x"].cuda(), d["residual"].cuda(), w13, w2t, d["rms"].cuda(), float(z["eps"]))
+    torch.cuda.synchronize()
+    tol = 2e-3 if str(z["dtype"]) == "float16" else 4e-3    # fp32 run of the reference never rounds the activations
+    assert close(o, torch.from_numpy(z["out"]), rtol=tol, atol=tol)
+
+
+def test_attention_and_ffn_share_one_workspace_in_a_chain():
+    """attention op -> FFN op -> attention op ... on one stream, PDL on, one workspace: a full decoder stack."""
+    from clusterfusion_b200 import cabi
+    import cabi_torch as ct
+    nl, kv, H, F = 4, 200, 4096, 11008
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device="cuda") * sc).half()
+    L = [dict(w_qkv=r(3 * H, H, sc=0.02), w_o=r(H, H, sc=0.02), k=r(kv, H), v=r(kv, H), n1=(1 + 0.1 * r(H).float()).half(),
+              w13=r(2 * F, H, sc=0.02), w2t=r(F, H, sc=0.02), n2=(1 + 0.1 * r(H).float()).half()) for _ in range(nl)]
+    x0, res0 = r(1, H), r(1, H)
+    cos = torch.rand(64, device="cuda"); sin = torch.rand(64, device="cuda")
+    ws = ct.workspace(H, 1, x0.device)
+
+    def chain(flags):
+        x, res, keep = x0, res0, []
+        for l in L:
+            o = torch.empty(1, H, dtype=torch.float16, device="cuda"); ro = torch.empty_like(o)
+            kn = torch.empty(H, dtype=torch.float16, device="cuda"); vn = torch.empty_like(kn)
+            a = cabi.CfLlamaArgs(variant=1, flags=flags, hidden=H, n_q_heads=32, n_kv_heads=32, head_dim=128, batch=1, kv_len=kv,
+                                 eps=1e-5, x=x.data_ptr(), residual_in=res.data_ptr(), residual_out=ro.data_ptr(),
+                                 w_qkv=l["w_qkv"].data_ptr(), w_o=l["w_o"].data_ptr(), rms_w=l["n1"].data_ptr(), out=o.data_ptr(),
+                                 k_new=kn.data_ptr(), v_new=vn.data_ptr(), k_cache=l["k"].data_ptr(), v_cache=l["v"].data_ptr(),
+                                 cos=cos.data_ptr(), sin=sin.data_ptr(), workspace=ws.data_ptr())
+            cabi.launch(a, ct.stream_handle())
+            f = torch.empty_like(o); rf = torch.empty_like(o)
+            b = cabi.CfFfnArgs(flags=flags, hidden=H, ffn=F, eps=1e-5, x=o.data_ptr(), residual_in=ro.data_ptr(),
+                               w_gate_up=l["w13"].data_ptr(), w_down_t=l["w2t"].data_ptr(), rms_w=l["n2"].data_ptr(),
+                               out=f.data_ptr(), residual_out=rf.data_ptr(), workspace=ws.data_ptr())
+            cabi.launch_ffn(b, ct.stream_handle())
+            keep += [o, ro, f, rf]
+            x, res = f, rf
+        torch.cuda.synchronize()
+        return keep
+
+    plain = chain(0)
+    # oracle for the first layer
+    l = L[0]
+    wo, wr, _, _ = O.sglang_layer(x0.cpu(), res0.cpu(), l["w_qkv"].cpu(), l["w_o"].cpu(), l["k"].cpu(), l["v"].cpu(), l["n1"].cpu(),
+                                  1e-5, cos.cpu(), sin.cpu(), n_heads=32, mode="eager")
+    assert close(plain[0], wo) and torch.equal(plain[1].cpu(), wr)
+    fo, fr = O.ffn_layer(plain[0].cpu(), plain[1].cpu(), l["w13"].cpu(), l["w2t"].cpu(), l["n2"].cpu(), 1e-5, mode="eager")
+    assert close(plain[2], fo, rtol=2e-3, atol=2e-3) and torch.equal(plain[3].cpu(), fr)
+    for _ in range(4):
+        pdl = chain(cabi.CF_FLAG_PDL)
+        for a_, b_ in zip(plain, pdl):
+            # fp32 atomic order moves last fp16 bits and 8 chained kernels compound them: allow a few stragglers,
+            # a real ordering bug would corrupt whole vectors
+            d_ = (a_.float() - b_.float()).abs()
+            bad = d_ > 6e-3 + 3e-3 * a_.float().abs()
+            assert float(bad.float().mean()) < 2e-3 and float(d_.max()) < 6e-2
+
+
 def test_decode_engine_fused_matches_eager_attention():
     """Whole-model decode loop (clusterfusion_b200/decode.py): fused attention op vs eager PyTorch attention, same
     random weights, CUDA-graphed and not; a few tokens from position 37."""
     from clusterfusion_b200.decode import LlamaDecodeEngine, ModelShape
     shp = ModelShape(n_layers=3, hidden=4096, n_heads=32, n_kv_heads=32, ffn=1024, vocab=2048)
     toks = {}
-    for mode, graph in (("eager", False), ("fused", False), ("fused", True)):
-        eng = LlamaDecodeEngine(shp, max_seq=128, device="cuda", seed=3, attn=mode)
+    for mode, graph in (("eager", False), ("fused", False), ("fused", True), ("fused+ffn", True)):
+        eng = LlamaDecodeEngine(shp, max_seq=128, device="cuda", seed=3, attn="eager" if mode == "eager" else "fused",
+                                ffn="fused" if mode == "fused+ffn" else "torch")
         eng.set_position(37)
         if graph:
             eng.capture()
@@ -489,6 +587,7 @@ def test_decode_engine_fused_matches_eager_attention():
     assert toks[("fused", False)] == toks[("fused", True)]
     # greedy tokens can legitimately diverge after a near-tie; the first ones must agree
     assert toks[("fused", True)][:3] == toks[("eager", False)][:3]
+    assert toks[("fused+ffn", True)][:3] == toks[("eager", False)][:3]
 
 
 def test_errors_are_loud():
