@@ -385,7 +385,8 @@ def run_ours(args, rank, world, local_rank):
     # ------------------------------------------------------------------ BASELINE config 4: Llama-3-8B GQA (32 Q / 8 KV), kv 8K
     gqa = ffn_res = None
     if not args.no_sweep:
-        gqa = run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
+        gqa = run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl, kvs=(1024, 8192))
+        gqa += run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl, cluster_kernel=True)
         ffn_res = run_ffn(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
     # ------------------------------------------------------------------ whole-model decode
     full = None
@@ -393,6 +394,9 @@ def run_ours(args, rank, world, local_rank):
         full = run_full_model(torch, dist, dev, world, peak)
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
+    ref_gpu = None
+    if world == 1 and not args.no_sweep:
+        ref_gpu = run_ref_gpu_kernel(torch, dev)
 
     # ------------------------------------------------------------------ Llama-2-70B head-parallel layer (N > 1 only)
     shard70 = None
@@ -452,6 +456,8 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "cpu_baseline": cpu,
     }
+    if ref_gpu is not None:
+        line["reference_gpu_kernel"] = ref_gpu
     if full is not None:
         line["full_model_decode"] = full
     if ffn_res is not None:
@@ -463,6 +469,67 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_ref_gpu_kernel(torch, dev, kvs=(1024, 16384), nsets=8):
+    """Baseline leg: the reference's OWN kernel (oracle/_ref = /root/reference/include/pybind.cpp + include/H100/*
+    recompiled unmodified for sm_100a by oracle/build_ref.sh) on this GPU, same shapes, 8 rotating layer sets.
+    us_per_call = CUDA events around its public operator (what a reference user gets: 3 memsets, 4 tensor-map encodes,
+    2 device syncs per call, llama_kernel_dispatch.cu:15-144); us_kernel = the kernel alone from CUPTI."""
+    import importlib.util
+    sos = sorted((ROOT / "oracle" / "_ref").glob("_clusterfusion_ref*.so"))
+    if not sos or dev.index != 0:           # the reference hard-codes cuda:0 (llama_kernel_dispatch.cu:18)
+        return {"unavailable": "oracle/_ref not built" if not sos else "reference kernel is cuda:0-only"}
+    try:
+        spec = importlib.util.spec_from_file_location("_clusterfusion_ref", sos[0])
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        out = []
+        for kv in kvs:
+            g = torch.Generator(device=dev).manual_seed(5)
+            r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * sc).half()
+            L = [dict(w_qkv=r(3 * HIDDEN, HIDDEN, sc=0.02), w_o=r(HIDDEN, HIDDEN, sc=0.02), k=r(kv, HIDDEN), v=r(kv, HIDDEN),
+                      rms=(1 + 0.1 * r(HIDDEN).float()).half()) for _ in range(nsets)]
+            x = r(1, HIDDEN)
+            a = float(kv) / (10000.0 ** (torch.arange(0, D, 2).float() / D))
+            cos = torch.repeat_interleave(a.cos(), 2).view(1, D).contiguous().to(dev)
+            sin = torch.repeat_interleave(a.sin(), 2).view(1, D).contiguous().to(dev)
+
+            def call(l):
+                return ref.llama_decoder_layer(x, l["w_qkv"], l["w_o"], l["k"], l["v"], l["rms"], cos, sin)
+            for l in L:
+                call(l)
+            torch.cuda.synchronize()
+            reps = 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                for l in L:
+                    call(l)
+            e1.record(); torch.cuda.synchronize()
+            us_call = e0.elapsed_time(e1) * 1e3 / (reps * nsets)
+            us_kernel = None
+            try:
+                from torch.profiler import profile, ProfilerActivity
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    for _ in range(3):
+                        for l in L:
+                            call(l)
+                    torch.cuda.synchronize()
+                ks = [e for e in prof.events() if "LlamaDecoderLayerKernel" in e.name]
+                if ks:
+                    us_kernel = sum(e.device_time for e in ks) / len(ks)
+            except Exception:
+                us_kernel = None
+            Bk = algorithmic_bytes(kv)
+            out.append({"kv_len": kv, "us_per_call": round(us_call, 2), "us_kernel": None if us_kernel is None else round(us_kernel, 2),
+                        "achieved_gbs_kernel": None if not us_kernel else round(Bk / (us_kernel * 1e-6) / 1e9, 1)})
+            del L
+            torch.cuda.empty_cache()
+        return {"what": "reference LlamaDecoderLayerKernel (include/H100/llama/kernel.cuh) recompiled unmodified for sm_100a",
+                "results": out}
+    except Exception as e:       # a baseline leg must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
 def run_ffn(torch, cabi, dev, timed_replays, peak, pdl=True, hidden=4096, ffn=11008, nl=8):
@@ -552,7 +619,8 @@ def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128):
     return out
 
 
-def run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=True, shape=(4096, 32, 8), kvs=(8192,), nl=8, tag="llama3-8b"):
+def run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=True, shape=(4096, 32, 8), kvs=(8192,), nl=8, tag="llama3-8b",
+               cluster_kernel=False):
     """Grouped-query kernel on one GPU (10-arg sglang form through the C ABI, CUDA graph of `nl` distinct layers)."""
     H, HQ, HKV = shape
     g = torch.Generator(device=dev).manual_seed(11)
@@ -567,7 +635,9 @@ def run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=True, shape=(4096, 32,
         x = r(1, H); res = r(1, H); cos = torch.rand(64, device=dev); sin = torch.rand(64, device=dev)
 
         def launch(h, rr, lay, stream):
-            a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_SGLANG, flags=(cabi.CF_FLAG_PDL if pdl else 0), hidden=H, n_q_heads=HQ,
+            a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_SGLANG,
+                                 flags=(cabi.CF_FLAG_PDL if pdl else 0) | (cabi.CF_FLAG_GQA_CLUSTER if cluster_kernel else 0),
+                                 hidden=H, n_q_heads=HQ,
                                  n_kv_heads=HKV, head_dim=128, batch=1, kv_len=kv, eps=1e-5, x=h.data_ptr(), residual_in=rr.data_ptr(),
                                  residual_out=lay["ro"].data_ptr(), w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(),
                                  rms_w=lay["rms"].data_ptr(), out=lay["o"].data_ptr(), k_new=lay["kn"].data_ptr(), v_new=lay["vn"].data_ptr(),
@@ -594,7 +664,9 @@ def run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=True, shape=(4096, 32,
         a = B / (us * 1e-6) / 1e9
         out.append({"model": tag, "hidden": H, "q_heads": HQ, "kv_heads": HKV, "kv_len": kv, "us_per_layer": round(us, 3),
                     "bytes": B, "achieved_gbs": round(a, 1), "frac_of_measured_peak": round(a / peak, 4),
-                    "frac_of_8tbs": round(a / 8000.0, 4), "kernel": "cfb::llama_decoder_layer_gqa_kernel<SGLANG,8|16,4>"})
+                    "frac_of_8tbs": round(a / 8000.0, 4),
+                    "kernel": "cfb::llama_decoder_layer_gqa_kernel<SGLANG,8|16,4> (first-generation cluster kernel)" if cluster_kernel
+                              else "cfb::llama_decoder_layer_gqa2_kernel<SGLANG,4> (G CTAs per group, L2 exchanges)"})
         del L, gr
         torch.cuda.empty_cache()
     return out

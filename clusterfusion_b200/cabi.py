@@ -20,6 +20,7 @@ LIB_PATH = Path(os.environ["CF_LIB_PATH"]) if os.environ.get("CF_LIB_PATH") else
 CF_VARIANT_CHAT, CF_VARIANT_SGLANG, CF_VARIANT_PAGED = 0, 1, 2
 CF_FLAG_OUT_FP32_PARTIAL = 0x1
 CF_FLAG_PDL = 0x2
+CF_FLAG_GQA_CLUSTER = 0x4
 
 EXPORTED_SYMBOLS = (
     "cf_abi_version",

@@ -13,6 +13,7 @@
 #include "../../include/clusterfusion_b200.h"
 #include "llama_decoder_kernel.cuh"
 #include "llama_decoder_gqa_kernel.cuh"
+#include "llama_decoder_gqa2_kernel.cuh"
 #include "llama_ffn_kernel.cuh"
 
 #include <cuda.h>
@@ -108,11 +109,11 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int CLUSTER, typename Kern>
-int launch_kernel(Kern kern, int smem_bytes, int slot, const cfb::KParams& kp, int n_clusters, int batch, bool pdl,
+template <int CLUSTER, typename Kern, typename Params>
+int launch_kernel(Kern kern, int smem_bytes, int slot, const Params& kp, int n_clusters, int batch, bool pdl,
                   cudaStream_t stream) {
-    static std::once_flag once[8][16];
-    static cudaError_t attr_err[8][16];
+    static std::once_flag once[12][16];
+    static cudaError_t attr_err[12][16];
     int dev = 0;
     cudaGetDevice(&dev);
     std::call_once(once[slot][dev & 15], [&] {
@@ -154,6 +155,34 @@ int launch_gqa(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cuda
                                   (CLUSTER == 16 ? 3 : 5) + VARIANT, kp, n_clusters, batch, pdl, stream);
 }
 
+// second-generation grouped-query kernel: G plain CTAs per (KV head, 4 query heads) group, exchanges through L2
+template <int VARIANT>
+int launch_gqa2(const cfb::G2Params& gp, int batch, bool pdl, cudaStream_t stream) {
+    return launch_kernel<1>(cfb::llama_decoder_layer_gqa2_kernel<VARIANT, 4>, cfb::SmemGqa2<4>::TOTAL, 8 + VARIANT,
+                            gp, gp.n_groups * gp.G, batch, pdl, stream);
+}
+
+int sm_count_of_current_device() {
+    static int sm_count[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sm_count[dev & 15] == 0) cudaDeviceGetAttribute(&sm_count[dev & 15], cudaDevAttrMultiProcessorCount, dev);
+    return sm_count[dev & 15];
+}
+
+// workspace carve-up (bytes): [scratch fp32 batch*hidden][counters u32 batch*32][qkv_acc][attn_buf][gcounters]
+size_t ws_off_counters(int hidden, int batch) { return (size_t)batch * hidden * sizeof(float); }
+size_t ws_off_qkv_acc(int hidden, int batch) { return ws_off_counters(hidden, batch) + (size_t)batch * 32 * sizeof(uint32_t); }
+size_t ws_off_attn_buf(int hidden, int batch) {
+    return ws_off_qkv_acc(hidden, batch) + (size_t)batch * cfb::G2_GROUPS_MAX * cfb::SmemGqa2<4>::R * sizeof(float);
+}
+size_t ws_off_gcounters(int hidden, int batch) {
+    return ws_off_attn_buf(hidden, batch) + (size_t)batch * cfb::G2_SLOTS * 4 * cfb::SmemGqa2<4>::PAY * sizeof(float);
+}
+size_t ws_total(int hidden, int batch) {
+    return ws_off_gcounters(hidden, batch) + (size_t)batch * cfb::G2_COUNTERS * sizeof(uint32_t);
+}
+
 bool device_is_sm100() {
     static int cached[16] = {0};   // 0 unknown, 1 yes, 2 no
     int dev = 0;
@@ -177,8 +206,9 @@ const char* cf_last_error_string(void) { return g_last_error.c_str(); }
 
 size_t cf_llama_workspace_bytes(int32_t hidden, int32_t batch) {
     if (hidden <= 0 || batch <= 0) return 0;
-    // fp32 scratch [batch][hidden] + counters [batch][16 + 1] (enough for any cluster size)
-    return (size_t)batch * hidden * sizeof(float) + (size_t)batch * 32 * sizeof(uint32_t);
+    // fp32 scratch [batch][hidden] + counters [batch][32] (any cluster size) + the grouped-query kernel's L2 exchange
+    // buffers (q|k|v accumulators, softmax-state slots, group counters): ~0.4 MB per request
+    return ws_total(hidden, batch);
 }
 
 uint64_t cf_llama_algorithmic_bytes(const CfLlamaArgs* a, uint64_t total_kv_rows) {
@@ -209,7 +239,7 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
             return fail(CF_ERR_BAD_SHAPE, "hidden must be a multiple of %d and <= %d (got %d)", CL * 256,
                         CL * ks_max, a->hidden);
     } else {
-        // grouped-query path: 16-CTA clusters, 4 query heads per cluster, nn.Linear weight layout
+        // grouped-query path: 4 query heads per group, nn.Linear weight layout
         if (chat) return fail(CF_ERR_BAD_SHAPE, "grouped-query attention needs the nn.Linear layout (SGLANG / PAGED)");
         if ((a->n_q_heads / a->n_kv_heads) % 4 != 0)
             return fail(CF_ERR_BAD_SHAPE, "grouped-query attention needs a multiple of 4 query heads per KV head (q=%d, kv=%d)",
@@ -280,9 +310,28 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     kp.flags = a->flags;
 
     const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
+    if (gqa && !(a->flags & CF_FLAG_GQA_CLUSTER)) {
+        // group kernel: G CTAs per group, G = largest power of two in [8, 64] with groups * G * batch <= #SMs
+        const int n_groups = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
+        if (n_groups > cfb::G2_GROUPS_MAX)
+            return fail(CF_ERR_BAD_SHAPE, "GQA: at most %d (KV head, 4 query heads) groups per call (got %d)", cfb::G2_GROUPS_MAX, n_groups);
+        const int n_sm = sm_count_of_current_device();
+        int G = cfb::G2_G_MAX;
+        while (G > 8 && (long long)n_groups * G * a->batch > n_sm) G >>= 1;
+        cfb::G2Params gp;
+        memset(&gp, 0, sizeof gp);
+        gp.k = kp;
+        char* ws = static_cast<char*>(a->workspace);
+        gp.qkv_acc = reinterpret_cast<float*>(ws + ws_off_qkv_acc(a->hidden, a->batch));
+        gp.attn_buf = reinterpret_cast<float*>(ws + ws_off_attn_buf(a->hidden, a->batch));
+        gp.gcounters = reinterpret_cast<unsigned*>(ws + ws_off_gcounters(a->hidden, a->batch));
+        gp.G = G;
+        gp.n_groups = n_groups;
+        return paged ? launch_gqa2<cfb::PAGED>(gp, a->batch, pdl, stream) : launch_gqa2<cfb::SGLANG>(gp, 1, pdl, stream);
+    }
     if (gqa) {
-        // at most four 16-CTA clusters are co-resident (1 CTA / SM, one cluster per GPC-sized slot): use 16 CTAs per
-        // cluster only when that covers the whole grid, otherwise 8 (all clusters resident at once)
+        // first-generation cluster kernel (CF_FLAG_GQA_CLUSTER; kept for A/B measurement).  At most four 16-CTA clusters
+        // are co-resident (1 CTA / SM): use 16 CTAs per cluster only when that covers the whole grid, otherwise 8
         const int n_clusters = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
         const bool wide = (long long)n_clusters * a->batch <= 4;
         if (paged) return wide ? launch_gqa<cfb::PAGED, 16>(kp, n_clusters, a->batch, pdl, stream)

@@ -1,0 +1,670 @@
+/*
+ * Grouped-query fused decoder attention half-layer, second generation ("group kernel").
+ *
+ * Why a second kernel: a B200 SM pulls at most ~64 GB/s through one 192 KB TMA ring (measured), so a
+ * layer only reaches the HBM roofline when >= ~110 SMs stream at once.  With grouped-query attention the natural unit
+ * of fusion is one KV head + its query heads: Llama-3-8B has 8 of them.  The cluster kernel
+ * (llama_decoder_gqa_kernel.cuh) can give a unit 8 CTAs (64 SMs: 48 % of the roofline) -- clusters of 16 with a
+ * 225 KB footprint are not co-resident beyond four (tools/cluster_probe.cu, profiles/), and DSMEM does not reach
+ * outside a cluster.  Here a unit ("group") is G CTAs, G = 2^k chosen so that groups x G ~ fills the 148 SMs
+ * (8B: 8 x 16 = 128; 70B shards: 8 x 16, 4 x 32, 2 x 64), and the two exchanges the fusion needs go through L2:
+ *
+ *   exchange 1  q|k|v:  the group's [(NQ+2)*128 x hidden] weight block is cut into 16-row x 256-col tiles, dealt to the
+ *               G CTAs as contiguous runs in row-block-major order (whole row blocks when G divides 6*8, so no
+ *               K-split and a deterministic sum); every CTA adds its row sums into the group's fp32 vector with
+ *               red.global.add, bumps the group counter (release), spins until it reads G (acquire), then loads the
+ *               768 floats back and applies RoPE itself.
+ *   exchange 2  softmax state: CTA r streams KV rows [r*chunk, ...) for all NQ query heads, writes its NQ x [m, l, o[128]]
+ *               to the group's slot r, bumps the second counter, spins, then merges all G states in rank order
+ *               (bit-identical on every CTA).
+ *
+ * L2 round trips are ~0.15 us (B300_MICROARCH: L2 hit 234-262 cycles, ATOMG 318); the TMA ring keeps landing the next
+ * phase's tiles while a CTA waits.  Everything else -- the single 24 x 8 KB self-issuing tile stream, fp32 reductions,
+ * fp16 rounding points of the eager model, fp32 red + last-arriver finalize of the O projection -- is as in the MHA
+ * kernel (llama_decoder_kernel.cuh).  nn.Linear weight layout only (SGLANG / PAGED), NQ = 4 query heads per group; a KV
+ * head with 8 query heads (70B) gets two groups.
+ *
+ * Cross-CTA spinning needs the waited-for CTAs to be resident or dispatched eventually: the launcher picks G with
+ * groups x G x batch <= #SMs whenever it can (1 CTA / SM), and CTAs of a group are contiguous in blockIdx.x, so a
+ * partially resident group only ever waits for blocks that are dispatched as earlier, complete groups drain.
+ *
+ * Reference: new capability (the reference kernels hard-code MHA, /root/reference/include/H100/llama/config.h:2-38,
+ * llama_kernel_dispatch.cu:63-64); same operator signatures (pybind.cpp:14-43).
+ */
+#pragma once
+
+#include "llama_decoder_gqa_kernel.cuh"
+
+namespace cfb {
+
+constexpr int G2_HIDDEN_MAX = 8192;
+constexpr int G2_RB_LOCAL_MAX = 8;        // 16-row blocks a CTA can touch in the QKV phase (6*8 / G + 1 partial, G >= 8 .. or 4096: G >= 4)
+constexpr int G2_OROWS_MAX = 1024;        // hidden / G
+constexpr int G2_GROUPS_MAX = 16;         // groups per request
+constexpr int G2_G_MAX = 64;              // CTAs per group
+constexpr int G2_SLOTS = 160;             // softmax-state slots per request (groups x G <= 148 whenever batch == 1)
+constexpr int G2_COUNTERS = 128;          // u32 per request: [0,64) O slices, [64] residual, [65 + 3*group + {0,1,2}]
+
+template <int NQ>
+struct SmemGqa2 {
+    static constexpr int R = (NQ + 2) * HEAD_DIM;                 // 768 rows of q(NQ heads) | k | v
+    static constexpr int PAY = HEAD_DIM + 4;                      // [m, l, -, -, o[128]]
+    static constexpr int RING = 0;
+    static constexpr int UNION = RING + NSTAGES * STAGE_BYTES;
+    //   phase QKV : xs fp16[hidden <= 8192] | part fp32[12 warps][G2_RB_LOCAL_MAX][16]
+    //   phase ATTN: attn_part fp32[12][132] | cta_state fp32[NQ][132]
+    //   phase O   : out_part fp32[NQ*128/256][G2_OROWS_MAX]
+    static constexpr int XS = UNION;
+    static constexpr int PART = UNION + G2_HIDDEN_MAX * 2;
+    static constexpr int QKV_BYTES = G2_HIDDEN_MAX * 2 + CONSUMER_WARPS * G2_RB_LOCAL_MAX * ROWS512 * 4;
+    static constexpr int ATTN_PART = UNION;
+    static constexpr int CTA_STATE = UNION + CONSUMER_WARPS * PAY * 4;
+    static constexpr int ATTN_BYTES = (CONSUMER_WARPS + NQ) * PAY * 4;
+    static constexpr int OUT_PART = UNION;
+    static constexpr int OUT_BYTES = (NQ * HEAD_DIM / 256) * G2_OROWS_MAX * 4;
+    static constexpr int UNION_SIZE = QKV_BYTES > ATTN_BYTES ? (QKV_BYTES > OUT_BYTES ? QKV_BYTES : OUT_BYTES)
+                                                             : (ATTN_BYTES > OUT_BYTES ? ATTN_BYTES : OUT_BYTES);
+    static constexpr int QKV_FIN = UNION + UNION_SIZE;                     // fp32[R] roped q*scale | k | v
+    static constexpr int AG2 = QKV_FIN + R * 4;                            // fp32[NQ*128] attention output
+    static constexpr int RED = AG2 + NQ * HEAD_DIM * 4;                    // fp32[32]
+    static constexpr int BARS = RED + 32 * 4;                              // u64 full[NSTAGES]
+    static constexpr int FLAGS = BARS + NSTAGES * 8;
+    static constexpr int TOTAL = FLAGS + 16;
+    static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
+};
+
+// extra kernel parameters of the group kernel (appended to KParams by composition)
+struct G2Params {
+    KParams k;
+    float* qkv_acc;        // fp32 [batch][G2_GROUPS_MAX][768], zero between launches
+    float* attn_buf;       // fp32 [batch][G2_SLOTS][NQ*132]
+    unsigned* gcounters;   // u32  [batch][G2_COUNTERS], zero between launches
+    int G;                 // CTAs per group (power of two)
+    int n_groups;          // groups per request
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_inc(unsigned* p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// 16 output rows x 256 input columns; ACCUMULATES the 16 row sums into acc[0..16) (owned by the calling warp)
+__device__ __forceinline__ void gemv_tile_16x256_acc(const uint4* tile, const float (&x8)[8], float* acc, uint32_t lane) {
+    float tmp[2];
+#pragma unroll
+    for (int grp = 0; grp < ROWS512 / 8; ++grp) {
+        float v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float w8[8];
+            unpack8(tile[(grp * 8 + r) * 32 + lane], w8);
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a = fmaf(x8[k], w8[k], a);
+            v[r] = a;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const bool hi = lane & 16;
+            const float send = hi ? v[r] : v[r + 4];
+            const float keep = hi ? v[r + 4] : v[r];
+            v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const bool hi = lane & 8;
+            const float send = hi ? v[r] : v[r + 2];
+            const float keep = hi ? v[r + 2] : v[r];
+            v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const bool hi = lane & 4;
+            const float send = hi ? v[0] : v[1];
+            const float keep = hi ? v[1] : v[0];
+            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        tmp[grp] = v[0];
+    }
+    if ((lane & 3) == 0) {
+        const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        acc[r] += tmp[0];
+        acc[8 + r] += tmp[1];
+    }
+}
+
+// one CTA-wide "arrive + wait for all G CTAs of the group" on a global counter.  Everything the CTA wrote before
+// (plain stores or reds, by any of its threads) is visible to every CTA that leaves the wait.
+__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned G, uint32_t tid) {
+    __threadfence();
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    if (tid == 0) {
+        red_release_inc(counter);
+        while (ld_acquire_u32(counter) < G) { __nanosleep(32); }
+    }
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+}
+
+template <int VARIANT, int NQ>
+__global__ void __launch_bounds__(BLOCK_THREADS, 1)
+llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
+{
+    using S = SmemGqa2<NQ>;
+    static_assert(VARIANT != CHAT, "GQA uses the nn.Linear weight layout");
+    constexpr bool kPaged = (VARIANT == PAGED);
+    const KParams& p = gp.k;
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t smem_base = dsm::smem_u32(smem);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t lane = tid & 31;
+    const int G = gp.G;
+    const uint32_t rank = blockIdx.x % G;            // CTA index inside the group
+    const uint32_t gid = blockIdx.x / G;             // group index inside the request
+    const uint32_t batch = blockIdx.y;
+
+    const int hidden = p.hidden;
+    const int Hq = p.n_heads, Hkv = p.n_kv_heads;
+    const int qsplit = (Hq / Hkv) / NQ;                 // groups per KV head
+    const int kvh = gid / qsplit;
+    const int qh0 = kvh * (Hq / Hkv) + (gid % qsplit) * NQ;     // first query head of this group
+    const bool writes_kv = (gid % qsplit) == 0;
+    const int OROWS = hidden / G;                        // this CTA's slice of the O output dim
+    const int kv_cols = Hkv * HEAD_DIM;
+    const int wins = hidden / 256;
+
+    const uint32_t full_u32 = smem_base + S::BARS;          // u64 full[NSTAGES]
+
+    int kv_len, kv_base = 0, new_slot = 0;
+    if constexpr (kPaged) {
+        kv_base = p.indptr[batch];
+        const int end = p.indptr[batch + 1] - 1;
+        kv_len = end - kv_base;
+        new_slot = p.indices[end];
+    } else {
+        kv_len = p.kv_len;
+    }
+    const int chunk = (((kv_len + G - 1) / G) + ROWS512 - 1) & ~(ROWS512 - 1);
+    const int row_begin = min((int)rank * chunk, kv_len);
+    const int row_end = min(row_begin + chunk, kv_len);
+    const uint32_t n_qkv_tiles = (uint32_t)((S::R / ROWS512) * wins / G);       // contiguous run of the group's tiles
+    const uint32_t t_first = rank * n_qkv_tiles;                                 // group-level index of this CTA's first tile
+    const int rb_first = t_first / wins;
+    const uint32_t n_kv_tiles = (row_end - row_begin + ROWS512 - 1) / ROWS512;
+    constexpr int owins = NQ * HEAD_DIM / 256;
+    const uint32_t n_o_tiles = (OROWS / ROWS512) * owins;
+
+    CF_MARK(0);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    // ---- tile stream: every warp requests, consumes and re-requests its own tiles (see llama_decoder_kernel.cuh) ----
+    const uint64_t pol = policy_evict_first();
+    const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
+    const __half* kpool = nullptr;
+    const __half* vpool = nullptr;
+    if constexpr (kPaged) {
+        kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
+        vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
+    }
+    auto issue_tile = [&](uint32_t g) {
+        if (g >= total_tiles) return;
+        const uint32_t s = ring_stage(g);
+        const uint32_t fb = full_u32 + 8 * s;
+        const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
+        if (g < n_qkv_tiles) {
+            if (lane == 0) {
+                constexpr int BPH = HEAD_DIM / ROWS512;          // 16-row blocks per head (8)
+                const uint32_t t = t_first + g;
+                const int rb = t / wins, win = t % wins;         // rb: 16-row block inside q(NQ*128) | k(128) | v(128)
+                int row0;
+                if (rb < NQ * BPH) row0 = qh0 * HEAD_DIM + rb * ROWS512;
+                else if (rb < NQ * BPH + BPH) row0 = Hq * HEAD_DIM + kvh * HEAD_DIM + (rb - NQ * BPH) * ROWS512;
+                else row0 = (Hq + Hkv) * HEAD_DIM + kvh * HEAD_DIM + (rb - NQ * BPH - BPH) * ROWS512;
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wqkv, win * 256, row0, fb, pol);
+            }
+        } else if (g < n_qkv_tiles + n_kv_tiles) {
+            const uint32_t i = g - n_qkv_tiles;
+            if constexpr (!kPaged) {
+                if (lane == 0) {
+                    const int r0 = row_begin + i * ROWS512;
+                    dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                    tma_load_2d(dst, &p.tm_k, kvh * HEAD_DIM, r0, fb, pol);
+                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, kvh * HEAD_DIM, r0, fb, pol);
+                }
+            } else {
+                const int r = row_begin + i * ROWS512 + (lane & 15);
+                const bool valid = r < row_end;
+                const long long slot = valid ? (long long)p.indices[kv_base + r] : 0;
+                const int nvalid = min(ROWS512, row_end - (row_begin + (int)i * ROWS512));
+                if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
+                __syncwarp();
+                if (valid) {
+                    const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
+                    if (lane < 16) bulk_load_1d(d, kpool + slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                    else bulk_load_1d(d + STAGE_BYTES / 2, vpool + slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                }
+            }
+        } else {
+            if (lane == 0) {
+                const uint32_t i = g - n_qkv_tiles - n_kv_tiles;
+                const int rb = i / owins, win = i % owins;       // Wo [out][in]: 16 output rows x 256 of this group's input cols
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wo, qh0 * HEAD_DIM + win * 256, rank * OROWS + rb * ROWS512, fb, pol);
+            }
+        }
+    };
+
+    if (lane == 0) {
+        dsm::mbar_init(full_u32 + 8 * warp, 1);
+        dsm::mbar_init(full_u32 + 8 * (warp + CONSUMER_WARPS), 1);
+        if (tid == 0) {
+            prefetch_tmap(&p.tm_wqkv);
+            prefetch_tmap(&p.tm_wo);
+            if constexpr (!kPaged) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); }
+        }
+        dsm::mbar_fence_init();
+    }
+    __syncwarp();
+    CF_MARK(12);
+    issue_tile(warp);
+    issue_tile(warp + CONSUMER_WARPS);
+
+    __half* xs = reinterpret_cast<__half*>(smem + S::XS);
+    float* part = reinterpret_cast<float*>(smem + S::PART);
+    float* attn_part = reinterpret_cast<float*>(smem + S::ATTN_PART);
+    float* cta_state = reinterpret_cast<float*>(smem + S::CTA_STATE);
+    float* out_part = reinterpret_cast<float*>(smem + S::OUT_PART);
+    float* qkv_fin = reinterpret_cast<float*>(smem + S::QKV_FIN);
+    float* ag2 = reinterpret_cast<float*>(smem + S::AG2);
+    float* red = reinterpret_cast<float*>(smem + S::RED);
+    uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
+
+    const __half* xg = p.x + (size_t)batch * hidden;
+    const __half* rg = p.residual_in + (size_t)batch * hidden;
+    __half* rout = p.residual_out + (size_t)batch * hidden;
+    const bool residual_inplace = (static_cast<const void*>(rout) == static_cast<const void*>(rg));
+    float* qkv_acc = gp.qkv_acc + ((size_t)batch * G2_GROUPS_MAX + gid) * S::R;
+    float* attn_buf = gp.attn_buf + ((size_t)batch * G2_SLOTS + (size_t)gid * G) * (NQ * S::PAY);
+    unsigned* gcnt = gp.gcounters + (size_t)batch * G2_COUNTERS;
+    unsigned* grp_cnt = gcnt + 65 + 3 * gid;
+
+    // zero this warp's accumulation slots (smem only: legal before griddepcontrol.wait)
+    for (int e = lane; e < G2_RB_LOCAL_MAX * ROWS512; e += 32) part[warp * G2_RB_LOCAL_MAX * ROWS512 + e] = 0.f;
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // ---- phase 0: fused residual add + RMSNorm over the FULL vector (every CTA needs all of it: rows are split) ----
+    {
+        float ss = 0.f;
+        for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+            float f[8], r8[8];
+            unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+            unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { f[k] = round_h(f[k] + r8[k]); ss += f[k] * f[k]; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) red[warp] = ss;
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w];
+        const float rstd = rsqrtf(tot / (float)hidden + p.eps);
+        const int own_lo = rank * OROWS, own_hi = own_lo + OROWS;       // residual_out slice written by group 0
+        for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+            float f[8], w8[8], r8[8];
+            unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+            unpack8(*reinterpret_cast<const uint4*>(p.rms_w + e), w8);
+            unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+            __align__(16) __half hs[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { hs[k] = __float2half_rn(f[k] + r8[k]); f[k] = __half2float(hs[k]); }
+            if (gid == 0 && !residual_inplace && e >= own_lo && e < own_hi)
+                *reinterpret_cast<uint4*>(rout + e) = *reinterpret_cast<const uint4*>(hs);
+            __align__(16) __half xn[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(round_h(f[k] * rstd) * w8[k]);
+            *reinterpret_cast<uint4*>(xs + e) = *reinterpret_cast<const uint4*>(xn);
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+    CF_MARK(1);
+
+    uint32_t gbase = 0;
+    // ---- phase 1: QKV GEMV over this CTA's run of tiles ---------------------------------------------------
+    for (uint32_t i = first_tile(gbase, warp); i < n_qkv_tiles; i += CONSUMER_WARPS) {
+        const uint32_t g = gbase + i, s = ring_stage(g);
+        const uint32_t t = t_first + i;
+        const int rb = t / wins, win = t % wins;
+        float x8[8];
+        unpack8(*reinterpret_cast<const uint4*>(xs + win * 256 + lane * 8), x8);
+        ring_wait_full(full_u32, g);
+        gemv_tile_16x256_acc(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), x8,
+                             part + (warp * G2_RB_LOCAL_MAX + (rb - rb_first)) * ROWS512, lane);
+        __syncwarp();
+        issue_tile(g + NSTAGES);
+    }
+    gbase += n_qkv_tiles;
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    CF_MARK(2);
+    {
+        const int rb_last = (t_first + n_qkv_tiles - 1) / wins;
+        const int n_loc = (rb_last - rb_first + 1) * ROWS512;
+        for (int o = tid; o < n_loc; o += CONSUMER_THREADS) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < CONSUMER_WARPS; ++w) a += part[w * G2_RB_LOCAL_MAX * ROWS512 + o];
+            red_add_f32(qkv_acc + rb_first * ROWS512 + o, a);
+        }
+    }
+    // ---- exchange 1 (through L2): all G CTAs have added their row sums ---------------------------------------
+    group_barrier(grp_cnt + 0, G, tid);
+    CF_MARK(3);
+
+    // ---- RoPE (NeoX), new K/V out ---------------------------------------------------------------------
+    {
+        constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;
+        const float* cosp = p.cos;
+        const float* sinp = p.sin;
+        if constexpr (kPaged) {
+            cosp = p.cos + p.positions[batch] * HEAD_DIM;
+            sinp = cosp + HEAD_DIM / 2;
+        }
+        for (int e = tid; e < S::R; e += CONSUMER_THREADS) {
+            const int hd = e >> 7, d = e & 127;                  // hd < NQ: query head; NQ: k; NQ+1: v
+            const float a = round_h(ld_cg_f32(qkv_acc + e));     // q / k / v leave the projection as fp16 (eager model)
+            if (hd <= NQ) {
+                const float b = round_h(ld_cg_f32(qkv_acc + (e ^ 64)));
+                const int i = d & 63;
+                const float rot = (d & 64) ? fmaf(a, cosp[i], b * sinp[i]) : fmaf(a, cosp[i], -b * sinp[i]);
+                const __half rh = __float2half_rn(rot);
+                qkv_fin[e] = hd < NQ ? __half2float(rh) * kScaleLog2 : __half2float(rh);
+                if (hd == NQ && rank == 0 && writes_kv) {
+                    if constexpr (kPaged) {
+                        __half* kp = reinterpret_cast<__half*>(p.k_pool_ptrs[p.layer_id]);
+                        kp[(size_t)new_slot * kv_cols + kvh * HEAD_DIM + d] = rh;
+                    } else {
+                        p.k_new[kvh * HEAD_DIM + d] = rh;
+                    }
+                }
+            } else {
+                qkv_fin[e] = a;
+                if (rank == 0 && writes_kv) {
+                    const __half vh = __float2half_rn(a);
+                    if constexpr (kPaged) {
+                        __half* vp = reinterpret_cast<__half*>(p.v_pool_ptrs[p.layer_id]);
+                        vp[(size_t)new_slot * kv_cols + kvh * HEAD_DIM + d] = vh;
+                    } else {
+                        p.v_new[kvh * HEAD_DIM + d] = vh;
+                    }
+                }
+            }
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+    CF_MARK(4);
+
+    // ---- phase 2: flash-decode, NQ query heads share each K/V tile -------------------------------------
+    {
+        const int sub = lane >> 4, c = lane & 15;
+        float q8[NQ][8], o8[NQ][8], m[NQ], l[NQ];
+#pragma unroll
+        for (int h = 0; h < NQ; ++h) {
+            m[h] = -INFINITY; l[h] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { q8[h][k] = qkv_fin[h * HEAD_DIM + c * 8 + k]; o8[h][k] = 0.f; }
+        }
+        for (uint32_t i = first_tile(gbase, warp); i < n_kv_tiles; i += CONSUMER_WARPS) {
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            ring_wait_full(full_u32, g);
+            const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+            const uint4* vt = kt + STAGE_BYTES / 32;
+            const int rows_left = row_end - (row_begin + (int)i * ROWS512);
+            float sc[NQ][8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int row = 2 * jj + sub;
+                float k8[8];
+                unpack8(kt[row * 16 + c], k8);
+#pragma unroll
+                for (int h = 0; h < NQ; ++h) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a = fmaf(q8[h][k], k8[k], a);
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    sc[h][jj] = (row < rows_left) ? a : -INFINITY;
+                }
+            }
+            float mu[NQ];
+#pragma unroll
+            for (int h = 0; h < NQ; ++h) {
+                float mx = sc[h][0];
+#pragma unroll
+                for (int jj = 1; jj < 8; ++jj) mx = fmaxf(mx, sc[h][jj]);
+                const float m_new = fmaxf(m[h], mx);
+                mu[h] = (m_new == -INFINITY) ? 0.f : m_new;
+                const float corr = dsm::exp2_diff(m[h], mu[h]);
+                l[h] *= corr;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o8[h][k] *= corr;
+                m[h] = m_new;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int row = 2 * jj + sub;
+                uint4 raw = vt[row * 16 + c];
+                if constexpr (kPaged) {
+                    if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
+                }
+                float v8[8];
+                unpack8(raw, v8);
+#pragma unroll
+                for (int h = 0; h < NQ; ++h) {
+                    const float pr = dsm::fast_exp2(sc[h][jj] - mu[h]);
+                    l[h] += pr;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o8[h][k] = fmaf(pr, v8[k], o8[h][k]);
+                }
+            }
+            __syncwarp();
+            issue_tile(g + NSTAGES);
+        }
+        gbase += n_kv_tiles;
+        CF_MARK(5);
+        // merge the two half-warps (they saw different rows) in registers
+#pragma unroll
+        for (int h = 0; h < NQ; ++h) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m[h], 16);
+            const float l2 = __shfl_xor_sync(0xffffffffu, l[h], 16);
+            const float M = fmaxf(m[h], m2);
+            const float w1 = dsm::exp2_diff(m[h], M), w2 = dsm::exp2_diff(m2, M);
+            l[h] = l[h] * w1 + l2 * w2;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float o2 = __shfl_xor_sync(0xffffffffu, o8[h][k], 16);
+                o8[h][k] = o8[h][k] * w1 + o2 * w2;
+            }
+            m[h] = M;
+        }
+        // block merge, one head at a time through a 12 x 132 float buffer; rank 0 folds in the current token
+#pragma unroll
+        for (int h = 0; h < NQ; ++h) {
+            if (sub == 0) {
+                float* slot = attn_part + warp * S::PAY;
+                if (c == 0) { slot[0] = m[h]; slot[1] = l[h]; }
+                *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[h][0], o8[h][1], o8[h][2], o8[h][3]);
+                *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[h][4], o8[h][5], o8[h][6], o8[h][7]);
+            }
+            if (warp == 0) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    a = fmaf(qkv_fin[h * HEAD_DIM + lane * 4 + k], qkv_fin[NQ * HEAD_DIM + lane * 4 + k], a);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) red[CONSUMER_WARPS] = a;
+            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            if (tid < HEAD_DIM) {
+                const bool with_new = (rank == 0);
+                float M = with_new ? red[CONSUMER_WARPS] : -INFINITY;
+#pragma unroll
+                for (int gI = 0; gI < CONSUMER_WARPS; ++gI) M = fmaxf(M, attn_part[gI * S::PAY]);
+                float L = 0.f, O = 0.f;
+#pragma unroll
+                for (int gI = 0; gI < CONSUMER_WARPS; ++gI) {
+                    const float w = dsm::exp2_diff(attn_part[gI * S::PAY], M);
+                    L = fmaf(attn_part[gI * S::PAY + 1], w, L);
+                    O = fmaf(attn_part[gI * S::PAY + 4 + tid], w, O);
+                }
+                if (with_new) {
+                    const float w = dsm::exp2_diff(red[CONSUMER_WARPS], M);
+                    L += w;
+                    O = fmaf(qkv_fin[(NQ + 1) * HEAD_DIM + tid], w, O);
+                }
+                float* st = cta_state + h * S::PAY;
+                st[4 + tid] = O;
+                if (tid == 0) { st[0] = M; st[1] = L; st[2] = 0.f; st[3] = 0.f; }
+            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        }
+        // ---- exchange 2 (through L2): publish this CTA's NQ softmax states, wait for the group, merge in rank order ----
+        {
+            float4* dstp = reinterpret_cast<float4*>(attn_buf + (size_t)rank * (NQ * S::PAY));
+            const float4* srcp = reinterpret_cast<const float4*>(cta_state);
+            for (int e = tid; e < NQ * S::PAY / 4; e += CONSUMER_THREADS) dstp[e] = srcp[e];
+        }
+        group_barrier(grp_cnt + 1, G, tid);
+        for (int e = tid; e < NQ * HEAD_DIM; e += CONSUMER_THREADS) {
+            const int h = e >> 7, d = e & 127;
+            const float* base = attn_buf + h * S::PAY;
+            float M = -INFINITY, L = 0.f, O = 0.f;
+#pragma unroll 4
+            for (int r = 0; r < G; ++r) {
+                const float* st = base + (size_t)r * (NQ * S::PAY);
+                const float mr = ld_cg_f32(st), lr = ld_cg_f32(st + 1), orr = ld_cg_f32(st + 4 + d);
+                const float Mn = fmaxf(M, mr);
+                const float a = dsm::exp2_diff(M, Mn), b = dsm::exp2_diff(mr, Mn);
+                L = L * a + lr * b;
+                O = O * a + orr * b;
+                M = Mn;
+            }
+            ag2[e] = round_h(O / L);                             // attention output leaves as fp16 (eager model)
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        // every CTA of the group has now passed exchange 1, and this CTA is done reading both exchange buffers:
+        // the last CTA to get here re-zeroes the group's buffers and counters for the next launch
+        if (tid == 0) {
+            __threadfence();
+            const unsigned prev = atomicAdd(grp_cnt + 2, 1u);
+            sflags[2] = (prev == (unsigned)G - 1u);
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        if (sflags[2]) {
+            __threadfence();
+            for (int e = tid; e < S::R; e += CONSUMER_THREADS) qkv_acc[e] = 0.f;
+            if (tid < 3) grp_cnt[tid] = 0u;
+        }
+    }
+    CF_MARK(6);
+
+    // ---- phase 3: O GEMV for output rows [rank*OROWS, +OROWS) over this group's NQ*128 input columns --------
+    {
+        for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            const int rb = i / owins, win = i % owins;
+            float a8[8];
+            {
+                const float4 a = *reinterpret_cast<const float4*>(ag2 + win * 256 + lane * 8);
+                const float4 b = *reinterpret_cast<const float4*>(ag2 + win * 256 + lane * 8 + 4);
+                a8[0] = a.x; a8[1] = a.y; a8[2] = a.z; a8[3] = a.w; a8[4] = b.x; a8[5] = b.y; a8[6] = b.z; a8[7] = b.w;
+            }
+            ring_wait_full(full_u32, g);
+            gemv_tile_16x256(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), a8,
+                             out_part + win * G2_OROWS_MAX + rb * ROWS512, lane);
+            __syncwarp();
+            issue_tile(g + NSTAGES);
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+    CF_MARK(7);
+
+    // ---- cross-group reduction: fp32 red into scratch, last arriver of the slice finalises ----------------
+    float* scratch = p.scratch + (size_t)batch * hidden + rank * OROWS;
+    for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4) {
+        float4 v = *reinterpret_cast<const float4*>(out_part + e);
+#pragma unroll
+        for (int w = 1; w < owins; ++w) {
+            const float4 u = *reinterpret_cast<const float4*>(out_part + w * G2_OROWS_MAX + e);
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+        red_add_v4(scratch + e, v);
+    }
+    __threadfence();
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(&gcnt[rank], 1u);
+        sflags[0] = (prev == (unsigned)gp.n_groups - 1u);
+    }
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    CF_MARK(8);
+    if (sflags[0]) {
+        __threadfence();
+        const bool fp32_out = p.flags & 1u;
+        for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4) {
+            const float4 v = ld_cg_v4(scratch + e);
+            *reinterpret_cast<float4*>(scratch + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const size_t off = (size_t)batch * hidden + rank * OROWS + e;
+            if (fp32_out) {
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
+            } else {
+                __align__(8) __half h4[4] = {__float2half_rn(v.x), __float2half_rn(v.y),
+                                             __float2half_rn(v.z), __float2half_rn(v.w)};
+                *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
+            }
+        }
+        if (tid == 0) gcnt[rank] = 0u;
+        if (residual_inplace) {
+            __threadfence();
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            if (tid == 0) {
+                const unsigned prev = atomicAdd(&gcnt[64], 1u);
+                sflags[1] = (prev == (unsigned)G - 1u);
+                if (sflags[1]) gcnt[64] = 0u;
+            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            if (sflags[1]) {
+                for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+                    float f[8], r8[8];
+                    unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+                    unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+                    __align__(16) __half hs[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) hs[k] = __float2half_rn(f[k] + r8[k]);
+                    *reinterpret_cast<uint4*>(rout + e) = *reinterpret_cast<const uint4*>(hs);
+                }
+            }
+        }
+    }
+    CF_MARK(9);
+}
+
+}  // namespace cfb

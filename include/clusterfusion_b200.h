@@ -59,6 +59,9 @@ enum {
                             in flight in the stream (true for a decoder stack: layer l+1's weights and cache are
                             not produced by layer l).                                                           */
 
+#define CF_FLAG_GQA_CLUSTER 0x4u /* grouped-query shapes: use the first-generation 8/16-CTA cluster kernel instead of the
+                                    group kernel (measurement / A-B only; slower on B200)              */
+
 typedef struct CfLlamaArgs {
     int32_t variant;    /* CF_VARIANT_*                                                             */
     uint32_t flags;     /* CF_FLAG_*                                                                */

@@ -38,7 +38,7 @@ def chat(x, w_qkv, w_o, k_cache, v_cache, rms_w, cos, sin, eps=1e-6):
 
 
 def sglang(x, residual, w_qkv, w_o, k_cache, v_cache, rms_w, eps, cos, sin, n_heads, n_kv_heads=None,
-           residual_out=None):
+           residual_out=None, flags=0):
     n_kv_heads = n_kv_heads or n_heads
     hidden = x.shape[-1]
     o = torch.empty(1, hidden, dtype=torch.float16, device=x.device)
@@ -46,7 +46,7 @@ def sglang(x, residual, w_qkv, w_o, k_cache, v_cache, rms_w, eps, cos, sin, n_he
     v = torch.empty(1, n_kv_heads, 128, dtype=torch.float16, device=x.device)
     if residual_out is None:
         residual_out = torch.empty_like(residual)
-    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_SGLANG, hidden=hidden, n_q_heads=n_heads, n_kv_heads=n_kv_heads,
+    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_SGLANG, flags=flags, hidden=hidden, n_q_heads=n_heads, n_kv_heads=n_kv_heads,
                          head_dim=128, batch=1, kv_len=k_cache.shape[0], eps=eps, x=_p(x), residual_in=_p(residual),
                          residual_out=_p(residual_out), w_qkv=_p(w_qkv), w_o=_p(w_o), rms_w=_p(rms_w), out=_p(o),
                          k_new=_p(k), v_new=_p(v), k_cache=_p(k_cache), v_cache=_p(v_cache), cos=_p(cos), sin=_p(sin),

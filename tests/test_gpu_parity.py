@@ -279,6 +279,54 @@ def test_gqa_llama3_8b_operator_vs_oracle(kv_len):
     assert close(o, want[0])
 
 
+@pytest.mark.parametrize("shape,kv_len", [(S8, 8192), (S8, 17), (S70, 64), (O.LayerShape(8192, 16, 2), 3000),
+                                          (O.LayerShape(8192, 8, 1), 1000), (O.LayerShape(4096, 8, 2), 555)])
+def test_gqa_group_kernel_and_cluster_kernel_agree_with_oracle(shape, kv_len):
+    """Both grouped-query kernels (default: G CTAs per group with L2 exchanges, G = 8 / 16 / 32 / 64 depending on the
+    shape; CF_FLAG_GQA_CLUSTER: the first-generation 8/16-CTA cluster kernel) against the oracle on the same inputs."""
+    import cabi_torch as ct
+    from clusterfusion_b200 import cabi
+    d = O.make_inputs(shape, kv_len, seed=kv_len + shape.n_heads, layout="sglang")
+    want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                          d["rms_w"], 1e-5, d["cos"], d["sin"], n_heads=shape.n_heads, n_kv_heads=shape.n_kv_heads, mode="eager")
+    c = cuda(d)
+    for flags in (0, cabi.CF_FLAG_GQA_CLUSTER):
+        o, r, k, v = ct.sglang(c["x"], c["residual"], c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"], c["rms_w"],
+                               1e-5, c["cos"], c["sin"], n_heads=shape.n_heads, n_kv_heads=shape.n_kv_heads, flags=flags)
+        torch.cuda.synchronize()
+        assert torch.equal(r.cpu(), want[1])
+        assert close(v, want[3])
+        assert close(k, want[2], atol=4e-3)
+        assert close(o, want[0])
+
+
+def test_gqa_group_kernel_repeatability_and_workspace_reset():
+    """200 back-to-back launches on one workspace (in-place residual included): the L2 exchange buffers and group counters
+    must come back zeroed every time, and results must agree to 1 fp16 ulp (fp32 cross-group red order is the only
+    order-dependent step)."""
+    import cabi_torch as ct
+    d = cuda(O.make_inputs(S8, 2048, seed=9, layout="sglang", theta=500000.0))
+    outs = []
+    for i in range(200):
+        res = d["residual"].clone() if i % 2 else d["residual"]
+        ro = res if i % 2 else None                       # odd launches update the residual in place
+        o, r, k, v = ct.sglang(d["x"], res, d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"], d["rms_w"], 1e-5,
+                               d["cos"], d["sin"], n_heads=32, n_kv_heads=8, residual_out=ro)
+        outs.append((o, r))
+    torch.cuda.synchronize()
+    ref = outs[0][0].float()
+    ulp = torch.maximum(ref.abs() * 2 ** -10, torch.full_like(ref, 2 ** -24))
+    for o, r in outs[1:]:
+        assert bool(((o.float() - ref).abs() <= ulp).all())
+        assert torch.equal(r, outs[0][1])
+    ws = ct.workspace(4096, 1, d["x"].device)
+    # scratch [hidden] fp32 + legacy counters + q|k|v accumulators must be all-zero again
+    n_zero_region = 4096 * 4 + 32 * 4 + 16 * 768 * 4
+    assert int(ws[:n_zero_region].count_nonzero()) == 0
+    assert int(ws[-128 * 4:].count_nonzero()) == 0
+
+
+
 def _gptj_to_neox_perm():
     perm = torch.empty(128, dtype=torch.long)         # neox index j holds gptj index perm[j]
     perm[:64] = torch.arange(0, 128, 2)
