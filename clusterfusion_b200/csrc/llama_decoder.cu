@@ -170,14 +170,21 @@ int sm_count_of_current_device() {
     return sm_count[dev & 15];
 }
 
-// workspace carve-up (bytes): [scratch fp32 batch*hidden][counters u32 batch*32][qkv_acc][attn_buf][gcounters]
-size_t ws_off_counters(int hidden, int batch) { return (size_t)batch * hidden * sizeof(float); }
-size_t ws_off_qkv_acc(int hidden, int batch) { return ws_off_counters(hidden, batch) + (size_t)batch * 32 * sizeof(uint32_t); }
-size_t ws_off_attn_buf(int hidden, int batch) {
-    return ws_off_qkv_acc(hidden, batch) + (size_t)batch * cfb::G2_GROUPS_MAX * cfb::SmemGqa2<4>::R * sizeof(float);
+// workspace carve-up (bytes): [header 256][scratch fp32 batch*hidden][counters u32 batch*32]
+//                              [qkv_ll u64][attn_ll u64][out_ll u64][gcounters u32 batch*128]
+// The header sits at a shape-independent offset: its epoch word tags every flag-in-data word of the group kernel, so
+// stale words left by launches of any other shape on the same workspace can never match.
+size_t ws_off_scratch() { return cfb::WS_HEADER_BYTES; }
+size_t ws_off_counters(int hidden, int batch) { return ws_off_scratch() + (size_t)batch * hidden * sizeof(float); }
+size_t ws_off_qkv_ll(int hidden, int batch) { return ws_off_counters(hidden, batch) + (size_t)batch * 32 * sizeof(uint32_t); }
+size_t ws_off_attn_ll(int hidden, int batch) {
+    return ws_off_qkv_ll(hidden, batch) + (size_t)batch * cfb::G2_GROUPS_MAX * 2 * cfb::SmemGqa2<4>::R * sizeof(uint64_t);
+}
+size_t ws_off_out_ll(int hidden, int batch) {
+    return ws_off_attn_ll(hidden, batch) + (size_t)batch * cfb::G2_SLOTS * 4 * cfb::SmemGqa2<4>::PAY * sizeof(uint64_t);
 }
 size_t ws_off_gcounters(int hidden, int batch) {
-    return ws_off_attn_buf(hidden, batch) + (size_t)batch * cfb::G2_SLOTS * 4 * cfb::SmemGqa2<4>::PAY * sizeof(float);
+    return ws_off_out_ll(hidden, batch) + (size_t)batch * cfb::G2_GROUPS_MAX * 4 * cfb::HEAD_DIM * sizeof(uint64_t);
 }
 size_t ws_total(int hidden, int batch) {
     return ws_off_gcounters(hidden, batch) + (size_t)batch * cfb::G2_COUNTERS * sizeof(uint32_t);
@@ -206,8 +213,8 @@ const char* cf_last_error_string(void) { return g_last_error.c_str(); }
 
 size_t cf_llama_workspace_bytes(int32_t hidden, int32_t batch) {
     if (hidden <= 0 || batch <= 0) return 0;
-    // fp32 scratch [batch][hidden] + counters [batch][32] (any cluster size) + the grouped-query kernel's L2 exchange
-    // buffers (q|k|v accumulators, softmax-state slots, group counters): ~0.4 MB per request
+    // header + fp32 scratch [batch][hidden] + counters [batch][32] (any cluster size) + the grouped-query kernel's L2
+    // exchange buffers (flag-in-data words for q|k|v, softmax states, merged attention output): ~0.95 MB per request
     return ws_total(hidden, batch);
 }
 
@@ -299,8 +306,8 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     kp.k_pool_ptrs = reinterpret_cast<const unsigned long long*>(a->k_pool_ptrs);
     kp.v_pool_ptrs = reinterpret_cast<const unsigned long long*>(a->v_pool_ptrs);
     kp.positions = reinterpret_cast<const long long*>(a->positions);
-    kp.scratch = static_cast<float*>(a->workspace);
-    kp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + (size_t)a->batch * a->hidden * sizeof(float));
+    kp.scratch = reinterpret_cast<float*>(static_cast<char*>(a->workspace) + ws_off_scratch());
+    kp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + ws_off_counters(a->hidden, a->batch));
     kp.eps = a->eps;
     kp.hidden = a->hidden;
     kp.n_heads = a->n_q_heads;
@@ -322,8 +329,10 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         memset(&gp, 0, sizeof gp);
         gp.k = kp;
         char* ws = static_cast<char*>(a->workspace);
-        gp.qkv_acc = reinterpret_cast<float*>(ws + ws_off_qkv_acc(a->hidden, a->batch));
-        gp.attn_buf = reinterpret_cast<float*>(ws + ws_off_attn_buf(a->hidden, a->batch));
+        gp.header = reinterpret_cast<unsigned*>(ws);
+        gp.qkv_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_qkv_ll(a->hidden, a->batch));
+        gp.attn_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_attn_ll(a->hidden, a->batch));
+        gp.out_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_out_ll(a->hidden, a->batch));
         gp.gcounters = reinterpret_cast<unsigned*>(ws + ws_off_gcounters(a->hidden, a->batch));
         gp.G = G;
         gp.n_groups = n_groups;
@@ -380,8 +389,8 @@ extern "C" int cf_llama_ffn_launch(const CfFfnArgs* a, void* stream_) {
     fp.rms_w = static_cast<const __half*>(a->rms_w);
     fp.out = a->out;
     fp.residual_out = static_cast<__half*>(a->residual_out);
-    fp.scratch = static_cast<float*>(a->workspace);
-    fp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + (size_t)a->hidden * sizeof(float));
+    fp.scratch = reinterpret_cast<float*>(static_cast<char*>(a->workspace) + ws_off_scratch());
+    fp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + ws_off_counters(a->hidden, 1));
     fp.eps = a->eps;
     fp.hidden = a->hidden;
     fp.ffn = a->ffn;

@@ -10,19 +10,24 @@
  * (8B: 8 x 16 = 128; 70B shards: 8 x 16, 4 x 32, 2 x 64), and the two exchanges the fusion needs go through L2:
  *
  *   exchange 1  q|k|v:  the group's [(NQ+2)*128 x hidden] weight block is cut into 16-row x 256-col tiles, dealt to the
- *               G CTAs as contiguous runs in row-block-major order (whole row blocks when G divides 6*8, so no
- *               K-split and a deterministic sum); every CTA adds its row sums into the group's fp32 vector with
- *               red.global.add, bumps the group counter (release), spins until it reads G (acquire), then loads the
- *               768 floats back and applies RoPE itself.
- *   exchange 2  softmax state: CTA r streams KV rows [r*chunk, ...) for all NQ query heads, writes its NQ x [m, l, o[128]]
- *               to the group's slot r, bumps the second counter, spins, then merges all G states in rank order
- *               (bit-identical on every CTA).
+ *               G CTAs as contiguous runs in row-block-major order (a row block is shared by at most two CTAs); every
+ *               CTA publishes its row sums, every CTA reads all 768 back, adds the (at most two) parts in a fixed order
+ *               and applies RoPE itself.
+ *   exchange 2  softmax state: CTA r streams KV rows [r*chunk, ...) for all NQ query heads and publishes its
+ *               NQ x [m, l, o[128]]; CTA j merges dims [j*512/G, ...) over all G states in rank order and publishes the
+ *               normalised fp16-rounded result; every CTA reads the 512 merged values (reduce-scatter + all-gather: an
+ *               all-to-all of full states would be 67-270 KB per CTA through a ~64 GB/s SM port).
  *
- * L2 round trips are ~0.15 us (B300_MICROARCH: L2 hit 234-262 cycles, ATOMG 318); the TMA ring keeps landing the next
- * phase's tiles while a CTA waits.  Everything else -- the single 24 x 8 KB self-issuing tile stream, fp32 reductions,
- * fp16 rounding points of the eager model, fp32 red + last-arriver finalize of the O projection -- is as in the MHA
- * kernel (llama_decoder_kernel.cuh).  nn.Linear weight layout only (SGLANG / PAGED), NQ = 4 query heads per group; a KV
- * head with 8 query heads (70B) gets two groups.
+ * Both exchanges use a flag-in-data protocol (what NCCL calls LL): every 64-bit word carries a float and the launch's
+ * epoch, written with one st.relaxed.gpu.b64 and polled with ld.relaxed.gpu.b64 until the epoch matches.  No fence, no
+ * counter, no atomics, nothing to re-zero: one L2 round trip per hop (B300_MICROARCH: L2 hit 234-262 cycles).  The first
+ * version used red.global.add + __threadfence + a counter + an acquire spin per exchange and cost 3.4 us + 6.4 us per
+ * layer (phase timeline, profiles/); the epoch lives in a 256-byte header at the start of the workspace and is bumped by
+ * the launch's last finalising CTA.  The TMA ring keeps landing the next phase's tiles while a CTA waits.
+ * Everything else -- the single 24 x 8 KB self-issuing tile stream, fp32 reductions, fp16 rounding points of the eager
+ * model, fp32 red + last-arriver finalize of the O projection -- is as in the MHA kernel (llama_decoder_kernel.cuh).
+ * nn.Linear weight layout only (SGLANG / PAGED), NQ = 4 query heads per group; a KV head with 8 query heads (70B) gets
+ * two groups.
  *
  * Cross-CTA spinning needs the waited-for CTAs to be resident or dispatched eventually: the launcher picks G with
  * groups x G x batch <= #SMs whenever it can (1 CTA / SM), and CTAs of a group are contiguous in blockIdx.x, so a
@@ -43,7 +48,8 @@ constexpr int G2_OROWS_MAX = 1024;        // hidden / G
 constexpr int G2_GROUPS_MAX = 16;         // groups per request
 constexpr int G2_G_MAX = 64;              // CTAs per group
 constexpr int G2_SLOTS = 160;             // softmax-state slots per request (groups x G <= 148 whenever batch == 1)
-constexpr int G2_COUNTERS = 128;          // u32 per request: [0,64) O slices, [64] residual, [65 + 3*group + {0,1,2}]
+constexpr int G2_COUNTERS = 128;          // u32 per request: [0,64) O slices, [64] finalised slices
+constexpr int WS_HEADER_BYTES = 256;      // workspace header: u32 [0] epoch, [1] finalised-slice count of the running launch
 
 template <int NQ>
 struct SmemGqa2 {
@@ -76,28 +82,29 @@ struct SmemGqa2 {
 // extra kernel parameters of the group kernel (appended to KParams by composition)
 struct G2Params {
     KParams k;
-    float* qkv_acc;        // fp32 [batch][G2_GROUPS_MAX][768], zero between launches
-    float* attn_buf;       // fp32 [batch][G2_SLOTS][NQ*132]
-    unsigned* gcounters;   // u32  [batch][G2_COUNTERS], zero between launches
+    unsigned long long* qkv_ll;    // (float, epoch) words [batch][G2_GROUPS_MAX][2 parts][768]
+    unsigned long long* attn_ll;   // (float, epoch) words [batch][G2_SLOTS][NQ*132]
+    unsigned long long* out_ll;    // (float, epoch) words [batch][G2_GROUPS_MAX][NQ*128]
+    unsigned* gcounters;           // u32 [batch][G2_COUNTERS], zero between launches
+    unsigned* header;              // u32 [64] at the start of the workspace: [0] epoch, [1] finalised slices
     int G;                 // CTAs per group (power of two)
     int n_groups;          // groups per request
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// ---- flag-in-data ("LL") words: low 32 bits = float payload, high 32 bits = epoch of the launch that wrote it ----
+__device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned flag) {
+    const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)flag << 32);
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-__device__ __forceinline__ void red_release_inc(unsigned* p) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
 }
-__device__ __forceinline__ float ld_cg_f32(const float* p) {
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_add_f32(float* p, float v) {
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+// spin until the word carries this launch's epoch (the first probe `w` was issued by the caller, batched with others)
+__device__ __forceinline__ float ll_resolve(const unsigned long long* p, unsigned long long w, unsigned flag) {
+    while ((unsigned)(w >> 32) != flag) w = ll_load(p);
+    return __uint_as_float((unsigned)w);
 }
 // 16 output rows x 256 input columns; ACCUMULATES the 16 row sums into acc[0..16) (owned by the calling warp)
 __device__ __forceinline__ void gemv_tile_16x256_acc(const uint4* tile, const float (&x8)[8], float* acc, uint32_t lane) {
@@ -143,18 +150,6 @@ __device__ __forceinline__ void gemv_tile_16x256_acc(const uint4* tile, const fl
         acc[r] += tmp[0];
         acc[8 + r] += tmp[1];
     }
-}
-
-// one CTA-wide "arrive + wait for all G CTAs of the group" on a global counter.  Everything the CTA wrote before
-// (plain stores or reds, by any of its threads) is visible to every CTA that leaves the wait.
-__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned G, uint32_t tid) {
-    __threadfence();
-    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-    if (tid == 0) {
-        red_release_inc(counter);
-        while (ld_acquire_u32(counter) < G) { __nanosleep(32); }
-    }
-    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
 }
 
 template <int VARIANT, int NQ>
@@ -297,25 +292,63 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     const __half* rg = p.residual_in + (size_t)batch * hidden;
     __half* rout = p.residual_out + (size_t)batch * hidden;
     const bool residual_inplace = (static_cast<const void*>(rout) == static_cast<const void*>(rg));
-    float* qkv_acc = gp.qkv_acc + ((size_t)batch * G2_GROUPS_MAX + gid) * S::R;
-    float* attn_buf = gp.attn_buf + ((size_t)batch * G2_SLOTS + (size_t)gid * G) * (NQ * S::PAY);
+    unsigned long long* qkv_ll = gp.qkv_ll + ((size_t)batch * G2_GROUPS_MAX + gid) * (2 * S::R);
+    unsigned long long* attn_ll = gp.attn_ll + ((size_t)batch * G2_SLOTS + (size_t)gid * G) * (NQ * S::PAY);
+    unsigned long long* out_ll = gp.out_ll + ((size_t)batch * G2_GROUPS_MAX + gid) * (NQ * HEAD_DIM);
     unsigned* gcnt = gp.gcounters + (size_t)batch * G2_COUNTERS;
-    unsigned* grp_cnt = gcnt + 65 + 3 * gid;
 
     // zero this warp's accumulation slots (smem only: legal before griddepcontrol.wait)
     for (int e = lane; e < G2_RB_LOCAL_MAX * ROWS512; e += 32) part[warp * G2_RB_LOCAL_MAX * ROWS512 + e] = 0.f;
 
+    // the RMSNorm weight does not depend on the previous kernel: fetch it before the dependency wait
+    constexpr int P0_ITERS = (G2_HIDDEN_MAX + CONSUMER_THREADS * 8 - 1) / (CONSUMER_THREADS * 8);     // 3
+    uint4 wraw[P0_ITERS];
+#pragma unroll
+    for (int it = 0; it < P0_ITERS; ++it) {
+        const int e = (it * CONSUMER_THREADS + tid) * 8;
+        wraw[it] = e < hidden ? *reinterpret_cast<const uint4*>(p.rms_w + e) : make_uint4(0, 0, 0, 0);
+    }
+
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // ---- phase 0: fused residual add + RMSNorm over the FULL vector (every CTA needs all of it: rows are split) ----
+    // this launch's epoch: every flag-in-data word written below carries it (header zeroed once by the caller,
+    // bumped by the previous launch's last finaliser; 0 is never used as a flag)
+    const unsigned epoch = __ldcg(gp.header);
+    const unsigned flag = epoch + 1u == 0u ? 1u : epoch + 1u;
+
+    // ---- phase 0: fused residual add + RMSNorm over the FULL vector (every CTA needs all of it: rows are split).
+    //      One pass: x and residual are loaded once and stay in registers across the block reduction. ----
     {
+        float f[P0_ITERS][8];
         float ss = 0.f;
-        for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
-            float f[8], r8[8];
-            unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
-            unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+        uint4 xr[P0_ITERS], rr[P0_ITERS];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { f[k] = round_h(f[k] + r8[k]); ss += f[k] * f[k]; }
+        for (int it = 0; it < P0_ITERS; ++it) {
+            const int e = (it * CONSUMER_THREADS + tid) * 8;
+            if (e < hidden) {
+                xr[it] = *reinterpret_cast<const uint4*>(xg + e);
+                rr[it] = *reinterpret_cast<const uint4*>(rg + e);
+            } else {
+                xr[it] = make_uint4(0, 0, 0, 0);
+                rr[it] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        const int own_lo = rank * OROWS, own_hi = own_lo + OROWS;       // residual_out slice written by group 0
+#pragma unroll
+        for (int it = 0; it < P0_ITERS; ++it) {
+            const int e = (it * CONSUMER_THREADS + tid) * 8;
+            float r8[8];
+            unpack8(xr[it], f[it]);
+            unpack8(rr[it], r8);
+            __align__(16) __half hs[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                hs[k] = __float2half_rn(f[it][k] + r8[k]);
+                f[it][k] = __half2float(hs[k]);
+                ss += f[it][k] * f[it][k];
+            }
+            if (gid == 0 && !residual_inplace && e >= own_lo && e < own_hi)
+                *reinterpret_cast<uint4*>(rout + e) = *reinterpret_cast<const uint4*>(hs);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -325,21 +358,17 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 #pragma unroll
         for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w];
         const float rstd = rsqrtf(tot / (float)hidden + p.eps);
-        const int own_lo = rank * OROWS, own_hi = own_lo + OROWS;       // residual_out slice written by group 0
-        for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
-            float f[8], w8[8], r8[8];
-            unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
-            unpack8(*reinterpret_cast<const uint4*>(p.rms_w + e), w8);
-            unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
-            __align__(16) __half hs[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { hs[k] = __float2half_rn(f[k] + r8[k]); f[k] = __half2float(hs[k]); }
-            if (gid == 0 && !residual_inplace && e >= own_lo && e < own_hi)
-                *reinterpret_cast<uint4*>(rout + e) = *reinterpret_cast<const uint4*>(hs);
-            __align__(16) __half xn[8];
+        for (int it = 0; it < P0_ITERS; ++it) {
+            const int e = (it * CONSUMER_THREADS + tid) * 8;
+            if (e < hidden) {
+                float w8[8];
+                unpack8(wraw[it], w8);
+                __align__(16) __half xn[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(round_h(f[k] * rstd) * w8[k]);
-            *reinterpret_cast<uint4*>(xs + e) = *reinterpret_cast<const uint4*>(xn);
+                for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(round_h(f[it][k] * rstd) * w8[k]);
+                *reinterpret_cast<uint4*>(xs + e) = *reinterpret_cast<const uint4*>(xn);
+            }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
@@ -362,6 +391,8 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     gbase += n_qkv_tiles;
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     CF_MARK(2);
+    // ---- exchange 1: publish this CTA's row sums as (value, epoch) words; part = position of this CTA among the
+    //      (at most two) CTAs that share the row block ------------------------------------------------------------
     {
         const int rb_last = (t_first + n_qkv_tiles - 1) / wins;
         const int n_loc = (rb_last - rb_first + 1) * ROWS512;
@@ -369,11 +400,11 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             float a = 0.f;
 #pragma unroll
             for (int w = 0; w < CONSUMER_WARPS; ++w) a += part[w * G2_RB_LOCAL_MAX * ROWS512 + o];
-            red_add_f32(qkv_acc + rb_first * ROWS512 + o, a);
+            const int rb = rb_first + o / ROWS512;
+            const int part_id = (int)rank - (int)((uint32_t)(rb * wins) / n_qkv_tiles);
+            ll_store(qkv_ll + part_id * S::R + rb_first * ROWS512 + o, a, flag);
         }
     }
-    // ---- exchange 1 (through L2): all G CTAs have added their row sums ---------------------------------------
-    group_barrier(grp_cnt + 0, G, tid);
     CF_MARK(3);
 
     // ---- RoPE (NeoX), new K/V out ---------------------------------------------------------------------
@@ -385,11 +416,25 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             cosp = p.cos + p.positions[batch] * HEAD_DIM;
             sinp = cosp + HEAD_DIM / 2;
         }
+        // read a projected row: sum of its 1 or 2 published parts, polled until they carry this launch's epoch
+        auto n_parts = [&](int e) {
+            const int rb = e / ROWS512;
+            return (int)((uint32_t)(rb * wins + wins - 1) / n_qkv_tiles) - (int)((uint32_t)(rb * wins) / n_qkv_tiles) + 1;
+        };
         for (int e = tid; e < S::R; e += CONSUMER_THREADS) {
             const int hd = e >> 7, d = e & 127;                  // hd < NQ: query head; NQ: k; NQ+1: v
-            const float a = round_h(ld_cg_f32(qkv_acc + e));     // q / k / v leave the projection as fp16 (eager model)
+            const int e2 = e ^ 64;
+            const bool two_a = n_parts(e) > 1, two_b = n_parts(e2) > 1;
+            // first probes of all (up to four) words back to back, then resolve
+            const unsigned long long wa0 = ll_load(qkv_ll + e), wb0 = ll_load(qkv_ll + e2);
+            const unsigned long long wa1 = two_a ? ll_load(qkv_ll + S::R + e) : 0ull;
+            const unsigned long long wb1 = two_b ? ll_load(qkv_ll + S::R + e2) : 0ull;
+            float av = ll_resolve(qkv_ll + e, wa0, flag), bv = ll_resolve(qkv_ll + e2, wb0, flag);
+            if (two_a) av += ll_resolve(qkv_ll + S::R + e, wa1, flag);
+            if (two_b) bv += ll_resolve(qkv_ll + S::R + e2, wb1, flag);
+            const float a = round_h(av);                         // q / k / v leave the projection as fp16 (eager model)
             if (hd <= NQ) {
-                const float b = round_h(ld_cg_f32(qkv_acc + (e ^ 64)));
+                const float b = round_h(bv);
                 const int i = d & 63;
                 const float rot = (d & 64) ? fmaf(a, cosp[i], b * sinp[i]) : fmaf(a, cosp[i], -b * sinp[i]);
                 const __half rh = __float2half_rn(rot);
@@ -546,43 +591,59 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             }
             dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
         }
-        // ---- exchange 2 (through L2): publish this CTA's NQ softmax states, wait for the group, merge in rank order ----
+        // ---- exchange 2, hop A: publish this CTA's NQ softmax states as (value, epoch) words ----------------------
+        for (int e = tid; e < NQ * S::PAY; e += CONSUMER_THREADS)
+            ll_store(attn_ll + (size_t)rank * (NQ * S::PAY) + e, cta_state[e], flag);
+        // this CTA owns merged dims [rank*S2, +S2) of the group's NQ*128: gather [m, l, o[S2]] of every rank ...
+        const int S2 = NQ * HEAD_DIM / G;                        // 64 / 32 / 16 / 8 for G = 8 / 16 / 32 / 64
+        const int hh = (rank * S2) >> 7, d0 = (rank * S2) & 127;
+        float* mg = attn_part;                                   // fp32 [G][S2 + 2], reuses the block-merge buffer
         {
-            float4* dstp = reinterpret_cast<float4*>(attn_buf + (size_t)rank * (NQ * S::PAY));
-            const float4* srcp = reinterpret_cast<const float4*>(cta_state);
-            for (int e = tid; e < NQ * S::PAY / 4; e += CONSUMER_THREADS) dstp[e] = srcp[e];
-        }
-        group_barrier(grp_cnt + 1, G, tid);
-        for (int e = tid; e < NQ * HEAD_DIM; e += CONSUMER_THREADS) {
-            const int h = e >> 7, d = e & 127;
-            const float* base = attn_buf + h * S::PAY;
-            float M = -INFINITY, L = 0.f, O = 0.f;
-#pragma unroll 4
-            for (int r = 0; r < G; ++r) {
-                const float* st = base + (size_t)r * (NQ * S::PAY);
-                const float mr = ld_cg_f32(st), lr = ld_cg_f32(st + 1), orr = ld_cg_f32(st + 4 + d);
-                const float Mn = fmaxf(M, mr);
-                const float a = dsm::exp2_diff(M, Mn), b = dsm::exp2_diff(mr, Mn);
-                L = L * a + lr * b;
-                O = O * a + orr * b;
-                M = Mn;
+            const int nw = G * (S2 + 2);                         // <= 640 words: at most two per thread
+            const unsigned long long* src[2];
+            unsigned long long w[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = tid + u * CONSUMER_THREADS;
+                const int r = i / (S2 + 2), j = i % (S2 + 2);
+                src[u] = attn_ll + (size_t)r * (NQ * S::PAY) + hh * S::PAY + (j < 2 ? j : 4 + d0 + (j - 2));
+                w[u] = i < nw ? ll_load(src[u]) : 0ull;
             }
-            ag2[e] = round_h(O / L);                             // attention output leaves as fp16 (eager model)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = tid + u * CONSUMER_THREADS;
+                if (i < nw) mg[i] = ll_resolve(src[u], w[u], flag);
+            }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-        // every CTA of the group has now passed exchange 1, and this CTA is done reading both exchange buffers:
-        // the last CTA to get here re-zeroes the group's buffers and counters for the next launch
-        if (tid == 0) {
-            __threadfence();
-            const unsigned prev = atomicAdd(grp_cnt + 2, 1u);
-            sflags[2] = (prev == (unsigned)G - 1u);
+        // ... merge them in rank order (deterministic) and publish the normalised, fp16-rounded slice (hop B)
+        if ((int)tid < S2) {
+            float M = -INFINITY;
+            for (int r = 0; r < G; ++r) M = fmaxf(M, mg[r * (S2 + 2)]);
+            float L = 0.f, O = 0.f;
+            for (int r = 0; r < G; ++r) {
+                const float w = dsm::exp2_diff(mg[r * (S2 + 2)], M);
+                L = fmaf(mg[r * (S2 + 2) + 1], w, L);
+                O = fmaf(mg[r * (S2 + 2) + 2 + tid], w, O);
+            }
+            ll_store(out_ll + rank * S2 + tid, round_h(O / L), flag);   // attention output leaves as fp16 (eager model)
+        }
+        // every CTA reads the whole merged attention output of the group
+        {
+            constexpr int NA = NQ * HEAD_DIM;                    // 512 words: at most two per thread
+            unsigned long long w[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * CONSUMER_THREADS;
+                w[u] = e < NA ? ll_load(out_ll + e) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * CONSUMER_THREADS;
+                if (e < NA) ag2[e] = ll_resolve(out_ll + e, w[u], flag);
+            }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-        if (sflags[2]) {
-            __threadfence();
-            for (int e = tid; e < S::R; e += CONSUMER_THREADS) qkv_acc[e] = 0.f;
-            if (tid < 3) grp_cnt[tid] = 0u;
-        }
     }
     CF_MARK(6);
 
@@ -628,6 +689,12 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     CF_MARK(8);
     if (sflags[0]) {
         __threadfence();
+        if (tid == 0) {
+            // a slice is finalised only after every group reached the end, so when the launch's last slice is, no CTA
+            // will read another flag-in-data word: bump the workspace epoch for the next launch
+            const unsigned prevf = atomicAdd(gp.header + 1, 1u);
+            if (prevf == gridDim.y * (unsigned)G - 1u) { gp.header[1] = 0u; gp.header[0] = epoch + 1u; }
+        }
         const bool fp32_out = p.flags & 1u;
         for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4) {
             const float4 v = ld_cg_v4(scratch + e);

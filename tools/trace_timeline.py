@@ -35,7 +35,12 @@ if NH == NKV:
     ncta = NH * 4
 else:
     ncl = NKV * ((NH // NKV) // 4)
-    ncta = ncl * (16 if ncl <= 4 else 8)
+    if flags & 4:                       # CF_FLAG_GQA_CLUSTER: first-generation cluster kernel
+        ncta = ncl * (16 if ncl <= 4 else 8)
+    else:                               # group kernel: G CTAs per group
+        G = 64
+        while G > 8 and ncl * G > 148: G //= 2
+        ncta = ncl * G
 trace = torch.zeros(nl, ncta, 16, dtype=torch.int64, device=dev)
 def launch(i, h):
     lay = layers[i]
