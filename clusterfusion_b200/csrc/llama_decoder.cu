@@ -171,7 +171,7 @@ int sm_count_of_current_device() {
 }
 
 // workspace carve-up (bytes): [header 256][scratch fp32 batch*hidden][counters u32 batch*32]
-//                              [qkv_ll u64][attn_ll u64][out_ll u64][gcounters u32 batch*128]
+//                              [qkv_ll u64][attn_ll u64][ag_ll u64][gcounters u32 batch*128][out_ll u64 (hidden/128)*hidden]
 // The header sits at a shape-independent offset: its epoch word tags every flag-in-data word of the group kernel, so
 // stale words left by launches of any other shape on the same workspace can never match.
 size_t ws_off_scratch() { return cfb::WS_HEADER_BYTES; }
@@ -180,14 +180,18 @@ size_t ws_off_qkv_ll(int hidden, int batch) { return ws_off_counters(hidden, bat
 size_t ws_off_attn_ll(int hidden, int batch) {
     return ws_off_qkv_ll(hidden, batch) + (size_t)batch * cfb::G2_GROUPS_MAX * 2 * cfb::SmemGqa2<4>::R * sizeof(uint64_t);
 }
-size_t ws_off_out_ll(int hidden, int batch) {
+size_t ws_off_ag_ll(int hidden, int batch) {
     return ws_off_attn_ll(hidden, batch) + (size_t)batch * cfb::G2_SLOTS * 4 * cfb::SmemGqa2<4>::PAY * sizeof(uint64_t);
 }
 size_t ws_off_gcounters(int hidden, int batch) {
-    return ws_off_out_ll(hidden, batch) + (size_t)batch * cfb::G2_GROUPS_MAX * 4 * cfb::HEAD_DIM * sizeof(uint64_t);
+    return ws_off_ag_ll(hidden, batch) + (size_t)batch * cfb::G2_GROUPS_MAX * 4 * cfb::HEAD_DIM * sizeof(uint64_t);
+}
+size_t ws_off_out_ll_b1(int hidden, int batch) {
+    return ws_off_gcounters(hidden, batch) + (size_t)batch * cfb::G2_COUNTERS * sizeof(uint32_t);
 }
 size_t ws_total(int hidden, int batch) {
-    return ws_off_gcounters(hidden, batch) + (size_t)batch * cfb::G2_COUNTERS * sizeof(uint32_t);
+    // batch == 1 launches reduce the O projection across clusters through (value, epoch) words [hidden/128][hidden]
+    return ws_off_out_ll_b1(hidden, batch) + (size_t)(hidden / 128) * hidden * sizeof(uint64_t);
 }
 
 bool device_is_sm100() {
@@ -214,7 +218,8 @@ const char* cf_last_error_string(void) { return g_last_error.c_str(); }
 size_t cf_llama_workspace_bytes(int32_t hidden, int32_t batch) {
     if (hidden <= 0 || batch <= 0) return 0;
     // header + fp32 scratch [batch][hidden] + counters [batch][32] (any cluster size) + the grouped-query kernel's L2
-    // exchange buffers (flag-in-data words for q|k|v, softmax states, merged attention output): ~0.95 MB per request
+    // exchange buffers (flag-in-data words for q|k|v, softmax states, merged attention output): ~0.95 MB per request,
+    // + the batch-1 cross-cluster output words (1 MB at hidden 4096, 4 MB at 8192)
     return ws_total(hidden, batch);
 }
 
@@ -308,6 +313,9 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     kp.positions = reinterpret_cast<const long long*>(a->positions);
     kp.scratch = reinterpret_cast<float*>(static_cast<char*>(a->workspace) + ws_off_scratch());
     kp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + ws_off_counters(a->hidden, a->batch));
+    kp.header = reinterpret_cast<unsigned*>(a->workspace);
+    kp.out_ll = a->batch == 1 ? reinterpret_cast<unsigned long long*>(static_cast<char*>(a->workspace) + ws_off_out_ll_b1(a->hidden, 1))
+                              : nullptr;
     kp.eps = a->eps;
     kp.hidden = a->hidden;
     kp.n_heads = a->n_q_heads;
@@ -329,10 +337,9 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         memset(&gp, 0, sizeof gp);
         gp.k = kp;
         char* ws = static_cast<char*>(a->workspace);
-        gp.header = reinterpret_cast<unsigned*>(ws);
         gp.qkv_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_qkv_ll(a->hidden, a->batch));
         gp.attn_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_attn_ll(a->hidden, a->batch));
-        gp.out_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_out_ll(a->hidden, a->batch));
+        gp.ag_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_ag_ll(a->hidden, a->batch));
         gp.gcounters = reinterpret_cast<unsigned*>(ws + ws_off_gcounters(a->hidden, a->batch));
         gp.G = G;
         gp.n_groups = n_groups;

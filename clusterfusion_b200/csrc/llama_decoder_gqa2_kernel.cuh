@@ -84,28 +84,13 @@ struct G2Params {
     KParams k;
     unsigned long long* qkv_ll;    // (float, epoch) words [batch][G2_GROUPS_MAX][2 parts][768]
     unsigned long long* attn_ll;   // (float, epoch) words [batch][G2_SLOTS][NQ*132]
-    unsigned long long* out_ll;    // (float, epoch) words [batch][G2_GROUPS_MAX][NQ*128]
+    unsigned long long* ag_ll;     // (float, epoch) words [batch][G2_GROUPS_MAX][NQ*128]
     unsigned* gcounters;           // u32 [batch][G2_COUNTERS], zero between launches
-    unsigned* header;              // u32 [64] at the start of the workspace: [0] epoch, [1] finalised slices
+                                   // (k.header: u32 [0] epoch, [1] finalised slices of a batch > 1 launch; k.out_ll: batch == 1)
     int G;                 // CTAs per group (power of two)
     int n_groups;          // groups per request
 };
 
-// ---- flag-in-data ("LL") words: low 32 bits = float payload, high 32 bits = epoch of the launch that wrote it ----
-__device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned flag) {
-    const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)flag << 32);
-    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
-    unsigned long long w;
-    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-    return w;
-}
-// spin until the word carries this launch's epoch (the first probe `w` was issued by the caller, batched with others)
-__device__ __forceinline__ float ll_resolve(const unsigned long long* p, unsigned long long w, unsigned flag) {
-    while ((unsigned)(w >> 32) != flag) w = ll_load(p);
-    return __uint_as_float((unsigned)w);
-}
 // 16 output rows x 256 input columns; ACCUMULATES the 16 row sums into acc[0..16) (owned by the calling warp)
 __device__ __forceinline__ void gemv_tile_16x256_acc(const uint4* tile, const float (&x8)[8], float* acc, uint32_t lane) {
     float tmp[2];
@@ -294,7 +279,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     const bool residual_inplace = (static_cast<const void*>(rout) == static_cast<const void*>(rg));
     unsigned long long* qkv_ll = gp.qkv_ll + ((size_t)batch * G2_GROUPS_MAX + gid) * (2 * S::R);
     unsigned long long* attn_ll = gp.attn_ll + ((size_t)batch * G2_SLOTS + (size_t)gid * G) * (NQ * S::PAY);
-    unsigned long long* out_ll = gp.out_ll + ((size_t)batch * G2_GROUPS_MAX + gid) * (NQ * HEAD_DIM);
+    unsigned long long* ag_ll = gp.ag_ll + ((size_t)batch * G2_GROUPS_MAX + gid) * (NQ * HEAD_DIM);
     unsigned* gcnt = gp.gcounters + (size_t)batch * G2_COUNTERS;
 
     // zero this warp's accumulation slots (smem only: legal before griddepcontrol.wait)
@@ -313,8 +298,8 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 
     // this launch's epoch: every flag-in-data word written below carries it (header zeroed once by the caller,
     // bumped by the previous launch's last finaliser; 0 is never used as a flag)
-    const unsigned epoch = __ldcg(gp.header);
-    const unsigned flag = epoch + 1u == 0u ? 1u : epoch + 1u;
+    const unsigned epoch = __ldcg(p.header);
+    const unsigned flag = ll_flag_of_epoch(epoch);
 
     // ---- phase 0: fused residual add + RMSNorm over the FULL vector (every CTA needs all of it: rows are split).
     //      One pass: x and residual are loaded once and stay in registers across the block reduction. ----
@@ -626,7 +611,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 L = fmaf(mg[r * (S2 + 2) + 1], w, L);
                 O = fmaf(mg[r * (S2 + 2) + 2 + tid], w, O);
             }
-            ll_store(out_ll + rank * S2 + tid, round_h(O / L), flag);   // attention output leaves as fp16 (eager model)
+            ll_store(ag_ll + rank * S2 + tid, round_h(O / L), flag);   // attention output leaves as fp16 (eager model)
         }
         // every CTA reads the whole merged attention output of the group
         {
@@ -635,12 +620,12 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int e = tid + u * CONSUMER_THREADS;
-                w[u] = e < NA ? ll_load(out_ll + e) : 0ull;
+                w[u] = e < NA ? ll_load(ag_ll + e) : 0ull;
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int e = tid + u * CONSUMER_THREADS;
-                if (e < NA) ag2[e] = ll_resolve(out_ll + e, w[u], flag);
+                if (e < NA) ag2[e] = ll_resolve(ag_ll + e, w[u], flag);
             }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
@@ -668,7 +653,44 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     }
     CF_MARK(7);
 
-    // ---- cross-group reduction: fp32 red into scratch, last arriver of the slice finalises ----------------
+    if (gridDim.y == 1) {
+        // ---- cross-group reduction, batch == 1: publish the fp32 partial of this rank's output slice as (value, epoch)
+        //      words; the n_groups CTAs that share the slice each sum 1/n_groups of its columns over all groups in group
+        //      order (deterministic; see ll_finalize_columns in llama_decoder_kernel.cuh) ----
+        unsigned long long* mine = p.out_ll + (size_t)gid * hidden + rank * OROWS;
+        for (int e = tid * 2; e < OROWS; e += CONSUMER_THREADS * 2) {
+            float2 v = *reinterpret_cast<const float2*>(out_part + e);
+#pragma unroll
+            for (int w = 1; w < owins; ++w) {
+                const float2 u = *reinterpret_cast<const float2*>(out_part + w * G2_OROWS_MAX + e);
+                v.x += u.x; v.y += u.y;
+            }
+            ll_store2(mine + e, v.x, v.y, flag);
+        }
+        CF_MARK(8);
+        const int ng = gp.n_groups;
+        const int lo = (int)((long long)gid * OROWS / ng), hi = (int)((long long)(gid + 1) * OROWS / ng);
+        ll_finalize_columns(p.out_ll, hidden, ng, rank * OROWS, lo, hi, flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
+        // a CTA that got here has seen every group's partial of its slice, and a group only gets past its exchanges once
+        // all of its CTAs are past phase 0: CTA 0 may bump the epoch and (in-place form) overwrite `residual`
+        if (blockIdx.x == 0) {
+            if (tid == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.header) : "memory");
+            if (residual_inplace) {
+                for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+                    float f[8], r8[8];
+                    unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+                    unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+                    __align__(16) __half hs[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) hs[k] = __float2half_rn(f[k] + r8[k]);
+                    *reinterpret_cast<uint4*>(rout + e) = *reinterpret_cast<const uint4*>(hs);
+                }
+            }
+        }
+        CF_MARK(9);
+        return;
+    }
+    // ---- cross-group reduction, batch > 1: fp32 red into scratch, last arriver of the slice finalises ----------------
     float* scratch = p.scratch + (size_t)batch * hidden + rank * OROWS;
     for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4) {
         float4 v = *reinterpret_cast<const float4*>(out_part + e);
@@ -692,8 +714,8 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         if (tid == 0) {
             // a slice is finalised only after every group reached the end, so when the launch's last slice is, no CTA
             // will read another flag-in-data word: bump the workspace epoch for the next launch
-            const unsigned prevf = atomicAdd(gp.header + 1, 1u);
-            if (prevf == gridDim.y * (unsigned)G - 1u) { gp.header[1] = 0u; gp.header[0] = epoch + 1u; }
+            const unsigned prevf = atomicAdd(p.header + 1, 1u);
+            if (prevf == gridDim.y * (unsigned)G - 1u) { p.header[1] = 0u; p.header[0] = epoch + 1u; }
         }
         const bool fp32_out = p.flags & 1u;
         for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4) {

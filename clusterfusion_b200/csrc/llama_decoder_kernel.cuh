@@ -76,6 +76,8 @@ struct alignas(64) KParams {
     const long long* positions;
     float* scratch;          // fp32 [batch][hidden], zero between launches
     unsigned* counters;      // [batch][CLUSTER + 1], zero between launches
+    unsigned long long* out_ll;   // batch == 1: (float, epoch) words [clusters][hidden] for the cross-head O reduction
+    unsigned* header;        // workspace header: u32 [0] launch epoch (tags every flag-in-data word)
     float eps;
     int hidden;
     int n_heads;             // query heads == clusters per request (MHA kernels)
@@ -146,6 +148,64 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// ---- flag-in-data ("LL") words: low 32 bits = float payload, high 32 bits = epoch of the launch that wrote it.
+//      A 64-bit scalar access is single-copy atomic, so a reader that sees the right epoch also sees the payload:
+//      no fence, no counter, nothing to re-zero -- one L2 round trip per hop. ----
+__device__ __forceinline__ unsigned long long ll_pack(float v, unsigned flag) {
+    return (unsigned long long)__float_as_uint(v) | ((unsigned long long)flag << 32);
+}
+__device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned flag) {
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(ll_pack(v, flag)) : "memory");
+}
+__device__ __forceinline__ void ll_store2(unsigned long long* p, float v0, float v1, unsigned flag) {   // p 16-byte aligned
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(ll_pack(v0, flag)), "l"(ll_pack(v1, flag)) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
+}
+// spin until the word carries this launch's epoch (the first probe `w` was issued by the caller, batched with others)
+__device__ __forceinline__ float ll_resolve(const unsigned long long* p, unsigned long long w, unsigned flag) {
+    while ((unsigned)(w >> 32) != flag) w = ll_load(p);
+    return __uint_as_float((unsigned)w);
+}
+__device__ __forceinline__ unsigned ll_flag_of_epoch(unsigned epoch) { return epoch + 1u == 0u ? 1u : epoch + 1u; }
+
+// Cross-cluster sum of per-cluster partial output slices without atomics (batch == 1 launches).
+// Cluster `cid` of `ncl` has published slice words out_ll[cid][slice0 .. slice0+n).  This CTA finalises columns
+// [lo, hi) of the slice (the ncl CTAs that share a slice split its columns), summing the ncl partials of a column in
+// cluster order -> the result is bit-identical from launch to launch.  4 threads per column poll ncl/4 words each.
+__device__ __forceinline__ void ll_finalize_columns(const unsigned long long* out_ll, int hidden, int ncl, int slice0, int lo,
+                                                    int hi, unsigned flag, void* out, bool fp32_out, uint32_t tid, int nthreads) {
+    const int ncols = hi - lo;
+    for (int i = tid; i < ((ncols * 4 + 31) & ~31); i += nthreads) {
+        const int col = i >> 2, sub = i & 3;
+        const bool active = col < ncols;
+        const int c0 = sub * ncl / 4, c1 = (sub + 1) * ncl / 4;
+        const unsigned long long* base = out_ll + slice0 + lo + (active ? col : 0);
+        float acc = 0.f;
+        if (active) {
+            for (int c = c0; c < c1; c += 8) {
+                unsigned long long w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = (c + j < c1) ? ll_load(base + (size_t)(c + j) * hidden) : 0ull;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c + j < c1) acc += ll_resolve(base + (size_t)(c + j) * hidden, w[j], flag);
+            }
+        }
+        // fixed-order combine of the 4 sub-sums: (s0 + s1) + (s2 + s3)
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (active && sub == 0) {
+            const int o = slice0 + lo + col;
+            if (fp32_out) static_cast<float*>(out)[o] = acc;
+            else static_cast<__half*>(out)[o] = __float2half_rn(acc);
+        }
+    }
+}
+
 __device__ __forceinline__ float4 ld_cg_v4(const float* addr) {
     float4 v;
     asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -364,25 +424,54 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     __half* rout = kChat ? nullptr : p.residual_out + (size_t)batch * hidden;
     const bool residual_inplace = !kChat && (static_cast<const void*>(rout) == static_cast<const void*>(rg));
 
+    // The RMSNorm weight slice does not depend on the previous kernel: fetch it before the dependency wait.
+    const int cpk = KS / 8;                    // 8-element chunks in this CTA's slice (<= 256 < CONSUMER_THREADS)
+    const int nchunks = hidden / 8;
+    uint4 wraw = make_uint4(0, 0, 0, 0);
+    if ((int)tid < cpk) wraw = *reinterpret_cast<const uint4*>(p.rms_w + rank * KS + tid * 8);
+
     // Programmatic dependent launch: everything above (and the whole producer warp) may run while the previous
     // kernel in the stream is still finishing; activations, outputs and the workspace may only be touched after it.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool ll_out = (gridDim.y == 1) && (p.out_ll != nullptr);
+    const unsigned flag = ll_out ? ll_flag_of_epoch(__ldcg(p.header)) : 0u;
 
     // ---- phase 0: RMSNorm ---------------------------------------------------------------------------
-    // every CTA reduces the full vector itself (8-16 KB from L2) -> no cluster round trip for a scalar
+    // every CTA reduces the full vector itself (8-16 KB from L2) -> no cluster round trip for a scalar.  One pass:
+    // chunk c = (j + rank*cpk) mod nchunks goes to thread j mod 384, so the chunks of this CTA's own slice are the
+    // FIRST chunk of threads 0..cpk-1 and stay in registers across the block reduction (one L2 round trip, not two).
     {
+        constexpr int P0_ITERS = (KS_MAX * 4 / 8 + CONSUMER_THREADS - 1) / CONSUMER_THREADS;     // hidden <= 4*KS_MAX: 3
+        uint4 xr[P0_ITERS], rr[P0_ITERS];
+#pragma unroll
+        for (int it = 0; it < P0_ITERS; ++it) {
+            const int j = tid + it * CONSUMER_THREADS;
+            const int c = (j + rank * cpk) % nchunks;
+            xr[it] = make_uint4(0, 0, 0, 0);
+            rr[it] = make_uint4(0, 0, 0, 0);
+            if (j < nchunks) {
+                xr[it] = *reinterpret_cast<const uint4*>(xg + c * 8);
+                if constexpr (!kChat) rr[it] = *reinterpret_cast<const uint4*>(rg + c * 8);
+            }
+        }
+        float f0[8];
         float ss = 0.f;
-        for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+#pragma unroll
+        for (int it = 0; it < P0_ITERS; ++it) {
             float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+            unpack8(xr[it], f);
             if constexpr (!kChat) {
                 float r8[8];
-                unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+                unpack8(rr[it], r8);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = round_h(f[k] + r8[k]);   // residual_out is fp16; norm the rounded sum
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) ss += f[k] * f[k];
+            for (int k = 0; k < 8; ++k) ss += f[k] * f[k];                  // chunks past the end are zeros
+            if (it == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f0[k] = f[k];
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -393,22 +482,20 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w];
         const float rstd = rsqrtf(tot / (float)hidden + p.eps);
         // normalised slice [rank*KS, +KS) -> fp32 smem, rounded where the eager fp16 model rounds
-        for (int e = tid * 8; e < KS; e += CONSUMER_THREADS * 8) {
-            const int ge = rank * KS + e;
-            float f[8], w8[8];
-            unpack8(*reinterpret_cast<const uint4*>(xg + ge), f);
-            unpack8(*reinterpret_cast<const uint4*>(p.rms_w + ge), w8);
+        if ((int)tid < cpk) {
+            const int e = tid * 8;
+            float w8[8];
+            unpack8(wraw, w8);
             if constexpr (!kChat) {
-                float r8[8];
-                unpack8(*reinterpret_cast<const uint4*>(rg + ge), r8);
-                __align__(16) __half hs[8];
+                if (head == 0 && !residual_inplace) {
+                    __align__(16) __half hs[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { hs[k] = __float2half_rn(f[k] + r8[k]); f[k] = __half2float(hs[k]); }
-                if (head == 0 && !residual_inplace)
-                    *reinterpret_cast<uint4*>(rout + ge) = *reinterpret_cast<const uint4*>(hs);
+                    for (int k = 0; k < 8; ++k) hs[k] = __float2half_rn(f0[k]);     // exact: f0 is already fp16-rounded
+                    *reinterpret_cast<uint4*>(rout + rank * KS + e) = *reinterpret_cast<const uint4*>(hs);
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) xs[e + k] = round_h(round_h(f[k] * rstd) * w8[k]);
+            for (int k = 0; k < 8; ++k) xs[e + k] = round_h(round_h(f0[k] * rstd) * w8[k]);
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
@@ -772,7 +859,49 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
 
     CF_MARK(7);   // O tiles consumed, block-reduced
-    // ---- cross-head reduction: fp32 red into scratch, last arriver of the slice finalises --------------
+    if (ll_out) {
+        // ---- cross-head reduction, batch == 1: every cluster publishes its fp32 partial of this rank's output slice as
+        //      (value, epoch) words; the 32 (n_heads) CTAs that share the slice each sum 1/n_heads of its columns over all
+        //      heads in head order and write the result.  No atomics, no fence, no scratch to re-zero, deterministic. ----
+        unsigned long long* mine = p.out_ll + (size_t)head * hidden + rank * KS;
+        for (int e = tid * 2; e < KS; e += CONSUMER_THREADS * 2) {
+            float2 v = *reinterpret_cast<const float2*>(out_part + e);
+            if constexpr (kChat) {
+#pragma unroll
+                for (int q = 1; q < HEAD_DIM / ROWS256; ++q) {
+                    const float2 w = *reinterpret_cast<const float2*>(out_part + q * KS + e);
+                    v.x += w.x; v.y += w.y;
+                }
+            }
+            ll_store2(mine + e, v.x, v.y, flag);
+        }
+        CF_MARK(8);   // partial published
+        const int nh = p.n_heads;
+        const int lo = (int)((long long)head * KS / nh), hi = (int)((long long)(head + 1) * KS / nh);
+        ll_finalize_columns(p.out_ll, hidden, nh, rank * KS, lo, hi, flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
+        // Any CTA that got here has seen every cluster's partial, so every CTA of the launch is past phase 0 (it read x,
+        // residual and the epoch before its cluster's first exchange): CTA 0 may now bump the epoch for the next launch
+        // and, for the in-place form, overwrite `residual` (the reference races here).
+        if (blockIdx.x == 0) {
+            if (tid == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.header) : "memory");
+            if constexpr (!kChat) {
+                if (residual_inplace) {
+                    for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+                        float f[8], r8[8];
+                        unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+                        unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+                        __align__(16) __half hs[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) hs[k] = __float2half_rn(f[k] + r8[k]);
+                        *reinterpret_cast<uint4*>(rout + e) = *reinterpret_cast<const uint4*>(hs);
+                    }
+                }
+            }
+        }
+        CF_MARK(9);   // CTA done
+        return;
+    }
+    // ---- cross-head reduction, batch > 1: fp32 red into scratch, last arriver of the slice finalises --------------
     float* scratch = p.scratch + (size_t)batch * hidden + rank * KS;
     for (int e = tid * 4; e < KS; e += CONSUMER_THREADS * 4) {
         float4 v = *reinterpret_cast<const float4*>(out_part + e);
