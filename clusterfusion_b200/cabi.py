@@ -21,6 +21,7 @@ CF_VARIANT_CHAT, CF_VARIANT_SGLANG, CF_VARIANT_PAGED = 0, 1, 2
 CF_FLAG_OUT_FP32_PARTIAL = 0x1
 CF_FLAG_PDL = 0x2
 CF_FLAG_GQA_CLUSTER = 0x4
+CF_FLAG_LL_OUT = 0x8
 
 EXPORTED_SYMBOLS = (
     "cf_abi_version",
@@ -64,6 +65,7 @@ class CfLlamaArgs(C.Structure):
         ("cos", C.c_void_p),
         ("sin", C.c_void_p),
         ("workspace", C.c_void_p),
+        ("workspace_batch", C.c_int32),
     ]
 
 

@@ -311,10 +311,12 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     kp.k_pool_ptrs = reinterpret_cast<const unsigned long long*>(a->k_pool_ptrs);
     kp.v_pool_ptrs = reinterpret_cast<const unsigned long long*>(a->v_pool_ptrs);
     kp.positions = reinterpret_cast<const long long*>(a->positions);
+    const int wsb = a->workspace_batch > 0 ? a->workspace_batch : a->batch;
+    if (wsb < a->batch) return fail(CF_ERR_BAD_SHAPE, "workspace_batch (%d) < batch (%d)", wsb, a->batch);
     kp.scratch = reinterpret_cast<float*>(static_cast<char*>(a->workspace) + ws_off_scratch());
-    kp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + ws_off_counters(a->hidden, a->batch));
+    kp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + ws_off_counters(a->hidden, wsb));
     kp.header = reinterpret_cast<unsigned*>(a->workspace);
-    kp.out_ll = a->batch == 1 ? reinterpret_cast<unsigned long long*>(static_cast<char*>(a->workspace) + ws_off_out_ll_b1(a->hidden, 1))
+    kp.out_ll = (a->batch == 1 && (gqa || (a->flags & CF_FLAG_LL_OUT))) ? reinterpret_cast<unsigned long long*>(static_cast<char*>(a->workspace) + ws_off_out_ll_b1(a->hidden, wsb))
                               : nullptr;
     kp.eps = a->eps;
     kp.hidden = a->hidden;
@@ -337,10 +339,10 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         memset(&gp, 0, sizeof gp);
         gp.k = kp;
         char* ws = static_cast<char*>(a->workspace);
-        gp.qkv_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_qkv_ll(a->hidden, a->batch));
-        gp.attn_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_attn_ll(a->hidden, a->batch));
-        gp.ag_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_ag_ll(a->hidden, a->batch));
-        gp.gcounters = reinterpret_cast<unsigned*>(ws + ws_off_gcounters(a->hidden, a->batch));
+        gp.qkv_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_qkv_ll(a->hidden, wsb));
+        gp.attn_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_attn_ll(a->hidden, wsb));
+        gp.ag_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_ag_ll(a->hidden, wsb));
+        gp.gcounters = reinterpret_cast<unsigned*>(ws + ws_off_gcounters(a->hidden, wsb));
         gp.G = G;
         gp.n_groups = n_groups;
         return paged ? launch_gqa2<cfb::PAGED>(gp, a->batch, pdl, stream) : launch_gqa2<cfb::SGLANG>(gp, 1, pdl, stream);

@@ -401,7 +401,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             cosp = p.cos + p.positions[batch] * HEAD_DIM;
             sinp = cosp + HEAD_DIM / 2;
         }
-        // read a projected row: sum of its 1 or 2 published parts, polled until they carry this launch's epoch
+        // read a projected row: sum of its 1 or 2 published parts, each validated by its own epoch
         auto n_parts = [&](int e) {
             const int rb = e / ROWS512;
             return (int)((uint32_t)(rb * wins + wins - 1) / n_qkv_tiles) - (int)((uint32_t)(rb * wins) / n_qkv_tiles) + 1;
@@ -653,7 +653,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     }
     CF_MARK(7);
 
-    if (gridDim.y == 1) {
+    if (gridDim.y == 1 && p.out_ll != nullptr) {
         // ---- cross-group reduction, batch == 1: publish the fp32 partial of this rank's output slice as (value, epoch)
         //      words; the n_groups CTAs that share the slice each sum 1/n_groups of its columns over all groups in group
         //      order (deterministic; see ll_finalize_columns in llama_decoder_kernel.cuh) ----
@@ -670,7 +670,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         CF_MARK(8);
         const int ng = gp.n_groups;
         const int lo = (int)((long long)gid * OROWS / ng), hi = (int)((long long)(gid + 1) * OROWS / ng);
-        ll_finalize_columns(p.out_ll, hidden, ng, rank * OROWS, lo, hi, flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
+        ll_finalize_columns(p.out_ll, hidden, ng, rank * OROWS, lo, hi, flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS, CONSUMER_BAR);
         // a CTA that got here has seen every group's partial of its slice, and a group only gets past its exchanges once
         // all of its CTAs are past phase 0: CTA 0 may bump the epoch and (in-place form) overwrite `residual`
         if (blockIdx.x == 0) {

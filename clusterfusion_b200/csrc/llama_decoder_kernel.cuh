@@ -167,7 +167,7 @@ __device__ __forceinline__ unsigned long long ll_load(const unsigned long long* 
 }
 // spin until the word carries this launch's epoch (the first probe `w` was issued by the caller, batched with others)
 __device__ __forceinline__ float ll_resolve(const unsigned long long* p, unsigned long long w, unsigned flag) {
-    while ((unsigned)(w >> 32) != flag) w = ll_load(p);
+    while ((unsigned)(w >> 32) != flag) { __nanosleep(40); w = ll_load(p); }
     return __uint_as_float((unsigned)w);
 }
 __device__ __forceinline__ unsigned ll_flag_of_epoch(unsigned epoch) { return epoch + 1u == 0u ? 1u : epoch + 1u; }
@@ -177,7 +177,8 @@ __device__ __forceinline__ unsigned ll_flag_of_epoch(unsigned epoch) { return ep
 // [lo, hi) of the slice (the ncl CTAs that share a slice split its columns), summing the ncl partials of a column in
 // cluster order -> the result is bit-identical from launch to launch.  4 threads per column poll ncl/4 words each.
 __device__ __forceinline__ void ll_finalize_columns(const unsigned long long* out_ll, int hidden, int ncl, int slice0, int lo,
-                                                    int hi, unsigned flag, void* out, bool fp32_out, uint32_t tid, int nthreads) {
+                                                    int hi, unsigned flag, void* out, bool fp32_out, uint32_t tid, int nthreads,
+                                                    int bar_id) {
     const int ncols = hi - lo;
     for (int i = tid; i < ((ncols * 4 + 31) & ~31); i += nthreads) {
         const int col = i >> 2, sub = i & 3;
@@ -860,9 +861,11 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
 
     CF_MARK(7);   // O tiles consumed, block-reduced
     if (ll_out) {
-        // ---- cross-head reduction, batch == 1: every cluster publishes its fp32 partial of this rank's output slice as
-        //      (value, epoch) words; the 32 (n_heads) CTAs that share the slice each sum 1/n_heads of its columns over all
-        //      heads in head order and write the result.  No atomics, no fence, no scratch to re-zero, deterministic. ----
+        // ---- cross-head reduction, opt-in (CF_FLAG_LL_OUT, batch == 1): every cluster publishes its fp32 partial of this
+        //      rank's output slice as (value, epoch) words; the n_heads CTAs that share the slice each sum 1/n_heads of its
+        //      columns over all heads in head order and write the result.  No atomics, bitwise reproducible -- but every
+        //      CTA then lives until the slowest cluster has published, which delays the next layer's CTAs in a PDL chain
+        //      (+2.5 us per layer, measured), so the red path below stays the default. ----
         unsigned long long* mine = p.out_ll + (size_t)head * hidden + rank * KS;
         for (int e = tid * 2; e < KS; e += CONSUMER_THREADS * 2) {
             float2 v = *reinterpret_cast<const float2*>(out_part + e);
@@ -878,7 +881,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         CF_MARK(8);   // partial published
         const int nh = p.n_heads;
         const int lo = (int)((long long)head * KS / nh), hi = (int)((long long)(head + 1) * KS / nh);
-        ll_finalize_columns(p.out_ll, hidden, nh, rank * KS, lo, hi, flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
+        ll_finalize_columns(p.out_ll, hidden, nh, rank * KS, lo, hi, flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS, CONSUMER_BAR);
         // Any CTA that got here has seen every cluster's partial, so every CTA of the launch is past phase 0 (it read x,
         // residual and the epoch before its cluster's first exchange): CTA 0 may now bump the epoch for the next launch
         // and, for the in-place form, overwrite `residual` (the reference races here).
@@ -901,7 +904,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         CF_MARK(9);   // CTA done
         return;
     }
-    // ---- cross-head reduction, batch > 1: fp32 red into scratch, last arriver of the slice finalises --------------
+    // ---- cross-head reduction (default): fp32 red into scratch, last arriver of the slice finalises ---------------
     float* scratch = p.scratch + (size_t)batch * hidden + rank * KS;
     for (int e = tid * 4; e < KS; e += CONSUMER_THREADS * 4) {
         float4 v = *reinterpret_cast<const float4*>(out_part + e);

@@ -39,19 +39,21 @@ void check_cuda_contig(const Tensor& t, const char* name, c10::ScalarType dtype)
     TORCH_CHECK(t.scalar_type() == dtype, name, " must have dtype ", dtype, " (got ", t.scalar_type(), ")");
 }
 
-// One zero-initialised workspace per (device, stream): the kernel leaves it zeroed, so it is
-// memset exactly once in the life of the process.  Grows (never shrinks) with hidden * batch.
-Tensor workspace_for(const Tensor& like, int hidden, int batch, cudaStream_t stream) {
+// One zero-initialised workspace per (device, stream, hidden): memset exactly once, opaque afterwards.  Its layout depends
+// on the batch it was sized for, so that batch is remembered and passed as CfLlamaArgs::workspace_batch; a larger batch gets
+// a fresh (zeroed) workspace sized for it, which then also serves the smaller ones.
+struct Workspace { Tensor buf; int batch; };
+Workspace workspace_for(const Tensor& like, int hidden, int batch, cudaStream_t stream) {
     static std::mutex mu;
-    static std::map<std::pair<int, void*>, Tensor> cache;
-    const size_t need = cf_llama_workspace_bytes(hidden, batch);
+    static std::map<std::tuple<int, void*, int>, Workspace> cache;
     std::lock_guard<std::mutex> lk(mu);
-    auto key = std::make_pair((int)like.get_device(), (void*)stream);
+    auto key = std::make_tuple((int)like.get_device(), (void*)stream, hidden);
     auto it = cache.find(key);
-    if (it == cache.end() || (size_t)it->second.numel() < need) {
-        Tensor ws = torch::zeros({(int64_t)need}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device()));
-        cache[key] = ws;
-        return ws;
+    if (it == cache.end() || it->second.batch < batch) {
+        const size_t need = cf_llama_workspace_bytes(hidden, batch);
+        Workspace w{torch::zeros({(int64_t)need}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device())), batch};
+        cache[key] = w;
+        return w;
     }
     return it->second;
 }
@@ -95,7 +97,7 @@ std::tuple<Tensor, Tensor, Tensor> llama_decoder_layer(
     Tensor o = torch::empty({1, hidden}, opt);
     Tensor k = torch::empty({1, n_heads, 128}, opt);
     Tensor v = torch::empty({1, n_heads, 128}, opt);
-    Tensor ws = workspace_for(input, (int)hidden, 1, stream);
+    Workspace ws = workspace_for(input, (int)hidden, 1, stream);
 
     CfLlamaArgs a{};
     a.variant = CF_VARIANT_CHAT;
@@ -107,7 +109,7 @@ std::tuple<Tensor, Tensor, Tensor> llama_decoder_layer(
     a.out = o.data_ptr(); a.k_new = k.data_ptr(); a.v_new = v.data_ptr();
     a.k_cache = k_cache.data_ptr(); a.v_cache = v_cache.data_ptr();
     a.cos = cos.data_ptr<float>(); a.sin = sin.data_ptr<float>();
-    a.workspace = ws.data_ptr();
+    a.workspace = ws.buf.data_ptr(); a.workspace_batch = ws.batch;
     if (g_pdl) a.flags |= CF_FLAG_PDL;
     run(a, stream);
     return std::make_tuple(o, k, v);
@@ -145,7 +147,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> llama_decoder_layer_sglang(
     Tensor o = torch::empty({1, hidden}, opt);
     Tensor k = torch::empty({1, kvd / 128, 128}, opt);
     Tensor v = torch::empty({1, kvd / 128, 128}, opt);
-    Tensor ws = workspace_for(input, (int)hidden, 1, stream);
+    Workspace ws = workspace_for(input, (int)hidden, 1, stream);
 
     CfLlamaArgs a{};
     a.variant = CF_VARIANT_SGLANG;
@@ -158,7 +160,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> llama_decoder_layer_sglang(
     a.out = o.data_ptr(); a.k_new = k.data_ptr(); a.v_new = v.data_ptr();
     a.k_cache = k_cache.data_ptr(); a.v_cache = v_cache.data_ptr();
     a.cos = cos.data_ptr<float>(); a.sin = sin.data_ptr<float>();
-    a.workspace = ws.data_ptr();
+    a.workspace = ws.buf.data_ptr(); a.workspace_batch = ws.batch;
     if (g_pdl) a.flags |= CF_FLAG_PDL;
     run(a, stream);
     return std::make_tuple(o, residual, k, v);
@@ -200,7 +202,7 @@ void llama_decoder_layer_batch_decode_sglang(
 
     const c10::cuda::CUDAGuard guard(input.device());
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
-    Tensor ws = workspace_for(input, (int)hidden, (int)bs, stream);
+    Workspace ws = workspace_for(input, (int)hidden, (int)bs, stream);
 
     CfLlamaArgs a{};
     a.variant = CF_VARIANT_PAGED;
@@ -216,7 +218,7 @@ void llama_decoder_layer_batch_decode_sglang(
     a.v_pool_ptrs = static_cast<const uint64_t*>(v_cache_ptrs.data_ptr());
     a.positions = positions.data_ptr<int64_t>();
     a.cos = cos_sin.data_ptr<float>();
-    a.workspace = ws.data_ptr();
+    a.workspace = ws.buf.data_ptr(); a.workspace_batch = ws.batch;
     if (g_pdl) a.flags |= CF_FLAG_PDL;
     run(a, stream);
 }
@@ -241,13 +243,13 @@ void llama_ffn_layer_out(Tensor output, Tensor residual_output, Tensor input, Te
     TORCH_CHECK(rms_weight.numel() == hidden, "rms_weight must be [hidden]");
     const c10::cuda::CUDAGuard guard(input.device());
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
-    Tensor ws = workspace_for(input, (int)hidden, 1, stream);
+    Workspace ws = workspace_for(input, (int)hidden, 1, stream);
     CfFfnArgs a{};
     a.flags = g_pdl ? CF_FLAG_PDL : 0u;
     a.hidden = (int)hidden; a.ffn = (int)ffn; a.eps = (float)eps;
     a.x = input.data_ptr(); a.residual_in = residual.data_ptr();
     a.w_gate_up = weight_gate_up.data_ptr(); a.w_down_t = weight_down_t.data_ptr(); a.rms_w = rms_weight.data_ptr();
-    a.out = output.data_ptr(); a.residual_out = residual_output.data_ptr(); a.workspace = ws.data_ptr();
+    a.out = output.data_ptr(); a.residual_out = residual_output.data_ptr(); a.workspace = ws.buf.data_ptr();
     const int rc = cf_llama_ffn_launch(&a, stream);
     TORCH_CHECK(rc == 0, "clusterfusion_b200: ffn launch failed (", rc, "): ", cf_last_error_string());
 }

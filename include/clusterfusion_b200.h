@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 1
+#define CF_ABI_VERSION 2
 
 enum {
     CF_VARIANT_CHAT = 0,   /* W^T weights, GPT-J interleaved RoPE, eps fixed by caller (1e-6), no residual   */
@@ -61,6 +61,11 @@ enum {
 
 #define CF_FLAG_GQA_CLUSTER 0x4u /* grouped-query shapes: use the first-generation 8/16-CTA cluster kernel instead of the
                                     group kernel (measurement / A-B only; slower on B200)              */
+
+#define CF_FLAG_LL_OUT 0x8u /* batch-1 MHA launches: reduce the O projection across clusters through flag-in-data words summed
+                               in head order (bitwise reproducible output, no atomics) instead of fp32 red.global.add + a
+                               last-arriver finalize.  Costs ~2.5 us per layer in a PDL chain: every CTA then lives until the
+                               slowest cluster has published, so the next layer's CTAs start later (measured). */
 
 typedef struct CfLlamaArgs {
     int32_t variant;    /* CF_VARIANT_*                                                             */
@@ -98,8 +103,12 @@ typedef struct CfLlamaArgs {
     const float* cos; /* CHAT: fp32 [128] pair-repeated; SGLANG: fp32 [>=64]; PAGED: cos_sin fp32 [max_pos,128] */
     const float* sin; /* CHAT / SGLANG as cos; PAGED: unused                                        */
 
-    void* workspace;  /* cf_llama_workspace_bytes() bytes, zero-filled ONCE by the caller; the kernel
-                         returns it zeroed.  One workspace per stream that may run concurrently.    */
+    void* workspace;  /* cf_llama_workspace_bytes(hidden, workspace_batch) bytes, zero-filled ONCE by the caller and
+                         opaque afterwards (a launch epoch, zeroed scratch / counters and stale exchange words
+                         live in it).  One workspace per stream that may run concurrently; its internal layout
+                         depends on (hidden, workspace_batch), so keep both fixed for the life of a workspace. */
+    int32_t workspace_batch; /* the batch the workspace was sized for; 0 means `batch`.  Lets one workspace sized for
+                                the largest batch serve smaller launches (batch <= workspace_batch).            */
 } CfLlamaArgs;
 
 /* Bytes of zero-initialised device workspace needed for a call with this hidden / batch. */

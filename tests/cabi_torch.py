@@ -22,13 +22,13 @@ def stream_handle():
     return torch.cuda.current_stream().cuda_stream
 
 
-def chat(x, w_qkv, w_o, k_cache, v_cache, rms_w, cos, sin, eps=1e-6):
+def chat(x, w_qkv, w_o, k_cache, v_cache, rms_w, cos, sin, eps=1e-6, flags=0):
     hidden = x.shape[-1]
     H = hidden // 128
     o = torch.empty(1, hidden, dtype=torch.float16, device=x.device)
     k = torch.empty(1, H, 128, dtype=torch.float16, device=x.device)
     v = torch.empty(1, H, 128, dtype=torch.float16, device=x.device)
-    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_CHAT, hidden=hidden, n_q_heads=H, n_kv_heads=H, head_dim=128,
+    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_CHAT, flags=flags, hidden=hidden, n_q_heads=H, n_kv_heads=H, head_dim=128,
                          batch=1, kv_len=k_cache.shape[0], eps=eps, x=_p(x), w_qkv=_p(w_qkv), w_o=_p(w_o),
                          rms_w=_p(rms_w), out=_p(o), k_new=_p(k), v_new=_p(v), k_cache=_p(k_cache),
                          v_cache=_p(v_cache), cos=_p(cos), sin=_p(sin),
