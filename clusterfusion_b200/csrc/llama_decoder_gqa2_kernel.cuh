@@ -58,14 +58,14 @@ struct SmemGqa2 {
     static constexpr int RING = 0;
     static constexpr int UNION = RING + NSTAGES * STAGE_BYTES;
     //   phase QKV : xs fp16[hidden <= 8192] | part fp32[12 warps][G2_RB_LOCAL_MAX][16]
-    //   phase ATTN: attn_part fp32[12][132] | cta_state fp32[NQ][132]
+    //   phase ATTN: attn_part fp32[12][NQ][132] | mg fp32[640]
     //   phase O   : out_part fp32[NQ*128/256][G2_OROWS_MAX]
     static constexpr int XS = UNION;
     static constexpr int PART = UNION + G2_HIDDEN_MAX * 2;
     static constexpr int QKV_BYTES = G2_HIDDEN_MAX * 2 + CONSUMER_WARPS * G2_RB_LOCAL_MAX * ROWS512 * 4;
-    static constexpr int ATTN_PART = UNION;
-    static constexpr int CTA_STATE = UNION + CONSUMER_WARPS * PAY * 4;
-    static constexpr int ATTN_BYTES = (CONSUMER_WARPS + NQ) * PAY * 4;
+    static constexpr int ATTN_PART = UNION;                                // fp32 [12 warps][NQ][132]
+    static constexpr int MG = UNION + CONSUMER_WARPS * NQ * PAY * 4;       // fp32 [G][S2 + 2] <= 640 floats
+    static constexpr int ATTN_BYTES = CONSUMER_WARPS * NQ * PAY * 4 + 640 * 4;
     static constexpr int OUT_PART = UNION;
     static constexpr int OUT_BYTES = (NQ * HEAD_DIM / 256) * G2_OROWS_MAX * 4;
     static constexpr int UNION_SIZE = QKV_BYTES > ATTN_BYTES ? (QKV_BYTES > OUT_BYTES ? QKV_BYTES : OUT_BYTES)
@@ -266,7 +266,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     __half* xs = reinterpret_cast<__half*>(smem + S::XS);
     float* part = reinterpret_cast<float*>(smem + S::PART);
     float* attn_part = reinterpret_cast<float*>(smem + S::ATTN_PART);
-    float* cta_state = reinterpret_cast<float*>(smem + S::CTA_STATE);
+    float* mg = reinterpret_cast<float*>(smem + S::MG);
     float* out_part = reinterpret_cast<float*>(smem + S::OUT_PART);
     float* qkv_fin = reinterpret_cast<float*>(smem + S::QKV_FIN);
     float* ag2 = reinterpret_cast<float*>(smem + S::AG2);
@@ -406,20 +406,35 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             const int rb = e / ROWS512;
             return (int)((uint32_t)(rb * wins + wins - 1) / n_qkv_tiles) - (int)((uint32_t)(rb * wins) / n_qkv_tiles) + 1;
         };
+        // one L2 round trip: every thread probes all words of its own two rows back to back, resolves them, and parks
+        // the fp16-rounded sums in shared memory (the activation buffer `xs` is dead by now) for the RoPE pairing
+        float* qkv_raw = reinterpret_cast<float*>(smem + S::XS);
+        {
+            static_assert(S::R == 2 * CONSUMER_THREADS, "two projected rows per thread");
+            unsigned long long w0[2], w1[2];
+            bool two[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * CONSUMER_THREADS;
+                two[u] = n_parts(e) > 1;
+                w0[u] = ll_load(qkv_ll + e);
+                w1[u] = two[u] ? ll_load(qkv_ll + S::R + e) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * CONSUMER_THREADS;
+                float v = ll_resolve(qkv_ll + e, w0[u], flag);
+                if (two[u]) v += ll_resolve(qkv_ll + S::R + e, w1[u], flag);
+                qkv_raw[e] = round_h(v);                         // q / k / v leave the projection as fp16 (eager model)
+            }
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
         for (int e = tid; e < S::R; e += CONSUMER_THREADS) {
             const int hd = e >> 7, d = e & 127;                  // hd < NQ: query head; NQ: k; NQ+1: v
-            const int e2 = e ^ 64;
-            const bool two_a = n_parts(e) > 1, two_b = n_parts(e2) > 1;
-            // first probes of all (up to four) words back to back, then resolve
-            const unsigned long long wa0 = ll_load(qkv_ll + e), wb0 = ll_load(qkv_ll + e2);
-            const unsigned long long wa1 = two_a ? ll_load(qkv_ll + S::R + e) : 0ull;
-            const unsigned long long wb1 = two_b ? ll_load(qkv_ll + S::R + e2) : 0ull;
-            float av = ll_resolve(qkv_ll + e, wa0, flag), bv = ll_resolve(qkv_ll + e2, wb0, flag);
-            if (two_a) av += ll_resolve(qkv_ll + S::R + e, wa1, flag);
-            if (two_b) bv += ll_resolve(qkv_ll + S::R + e2, wb1, flag);
-            const float a = round_h(av);                         // q / k / v leave the projection as fp16 (eager model)
+            const float a = qkv_raw[e];
+            const float bv = qkv_raw[e ^ 64];
             if (hd <= NQ) {
-                const float b = round_h(bv);
+                const float b = bv;
                 const int i = d & 63;
                 const float rot = (d & 64) ? fmaf(a, cosp[i], b * sinp[i]) : fmaf(a, cosp[i], -b * sinp[i]);
                 const __half rh = __float2half_rn(rot);
@@ -534,55 +549,55 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             }
             m[h] = M;
         }
-        // block merge, one head at a time through a 12 x 132 float buffer; rank 0 folds in the current token
+        // block merge of all NQ heads in one round: every warp writes its NQ states, then thread (h, d) folds the 12
+        // warps (and, on rank 0, the current token) in warp order and publishes the result straight from registers as
+        // (value, epoch) words -- exchange 2, hop A.
 #pragma unroll
         for (int h = 0; h < NQ; ++h) {
             if (sub == 0) {
-                float* slot = attn_part + warp * S::PAY;
+                float* slot = attn_part + (warp * NQ + h) * S::PAY;
                 if (c == 0) { slot[0] = m[h]; slot[1] = l[h]; }
                 *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[h][0], o8[h][1], o8[h][2], o8[h][3]);
                 *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[h][4], o8[h][5], o8[h][6], o8[h][7]);
             }
-            if (warp == 0) {
-                float a = 0.f;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    a = fmaf(qkv_fin[h * HEAD_DIM + lane * 4 + k], qkv_fin[NQ * HEAD_DIM + lane * 4 + k], a);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                if (lane == 0) red[CONSUMER_WARPS] = a;
-            }
-            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-            if (tid < HEAD_DIM) {
-                const bool with_new = (rank == 0);
-                float M = with_new ? red[CONSUMER_WARPS] : -INFINITY;
-#pragma unroll
-                for (int gI = 0; gI < CONSUMER_WARPS; ++gI) M = fmaxf(M, attn_part[gI * S::PAY]);
-                float L = 0.f, O = 0.f;
-#pragma unroll
-                for (int gI = 0; gI < CONSUMER_WARPS; ++gI) {
-                    const float w = dsm::exp2_diff(attn_part[gI * S::PAY], M);
-                    L = fmaf(attn_part[gI * S::PAY + 1], w, L);
-                    O = fmaf(attn_part[gI * S::PAY + 4 + tid], w, O);
-                }
-                if (with_new) {
-                    const float w = dsm::exp2_diff(red[CONSUMER_WARPS], M);
-                    L += w;
-                    O = fmaf(qkv_fin[(NQ + 1) * HEAD_DIM + tid], w, O);
-                }
-                float* st = cta_state + h * S::PAY;
-                st[4 + tid] = O;
-                if (tid == 0) { st[0] = M; st[1] = L; st[2] = 0.f; st[3] = 0.f; }
-            }
-            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
         }
-        // ---- exchange 2, hop A: publish this CTA's NQ softmax states as (value, epoch) words ----------------------
-        for (int e = tid; e < NQ * S::PAY; e += CONSUMER_THREADS)
-            ll_store(attn_ll + (size_t)rank * (NQ * S::PAY) + e, cta_state[e], flag);
+        if (warp < NQ) {                                         // score of the current token against query head `warp`
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                a = fmaf(qkv_fin[warp * HEAD_DIM + lane * 4 + k], qkv_fin[NQ * HEAD_DIM + lane * 4 + k], a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) red[CONSUMER_WARPS + warp] = a;
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        for (int e = tid; e < NQ * HEAD_DIM; e += CONSUMER_THREADS) {
+            const int h = e >> 7, d = e & 127;
+            const bool with_new = (rank == 0);
+            const float s_new = red[CONSUMER_WARPS + h];
+            float M = with_new ? s_new : -INFINITY;
+#pragma unroll
+            for (int gI = 0; gI < CONSUMER_WARPS; ++gI) M = fmaxf(M, attn_part[(gI * NQ + h) * S::PAY]);
+            float L = 0.f, O = 0.f;
+#pragma unroll
+            for (int gI = 0; gI < CONSUMER_WARPS; ++gI) {
+                const float* sl = attn_part + (gI * NQ + h) * S::PAY;
+                const float w = dsm::exp2_diff(sl[0], M);
+                L = fmaf(sl[1], w, L);
+                O = fmaf(sl[4 + d], w, O);
+            }
+            if (with_new) {
+                const float w = dsm::exp2_diff(s_new, M);
+                L += w;
+                O = fmaf(qkv_fin[(NQ + 1) * HEAD_DIM + d], w, O);
+            }
+            unsigned long long* st = attn_ll + (size_t)rank * (NQ * S::PAY) + h * S::PAY;
+            ll_store(st + 4 + d, O, flag);
+            if (d == 0) { ll_store(st, M, flag); ll_store(st + 1, L, flag); }
+        }
         // this CTA owns merged dims [rank*S2, +S2) of the group's NQ*128: gather [m, l, o[S2]] of every rank ...
         const int S2 = NQ * HEAD_DIM / G;                        // 64 / 32 / 16 / 8 for G = 8 / 16 / 32 / 64
         const int hh = (rank * S2) >> 7, d0 = (rank * S2) & 127;
-        float* mg = attn_part;                                   // fp32 [G][S2 + 2], reuses the block-merge buffer
         {
             const int nw = G * (S2 + 2);                         // <= 640 words: at most two per thread
             const unsigned long long* src[2];

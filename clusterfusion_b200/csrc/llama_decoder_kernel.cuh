@@ -167,7 +167,7 @@ __device__ __forceinline__ unsigned long long ll_load(const unsigned long long* 
 }
 // spin until the word carries this launch's epoch (the first probe `w` was issued by the caller, batched with others)
 __device__ __forceinline__ float ll_resolve(const unsigned long long* p, unsigned long long w, unsigned flag) {
-    while ((unsigned)(w >> 32) != flag) { __nanosleep(40); w = ll_load(p); }
+    while ((unsigned)(w >> 32) != flag) w = ll_load(p);
     return __uint_as_float((unsigned)w);
 }
 __device__ __forceinline__ unsigned ll_flag_of_epoch(unsigned epoch) { return epoch + 1u == 0u ? 1u : epoch + 1u; }

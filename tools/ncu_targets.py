@@ -1,0 +1,43 @@
+"""Plain (graph-free) launch loops for ncu captures of the kernels bench.py's headline arm does not launch:
+    python tools/ncu_targets.py gqa 8192     # group kernel, Llama-3-8B shapes
+    python tools/ncu_targets.py ffn          # fused FFN half-layer, Llama-2-7B shapes
+8 distinct layer sets, 3 passes (24 launches); capture with  ncu --set full -k regex:<kernel> -s 8 -c 3 ..."""
+import sys, torch
+sys.path.insert(0, ".")
+from clusterfusion_b200 import cabi
+cabi.load()
+dev = torch.device("cuda", 0)
+what = sys.argv[1]
+r = lambda *s, sc=1.0: (torch.randn(*s, device=dev) * sc).half()
+st = torch.cuda.current_stream().cuda_stream
+if what == "gqa":
+    kv = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+    H, HQ, HKV = 4096, 32, 8
+    ws = torch.zeros(cabi.workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
+    L = [dict(w_qkv=r((HQ + 2 * HKV) * 128, H, sc=0.02), w_o=r(H, HQ * 128, sc=0.02), k=r(kv, HKV * 128), v=r(kv, HKV * 128),
+              rms=(1 + 0.1 * r(H).float()).half(), o=torch.empty(1, H, dtype=torch.float16, device=dev),
+              ro=torch.empty(1, H, dtype=torch.float16, device=dev), kn=torch.empty(HKV * 128, dtype=torch.float16, device=dev),
+              vn=torch.empty(HKV * 128, dtype=torch.float16, device=dev)) for _ in range(8)]
+    x = r(1, H); res = r(1, H); cos = torch.rand(64, device=dev); sin = torch.rand(64, device=dev)
+    for _ in range(3):
+        for lay in L:
+            a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_SGLANG, flags=0, hidden=H, n_q_heads=HQ, n_kv_heads=HKV, head_dim=128, batch=1,
+                                 kv_len=kv, eps=1e-5, x=x.data_ptr(), residual_in=res.data_ptr(), residual_out=lay["ro"].data_ptr(),
+                                 w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(), out=lay["o"].data_ptr(),
+                                 k_new=lay["kn"].data_ptr(), v_new=lay["vn"].data_ptr(), k_cache=lay["k"].data_ptr(), v_cache=lay["v"].data_ptr(),
+                                 cos=cos.data_ptr(), sin=sin.data_ptr(), workspace=ws.data_ptr())
+            cabi.launch(a, st)
+else:
+    H, F = 4096, 11008
+    ws = torch.zeros(cabi.workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
+    L = [dict(w13=r(2 * F, H, sc=0.02), w2t=r(F, H, sc=0.02), rms=(1 + 0.1 * r(H).float()).half(),
+              o=torch.empty(1, H, dtype=torch.float16, device=dev), ro=torch.empty(1, H, dtype=torch.float16, device=dev)) for _ in range(8)]
+    x, res = r(1, H), r(1, H)
+    for _ in range(3):
+        for lay in L:
+            a = cabi.CfFfnArgs(flags=0, hidden=H, ffn=F, eps=1e-5, x=x.data_ptr(), residual_in=res.data_ptr(), w_gate_up=lay["w13"].data_ptr(),
+                               w_down_t=lay["w2t"].data_ptr(), rms_w=lay["rms"].data_ptr(), out=lay["o"].data_ptr(),
+                               residual_out=lay["ro"].data_ptr(), workspace=ws.data_ptr())
+            cabi.launch_ffn(a, st)
+torch.cuda.synchronize()
+print("done", what)
