@@ -149,12 +149,14 @@ def test_paged_form_vs_reference_kernel(ref):
     assert torch.equal(r, want_r)
     assert err(k_pool, kp) < 4e-3 and err(v_pool, vp) < 1e-3
     # The reference kernel zeroes its slice of `output` inside the kernel with no grid-wide ordering against the other
-    # clusters' atomicAdds (kernel_batch_sglang.cuh:608-610 vs :643): launches where the race fires lose
-    # contributions.  Six attempts, best one compared; all errors printed.
-    runs = [run(ref.llama_decoder_layer_batch_decode_sglang) for _ in range(6)]
+    # clusters' atomicAdds (kernel_batch_sglang.cuh:608-610 vs :643): a cluster that zeroes late wipes what
+    # earlier clusters added.  On B200 that happens on every launch (observed max-abs error 0.19-0.26 on six of six),
+    # so its `output` cannot serve as a pin; what it writes race-free -- residual_output and the new token's K / V rows in
+    # the pool (RoPE position lookup, slot = last index of the request) -- is compared, and its output error is printed.
+    runs = [run(ref.llama_decoder_layer_batch_decode_sglang) for _ in range(3)]
     errs = [err(x[0], want_o) for x in runs]
-    print(f"reference paged kernel, 6 launches: max-abs errors {[round(e, 4) for e in errs]}")
-    r_o, r_r, r_k_pool, r_v_pool = runs[errs.index(min(errs))]
-    assert torch.equal(r_r, want_r)
-    assert err(r_o, want_o) < 5e-2 and err(o, r_o) < 5e-2
-    assert err(r_k_pool, kp) < 1e-2 and err(r_v_pool, vp) < 1e-2
+    print(f"reference paged kernel, 3 launches: max-abs output errors {[round(e, 4) for e in errs]} (racy, not asserted)")
+    for r_o, r_r, r_k_pool, r_v_pool in runs:
+        assert torch.equal(r_r, want_r)
+        assert err(r_k_pool, kp) < 1e-2 and err(r_v_pool, vp) < 1e-2
+        assert err(k_pool, r_k_pool) < 1e-2 and err(v_pool, r_v_pool) < 1e-2
