@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "cf_abi_version",
     "cf_last_error_string",
     "cf_llama_workspace_bytes",
+    "cf_rmsnorm_launch",
     "cf_llama_algorithmic_bytes",
     "cf_llama_decoder_layer_launch",
     "cf_llama_ffn_launch",
@@ -115,6 +116,8 @@ def load() -> C.CDLL:
     lib.cf_llama_decoder_layer_launch.argtypes = [C.POINTER(CfLlamaArgs), C.c_void_p]
     lib.cf_llama_ffn_launch.restype = C.c_int
     lib.cf_llama_ffn_launch.argtypes = [C.POINTER(CfFfnArgs), C.c_void_p]
+    lib.cf_rmsnorm_launch.restype = C.c_int
+    lib.cf_rmsnorm_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_uint32, C.c_void_p]
     lib.cf_test_cluster_reduce.restype = C.c_int
     lib.cf_test_cluster_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_int32, C.c_void_p]

@@ -15,6 +15,7 @@
 #include "llama_decoder_gqa_kernel.cuh"
 #include "llama_decoder_gqa2_kernel.cuh"
 #include "llama_ffn_kernel.cuh"
+#include "rmsnorm_kernel.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -425,6 +426,36 @@ extern "C" int cf_llama_ffn_launch(const CfFfnArgs* a, void* stream_) {
     cfg.numAttrs = (a->flags & CF_FLAG_PDL) ? 1 : 0;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, cfb::llama_ffn_layer_kernel, fp);
     if (e != cudaSuccess) return fail((int)e, "ffn kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int cf_rmsnorm_launch(const void* x, const void* weight, void* out, int32_t batch, int32_t hidden, float eps,
+                                 uint32_t flags, void* stream_) {
+    if (!x || !weight || !out) return fail(CF_ERR_NULL_ARG, "rmsnorm: x / weight / out must be non-NULL");
+    if (batch < 1 || batch > (1 << 20)) return fail(CF_ERR_BAD_SHAPE, "rmsnorm: bad batch %d", batch);
+    const int slice_max = cfb::NORM_THREADS * 8 * cfb::NORM_ITERS;
+    if (hidden <= 0 || hidden % (8 * cfb::NORM_CLUSTER) != 0 || hidden / cfb::NORM_CLUSTER > slice_max)
+        return fail(CF_ERR_BAD_SHAPE, "rmsnorm: hidden must be a multiple of %d and <= %d (got %d)", 8 * cfb::NORM_CLUSTER,
+                    slice_max * cfb::NORM_CLUSTER, hidden);
+    if (!aligned16(x) || !aligned16(weight) || !aligned16(out)) return fail(CF_ERR_BAD_ALIGNMENT, "rmsnorm: tensors must be 16-byte aligned");
+    if (!device_is_sm100()) return fail(CF_ERR_NO_DEVICE, "current CUDA device is not compute capability 10.x");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(batch * cfb::NORM_CLUSTER, 1, 1);
+    cfg.blockDim = dim3(cfb::NORM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = static_cast<cudaStream_t>(stream_);
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cfb::NORM_CLUSTER;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (flags & CF_FLAG_PDL) ? 2 : 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, cfb::rmsnorm_cluster_kernel, static_cast<const __half*>(x),
+                                             static_cast<const __half*>(weight), static_cast<__half*>(out), (int)hidden, eps);
+    if (e != cudaSuccess) return fail((int)e, "rmsnorm kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 

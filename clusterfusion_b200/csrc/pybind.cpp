@@ -264,6 +264,21 @@ std::tuple<Tensor, Tensor> llama_ffn_layer(Tensor input, Tensor residual, Tensor
     return std::make_tuple(out, res_out);
 }
 
+// rmsnorm(input [batch, hidden], weight [hidden]) -> fp16 [batch, hidden]; eps = 1e-6 as in the reference kernel
+// (/root/reference/include/H100/norm/kernel.cuh:28; signature pybind.cpp:61-64)
+Tensor rmsnorm(Tensor input, Tensor weight) {
+    check_cuda_contig(input, "input", torch::kHalf);
+    check_cuda_contig(weight, "weight", torch::kHalf);
+    TORCH_CHECK(input.dim() == 2 && weight.numel() == input.size(1), "rmsnorm: input [batch, hidden], weight [hidden]");
+    const c10::cuda::CUDAGuard guard(input.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
+    Tensor out = torch::empty_like(input);
+    const int rc = cf_rmsnorm_launch(input.data_ptr(), weight.data_ptr(), out.data_ptr(), (int)input.size(0), (int)input.size(1),
+                                     1e-6f, g_pdl ? CF_FLAG_PDL : 0u, stream);
+    TORCH_CHECK(rc == 0, "clusterfusion_b200: rmsnorm launch failed (", rc, "): ", cf_last_error_string());
+    return out;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -276,6 +291,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     // fused FFN half-layer (new op; the reference's FFN is eager PyTorch): (out, residual_out) = f(input, residual, [W1;W3], W2^T, w, eps)
     m.def("llama_ffn_layer", &llama_ffn_layer, "");
     m.def("llama_ffn_layer_out", &llama_ffn_layer_out, "");
+    m.def("rmsnorm", &rmsnorm, "");
     m.def("set_pdl", [](bool on) { g_pdl = on; }, "enable / disable programmatic dependent launch for all ops of this module");
     m.def("get_pdl", []() { return g_pdl; });
     m.def("abi_version", []() { return cf_abi_version(); });

@@ -141,6 +141,13 @@ typedef struct CfFfnArgs {
 
 int cf_llama_ffn_launch(const CfFfnArgs* args, void* stream);
 
+/* ---- standalone cluster RMSNorm -- replaces the reference op `rmsnorm(input, weight)`
+ * (/root/reference/include/H100/norm/norm_kernel_dispatch.cu:4-26, kernel.cuh:8-76, pybind.cpp:61-64, :114):
+ * out[b] = fp16(x[b] * rsqrt(mean(x[b]^2) + eps) * weight), fp32 math.  x, out fp16 [batch, hidden]; weight fp16 [hidden];
+ * hidden a multiple of 16, <= 16384 (the reference binary is fixed at 64 x 8192, eps 1e-6).  flags: CF_FLAG_PDL.      */
+int cf_rmsnorm_launch(const void* x, const void* weight, void* out, int32_t batch, int32_t hidden, float eps,
+                      uint32_t flags, void* stream);
+
 /* Unit-test hook for the device primitive in include/dsm.cuh:
  * launches n_clusters clusters of `cluster_size` CTAs; CTA r of cluster c contributes
  * in[(c*cluster_size + r)*n .. +n) (float); stage 0 = LINEAR (sum), 1 = ATTN (softmax-state merge of

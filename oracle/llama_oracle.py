@@ -290,6 +290,19 @@ def paged_layer(
 
 
 # --------------------------------------------------------------------------------------
+# standalone rmsnorm op
+# --------------------------------------------------------------------------------------
+def rmsnorm_op(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """``clusterfusion.rmsnorm(input, weight)``: restates /root/reference/include/H100/norm/kernel.cuh:28-75 -- sum of
+    squares, ``rsqrt(sum / hidden + eps)`` (eps 1e-6 hard-coded, :28) and ``x * rms_rcp * w`` all in fp32, one rounding to
+    fp16 (:71).  The reference's own check compares against ``flashinfer.norm.rmsnorm`` (tests/test_norm.py:12), same
+    definition.  x fp16 [batch, hidden], w fp16 [hidden] -> fp16 [batch, hidden]."""
+    xf = x.float()
+    r = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return (xf * r * w.float()).half()
+
+
+# --------------------------------------------------------------------------------------
 # FFN half-layer (SURVEY.md section 8 row f1; the reference ships no fused FFN kernel, only the eager module)
 # --------------------------------------------------------------------------------------
 def ffn_layer(

@@ -51,7 +51,7 @@ def test_argument_errors_without_gpu():
 
 def test_pybind_surface_matches_reference_names():
     import clusterfusion
-    for name in ("llama_decoder_layer", "llama_decoder_layer_sglang", "llama_decoder_layer_batch_decode_sglang"):
+    for name in ("llama_decoder_layer", "llama_decoder_layer_sglang", "llama_decoder_layer_batch_decode_sglang", "rmsnorm"):
         assert callable(getattr(clusterfusion, name))
     doc = clusterfusion.llama_decoder_layer.__doc__
     assert doc.count("llama_decoder_layer(") >= 2        # 8-arg form + the README's 15-arg form

@@ -655,6 +655,23 @@ def test_decode_engine_fused_matches_eager_attention():
     assert toks[("fused+ffn", True)][:3] == toks[("eager", False)][:3]
 
 
+# ---------------------------------------------------------------------------------------------------
+# standalone cluster RMSNorm op (row f4)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch,hidden", [(64, 8192), (1, 4096), (7, 1024), (3, 16384), (5, 48)])
+def test_rmsnorm_operator_vs_oracle(batch, hidden):
+    import clusterfusion
+    g = torch.Generator().manual_seed(batch * 131 + hidden)
+    x = torch.randn(batch, hidden, generator=g).half()
+    w = torch.randn(hidden, generator=g).half()
+    want = O.rmsnorm_op(x, w, 1e-6)
+    got = clusterfusion.rmsnorm(x.cuda(), w.cuda())
+    torch.cuda.synchronize()
+    # one fp16 rounding of an fp32 product on both sides: at most 1 ulp apart (rsqrt.approx vs torch.rsqrt)
+    assert torch.allclose(got.float().cpu(), want.float(), rtol=1e-3, atol=1e-3)
+    assert float((got.float().cpu() - want.float()).abs().max()) <= float(want.float().abs().max()) * 2 ** -10
+
+
 def test_errors_are_loud():
     import clusterfusion
     d = cuda(O.make_inputs(S7, 4, seed=1, layout="chat"))

@@ -160,3 +160,17 @@ def test_paged_form_vs_reference_kernel(ref):
         assert torch.equal(r_r, want_r)
         assert err(r_k_pool, kp) < 1e-2 and err(r_v_pool, vp) < 1e-2
         assert err(k_pool, r_k_pool) < 1e-2 and err(v_pool, r_v_pool) < 1e-2
+
+
+def test_rmsnorm_vs_reference_kernel(ref):
+    """The reference's standalone op is fixed at 64 x 8192 (include/H100/norm/config.h:1-2)."""
+    import clusterfusion
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(64, 8192, generator=g).half()
+    w = torch.randn(8192, generator=g).half()
+    want = O.rmsnorm_op(x, w, 1e-6)
+    r = ref.rmsnorm(x.cuda(), w.cuda())
+    o = clusterfusion.rmsnorm(x.cuda(), w.cuda())
+    torch.cuda.synchronize()
+    print(f"rmsnorm: |ours-oracle|={err(o, want):.2e} |ref-oracle|={err(r, want):.2e} |ours-ref|={err(o, r):.2e}")
+    assert err(o, want) < 4e-3 and err(r, want) < 4e-3 and err(o, r) < 4e-3        # values up to ~16: 1 fp16 ulp = 7.8e-3 / 2

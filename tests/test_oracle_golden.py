@@ -189,3 +189,22 @@ def test_ffn_oracle_matches_reference_feedforward(name):
     out2, _ = O.ffn_layer(d["x"], d["residual"], w13, w2t, d["rms"], float(g["eps"]), mode="eager" if mode == "fp32" else "fp32")
     # across flavours the fp16 rounding of the 11008 activations shows: |out| ~ 2, a few 1e-3 apart
     assert torch.allclose(out.float(), out2.float(), rtol=4e-3, atol=4e-3)
+
+
+def test_rmsnorm_op_oracle_definition():
+    """Standalone op (row f4): fp32 math, one rounding; rows are independent; weight == 1 and unit-RMS rows are fixed points."""
+    import torch
+    from oracle import llama_oracle as O
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(5, 512, generator=g).half()
+    w = torch.randn(512, generator=g).half()
+    y = O.rmsnorm_op(x, w)
+    assert y.dtype == torch.float16 and y.shape == x.shape
+    for b in range(5):
+        assert torch.equal(y[b:b + 1], O.rmsnorm_op(x[b:b + 1], w))
+    xf = x.double()
+    want = (xf / torch.sqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * w.double()).half()
+    assert float((y.float() - want.float()).abs().max()) <= float(want.float().abs().max()) * 2 ** -10
+    ones = torch.ones(512).half()
+    unit = torch.ones(1, 512).half()
+    assert torch.equal(O.rmsnorm_op(unit, ones), unit)
