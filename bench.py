@@ -383,11 +383,12 @@ def run_ours(args, rank, world, local_rank):
             del Ls, g2
             torch.cuda.empty_cache()
     # ------------------------------------------------------------------ BASELINE config 4: Llama-3-8B GQA (32 Q / 8 KV), kv 8K
-    gqa = ffn_res = None
+    gqa = ffn_res = batched = None
     if not args.no_sweep:
         gqa = run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl, kvs=(1024, 8192))
         gqa += run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl, cluster_kernel=True)
         ffn_res = run_ffn(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
+        batched = run_batched_paged(torch, cabi, dev, timed_replays, peak)
     # ------------------------------------------------------------------ whole-model decode
     full = None
     if not args.no_sweep and not args.no_full_model:
@@ -462,6 +463,8 @@ def run_ours(args, rank, world, local_rank):
         line["full_model_decode"] = full
     if ffn_res is not None:
         line["fused_ffn_half_layer"] = ffn_res
+    if batched is not None:
+        line["batched_paged_decode"] = batched
     if gqa is not None:
         line["llama3_8b_gqa"] = gqa
     if shard70 is not None:
@@ -530,6 +533,70 @@ def run_ref_gpu_kernel(torch, dev, kvs=(1024, 16384), nsets=8):
                 "results": out}
     except Exception as e:       # a baseline leg must never take the bench down
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+def run_batched_paged(torch, cabi, dev, timed_replays, peak, kv=1024, nl=8, batches=(1, 4, 8)):
+    """Row f3: 15-argument paged form at batch > 1, Llama-2-7B shapes, kv rows per request = `kv`.  The batched kernel
+    streams every weight tile once per chunk of 4 requests; CF_FLAG_PER_REQUEST launches one cluster per (request, head)
+    like the reference (grid 32*4*bs, llama_kernel_batch_sglang_dispatch.cu:89)."""
+    g = torch.Generator(device=dev).manual_seed(31)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * sc).half()
+    out = []
+    L = [dict(w_qkv=r(3 * HIDDEN, HIDDEN, sc=0.02), w_o=r(HIDDEN, HIDDEN, sc=0.02), rms=(1 + 0.1 * r(HIDDEN).float()).half())
+         for _ in range(nl)]
+    for bs in batches:
+        nslots = bs * (kv + 1)
+        pools = [(r(nslots, HIDDEN), r(nslots, HIDDEN)) for _ in range(nl)]
+        kptrs = torch.tensor([pk.data_ptr() for pk, _ in pools], dtype=torch.uint64).to(dev)
+        vptrs = torch.tensor([pv.data_ptr() for _, pv in pools], dtype=torch.uint64).to(dev)
+        indptr = torch.arange(0, bs + 1, dtype=torch.int32, device=dev) * (kv + 1)
+        indices = torch.randperm(nslots, generator=torch.Generator().manual_seed(bs)).int().to(dev)
+        positions = torch.full((bs,), kv, dtype=torch.int64, device=dev)
+        inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2).float() / D))
+        ang = torch.outer(torch.arange(kv + 1).float(), inv)
+        cos_sin = torch.cat([ang.cos(), ang.sin()], 1).contiguous().to(dev)
+        ws = torch.zeros(cabi.workspace_bytes(HIDDEN, bs), dtype=torch.uint8, device=dev)
+        x = r(bs, HIDDEN); res = r(bs, HIDDEN)
+        bufs = [(torch.empty(bs, HIDDEN, dtype=torch.float16, device=dev), torch.empty(bs, HIDDEN, dtype=torch.float16, device=dev))
+                for _ in range(nl)]
+        row = {"batch": bs, "kv_len": kv}
+        for name, fl in (("batched", 0), ("per_request", cabi.CF_FLAG_PER_REQUEST)):
+            if bs == 1 and name == "per_request":
+                continue
+
+            def launch(h, rr, li, st):
+                a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=fl | cabi.CF_FLAG_PDL, hidden=HIDDEN, n_q_heads=HEADS,
+                                     n_kv_heads=HEADS, head_dim=D, batch=bs, layer_id=li, eps=1e-5, x=h.data_ptr(), residual_in=rr.data_ptr(),
+                                     residual_out=bufs[li][1].data_ptr(), w_qkv=L[li]["w_qkv"].data_ptr(), w_o=L[li]["w_o"].data_ptr(),
+                                     rms_w=L[li]["rms"].data_ptr(), out=bufs[li][0].data_ptr(), indptr=indptr.data_ptr(),
+                                     indices=indices.data_ptr(), k_pool_ptrs=kptrs.data_ptr(), v_pool_ptrs=vptrs.data_ptr(),
+                                     positions=positions.data_ptr(), cos=cos_sin.data_ptr(), workspace=ws.data_ptr())
+                cabi.launch(a, st)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                launch(x, res, 0, side.cuda_stream)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                st = torch.cuda.current_stream().cuda_stream
+                h, rr = x, res
+                for li in range(nl):
+                    launch(h, rr, li, st)
+                    h, rr = bufs[li]
+            ms = timed_replays(gr, 30, 5)
+            us = ms * 1e3 / (30 * nl)
+            B = 2 * 4 * HIDDEN * HIDDEN + bs * 4 * kv * HIDDEN          # weights once + every request's K and V
+            row[name] = {"us_per_layer": round(us, 2), "tokens_per_s_32_layers": round(bs * 1e6 / (us * LAYERS), 1),
+                         "achieved_gbs_weights_once": round(B / (us * 1e-6) / 1e9, 1)}
+            del gr
+        if "per_request" in row:
+            row["speedup_vs_per_request"] = round(row["per_request"]["us_per_layer"] / row["batched"]["us_per_layer"], 2)
+        out.append(row)
+        del pools, ws
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_ffn(torch, cabi, dev, timed_replays, peak, pdl=True, hidden=4096, ffn=11008, nl=8):

@@ -14,6 +14,7 @@
 #include "llama_decoder_kernel.cuh"
 #include "llama_decoder_gqa_kernel.cuh"
 #include "llama_decoder_gqa2_kernel.cuh"
+#include "llama_decoder_batch_kernel.cuh"
 #include "llama_ffn_kernel.cuh"
 #include "rmsnorm_kernel.cuh"
 
@@ -326,6 +327,7 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     kp.kv_len = (int)a->kv_len;
     kp.layer_id = a->layer_id;
     kp.flags = a->flags;
+    kp.batch = a->batch;
 
     const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
     if (gqa && !(a->flags & CF_FLAG_GQA_CLUSTER)) {
@@ -358,6 +360,11 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         return wide ? launch_gqa<cfb::SGLANG, 16>(kp, n_clusters, 1, pdl, stream)
                     : launch_gqa<cfb::SGLANG, 8>(kp, n_clusters, 1, pdl, stream);
     }
+    // batched paged decode: one cluster per head serves chunks of 4 requests, weights streamed once per chunk
+    if (paged && a->batch >= 2 && a->hidden / CL <= cfb::BK_KS_MAX && a->residual_out != a->residual_in &&
+        !(a->flags & CF_FLAG_PER_REQUEST))
+        return launch_kernel<CL>(cfb::llama_decoder_layer_batch_kernel<4>, cfb::SmemB<4>::TOTAL, 11, kp, a->n_q_heads,
+                                 (a->batch + 3) / 4, pdl, stream);
     switch (a->variant) {
         case CF_VARIANT_CHAT: return launch<cfb::CHAT, CL>(kp, a->n_q_heads, 1, pdl, stream);
         case CF_VARIANT_SGLANG: return launch<cfb::SGLANG, CL>(kp, a->n_q_heads, 1, pdl, stream);

@@ -1,0 +1,620 @@
+/*
+ * Batched paged decode with the weights streamed ONCE per chunk of BC requests.
+ *
+ * The reference's batch kernel launches one cluster per (request, head) -- grid 32*4*bs,
+ * /root/reference/include/H100/llama/llama_kernel_batch_sglang_dispatch.cu:89 -- so every request re-streams all of
+ * Wqkv and Wo (kernel_batch_sglang.cuh:43-664); so did this repo's first paged path (grid (Hq*4, bs) of the MHA
+ * kernel).  On B200 a CTA ingests at most ~64 GB/s, so bs requests cost bs layers.  Here one 4-CTA cluster per head
+ * serves a chunk of BC = 4 requests: every Wqkv / Wo tile that lands in shared memory is multiplied against the BC
+ * activation vectors held in registers (BC x the FMAs per byte -- still under the CUDA-core issue limit at BC = 4), the
+ * chunk's K/V pages follow in the same tile stream, and the two cluster exchanges carry all BC requests at once:
+ *
+ *   exchange 1  BC x (q|k|v) = 6 KB of fp32 partial sums per CTA: reduce-scatter (cluster_scatter, slice r folded in
+ *               rank order by CTA r) + all-gather (cluster_reduce<.., QUK_DEEPSEEK>) -- an all-to-all of 6 KB vectors
+ *               would need 24 KB of receive slots;
+ *   exchange 2  BC softmax states [m, l, o[128]] per CTA, all-gathered and merged in rank order.
+ *
+ * QKV tile order: tile g -> row block (g % 12) + 12 * (g / (12*wins)), window (g / 12) % wins, so a warp owns whole row
+ * blocks and sums their windows in registers (no per-window slots in shared memory; deterministic).
+ * Same decomposition otherwise as llama_decoder_kernel.cuh (K-split QKV, sequence-split KV, N-split O, 24 x 8 KB
+ * self-issuing ring, fp32 red + last-arriver finalize per request).  PAGED variant, MHA, hidden <= 4096, page size 1.
+ */
+#pragma once
+
+#include "llama_decoder_kernel.cuh"
+
+namespace cfb {
+
+constexpr int BK_KS_MAX = 1024;             // hidden / CLUSTER
+
+template <int BC>
+struct SmemB {
+    static constexpr int CL = 4;
+    static constexpr int QKV_OUT = 3 * HEAD_DIM;                          // 384
+    static constexpr int SLICE1 = BC * QKV_OUT / CL;                      // floats per CTA slice in exchange 1 (BC * 96)
+    static constexpr int PAY = HEAD_DIM + 4;                              // [m, l, -, -, o[128]]
+    static constexpr int RING = 0;
+    static constexpr int UNION = RING + NSTAGES * STAGE_BYTES;
+    //   phase QKV : xs fp16 [BC][BK_KS_MAX]            phase ATTN: attn_part fp32 [24][132]
+    static constexpr int XS = UNION;
+    static constexpr int ATTN_PART = UNION;
+    static constexpr int UNION_BYTES = (BC * BK_KS_MAX * 2 > 24 * PAY * 4) ? BC * BK_KS_MAX * 2 : 24 * PAY * 4;
+    // X1: exchange-1 buffers; all dead after RoPE
+    static constexpr int X1 = UNION + UNION_BYTES;
+    static constexpr int QKV_SRC = X1;                                    // fp32 [BC][384]   this CTA's partial sums
+    static constexpr int RED1 = QKV_SRC + BC * QKV_OUT * 4;               // fp32 [SLICE1]    my folded slice
+    static constexpr int AG_RECV = RED1 + SLICE1 * 4;                     // fp32 [CL][SLICE1] = full [BC][384]
+    static constexpr int X1_BYTES = BC * QKV_OUT * 4 + SLICE1 * 4 + CL * SLICE1 * 4;
+    // exchange-2 buffers alias X1 (a peer can only push them after it finished exchange 1, which needed this CTA's
+    // all-gather contribution, which this CTA sends after it is done with QKV_SRC / RED1; AG_RECV is read before then)
+    static constexpr int ATTN_SRC = X1;                                   // fp32 [BC][132]
+    static constexpr int ATTN_RECV = ATTN_SRC + BC * PAY * 4;             // fp32 [CL][BC][132]
+    static_assert((1 + CL) * BC * PAY * 4 <= X1_BYTES, "exchange-2 buffers must fit into the exchange-1 region");
+    static constexpr int RS_RECV = X1 + X1_BYTES;                         // fp32 [CL][SLICE1]  reduce-scatter slots
+    static constexpr int QKV_FIN = RS_RECV;                               // fp32 [BC][384]  (RS_RECV is dead after the fold)
+    static_assert(CL * SLICE1 == BC * QKV_OUT, "QKV_FIN aliases RS_RECV exactly");
+    // phase O: out_part fp32 [BC][BK_KS_MAX] aliases X1 + RS_RECV (everything there is dead once attn_out is written)
+    static constexpr int OUT_PART = X1;
+    static_assert(BC * BK_KS_MAX * 4 <= X1_BYTES + CL * SLICE1 * 4, "out_part must fit");
+    static constexpr int ATTN_OUT = RS_RECV + CL * SLICE1 * 4;            // fp32 [BC][128]
+    static constexpr int RED = ATTN_OUT + BC * HEAD_DIM * 4;              // fp32 [12 warps][BC] + [BC] new-token scores
+    static constexpr int BARS = RED + (CONSUMER_WARPS + 1) * BC * 4;      // u64 full[NSTAGES], xbar[3]
+    static constexpr int FLAGS = BARS + (NSTAGES + 3) * 8;                // u32 [BC]
+    static constexpr int TOTAL = FLAGS + ((BC * 4 + 15) & ~15);
+    static_assert(BARS % 8 == 0, "mbarrier alignment");
+    static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
+};
+
+template <int BC>
+__global__ void __launch_bounds__(BLOCK_THREADS, 1)
+llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
+{
+    using S = SmemB<BC>;
+    constexpr int CLUSTER = S::CL;
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t smem_base = dsm::smem_u32(smem);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t lane = tid & 31;
+    const uint32_t rank = dsm::cluster_ctarank();
+    const uint32_t head = blockIdx.x / CLUSTER;
+    const int b0 = blockIdx.y * BC;                       // first request of this chunk
+    const int nb = min(BC, p.batch - b0);      // live requests in the chunk (>= 1)
+
+    const int hidden = p.hidden;
+    const int KS = hidden / CLUSTER;
+    const int wins = KS / 256;
+    const int kv_cols = p.n_kv_heads * HEAD_DIM;
+
+    const uint32_t full_u32 = smem_base + S::BARS;
+    const uint32_t xbar_u32 = full_u32 + NSTAGES * 8;
+
+    // ---- per-request KV ranges ---------------------------------------------------------------------------
+    int kv_base[BC], row_begin[BC], row_end[BC], new_slot[BC];
+    uint32_t kv_tile0[BC + 1];                             // first KV tile (phase-local index) of request b
+    kv_tile0[0] = 0;
+#pragma unroll
+    for (int b = 0; b < BC; ++b) {
+        int len = 0;
+        kv_base[b] = 0; new_slot[b] = 0;
+        if (b < nb) {
+            kv_base[b] = p.indptr[b0 + b];
+            const int end = p.indptr[b0 + b + 1] - 1;
+            len = end - kv_base[b];
+            new_slot[b] = p.indices[end];
+        }
+        const int chunk = (((len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);
+        row_begin[b] = min((int)rank * chunk, len);
+        row_end[b] = min(row_begin[b] + chunk, len);
+        kv_tile0[b + 1] = kv_tile0[b] + (row_end[b] - row_begin[b] + ROWS512 - 1) / ROWS512;
+    }
+    const uint32_t n_qkv_tiles = (uint32_t)(S::QKV_OUT / ROWS512) * wins;       // 24 row blocks x wins windows
+    const uint32_t n_kv_tiles = kv_tile0[BC];
+    const uint32_t n_o_tiles = (uint32_t)(KS / ROWS256);
+    const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    const uint64_t pol = policy_evict_first();
+    const __half* kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
+    const __half* vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
+
+    auto issue_tile = [&](uint32_t g) {
+        if (g >= total_tiles) return;
+        const uint32_t s = ring_stage(g);
+        const uint32_t fb = full_u32 + 8 * s;
+        const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
+        if (g < n_qkv_tiles) {
+            if (lane == 0) {
+                // warp-owned row blocks: rb = (g % 12) + 12 * (g / (12*wins)), window = (g / 12) % wins
+                const int rb = (int)(g % CONSUMER_WARPS) + CONSUMER_WARPS * (int)(g / (CONSUMER_WARPS * wins));
+                const int win = (int)(g / CONSUMER_WARPS) % wins;
+                const int j = rb / (HEAD_DIM / ROWS512), sub = rb % (HEAD_DIM / ROWS512);
+                const int row0 = (j == 0) ? head * HEAD_DIM
+                               : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
+                                          : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wqkv, rank * KS + win * 256, row0 + sub * ROWS512, fb, pol);
+            }
+        } else if (g < n_qkv_tiles + n_kv_tiles) {
+            const uint32_t t = g - n_qkv_tiles;
+            int b = 0;
+#pragma unroll
+            for (int q = 1; q < BC; ++q) b += (t >= kv_tile0[q]) ? 1 : 0;
+            int rbeg = row_begin[0], rend = row_end[0], kb = kv_base[0];
+            uint32_t t0 = kv_tile0[0];
+#pragma unroll
+            for (int q = 1; q < BC; ++q)
+                if (b == q) { rbeg = row_begin[q]; rend = row_end[q]; kb = kv_base[q]; t0 = kv_tile0[q]; }
+            const int i = (int)(t - t0);
+            // paged KV, page size 1: one 256-byte bulk copy per row per tensor; lanes 0-15 fetch K rows, 16-31 V rows
+            const int r = rbeg + i * ROWS512 + (lane & 15);
+            const bool valid = r < rend;
+            const long long slot = valid ? (long long)p.indices[kb + r] : 0;
+            const int nvalid = min(ROWS512, rend - (rbeg + i * ROWS512));
+            if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
+            __syncwarp();
+            if (valid) {
+                const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
+                if (lane < 16) bulk_load_1d(d, kpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                else bulk_load_1d(d + STAGE_BYTES / 2, vpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+            }
+        } else {
+            if (lane == 0) {
+                const uint32_t i = g - n_qkv_tiles - n_kv_tiles;     // Wo [out][in]: 32 output rows x this head's 128 input cols
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wo, head * HEAD_DIM, rank * KS + i * ROWS256, fb, pol);
+            }
+        }
+    };
+
+    if (lane == 0) {
+        dsm::mbar_init(full_u32 + 8 * warp, 1);
+        dsm::mbar_init(full_u32 + 8 * (warp + CONSUMER_WARPS), 1);
+        if (tid == 0) {
+            prefetch_tmap(&p.tm_wqkv);
+            prefetch_tmap(&p.tm_wo);
+            cluster_reduce_arm<CLUSTER>(xbar_u32, S::SLICE1 * 4);
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::SLICE1 * 4);
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 16, BC * S::PAY * 4);
+        }
+        dsm::mbar_fence_init();
+    }
+    __syncwarp();
+    issue_tile(warp);
+    issue_tile(warp + CONSUMER_WARPS);
+    dsm::cluster_arrive();
+
+    __half* xs = reinterpret_cast<__half*>(smem + S::XS);
+    float* attn_part = reinterpret_cast<float*>(smem + S::ATTN_PART);
+    float* qkv_src = reinterpret_cast<float*>(smem + S::QKV_SRC);
+    float* rs_recv = reinterpret_cast<float*>(smem + S::RS_RECV);
+    float* red1 = reinterpret_cast<float*>(smem + S::RED1);
+    float* ag_recv = reinterpret_cast<float*>(smem + S::AG_RECV);
+    float* qkv_fin = reinterpret_cast<float*>(smem + S::QKV_FIN);
+    float* attn_src = reinterpret_cast<float*>(smem + S::ATTN_SRC);
+    float* attn_recv = reinterpret_cast<float*>(smem + S::ATTN_RECV);
+    float* attn_out = reinterpret_cast<float*>(smem + S::ATTN_OUT);
+    float* out_part = reinterpret_cast<float*>(smem + S::OUT_PART);
+    float* red = reinterpret_cast<float*>(smem + S::RED);
+    uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // ---- phase 0: fused residual add + RMSNorm for the BC requests of the chunk ---------------------------
+    {
+        float ss[BC];
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
+            ss[b] = 0.f;
+            if (b < nb) {
+                const __half* xg = p.x + (size_t)(b0 + b) * hidden;
+                const __half* rg = p.residual_in + (size_t)(b0 + b) * hidden;
+                for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+                    float f[8], r8[8];
+                    unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+                    unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { const float h = round_h(f[k] + r8[k]); ss[b] = fmaf(h, h, ss[b]); }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
+            if (lane == 0) red[warp * BC + b] = ss[b];
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w * BC + b];
+            const float rstd = rsqrtf(tot / (float)hidden + p.eps);
+            for (int e = tid * 8; e < KS; e += CONSUMER_THREADS * 8) {
+                __align__(16) __half xn[8];
+                if (b < nb) {
+                    const int ge = rank * KS + e;
+                    const __half* xg = p.x + (size_t)(b0 + b) * hidden;
+                    const __half* rg = p.residual_in + (size_t)(b0 + b) * hidden;
+                    float f[8], w8[8], r8[8];
+                    unpack8(*reinterpret_cast<const uint4*>(xg + ge), f);
+                    unpack8(*reinterpret_cast<const uint4*>(p.rms_w + ge), w8);
+                    unpack8(*reinterpret_cast<const uint4*>(rg + ge), r8);
+                    __align__(16) __half hs[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { hs[k] = __float2half_rn(f[k] + r8[k]); f[k] = __half2float(hs[k]); }
+                    if (head == 0)
+                        *reinterpret_cast<uint4*>(p.residual_out + (size_t)(b0 + b) * hidden + ge) = *reinterpret_cast<const uint4*>(hs);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(round_h(f[k] * rstd) * w8[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(0.f);
+                }
+                *reinterpret_cast<uint4*>(xs + b * BK_KS_MAX + e) = *reinterpret_cast<const uint4*>(xn);
+            }
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+
+    uint32_t gbase = 0;
+    // ---- phase 1: QKV GEMV, every weight tile against the BC activation vectors --------------------------------
+    {
+        float acc[BC][2];
+        for (uint32_t i = warp; i < n_qkv_tiles; i += CONSUMER_WARPS) {        // phase starts at ring index 0
+            const uint32_t g = i, s = ring_stage(g);
+            const int k = (int)(i / CONSUMER_WARPS);
+            const int win = k % wins;
+            const int rb = (int)warp + CONSUMER_WARPS * (k / wins);
+            if (win == 0) {
+#pragma unroll
+                for (int b = 0; b < BC; ++b) { acc[b][0] = 0.f; acc[b][1] = 0.f; }
+            }
+            float x8[BC][8];
+#pragma unroll
+            for (int b = 0; b < BC; ++b) unpack8(*reinterpret_cast<const uint4*>(xs + b * BK_KS_MAX + win * 256 + lane * 8), x8[b]);
+            ring_wait_full(full_u32, g);
+            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+#pragma unroll
+            for (int grp = 0; grp < ROWS512 / 8; ++grp) {
+                float v[BC][8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    float w8[8];
+                    unpack8(tile[(grp * 8 + r) * 32 + lane], w8);
+#pragma unroll
+                    for (int b = 0; b < BC; ++b) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) a = fmaf(x8[b][kk], w8[kk], a);
+                        v[b][r] = a;
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < BC; ++b) {
+                    // transpose-reduce 8 values over 32 lanes: 4 + 2 + 1 + 1 + 1 shuffles
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const bool hi = lane & 16;
+                        const float send = hi ? v[b][r] : v[b][r + 4];
+                        const float keep = hi ? v[b][r + 4] : v[b][r];
+                        v[b][r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const bool hi = lane & 8;
+                        const float send = hi ? v[b][r] : v[b][r + 2];
+                        const float keep = hi ? v[b][r + 2] : v[b][r];
+                        v[b][r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    {
+                        const bool hi = lane & 4;
+                        const float send = hi ? v[b][0] : v[b][1];
+                        const float keep = hi ? v[b][1] : v[b][0];
+                        v[b][0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    v[b][0] += __shfl_xor_sync(0xffffffffu, v[b][0], 2);
+                    v[b][0] += __shfl_xor_sync(0xffffffffu, v[b][0], 1);
+                    acc[b][grp] += v[b][0];            // meaningful on lanes with (lane & 3) == 0: row = lane bits (4,3,2)
+                }
+            }
+            if (win == wins - 1 && (lane & 3) == 0) {
+                const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+#pragma unroll
+                for (int b = 0; b < BC; ++b) {
+                    qkv_src[b * S::QKV_OUT + rb * ROWS512 + r] = acc[b][0];
+                    qkv_src[b * S::QKV_OUT + rb * ROWS512 + 8 + r] = acc[b][1];
+                }
+            }
+            __syncwarp();
+            issue_tile(g + NSTAGES);
+        }
+    }
+    gbase += n_qkv_tiles;
+
+    // ---- exchange 1: reduce-scatter (sum, rank order) + all-gather of BC x (q|k|v) ---------------------------
+    dsm::cluster_wait();
+    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+    cluster_scatter<CLUSTER, CONSUMER_THREADS, CONSUMER_BAR>(S::SLICE1 * 4, tid, rank, smem_base + S::RS_RECV, xbar_u32, ph0,
+                                                             qkv_src, rs_recv);
+    for (int e = tid; e < S::SLICE1; e += CONSUMER_THREADS) {
+        float a = 0.f;
+#pragma unroll
+        for (int r = 0; r < CLUSTER; ++r) a += rs_recv[r * S::SLICE1 + e];
+        red1[e] = round_h(a);                                    // q / k / v leave the projection as fp16 (eager model)
+    }
+    cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
+        S::SLICE1 * 4, tid, S::SLICE1, rank, smem_base + S::RED1, smem_base + S::AG_RECV, xbar_u32 + 8, ph1, red1, ag_recv);
+
+    // ---- RoPE (NeoX) per request, new K/V rows into the pool ---------------------------------------------------
+    {
+        constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;
+        for (int f = tid; f < BC * S::QKV_OUT; f += CONSUMER_THREADS) {
+            const int b = f / S::QKV_OUT, e = f % S::QKV_OUT;
+            const int which = e >> 7, d = e & 127;               // 0: q, 1: k, 2: v
+            const float a = ag_recv[f];
+            float outv = a;
+            if (b < nb) {
+                if (which < 2) {
+                    const float* cosp = p.cos + p.positions[b0 + b] * HEAD_DIM;
+                    const float* sinp = cosp + HEAD_DIM / 2;
+                    const float bb = ag_recv[f ^ 64];
+                    const int i = d & 63;
+                    const float rot = (d & 64) ? fmaf(a, cosp[i], bb * sinp[i]) : fmaf(a, cosp[i], -bb * sinp[i]);
+                    const __half rh = __float2half_rn(rot);
+                    outv = which == 0 ? __half2float(rh) * kScaleLog2 : __half2float(rh);
+                    if (which == 1 && rank == 0) {
+                        __half* kp = reinterpret_cast<__half*>(p.k_pool_ptrs[p.layer_id]);
+                        int ns = new_slot[0];
+#pragma unroll
+                        for (int q = 1; q < BC; ++q) if (b == q) ns = new_slot[q];
+                        kp[(size_t)ns * kv_cols + head * HEAD_DIM + d] = rh;
+                    }
+                } else if (rank == 0) {
+                    __half* vp = reinterpret_cast<__half*>(p.v_pool_ptrs[p.layer_id]);
+                    int ns = new_slot[0];
+#pragma unroll
+                    for (int q = 1; q < BC; ++q) if (b == q) ns = new_slot[q];
+                    vp[(size_t)ns * kv_cols + head * HEAD_DIM + d] = __float2half_rn(a);
+                }
+            }
+            qkv_fin[f] = outv;        // aliases rs_recv: every thread finished folding it before the all-gather barrier
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+    // exchange-2 receive slots alias ag_recv: tell the peers this CTA is done reading it (waited on before exchange 2)
+    dsm::cluster_arrive();
+
+    // ---- phase 2: flash-decode, request after request through the same tile stream -----------------------------
+    {
+        const int sub = lane >> 4, c = lane & 15;
+        float m[BC], l[BC], o8[BC][8];
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
+            m[b] = -INFINITY; l[b] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o8[b][k] = 0.f;
+            float q8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q8[k] = qkv_fin[b * S::QKV_OUT + c * 8 + k];
+            const uint32_t nt = kv_tile0[b + 1] - kv_tile0[b];
+            const uint32_t gb = gbase + kv_tile0[b];
+            for (uint32_t i = first_tile(gb, warp); i < nt; i += CONSUMER_WARPS) {
+                const uint32_t g = gb + i, s = ring_stage(g);
+                ring_wait_full(full_u32, g);
+                const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+                const uint4* vt = kt + STAGE_BYTES / 32;
+                const int rows_left = row_end[b] - (row_begin[b] + (int)i * ROWS512);     // >= 1
+                float sc[ROWS512 / 2];
+#pragma unroll
+                for (int jj = 0; jj < ROWS512 / 2; ++jj) {
+                    const int row = 2 * jj + sub;
+                    float k8[8];
+                    unpack8(kt[row * 16 + c], k8);
+                    float a = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a = fmaf(q8[k], k8[k], a);
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    sc[jj] = (row < rows_left) ? a : -INFINITY;
+                }
+                float mx = sc[0];
+#pragma unroll
+                for (int jj = 1; jj < ROWS512 / 2; ++jj) mx = fmaxf(mx, sc[jj]);
+                const float m_new = fmaxf(m[b], mx);
+                const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                const float corr = dsm::exp2_diff(m[b], m_use);
+                l[b] *= corr;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o8[b][k] *= corr;
+#pragma unroll
+                for (int jj = 0; jj < ROWS512 / 2; ++jj) {
+                    const int row = 2 * jj + sub;
+                    const float pr = dsm::fast_exp2(sc[jj] - m_use);       // -inf -> 0
+                    l[b] += pr;
+                    uint4 raw = vt[row * 16 + c];
+                    if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);    // rows past the end were never copied
+                    float v8[8];
+                    unpack8(raw, v8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o8[b][k] = fmaf(pr, v8[k], o8[b][k]);
+                }
+                m[b] = m_new;
+                __syncwarp();
+                issue_tile(g + NSTAGES);
+            }
+        }
+        gbase += n_kv_tiles;
+        // block merge, one request per round through the 24 x 132 buffer; rank 0 folds in the request's current token
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
+            {
+                const int grp = warp * 2 + sub;
+                float* slot = attn_part + grp * S::PAY;
+                if (c == 0) { slot[0] = m[b]; slot[1] = l[b]; }
+                *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[b][0], o8[b][1], o8[b][2], o8[b][3]);
+                *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[b][4], o8[b][5], o8[b][6], o8[b][7]);
+            }
+            if (warp == 0) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    a = fmaf(qkv_fin[b * S::QKV_OUT + lane * 4 + k], qkv_fin[b * S::QKV_OUT + HEAD_DIM + lane * 4 + k], a);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) red[CONSUMER_WARPS * BC + b] = a;
+            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            if (tid < HEAD_DIM) {
+                const bool with_new = (rank == 0);
+                const float s_new = red[CONSUMER_WARPS * BC + b];
+                float M = with_new ? s_new : -INFINITY;
+#pragma unroll
+                for (int gI = 0; gI < 2 * CONSUMER_WARPS; ++gI) M = fmaxf(M, attn_part[gI * S::PAY]);
+                float L = 0.f, Ov = 0.f;
+#pragma unroll
+                for (int gI = 0; gI < 2 * CONSUMER_WARPS; ++gI) {
+                    const float w = dsm::exp2_diff(attn_part[gI * S::PAY], M);
+                    L = fmaf(attn_part[gI * S::PAY + 1], w, L);
+                    Ov = fmaf(attn_part[gI * S::PAY + 4 + tid], w, Ov);
+                }
+                if (with_new) {
+                    const float w = dsm::exp2_diff(s_new, M);
+                    L += w;
+                    Ov = fmaf(qkv_fin[b * S::QKV_OUT + 2 * HEAD_DIM + tid], w, Ov);
+                }
+                float* st = attn_src + b * S::PAY;       // aliases qkv_src / red1: dead since the all-gather
+                st[4 + tid] = Ov;
+                if (tid == 0) { st[0] = M; st[1] = L; st[2] = 0.f; st[3] = 0.f; }
+            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        }
+        // ---- exchange 2: all-gather of the BC softmax states, merged in rank order -------------------------------
+        dsm::cluster_wait();          // every peer is past RoPE: its exchange-1 buffers may now be overwritten
+        cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
+            BC * S::PAY * 4, tid, BC * S::PAY, rank, smem_base + S::ATTN_SRC, smem_base + S::ATTN_RECV, xbar_u32 + 16, ph2,
+            attn_src, attn_recv);
+        for (int f = tid; f < BC * HEAD_DIM; f += CONSUMER_THREADS) {
+            const int b = f >> 7, d = f & 127;
+            float M = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < CLUSTER; ++r) M = fmaxf(M, attn_recv[(r * BC + b) * S::PAY]);
+            float L = 0.f, Ov = 0.f;
+#pragma unroll
+            for (int r = 0; r < CLUSTER; ++r) {
+                const float* st = attn_recv + (r * BC + b) * S::PAY;
+                const float w = dsm::exp2_diff(st[0], M);
+                L = fmaf(st[1], w, L);
+                Ov = fmaf(st[4 + d], w, Ov);
+            }
+            attn_out[f] = (b < nb) ? round_h(Ov / L) : 0.f;          // attention output leaves as fp16 (eager model)
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+
+    // ---- phase 3: O GEMV for output columns [rank*KS, +KS), every Wo tile against the BC attention outputs ----------
+    {
+        // tile = 32 output rows x 128 input cols; lane (sub, c): rows sub+2s, input cols c*8..+8
+        const int sub = lane >> 4, c = lane & 15;
+        float a8[BC][8];
+#pragma unroll
+        for (int b = 0; b < BC; ++b)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a8[b][k] = attn_out[b * HEAD_DIM + c * 8 + k];
+        for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            ring_wait_full(full_u32, g);
+            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+#pragma unroll
+            for (int grp = 0; grp < ROWS256 / 16; ++grp) {
+                float v[BC][8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int row = 2 * (grp * 8 + r) + sub;
+                    float w8[8];
+                    unpack8(tile[row * 16 + c], w8);
+#pragma unroll
+                    for (int b = 0; b < BC; ++b) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) a = fmaf(a8[b][k], w8[k], a);
+                        v[b][r] = a;
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < BC; ++b) {
+                    // transpose-reduce 8 values over the 16 lanes of a half-warp: 4 + 2 + 1 + 1 shuffles
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const bool hi = lane & 8;
+                        const float send = hi ? v[b][r] : v[b][r + 4];
+                        const float keep = hi ? v[b][r + 4] : v[b][r];
+                        v[b][r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const bool hi = lane & 4;
+                        const float send = hi ? v[b][r] : v[b][r + 2];
+                        const float keep = hi ? v[b][r + 2] : v[b][r];
+                        v[b][r] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    {
+                        const bool hi = lane & 2;
+                        const float send = hi ? v[b][0] : v[b][1];
+                        const float keep = hi ? v[b][1] : v[b][0];
+                        v[b][0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    v[b][0] += __shfl_xor_sync(0xffffffffu, v[b][0], 1);
+                    if ((lane & 1) == 0) {
+                        const int r = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        out_part[b * BK_KS_MAX + i * ROWS256 + 2 * (grp * 8 + r) + sub] = v[b][0];
+                    }
+                }
+            }
+            __syncwarp();
+            issue_tile(g + NSTAGES);
+        }
+    }
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+
+    // ---- cross-head reduction per request: fp32 red into scratch, last arriver of the slice finalises --------------
+#pragma unroll
+    for (int b = 0; b < BC; ++b) {
+        if (b < nb) {
+            float* scratch = p.scratch + (size_t)(b0 + b) * hidden + rank * KS;
+            for (int e = tid * 4; e < KS; e += CONSUMER_THREADS * 4)
+                red_add_v4(scratch + e, *reinterpret_cast<const float4*>(out_part + b * BK_KS_MAX + e));
+        }
+    }
+    __threadfence();
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    if (tid < (uint32_t)nb) {
+        unsigned* counters = p.counters + (size_t)(b0 + tid) * (CLUSTER + 1);
+        const unsigned prev = atomicAdd(&counters[rank], 1u);
+        sflags[tid] = (prev == (unsigned)p.n_heads - 1u);
+    }
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    for (int b = 0; b < nb; ++b) {
+        if (!sflags[b]) continue;
+        __threadfence();
+        float* scratch = p.scratch + (size_t)(b0 + b) * hidden + rank * KS;
+        const bool fp32_out = p.flags & 1u;
+        for (int e = tid * 4; e < KS; e += CONSUMER_THREADS * 4) {
+            const float4 v = ld_cg_v4(scratch + e);
+            *reinterpret_cast<float4*>(scratch + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const size_t off = (size_t)(b0 + b) * hidden + rank * KS + e;
+            if (fp32_out) {
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
+            } else {
+                __align__(8) __half h4[4] = {__float2half_rn(v.x), __float2half_rn(v.y),
+                                             __float2half_rn(v.z), __float2half_rn(v.w)};
+                *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
+            }
+        }
+        if (tid == 0) p.counters[(size_t)(b0 + b) * (CLUSTER + 1) + rank] = 0u;
+    }
+}
+
+}  // namespace cfb

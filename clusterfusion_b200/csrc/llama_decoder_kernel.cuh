@@ -85,6 +85,7 @@ struct alignas(64) KParams {
     int kv_len;
     int layer_id;
     unsigned flags;
+    int batch;               // requests in the launch (batched paged kernel)
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -67,6 +67,10 @@ enum {
                                last-arriver finalize.  Costs ~2.5 us per layer in a PDL chain: every CTA then lives until the
                                slowest cluster has published, so the next layer's CTAs start later (measured). */
 
+#define CF_FLAG_PER_REQUEST 0x10u /* PAGED, batch >= 2, MHA: launch one cluster per (request, head) as the reference does
+                                     (weights re-streamed per request) instead of the batched kernel that streams every
+                                     weight tile once per chunk of 4 requests (measurement / A-B)                          */
+
 typedef struct CfLlamaArgs {
     int32_t variant;    /* CF_VARIANT_*                                                             */
     uint32_t flags;     /* CF_FLAG_*                                                                */

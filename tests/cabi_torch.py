@@ -56,10 +56,10 @@ def sglang(x, residual, w_qkv, w_o, k_cache, v_cache, rms_w, eps, cos, sin, n_he
 
 
 def paged(out, residual_out, x, residual, w_qkv, w_o, indptr, indices, k_ptrs, v_ptrs, layer_id, rms_w, eps,
-          positions, cos_sin, n_heads, n_kv_heads=None):
+          positions, cos_sin, n_heads, n_kv_heads=None, flags=0):
     n_kv_heads = n_kv_heads or n_heads
     bs, hidden = x.shape
-    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, hidden=hidden, n_q_heads=n_heads, n_kv_heads=n_kv_heads,
+    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=flags, hidden=hidden, n_q_heads=n_heads, n_kv_heads=n_kv_heads,
                          head_dim=128, batch=bs, layer_id=layer_id, eps=eps, x=_p(x), residual_in=_p(residual),
                          residual_out=_p(residual_out), w_qkv=_p(w_qkv), w_o=_p(w_o), rms_w=_p(rms_w), out=_p(out),
                          indptr=_p(indptr), indices=_p(indices), k_pool_ptrs=_p(k_ptrs), v_pool_ptrs=_p(v_ptrs),

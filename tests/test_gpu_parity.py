@@ -254,6 +254,44 @@ def test_paged_operator_vs_oracle(lens):
     assert close(out2, want_o)
 
 
+@pytest.mark.parametrize("lens", [[40, 0, 513, 7, 128, 1], [300] * 8, [17, 2]])
+def test_batched_paged_kernel_matches_per_request_kernel_and_oracle(lens):
+    """Row f3: the batched kernel (weights streamed once per chunk of 4 requests; chunks of 4 + a ragged tail) against
+    the oracle and against the per-request launch (CF_FLAG_PER_REQUEST, the reference's grid shape)."""
+    import cabi_torch as ct
+    from clusterfusion_b200 import cabi
+    bs = len(lens)
+    nslots = sum(lens) + bs + 5
+    d = O.make_inputs(S7, nslots, seed=300 + bs, layout="sglang", bs=bs)
+    slots = torch.randperm(nslots, generator=torch.Generator().manual_seed(4))
+    indptr, indices, off = [0], [], 0
+    for L in lens:
+        indices += slots[off:off + L + 1].tolist(); off += L + 1; indptr.append(len(indices))
+    indptr = torch.tensor(indptr, dtype=torch.int32); indices = torch.tensor(indices, dtype=torch.int32)
+    positions = torch.tensor(lens, dtype=torch.int64)
+    cos_sin = torch.stack([torch.cat([O.rope_angles(p).cos(), O.rope_angles(p).sin()]) for p in range(max(lens) + 1)])
+    kp, vp = d["k_cache"].clone(), d["v_cache"].clone()
+    want_o, want_r = O.paged_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], indptr, indices, kp, vp,
+                                   d["rms_w"], 1e-5, positions, cos_sin, n_heads=32, mode="eager")
+    c = cuda(d)
+    res = {}
+    for name, flags in (("batched", 0), ("per_request", cabi.CF_FLAG_PER_REQUEST)):
+        kpool, vpool = c["k_cache"].clone(), c["v_cache"].clone()
+        kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
+        vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
+        out = torch.full((bs, 4096), float("nan"), dtype=torch.float16, device="cuda"); rout = torch.empty_like(out)
+        for _ in range(3):        # repeated launches on one workspace: scratch / counters must come back zeroed
+            kpool.copy_(c["k_cache"]); vpool.copy_(c["v_cache"])
+            ct.paged(out, rout, c["x"], c["residual"], c["weight_qkv"], c["weight_o"], indptr.cuda(), indices.cuda(), kptrs, vptrs,
+                     0, c["rms_w"], 1e-5, positions.cuda(), cos_sin.cuda(), n_heads=32, flags=flags)
+        torch.cuda.synchronize()
+        assert torch.equal(rout.cpu(), want_r), name
+        assert close(out, want_o), name
+        assert close(kpool, kp, atol=4e-3) and close(vpool, vp), name
+        res[name] = out
+    assert close(res["batched"], res["per_request"])
+
+
 # ---------------------------------------------------------------------------------------------------
 # grouped-query attention: Llama-3-8B (32 Q / 8 KV) and the Llama-2-70B head-parallel shards
 # ---------------------------------------------------------------------------------------------------
