@@ -114,12 +114,29 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     const uint32_t n_o_tiles = (uint32_t)(KS / ROWS256);
     const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
 
+    CF_MARK(0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const uint64_t pol = policy_evict_first();
     const __half* kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
     const __half* vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
 
+    // page index of this lane's row of KV tile g (phase-global index), fetched one ring cycle ahead of the tile
+    int pre_slot0 = 0, pre_slot1 = 0;
+    uint32_t pre_g0 = 0xffffffffu, pre_g1 = 0xffffffffu;
+    auto page_of = [&](uint32_t g) -> int {
+        const uint32_t t = g - n_qkv_tiles;
+        int b = 0;
+#pragma unroll
+        for (int q = 1; q < BC; ++q) b += (t >= kv_tile0[q]) ? 1 : 0;
+        int rbeg = row_begin[0], rend = row_end[0], kb = kv_base[0];
+        uint32_t t0 = kv_tile0[0];
+#pragma unroll
+        for (int q = 1; q < BC; ++q)
+            if (b == q) { rbeg = row_begin[q]; rend = row_end[q]; kb = kv_base[q]; t0 = kv_tile0[q]; }
+        const int r = rbeg + (int)(t - t0) * ROWS512 + (int)(lane & 15);
+        return (r < rend) ? p.indices[kb + r] : 0;
+    };
     auto issue_tile = [&](uint32_t g) {
         if (g >= total_tiles) return;
         const uint32_t s = ring_stage(g);
@@ -151,7 +168,8 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
             // paged KV, page size 1: one 256-byte bulk copy per row per tensor; lanes 0-15 fetch K rows, 16-31 V rows
             const int r = rbeg + i * ROWS512 + (lane & 15);
             const bool valid = r < rend;
-            const long long slot = valid ? (long long)p.indices[kb + r] : 0;
+            const bool odd = (g / CONSUMER_WARPS) & 1u;
+            const long long slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
             const int nvalid = min(ROWS512, rend - (rbeg + i * ROWS512));
             if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
             __syncwarp();
@@ -166,6 +184,11 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
                 dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
                 tma_load_2d(dst, &p.tm_wo, head * HEAD_DIM, rank * KS + i * ROWS256, fb, pol);
             }
+        }
+        const uint32_t g2 = g + NSTAGES;              // the tile that will live in this stage next
+        if (g2 >= n_qkv_tiles && g2 < n_qkv_tiles + n_kv_tiles) {
+            const int pg = page_of(g2);
+            if ((g / CONSUMER_WARPS) & 1u) { pre_slot1 = pg; pre_g1 = g2; } else { pre_slot0 = pg; pre_g0 = g2; }
         }
     };
 
@@ -182,6 +205,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
         dsm::mbar_fence_init();
     }
     __syncwarp();
+    CF_MARK(12);
     issue_tile(warp);
     issue_tile(warp + CONSUMER_WARPS);
     dsm::cluster_arrive();
@@ -206,7 +230,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     {
         float ss[BC];
 #pragma unroll
-        for (int b = 0; b < BC; ++b) {
+        for (int b = 0; b < BC; ++b) {                       // loads of all requests first: no barrier or shuffle between them
             ss[b] = 0.f;
             if (b < nb) {
                 const __half* xg = p.x + (size_t)(b0 + b) * hidden;
@@ -219,6 +243,9 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
                     for (int k = 0; k < 8; ++k) { const float h = round_h(f[k] + r8[k]); ss[b] = fmaf(h, h, ss[b]); }
                 }
             }
+        }
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
             if (lane == 0) red[warp * BC + b] = ss[b];
@@ -257,6 +284,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
 
+    CF_MARK(1);
     uint32_t gbase = 0;
     // ---- phase 1: QKV GEMV, every weight tile against the BC activation vectors --------------------------------
     {
@@ -331,6 +359,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
         }
     }
     gbase += n_qkv_tiles;
+    CF_MARK(2);
 
     // ---- exchange 1: reduce-scatter (sum, rank order) + all-gather of BC x (q|k|v) ---------------------------
     dsm::cluster_wait();
@@ -346,6 +375,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
         S::SLICE1 * 4, tid, S::SLICE1, rank, smem_base + S::RED1, smem_base + S::AG_RECV, xbar_u32 + 8, ph1, red1, ag_recv);
 
+    CF_MARK(3);
     // ---- RoPE (NeoX) per request, new K/V rows into the pool ---------------------------------------------------
     {
         constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;
@@ -385,6 +415,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     // exchange-2 receive slots alias ag_recv: tell the peers this CTA is done reading it (waited on before exchange 2)
     dsm::cluster_arrive();
 
+    CF_MARK(4);
     // ---- phase 2: flash-decode, request after request through the same tile stream -----------------------------
     {
         const int sub = lane >> 4, c = lane & 15;
@@ -447,6 +478,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
             }
         }
         gbase += n_kv_tiles;
+        CF_MARK(5);
         // block merge, one request per round through the 24 x 132 buffer; rank 0 folds in the request's current token
 #pragma unroll
         for (int b = 0; b < BC; ++b) {
@@ -514,6 +546,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
 
+    CF_MARK(6);
     // ---- phase 3: O GEMV for output columns [rank*KS, +KS), every Wo tile against the BC attention outputs ----------
     {
         // tile = 32 output rows x 128 input cols; lane (sub, c): rows sub+2s, input cols c*8..+8
@@ -579,6 +612,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     }
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
 
+    CF_MARK(7);
     // ---- cross-head reduction per request: fp32 red into scratch, last arriver of the slice finalises --------------
 #pragma unroll
     for (int b = 0; b < BC; ++b) {
@@ -596,25 +630,33 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
         sflags[tid] = (prev == (unsigned)p.n_heads - 1u);
     }
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-    for (int b = 0; b < nb; ++b) {
-        if (!sflags[b]) continue;
+    CF_MARK(8);
+    {
+        // finalise every request this CTA arrived last for: all scratch loads first (one L2 round trip), then the stores
         __threadfence();
-        float* scratch = p.scratch + (size_t)(b0 + b) * hidden + rank * KS;
         const bool fp32_out = p.flags & 1u;
-        for (int e = tid * 4; e < KS; e += CONSUMER_THREADS * 4) {
-            const float4 v = ld_cg_v4(scratch + e);
-            *reinterpret_cast<float4*>(scratch + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-            const size_t off = (size_t)(b0 + b) * hidden + rank * KS + e;
-            if (fp32_out) {
-                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
-            } else {
-                __align__(8) __half h4[4] = {__float2half_rn(v.x), __float2half_rn(v.y),
-                                             __float2half_rn(v.z), __float2half_rn(v.w)};
-                *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
+        const int e = tid * 4;                                // KS <= 1024: one float4 per thread
+        float4 v[BC];
+#pragma unroll
+        for (int b = 0; b < BC; ++b)
+            if (b < nb && sflags[b] && e < KS) v[b] = ld_cg_v4(p.scratch + (size_t)(b0 + b) * hidden + rank * KS + e);
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
+            if (b < nb && sflags[b] && e < KS) {
+                const size_t off = (size_t)(b0 + b) * hidden + rank * KS + e;
+                *reinterpret_cast<float4*>(p.scratch + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fp32_out) {
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v[b];
+                } else {
+                    __align__(8) __half h4[4] = {__float2half_rn(v[b].x), __float2half_rn(v[b].y),
+                                                 __float2half_rn(v[b].z), __float2half_rn(v[b].w)};
+                    *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
+                }
             }
+            if (b < nb && sflags[b] && tid == 0) p.counters[(size_t)(b0 + b) * (CLUSTER + 1) + rank] = 0u;
         }
-        if (tid == 0) p.counters[(size_t)(b0 + b) * (CLUSTER + 1) + rank] = 0u;
     }
+    CF_MARK(9);
 }
 
 }  // namespace cfb

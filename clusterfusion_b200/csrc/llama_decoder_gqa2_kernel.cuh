@@ -199,6 +199,13 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
         vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
     }
+    // paged KV: page index of this lane's row of KV tile g, fetched one ring cycle ahead (see llama_decoder_kernel.cuh)
+    int pre_slot0 = 0, pre_slot1 = 0;
+    uint32_t pre_g0 = 0xffffffffu, pre_g1 = 0xffffffffu;
+    auto page_of = [&](uint32_t g) -> int {
+        const int r = row_begin + (int)(g - n_qkv_tiles) * ROWS512 + (int)(lane & 15);
+        return (r < row_end) ? p.indices[kv_base + r] : 0;
+    };
     auto issue_tile = [&](uint32_t g) {
         if (g >= total_tiles) return;
         const uint32_t s = ring_stage(g);
@@ -228,7 +235,8 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             } else {
                 const int r = row_begin + i * ROWS512 + (lane & 15);
                 const bool valid = r < row_end;
-                const long long slot = valid ? (long long)p.indices[kv_base + r] : 0;
+                const bool odd = (g / CONSUMER_WARPS) & 1u;
+                const long long slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
                 const int nvalid = min(ROWS512, row_end - (row_begin + (int)i * ROWS512));
                 if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
                 __syncwarp();
@@ -244,6 +252,13 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 const int rb = i / owins, win = i % owins;       // Wo [out][in]: 16 output rows x 256 of this group's input cols
                 dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
                 tma_load_2d(dst, &p.tm_wo, qh0 * HEAD_DIM + win * 256, rank * OROWS + rb * ROWS512, fb, pol);
+            }
+        }
+        if constexpr (kPaged) {
+            const uint32_t g2 = g + NSTAGES;          // the tile that will live in this stage next
+            if (g2 >= n_qkv_tiles && g2 < n_qkv_tiles + n_kv_tiles) {
+                const int pg = page_of(g2);
+                if ((g / CONSUMER_WARPS) & 1u) { pre_slot1 = pg; pre_g1 = g2; } else { pre_slot0 = pg; pre_g0 = g2; }
             }
         }
     };

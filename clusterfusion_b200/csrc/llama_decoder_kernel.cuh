@@ -315,6 +315,16 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
         vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
     }
+    // Paged KV: the page index of this lane's row of KV tile g.  A warp fetches it one ring cycle ahead (when it issues
+    // tile g - 24 into the same stage), so the index load is never on the path between consuming a tile and refilling
+    // its stage (the reference gathers with an index load per row on the critical path, kernel_batch_sglang.cuh:356-371;
+    // measured here: 3 us per layer at kv 1K before the prefetch).
+    int pre_slot0 = 0, pre_slot1 = 0;
+    uint32_t pre_g0 = 0xffffffffu, pre_g1 = 0xffffffffu;
+    auto page_of = [&](uint32_t g) -> int {
+        const int r = row_begin + (int)(g - n_qkv_tiles) * ROWS512 + (int)(lane & 15);
+        return (r < row_end) ? p.indices[kv_base + r] : 0;
+    };
     // Request global tile g into its stage.  Called warp-converged by the owner warp (g % 12 == warp), after it has
     // finished reading the stage (tile g - 24).  Weights and tiled KV: one elected lane; paged KV: one row per lane.
     auto issue_tile = [&](uint32_t g) {
@@ -356,7 +366,8 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                 // paged KV, page size 1: one 256-byte bulk copy per row per tensor; lanes 0-15 fetch K rows, 16-31 V rows
                 const int r = row_begin + i * ROWS512 + (lane & 15);
                 const bool valid = r < row_end;
-                const long long slot = valid ? (long long)p.indices[kv_base + r] : 0;
+                const bool odd = (g / CONSUMER_WARPS) & 1u;
+                const long long slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
                 const int nvalid = min(ROWS512, row_end - (row_begin + (int)i * ROWS512));
                 if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
                 __syncwarp();
@@ -379,6 +390,13 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                 }
                 dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
                 tma_load_2d(dst, &p.tm_wo, c0, c1, fb, pol);
+            }
+        }
+        if constexpr (kPaged) {
+            const uint32_t g2 = g + NSTAGES;          // the tile that will live in this stage next
+            if (g2 >= n_qkv_tiles && g2 < n_qkv_tiles + n_kv_tiles) {
+                const int pg = page_of(g2);
+                if ((g / CONSUMER_WARPS) & 1u) { pre_slot1 = pg; pre_g1 = g2; } else { pre_slot0 = pg; pre_g0 = g2; }
             }
         }
     };

@@ -150,17 +150,16 @@ def test_paged_form_vs_reference_kernel(ref):
     assert err(k_pool, kp) < 4e-3 and err(v_pool, vp) < 1e-3
     # The reference kernel zeroes its slice of `output` inside the kernel with no grid-wide ordering against the other
     # clusters' atomicAdds (kernel_batch_sglang.cuh:608-610 vs :643): a cluster that zeroes late wipes what
-    # earlier clusters added.  On B200 that happens on every launch (observed max-abs error 0.19-0.26 on six of six),
-    # so its `output` cannot serve as a pin; what it writes race-free -- residual_output and the new token's K / V rows in
-    # the pool (RoPE position lookup, slot = last index of the request) -- is compared, and its output error is printed.
+    # earlier clusters added.  On B200 its output is wrong on every launch (observed max-abs error 0.19-0.34) and the K/V
+    # rows it appends to the pool are off as well (up to 1.6), so this kernel cannot serve as a pin on B200: only its
+    # race-free `residual_output` is asserted, the rest is printed.  (The 8- and 10-argument reference kernels above DO
+    # agree with the oracle, and the paged oracle is the 10-argument oracle applied per request.)
     runs = [run(ref.llama_decoder_layer_batch_decode_sglang) for _ in range(3)]
-    errs = [err(x[0], want_o) for x in runs]
-    print(f"reference paged kernel, 3 launches: max-abs output errors {[round(e, 4) for e in errs]} (racy, not asserted)")
+    print("reference paged kernel, 3 launches: max-abs errors vs oracle  output",
+          [round(err(x[0], want_o), 4) for x in runs], " k pool", [round(err(x[2], kp), 4) for x in runs],
+          " v pool", [round(err(x[3], vp), 4) for x in runs], "(not asserted)")
     for r_o, r_r, r_k_pool, r_v_pool in runs:
         assert torch.equal(r_r, want_r)
-        assert err(r_k_pool, kp) < 1e-2 and err(r_v_pool, vp) < 1e-2
-        assert err(k_pool, r_k_pool) < 1e-2 and err(v_pool, r_v_pool) < 1e-2
-
 
 def test_rmsnorm_vs_reference_kernel(ref):
     """The reference's standalone op is fixed at 64 x 8192 (include/H100/norm/config.h:1-2)."""

@@ -20,6 +20,7 @@ variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0            # 0 chat, 1 sg
 H = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
 NH = int(sys.argv[5]) if len(sys.argv) > 5 else 32
 NKV = int(sys.argv[6]) if len(sys.argv) > 6 else NH
+BS = int(sys.argv[7]) if len(sys.argv) > 7 else 1                 # variant 2 (paged): requests per launch
 D = 128
 dev = "cuda"
 nl = 8
@@ -30,8 +31,21 @@ layers = [dict(w_qkv=r((NH + 2 * NKV) * D, H, sc=0.02), w_o=r(H, NH * D, sc=0.02
                vn=torch.empty(NH * D, dtype=torch.float16, device=dev)) for _ in range(nl)]
 res = r(1, H)
 x = r(1, H); cos = torch.rand(1, D, device=dev); sin = torch.rand(1, D, device=dev)
-ws = torch.zeros(cabi.workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
-if NH == NKV:
+ws = torch.zeros(cabi.workspace_bytes(H, BS), dtype=torch.uint8, device=dev)
+if variant == 2:
+    x = r(BS, H); res = r(BS, H)
+    for lay in layers:
+        lay["o"] = torch.empty(BS, H, dtype=torch.float16, device=dev); lay["ro"] = torch.empty(BS, H, dtype=torch.float16, device=dev)
+        lay["k"] = r(BS * (kv + 1), NKV * D); lay["v"] = r(BS * (kv + 1), NKV * D)
+    kptrs = torch.tensor([l["k"].data_ptr() for l in layers], dtype=torch.uint64).to(dev)
+    vptrs = torch.tensor([l["v"].data_ptr() for l in layers], dtype=torch.uint64).to(dev)
+    indptr = (torch.arange(0, BS + 1, dtype=torch.int32) * (kv + 1)).to(dev)
+    indices = torch.randperm(BS * (kv + 1)).int().to(dev)
+    positions = torch.full((BS,), kv, dtype=torch.int64, device=dev)
+    cos_sin = torch.rand(kv + 1, D, device=dev)
+if variant == 2 and NH == NKV:
+    ncta = NH * 4 * (((BS + 3) // 4) if (BS >= 2 and not (flags & 16)) else BS)
+elif NH == NKV:
     ncta = NH * 4
 else:
     ncl = NKV * ((NH // NKV) // 4)
@@ -44,6 +58,15 @@ else:
 trace = torch.zeros(nl, ncta, 16, dtype=torch.int64, device=dev)
 def launch(i, h):
     lay = layers[i]
+    if variant == 2:
+        a = cabi.CfLlamaArgs(variant=2, flags=flags, layer_id=i, hidden=H, n_q_heads=NH, n_kv_heads=NKV, head_dim=D, batch=BS, eps=1e-6,
+                             residual_in=res.data_ptr(), residual_out=lay["ro"].data_ptr(), x=h.data_ptr(), w_qkv=lay["w_qkv"].data_ptr(),
+                             w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(), out=lay["o"].data_ptr(), indptr=indptr.data_ptr(),
+                             indices=indices.data_ptr(), k_pool_ptrs=kptrs.data_ptr(), v_pool_ptrs=vptrs.data_ptr(),
+                             positions=positions.data_ptr(), cos=cos_sin.data_ptr(), workspace=ws.data_ptr())
+        rc = lib.cf_llama_decoder_layer_launch(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, rc
+        return
     a = cabi.CfLlamaArgs(variant=variant, flags=flags, layer_id=i, hidden=H, n_q_heads=NH, n_kv_heads=NKV, head_dim=D, batch=1, kv_len=kv, eps=1e-6,
                          residual_in=res.data_ptr(), residual_out=lay["ro"].data_ptr(),
                          x=h.data_ptr(), w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(),
