@@ -749,49 +749,58 @@ def run_70b_sharded(torch, dist, dev, rank, world, peak):
     r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * sc).half()
     res = []
     for kvs in (1024, 16384):
-        layers = [(sharded.ShardedDecoderLayer(r((nq + 2 * nkv) * 128, H70, sc=0.02), r(H70, nq * 128, sc=0.02),
-                                               (1 + 0.1 * r(H70).float()).half(), nq, nkv, H70, 1e-5, None, world),
-                   r(kvs, nkv * 128), r(kvs, nkv * 128)) for _ in range(nl)]
-        torch.manual_seed(3)
-        x = torch.randn(1, H70, device=dev).half(); resid = torch.randn(1, H70, device=dev).half()
-        dist.broadcast(x, 0); dist.broadcast(resid, 0)
-        cos = torch.rand(64, device=dev); sin = torch.rand(64, device=dev)
+        for fused in (False, True):
+            layers = [(sharded.ShardedDecoderLayer(r((nq + 2 * nkv) * 128, H70, sc=0.02), r(H70, nq * 128, sc=0.02),
+                                                   (1 + 0.1 * r(H70).float()).half(), nq, nkv, H70, 1e-5, None, world, rank=rank,
+                                                   fused_allreduce=fused),
+                       r(kvs, nkv * 128), r(kvs, nkv * 128)) for _ in range(nl)]
+            torch.manual_seed(3)
+            x = torch.randn(1, H70, device=dev).half(); resid = torch.randn(1, H70, device=dev).half()
+            dist.broadcast(x, 0); dist.broadcast(resid, 0)
+            cos = torch.rand(64, device=dev); sin = torch.rand(64, device=dev)
 
-        def step():
-            h, rr = x, resid
-            for lay, kc, vc in layers:
-                h, rr, _, _ = lay.forward(h, rr, kc, vc, cos, sin)
-            return h
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        gr = None
-        try:
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
+            def step():
+                h, rr = x, resid
+                for lay, kc, vc in layers:
+                    h, rr, _, _ = lay.forward(h, rr, kc, vc, cos, sin, pdl=fused)
+                return h
+            for _ in range(3):
                 step()
-            run = gr.replay
-        except Exception:
-            gr, run = None, step
-        for _ in range(5):
-            run()
-        dist.barrier(); torch.cuda.synchronize()
-        reps = 200 if kvs <= 1024 else 60
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            run()
-        e1.record(); torch.cuda.synchronize(); dist.barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        us = float(t.item()) * 1e3 / (reps * nl)
-        bytes_gpu = (2 * (HQ + 2 * HKV) * 128 * H70 + 2 * HQ * 128 * H70 + 4 * kvs * HKV * 128) // world
-        res.append({"kv_len": kvs, "world": world, "us_per_layer": round(us, 2), "bytes_per_gpu": bytes_gpu,
-                    "achieved_gbs_per_gpu": round(bytes_gpu / (us * 1e-6) / 1e9, 1),
-                    "collective": "1 x NCCL all_reduce(fp32[8192]) per layer", "cuda_graph": gr is not None,
-                    "tokens_per_s_attn_half_80_layers": round(1e6 / (us * 80), 1)})
-        del layers, gr
-        torch.cuda.empty_cache()
+            torch.cuda.synchronize()
+            dist.barrier()
+            gr = None
+            try:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    step()
+                run = gr.replay
+            except Exception:
+                gr, run = None, step
+            for _ in range(5):
+                run()
+            dist.barrier(); torch.cuda.synchronize()
+            reps = 200 if kvs <= 1024 else 60
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                run()
+            e1.record(); torch.cuda.synchronize(); dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            us = float(t.item()) * 1e3 / (reps * nl)
+            timeouts = sum(int(lay.ws[8:12].view(torch.int32).item()) for lay, _, _ in layers)
+            bytes_gpu = (2 * (HQ + 2 * HKV) * 128 * H70 + 2 * HQ * 128 * H70 + 4 * kvs * HKV * 128) // world
+            res.append({"kv_len": kvs, "world": world, "us_per_layer": round(us, 2), "bytes_per_gpu": bytes_gpu,
+                        "achieved_gbs_per_gpu": round(bytes_gpu / (us * 1e-6) / 1e9, 1),
+                        "collective": ("all-reduce fused into the kernel: 8-byte flag-in-data stores to every peer over NVLink, "
+                                       "rank-ordered sum; no NCCL call" if fused else "1 x NCCL all_reduce(fp32[8192]) per layer + fp32->fp16 cast"),
+                        "fused_allreduce": fused, "cuda_graph": gr is not None, "peer_poll_timeouts": timeouts,
+                        "tokens_per_s_attn_half_80_layers": round(1e6 / (us * 80), 1)})
+            for lay, _, _ in layers:
+                if lay.tp is not None:
+                    lay.tp.close()
+            del layers, gr
+            torch.cuda.empty_cache()
     return res
 
 

@@ -29,6 +29,11 @@ EXPORTED_SYMBOLS = (
     "cf_last_error_string",
     "cf_llama_workspace_bytes",
     "cf_rmsnorm_launch",
+    "cf_tp_exchange_bytes",
+    "cf_ipc_alloc",
+    "cf_ipc_open",
+    "cf_ipc_close",
+    "cf_ipc_free",
     "cf_llama_algorithmic_bytes",
     "cf_llama_decoder_layer_launch",
     "cf_llama_ffn_launch",
@@ -68,6 +73,9 @@ class CfLlamaArgs(C.Structure):
         ("sin", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_batch", C.c_int32),
+        ("tp_rank", C.c_int32),
+        ("tp_world", C.c_int32),
+        ("tp_peer", C.c_void_p * 8),
     ]
 
 
@@ -117,6 +125,16 @@ def load() -> C.CDLL:
     lib.cf_llama_decoder_layer_launch.argtypes = [C.POINTER(CfLlamaArgs), C.c_void_p]
     lib.cf_llama_ffn_launch.restype = C.c_int
     lib.cf_llama_ffn_launch.argtypes = [C.POINTER(CfFfnArgs), C.c_void_p]
+    lib.cf_tp_exchange_bytes.restype = C.c_size_t
+    lib.cf_tp_exchange_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.cf_ipc_alloc.restype = C.c_int
+    lib.cf_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.cf_ipc_open.restype = C.c_int
+    lib.cf_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.cf_ipc_close.restype = C.c_int
+    lib.cf_ipc_close.argtypes = [C.c_void_p]
+    lib.cf_ipc_free.restype = C.c_int
+    lib.cf_ipc_free.argtypes = [C.c_void_p]
     lib.cf_rmsnorm_launch.restype = C.c_int
     lib.cf_rmsnorm_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_uint32, C.c_void_p]
     lib.cf_test_cluster_reduce.restype = C.c_int

@@ -328,6 +328,20 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     kp.layer_id = a->layer_id;
     kp.flags = a->flags;
     kp.batch = a->batch;
+    kp.tp_rank = 0;
+    kp.tp_world = 1;
+    if (a->tp_world > 1) {
+        if (a->tp_world > 8 || a->tp_rank < 0 || a->tp_rank >= a->tp_world)
+            return fail(CF_ERR_BAD_SHAPE, "tp_world must be in [2, 8] and 0 <= tp_rank < tp_world (got rank %d of %d)", a->tp_rank, a->tp_world);
+        if (!gqa || a->batch != 1 || (a->flags & CF_FLAG_GQA_CLUSTER))
+            return fail(CF_ERR_BAD_SHAPE, "the fused all-reduce needs a grouped-query shape, batch 1 and the group kernel");
+        for (int r = 0; r < a->tp_world; ++r) {
+            if (!a->tp_peer[r] || !aligned16(a->tp_peer[r])) return fail(CF_ERR_NULL_ARG, "tp_peer[%d] must be a 16-byte aligned device pointer", r);
+            kp.tp_peer[r] = static_cast<unsigned long long*>(a->tp_peer[r]);
+        }
+        kp.tp_rank = a->tp_rank;
+        kp.tp_world = a->tp_world;
+    }
 
     const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
     if (gqa && !(a->flags & CF_FLAG_GQA_CLUSTER)) {
@@ -434,6 +448,48 @@ extern "C" int cf_llama_ffn_launch(const CfFfnArgs* a, void* stream_) {
     const cudaError_t e = cudaLaunchKernelEx(&cfg, cfb::llama_ffn_layer_kernel, fp);
     if (e != cudaSuccess) return fail((int)e, "ffn kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+extern "C" size_t cf_tp_exchange_bytes(int32_t hidden, int32_t tp_world) {
+    if (hidden <= 0 || tp_world < 1) return 0;
+    return (size_t)2 * tp_world * hidden * sizeof(uint64_t);          // [2 parities][tp_world][hidden] (float, epoch) words
+}
+
+extern "C" int cf_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!dev_ptr || !handle || bytes == 0) return fail(CF_ERR_NULL_ARG, "cf_ipc_alloc: bad arguments");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        if (p) cudaFree(p);
+        return fail((int)e, "cf_ipc_alloc: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, 64);
+    *dev_ptr = p;
+    return 0;
+}
+
+extern "C" int cf_ipc_open(const unsigned char handle[64], void** dev_ptr) {
+    if (!dev_ptr || !handle) return fail(CF_ERR_NULL_ARG, "cf_ipc_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    const cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail((int)e, "cf_ipc_open: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int cf_ipc_close(void* dev_ptr) {
+    const cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    return e == cudaSuccess ? 0 : fail((int)e, "cf_ipc_close: %s", cudaGetErrorString(e));
+}
+
+extern "C" int cf_ipc_free(void* dev_ptr) {
+    const cudaError_t e = cudaFree(dev_ptr);
+    return e == cudaSuccess ? 0 : fail((int)e, "cf_ipc_free: %s", cudaGetErrorString(e));
 }
 
 extern "C" int cf_rmsnorm_launch(const void* x, const void* weight, void* out, int32_t batch, int32_t hidden, float eps,

@@ -315,6 +315,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     // bumped by the previous launch's last finaliser; 0 is never used as a flag)
     const unsigned epoch = __ldcg(p.header);
     const unsigned flag = ll_flag_of_epoch(epoch);
+    const unsigned tp_flag = p.tp_world > 1 ? ll_flag_of_epoch(__ldcg(p.header + 3)) : 0u;
 
     // ---- phase 0: fused residual add + RMSNorm over the FULL vector (every CTA needs all of it: rows are split).
     //      One pass: x and residual are loaded once and stay in registers across the block reduction. ----
@@ -700,11 +701,14 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         CF_MARK(8);
         const int ng = gp.n_groups;
         const int lo = (int)((long long)gid * OROWS / ng), hi = (int)((long long)(gid + 1) * OROWS / ng);
-        ll_finalize_columns(p.out_ll, hidden, ng, rank * OROWS, lo, hi, flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS, CONSUMER_BAR);
+        ll_finalize_columns(p, p.out_ll, hidden, ng, rank * OROWS, lo, hi, flag, tp_flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
         // a CTA that got here has seen every group's partial of its slice, and a group only gets past its exchanges once
         // all of its CTAs are past phase 0: CTA 0 may bump the epoch and (in-place form) overwrite `residual`
         if (blockIdx.x == 0) {
-            if (tid == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.header) : "memory");
+            if (tid == 0) {
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.header) : "memory");
+                if (p.tp_world > 1) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.header + 3) : "memory");
+            }
             if (residual_inplace) {
                 for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
                     float f[8], r8[8];

@@ -86,6 +86,9 @@ struct alignas(64) KParams {
     int layer_id;
     unsigned flags;
     int batch;               // requests in the launch (batched paged kernel)
+    // head-parallel shards (Llama-2-70B): fused all-reduce of the O-projection partial over NVLink peer memory
+    unsigned long long* tp_peer[8];   // rank r's exchange buffer: (float, epoch) words [2 parities][tp_world][hidden]
+    int tp_rank, tp_world;            // tp_world <= 1: no peer stage
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -171,15 +174,57 @@ __device__ __forceinline__ float ll_resolve(const unsigned long long* p, unsigne
     while ((unsigned)(w >> 32) != flag) w = ll_load(p);
     return __uint_as_float((unsigned)w);
 }
+
 __device__ __forceinline__ unsigned ll_flag_of_epoch(unsigned epoch) { return epoch + 1u == 0u ? 1u : epoch + 1u; }
+
+// ---- the same words at SYSTEM scope: peer GPUs' memory over NVLink (an aligned 64-bit store is one transaction) ----
+__device__ __forceinline__ void ll_store_sys(unsigned long long* p, float v, unsigned flag) {
+    asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(ll_pack(v, flag)) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load_sys(const unsigned long long* p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
+}
+
+// Fused all-reduce stage for head-parallel shards.  `v` is this rank's fp32 partial of output column `col` (already summed
+// over the rank's own clusters).  The rank pushes it as a (value, epoch) word into slot [parity][tp_rank][col] of EVERY
+// rank's exchange buffer (its own included) with one 8-byte store per peer over NVLink, then polls its own buffer until
+// all tp_world slots of the column carry this launch's epoch and adds them in rank order: every rank computes the
+// bit-identical sum, with no NCCL launch, no extra kernel and no separate fp32 -> fp16 pass (one collective per layer is
+// the whole communication of the 70B config; NCCL's latency for 32 KB is several times this kernel's tail).
+// Double-buffered on the epoch parity: a rank can be at most one launch ahead of its slowest peer (it needs that peer's
+// words of launch L+1 to finish L+1, and the peer publishes them only after it has read everything of launch L).
+// The poll is bounded (about a second) so that a desynchronised peer shows up as a NaN + an error word, not as a hang.
+// `flag` comes from the peer stage's own launch counter (header[3], read at kernel start and bumped only by launches that
+// use the stage), so launches without a peer stage on the same workspace cannot break the strict parity alternation.
+__device__ __forceinline__ float tp_allreduce_column(const KParams& p, float v, int col, unsigned flag) {
+    const size_t par = (size_t)(flag & 1u) * p.tp_world;
+    for (int r = 0; r < p.tp_world; ++r)
+        ll_store_sys(p.tp_peer[r] + (par + p.tp_rank) * p.hidden + col, v, flag);
+    const unsigned long long* mine = p.tp_peer[p.tp_rank] + par * p.hidden + col;
+    float acc = 0.f;
+    for (int r = 0; r < p.tp_world; ++r) {
+        unsigned long long w = ll_load_sys(mine + (size_t)r * p.hidden);
+        unsigned spins = 0;
+        while ((unsigned)(w >> 32) != flag) {
+            if (++spins > (1u << 23)) { p.header[2] = 1u; w = ll_pack(__int_as_float(0x7fc00000), flag); break; }
+            __nanosleep(64);
+            w = ll_load_sys(mine + (size_t)r * p.hidden);
+        }
+        acc += __uint_as_float((unsigned)w);
+    }
+    return acc;
+}
 
 // Cross-cluster sum of per-cluster partial output slices without atomics (batch == 1 launches).
 // Cluster `cid` of `ncl` has published slice words out_ll[cid][slice0 .. slice0+n).  This CTA finalises columns
 // [lo, hi) of the slice (the ncl CTAs that share a slice split its columns), summing the ncl partials of a column in
 // cluster order -> the result is bit-identical from launch to launch.  4 threads per column poll ncl/4 words each.
-__device__ __forceinline__ void ll_finalize_columns(const unsigned long long* out_ll, int hidden, int ncl, int slice0, int lo,
-                                                    int hi, unsigned flag, void* out, bool fp32_out, uint32_t tid, int nthreads,
-                                                    int bar_id) {
+// With head-parallel shards (p.tp_world > 1) the column then goes through tp_allreduce_column before it is written.
+__device__ __forceinline__ void ll_finalize_columns(const KParams& p, const unsigned long long* out_ll, int hidden, int ncl,
+                                                    int slice0, int lo, int hi, unsigned flag, unsigned tp_flag, void* out,
+                                                    bool fp32_out, uint32_t tid, int nthreads) {
     const int ncols = hi - lo;
     for (int i = tid; i < ((ncols * 4 + 31) & ~31); i += nthreads) {
         const int col = i >> 2, sub = i & 3;
@@ -202,6 +247,7 @@ __device__ __forceinline__ void ll_finalize_columns(const unsigned long long* ou
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         if (active && sub == 0) {
             const int o = slice0 + lo + col;
+            if (p.tp_world > 1) acc = tp_allreduce_column(p, acc, o, tp_flag);
             if (fp32_out) static_cast<float*>(out)[o] = acc;
             else static_cast<__half*>(out)[o] = __float2half_rn(acc);
         }
@@ -455,6 +501,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const bool ll_out = (gridDim.y == 1) && (p.out_ll != nullptr);
     const unsigned flag = ll_out ? ll_flag_of_epoch(__ldcg(p.header)) : 0u;
+    const unsigned tp_flag = (ll_out && p.tp_world > 1) ? ll_flag_of_epoch(__ldcg(p.header + 3)) : 0u;
 
     // ---- phase 0: RMSNorm ---------------------------------------------------------------------------
     // every CTA reduces the full vector itself (8-16 KB from L2) -> no cluster round trip for a scalar.  One pass:
@@ -900,12 +947,15 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         CF_MARK(8);   // partial published
         const int nh = p.n_heads;
         const int lo = (int)((long long)head * KS / nh), hi = (int)((long long)(head + 1) * KS / nh);
-        ll_finalize_columns(p.out_ll, hidden, nh, rank * KS, lo, hi, flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS, CONSUMER_BAR);
+        ll_finalize_columns(p, p.out_ll, hidden, nh, rank * KS, lo, hi, flag, tp_flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
         // Any CTA that got here has seen every cluster's partial, so every CTA of the launch is past phase 0 (it read x,
         // residual and the epoch before its cluster's first exchange): CTA 0 may now bump the epoch for the next launch
         // and, for the in-place form, overwrite `residual` (the reference races here).
         if (blockIdx.x == 0) {
-            if (tid == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.header) : "memory");
+            if (tid == 0) {
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.header) : "memory");
+                if (p.tp_world > 1) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.header + 3) : "memory");
+            }
             if constexpr (!kChat) {
                 if (residual_inplace) {
                     for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {

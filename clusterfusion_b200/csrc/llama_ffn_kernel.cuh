@@ -116,40 +116,68 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
     float* red = reinterpret_cast<float*>(smem + S::RED);
     uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
 
+    // the RMSNorm weight does not depend on the previous kernel: fetch it before the dependency wait
+    constexpr int P0_ITERS = (FFN_HIDDEN_MAX / 8 + CONSUMER_THREADS - 1) / CONSUMER_THREADS;      // 3
+    uint4 wraw[P0_ITERS];
+#pragma unroll
+    for (int it = 0; it < P0_ITERS; ++it) {
+        const int e = (it * CONSUMER_THREADS + tid) * 8;
+        wraw[it] = e < hidden ? *reinterpret_cast<const uint4*>(p.rms_w + e) : make_uint4(0, 0, 0, 0);
+    }
+    for (int e = tid; e < FFN_NB_MAX * 2 * FFN_BLOCK; e += CONSUMER_THREADS) gu[e] = 0.f;
+
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // ---- phase 0: h = x + residual, RMSNorm (every CTA reduces the whole vector itself) ------------------
+    // ---- phase 0: h = x + residual, RMSNorm (every CTA reduces the whole vector itself).  One pass: x and residual are
+    //      loaded once and stay in registers across the block reduction. --------------------------------------------
     {
+        uint4 xr[P0_ITERS], rr[P0_ITERS];
+#pragma unroll
+        for (int it = 0; it < P0_ITERS; ++it) {
+            const int e = (it * CONSUMER_THREADS + tid) * 8;
+            xr[it] = e < hidden ? *reinterpret_cast<const uint4*>(p.x + e) : make_uint4(0, 0, 0, 0);
+            rr[it] = e < hidden ? *reinterpret_cast<const uint4*>(p.residual_in + e) : make_uint4(0, 0, 0, 0);
+        }
+        float f[P0_ITERS][8];
         float ss = 0.f;
-        for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
-            float f[8], r8[8];
-            unpack8(*reinterpret_cast<const uint4*>(p.x + e), f);
-            unpack8(*reinterpret_cast<const uint4*>(p.residual_in + e), r8);
+#pragma unroll
+        for (int it = 0; it < P0_ITERS; ++it) {
+            const int e = (it * CONSUMER_THREADS + tid) * 8;
+            float r8[8];
+            unpack8(xr[it], f[it]);
+            unpack8(rr[it], r8);
             __align__(16) __half hs[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                hs[k] = __float2half_rn(f[k] + r8[k]);
-                f[k] = __half2float(hs[k]);
-                ss += f[k] * f[k];
-                xs[e + k] = f[k];                               // un-normalised for now
+                hs[k] = __float2half_rn(f[it][k] + r8[k]);
+                f[it][k] = __half2float(hs[k]);
+                ss += f[it][k] * f[it][k];
             }
-            if (cta == 0 && p.residual_out != p.residual_in)
+            if (cta == 0 && e < hidden && p.residual_out != p.residual_in)
                 *reinterpret_cast<uint4*>(p.residual_out + e) = *reinterpret_cast<const uint4*>(hs);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if (lane == 0) red[warp] = ss;
-        for (int e = tid; e < FFN_NB_MAX * 2 * FFN_BLOCK; e += CONSUMER_THREADS) gu[e] = 0.f;
         __syncthreads();
         float tot = 0.f;
 #pragma unroll
         for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w];
         const float rstd = rsqrtf(tot / (float)hidden + p.eps);
-        for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
-            float w8[8];
-            unpack8(*reinterpret_cast<const uint4*>(p.rms_w + e), w8);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) xs[e + k] = round_h(round_h(xs[e + k] * rstd) * w8[k]);
+        for (int it = 0; it < P0_ITERS; ++it) {
+            const int e = (it * CONSUMER_THREADS + tid) * 8;
+            if (e < hidden) {
+                float w8[8];
+                unpack8(wraw[it], w8);
+                float4 lo, hi;
+                lo.x = round_h(round_h(f[it][0] * rstd) * w8[0]); lo.y = round_h(round_h(f[it][1] * rstd) * w8[1]);
+                lo.z = round_h(round_h(f[it][2] * rstd) * w8[2]); lo.w = round_h(round_h(f[it][3] * rstd) * w8[3]);
+                hi.x = round_h(round_h(f[it][4] * rstd) * w8[4]); hi.y = round_h(round_h(f[it][5] * rstd) * w8[5]);
+                hi.z = round_h(round_h(f[it][6] * rstd) * w8[6]); hi.w = round_h(round_h(f[it][7] * rstd) * w8[7]);
+                *reinterpret_cast<float4*>(xs + e) = lo;
+                *reinterpret_cast<float4*>(xs + e + 4) = hi;
+            }
         }
         __syncthreads();
     }

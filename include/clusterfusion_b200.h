@@ -113,6 +113,17 @@ typedef struct CfLlamaArgs {
                          depends on (hidden, workspace_batch), so keep both fixed for the life of a workspace. */
     int32_t workspace_batch; /* the batch the workspace was sized for; 0 means `batch`.  Lets one workspace sized for
                                 the largest batch serve smaller launches (batch <= workspace_batch).            */
+
+    /* Head-parallel shards with the all-reduce FUSED into the kernel (Llama-2-70B config; grouped-query shapes, batch 1).
+     * tp_world in [2, 8] enables it: every rank launches the same call on its shard; the kernel pushes its fp32
+     * O-projection partial into every rank's exchange buffer over NVLink peer memory and sums all ranks' partials in rank
+     * order, so `out` (fp16, or fp32 with CF_FLAG_OUT_FP32_PARTIAL) already holds the all-reduced, rank-identical result:
+     * no NCCL call, no extra kernel.  tp_peer[r] = device pointer, valid on THIS device, to rank r's exchange buffer
+     * (cf_tp_exchange_bytes(hidden, tp_world) bytes, zero-filled once; tp_peer[tp_rank] is the local one; peers' come
+     * from cf_ipc_open).  All ranks must issue the same sequence of tp launches on their workspace.  0 / 1: disabled.  */
+    int32_t tp_rank;
+    int32_t tp_world;
+    void* tp_peer[8];
 } CfLlamaArgs;
 
 /* Bytes of zero-initialised device workspace needed for a call with this hidden / batch. */
@@ -120,6 +131,16 @@ size_t cf_llama_workspace_bytes(int32_t hidden, int32_t batch);
 
 /* Validate, encode (cached) TMA descriptors, launch the fused kernel on `stream`. */
 int cf_llama_decoder_layer_launch(const CfLlamaArgs* args, void* stream);
+
+/* ---- peer memory for the fused all-reduce: cudaMalloc'ed, zero-filled buffers that other processes on the node can map.
+ * cf_ipc_alloc: allocate + zero `bytes` on the current device, return the device pointer and a 64-byte handle to send to the
+ * peers (any transport: torch.distributed all_gather_object, MPI, a file).  cf_ipc_open: map a peer's handle on the current
+ * device (peer access over NVLink).  cf_ipc_close / cf_ipc_free undo them.  All return 0 or a cudaError_t.                */
+size_t cf_tp_exchange_bytes(int32_t hidden, int32_t tp_world);
+int cf_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]);
+int cf_ipc_open(const unsigned char handle[64], void** dev_ptr);
+int cf_ipc_close(void* dev_ptr);
+int cf_ipc_free(void* dev_ptr);
 
 /* Algorithmic HBM bytes of one call (SURVEY.md section 8d formula) -- used by bench / tests. */
 uint64_t cf_llama_algorithmic_bytes(const CfLlamaArgs* args, uint64_t total_kv_rows);

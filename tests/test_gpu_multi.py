@@ -13,7 +13,16 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, fused=False):
+    try:
+        _worker_body(rank, world, port, q, fused)
+    except BaseException as e:          # surface the failure in the parent instead of a queue timeout
+        import traceback
+        q.put(("error", f"rank {rank}: {e!r}\n{traceback.format_exc()}"))
+        raise
+
+
+def _worker_body(rank, world, port, q, fused):
     import torch.distributed as dist
     from oracle import llama_oracle as O
     from clusterfusion_b200 import sharded
@@ -26,13 +35,18 @@ def _worker(rank, world, port, q):
     c = {k: v.cuda() for k, v in d.items()}
     sh = sharded.shard_layer(c["weight_qkv"], c["weight_o"], 64, 8, rank, world)
     lay = sharded.ShardedDecoderLayer(sh["w_qkv"], sh["w_o"], c["rms_w"], sh["n_q_heads"], sh["n_kv_heads"], 8192, 1e-5,
-                                      None, world)
+                                      None, world, rank=rank, fused_allreduce=fused)
     kc = sharded.shard_kv(c["k_cache"], 8, rank, world); vc = sharded.shard_kv(c["v_cache"], 8, rank, world)
     outs = []
-    for it in range(3):
+    for it in range(7 if fused else 3):        # fused: both parities of the exchange double buffer, several times
         o, r, k, v = lay.forward(c["x"], c["residual"], kc, vc, c["cos"], c["sin"], pdl=(it == 2))
         torch.cuda.synchronize()
         outs.append(o.clone())
+    if fused:
+        hdr = lay.ws[:16].view(torch.int32).cpu()
+        assert int(hdr[2]) == 0, "a peer poll timed out"
+        assert int(hdr[3]) == 7, "one peer-stage launch counted per forward"
+        assert all(torch.equal(outs[0], x_) for x_ in outs[1:]), "fused all-reduce is deterministic (rank-ordered sums)"
     ks = [torch.empty_like(k) for _ in range(world)]; vs = [torch.empty_like(v) for _ in range(world)]
     dist.all_gather(ks, k.contiguous()); dist.all_gather(vs, v.contiguous())
     allo = [torch.empty_like(o) for _ in range(world)]
@@ -44,8 +58,10 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_70b_head_parallel_nccl(world):
+@pytest.mark.parametrize("world,fused", [(2, False), (2, True)])
+def test_70b_head_parallel_nccl(world, fused):
+    """fused=False: kernel + ONE NCCL all-reduce; fused=True: the all-reduce happens inside the kernel over NVLink peer
+    memory (no NCCL call on the data path).  Both against the full-layer oracle; ranks must agree bit for bit."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -53,12 +69,14 @@ def test_70b_head_parallel_nccl(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, fused)) for r in range(world)]
     for p in procs:
         p.start()
-    o0, o2, r, k, v, same = q.get(timeout=300)
+    got = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
+    assert got[0] is not "error" and not (isinstance(got[0], str) and got[0] == "error"), got[1]
+    o0, o2, r, k, v, same = got
     shape = O.LayerShape(8192, 64, 8)
     d = O.make_inputs(shape, 300, seed=70, layout="sglang")
     want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"], d["rms_w"],
