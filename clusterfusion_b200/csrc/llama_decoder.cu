@@ -62,7 +62,7 @@ EncodeTiledFn get_encode_fn() {
 struct MapKey {
     const void* ptr;
     uint64_t rows, cols;
-    uint32_t box_c, box_r;
+    uint32_t box_c, box_r;      // bit 31 of box_r: 128-byte swizzle
     bool operator==(const MapKey& o) const {
         return ptr == o.ptr && rows == o.rows && cols == o.cols && box_c == o.box_c && box_r == o.box_r;
     }
@@ -81,8 +81,8 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
 // 2-D fp16 row-major tensor [rows][cols], box {box_c, box_r}; OOB rows/cols read as zero.
 int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_c,
-                   uint32_t box_r) {
-    const MapKey key{ptr, rows, cols, box_c, box_r};
+                   uint32_t box_r, bool swizzle128 = false) {
+    const MapKey key{ptr, rows, cols, box_c, box_r | (swizzle128 ? 0x80000000u : 0u)};
     {
         std::lock_guard<std::mutex> lk(g_map_mutex);
         auto it = g_map_cache.find(key);
@@ -96,7 +96,7 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
     const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu",
                                        (int)r, (unsigned long long)rows, (unsigned long long)cols);
@@ -296,8 +296,10 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         // kv_len == 0: no tile is ever requested; point the maps at any valid address
         const void* kc = a->kv_len ? a->k_cache : a->x;
         const void* vc = a->kv_len ? a->v_cache : a->x;
-        if ((rc = get_tensor_map(&kp.tm_k, kc, a->kv_len, kvd, 128, cfb::ROWS512))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_v, vc, a->kv_len, kvd, 128, cfb::ROWS512))) return rc;
+        // group kernel (tensor-core attention): 64-dim half rows, 128-byte swizzled, so ldmatrix is conflict-free
+        const bool mma_kv = gqa && !(a->flags & CF_FLAG_GQA_CLUSTER);
+        if ((rc = get_tensor_map(&kp.tm_k, kc, a->kv_len, kvd, mma_kv ? 64 : 128, cfb::ROWS512, mma_kv))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_v, vc, a->kv_len, kvd, mma_kv ? 64 : 128, cfb::ROWS512, mma_kv))) return rc;
     }
     kp.x = static_cast<const __half*>(a->x);
     kp.residual_in = static_cast<const __half*>(a->residual_in);

@@ -144,6 +144,11 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     using S = SmemGqa2<NQ>;
     static_assert(VARIANT != CHAT, "GQA uses the nn.Linear weight layout");
     constexpr bool kPaged = (VARIANT == PAGED);
+    // contiguous KV arrives through TMA and can be laid out 128-byte-swizzled, which makes ldmatrix conflict-free: that
+    // variant runs QK^T and PV on the tensor cores (mma.sync m16n8k16).  Page-size-1 KV lands as linear 256-byte rows
+    // (bulk copies cannot swizzle) and keeps the CUDA-core loop.
+    constexpr bool kMma = !kPaged;
+    constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;      // 1/sqrt(128) * log2(e)
     const KParams& p = gp.k;
 
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -229,8 +234,11 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 if (lane == 0) {
                     const int r0 = row_begin + i * ROWS512;
                     dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                    // stage = K dims 0-63 | K dims 64-127 | V dims 0-63 | V dims 64-127, each [16 rows][128 B] swizzled
                     tma_load_2d(dst, &p.tm_k, kvh * HEAD_DIM, r0, fb, pol);
-                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, kvh * HEAD_DIM, r0, fb, pol);
+                    tma_load_2d(dst + 2048, &p.tm_k, kvh * HEAD_DIM + 64, r0, fb, pol);
+                    tma_load_2d(dst + 4096, &p.tm_v, kvh * HEAD_DIM, r0, fb, pol);
+                    tma_load_2d(dst + 6144, &p.tm_v, kvh * HEAD_DIM + 64, r0, fb, pol);
                 }
             } else {
                 const int r = row_begin + i * ROWS512 + (lane & 15);
@@ -410,7 +418,6 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 
     // ---- RoPE (NeoX), new K/V out ---------------------------------------------------------------------
     {
-        constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;
         const float* cosp = p.cos;
         const float* sinp = p.sin;
         if constexpr (kPaged) {
@@ -454,7 +461,8 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 const int i = d & 63;
                 const float rot = (d & 64) ? fmaf(a, cosp[i], b * sinp[i]) : fmaf(a, cosp[i], -b * sinp[i]);
                 const __half rh = __float2half_rn(rot);
-                qkv_fin[e] = hd < NQ ? __half2float(rh) * kScaleLog2 : __half2float(rh);
+                // CUDA-core loop: q pre-scaled in fp32; mma loop: q must stay an exact fp16 value, the scale goes onto S
+                qkv_fin[e] = (hd < NQ && !kMma) ? __half2float(rh) * kScaleLog2 : __half2float(rh);
                 if (hd == NQ && rank == 0 && writes_kv) {
                     if constexpr (kPaged) {
                         __half* kp = reinterpret_cast<__half*>(p.k_pool_ptrs[p.layer_id]);
@@ -482,101 +490,199 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 
     // ---- phase 2: flash-decode, NQ query heads share each K/V tile -------------------------------------
     {
-        const int sub = lane >> 4, c = lane & 15;
-        float q8[NQ][8], o8[NQ][8], m[NQ], l[NQ];
+        if constexpr (kMma) {
+            // ---- tensor-core loop.  Per 16-key tile and warp: S[head][key] = Q K^T (M = 16 rows of which NQ = 4 are real
+            // heads, N = 2 x 8 keys, K = 128 dims: 16 mma), online softmax on the C fragments (a head's 16 scores sit in one
+            // quad), then O[head][dim] += P V (P's C fragments are the A fragments of the second product: 16 mma).  ~150
+            // instructions per tile instead of ~1150 on the CUDA cores, where 4 heads x 2 FMA per K/V byte made this phase
+            // issue-bound (7.3 us for 33.5 MB at kv 8K).  P is rounded to fp16 for the product, like the probabilities of the
+            // eager fp16 model.
+            const int g4 = lane >> 2, t4 = lane & 3;              // fragment coordinates: row / column pair
+            uint32_t qa[8][2];                                    // A fragments of Q: [k-step][k lo / k hi], rows >= NQ are zero
 #pragma unroll
-        for (int h = 0; h < NQ; ++h) {
-            m[h] = -INFINITY; l[h] = 0.f;
+            for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { q8[h][k] = qkv_fin[h * HEAD_DIM + c * 8 + k]; o8[h][k] = 0.f; }
-        }
-        for (uint32_t i = first_tile(gbase, warp); i < n_kv_tiles; i += CONSUMER_WARPS) {
-            const uint32_t g = gbase + i, s = ring_stage(g);
-            ring_wait_full(full_u32, g);
-            const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
-            const uint4* vt = kt + STAGE_BYTES / 32;
-            const int rows_left = row_end - (row_begin + (int)i * ROWS512);
-            float sc[NQ][8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const int row = 2 * jj + sub;
-                float k8[8];
-                unpack8(kt[row * 16 + c], k8);
-#pragma unroll
-                for (int h = 0; h < NQ; ++h) {
-                    float a = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) a = fmaf(q8[h][k], k8[k], a);
-                    a += __shfl_xor_sync(0xffffffffu, a, 1);
-                    a += __shfl_xor_sync(0xffffffffu, a, 2);
-                    a += __shfl_xor_sync(0xffffffffu, a, 4);
-                    a += __shfl_xor_sync(0xffffffffu, a, 8);
-                    sc[h][jj] = (row < rows_left) ? a : -INFINITY;
+                for (int hi = 0; hi < 2; ++hi) {
+                    const int d = ks * 16 + hi * 8 + t4 * 2;
+                    const float q0 = g4 < NQ ? qkv_fin[g4 * HEAD_DIM + d] : 0.f;
+                    const float q1 = g4 < NQ ? qkv_fin[g4 * HEAD_DIM + d + 1] : 0.f;
+                    const __half2 h2 = __floats2half2_rn(q0, q1);
+                    qa[ks][hi] = *reinterpret_cast<const uint32_t*>(&h2);
                 }
             }
-            float mu[NQ];
+            float oacc[16][4];
 #pragma unroll
+            for (int t = 0; t < 16; ++t) { oacc[t][0] = 0.f; oacc[t][1] = 0.f; oacc[t][2] = 0.f; oacc[t][3] = 0.f; }
+            float mrun = -INFINITY, lrun = 0.f;                   // this lane's head g4 (replicated over the quad; l is a quad-partial)
+            const int lrow = lane & 7, lmat = lane >> 3;
+            for (uint32_t i = first_tile(gbase, warp); i < n_kv_tiles; i += CONSUMER_WARPS) {
+                const uint32_t g = gbase + i, s = ring_stage(g);
+                ring_wait_full(full_u32, g);
+                const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
+                const int rows_left = row_end - (row_begin + (int)i * ROWS512);
+                // S = Q K^T
+                float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const int key = (lmat >> 1) * 8 + lrow, chunk = (ks & 3) * 2 + (lmat & 1);
+                    const uint32_t addr = st + (ks >> 2) * 2048 + key * 128 + ((chunk ^ (key & 7)) << 4);
+                    uint32_t b0, b1, b2, b3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(sc[0][0]), "+f"(sc[0][1]), "+f"(sc[0][2]), "+f"(sc[0][3])
+                                 : "r"(qa[ks][0]), "r"(0u), "r"(qa[ks][1]), "r"(0u), "r"(b0), "r"(b1));
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(sc[1][0]), "+f"(sc[1][1]), "+f"(sc[1][2]), "+f"(sc[1][3])
+                                 : "r"(qa[ks][0]), "r"(0u), "r"(qa[ks][1]), "r"(0u), "r"(b2), "r"(b3));
+                }
+                // online softmax for head g4: scores of keys 2*t4, 2*t4+1 (n-tile 0) and 8+2*t4, 9+2*t4 (n-tile 1)
+                float s4[4];
+                s4[0] = (2 * t4 < rows_left) ? sc[0][0] * kScaleLog2 : -INFINITY;
+                s4[1] = (2 * t4 + 1 < rows_left) ? sc[0][1] * kScaleLog2 : -INFINITY;
+                s4[2] = (8 + 2 * t4 < rows_left) ? sc[1][0] * kScaleLog2 : -INFINITY;
+                s4[3] = (9 + 2 * t4 < rows_left) ? sc[1][1] * kScaleLog2 : -INFINITY;
+                float mx = fmaxf(fmaxf(s4[0], s4[1]), fmaxf(s4[2], s4[3]));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                const float m_new = fmaxf(mrun, mx);
+                const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                const float corr = dsm::exp2_diff(mrun, m_use);
+                mrun = m_new;
+                float pr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pr[k] = dsm::fast_exp2(s4[k] - m_use);           // -inf -> 0
+                const __half2 p01 = __floats2half2_rn(pr[0], pr[1]), p23 = __floats2half2_rn(pr[2], pr[3]);
+                // the row sum uses the same fp16-rounded probabilities that multiply V
+                lrun = lrun * corr + (__low2float(p01) + __high2float(p01)) + (__low2float(p23) + __high2float(p23));
+                const uint32_t pa0 = *reinterpret_cast<const uint32_t*>(&p01), pa2 = *reinterpret_cast<const uint32_t*>(&p23);
+                // O = O * corr + P V
+#pragma unroll
+                for (int jd = 0; jd < 8; ++jd) {
+                    const int key = (lmat & 1) * 8 + lrow, chunk = (jd & 3) * 2 + (lmat >> 1);
+                    const uint32_t addr = st + 4096 + (jd >> 2) * 2048 + key * 128 + ((chunk ^ (key & 7)) << 4);
+                    uint32_t b0, b1, b2, b3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+                    oacc[2 * jd][0] *= corr; oacc[2 * jd][1] *= corr;
+                    oacc[2 * jd + 1][0] *= corr; oacc[2 * jd + 1][1] *= corr;
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(oacc[2 * jd][0]), "+f"(oacc[2 * jd][1]), "+f"(oacc[2 * jd][2]), "+f"(oacc[2 * jd][3])
+                                 : "r"(pa0), "r"(0u), "r"(pa2), "r"(0u), "r"(b0), "r"(b1));
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(oacc[2 * jd + 1][0]), "+f"(oacc[2 * jd + 1][1]), "+f"(oacc[2 * jd + 1][2]), "+f"(oacc[2 * jd + 1][3])
+                                 : "r"(pa0), "r"(0u), "r"(pa2), "r"(0u), "r"(b2), "r"(b3));
+                }
+                __syncwarp();
+                issue_tile(g + NSTAGES);
+            }
+            // this warp's state of head g4 -> slot [warp][head]; l is summed over the quad first
+            lrun += __shfl_xor_sync(0xffffffffu, lrun, 1);
+            lrun += __shfl_xor_sync(0xffffffffu, lrun, 2);
+            if (g4 < NQ) {
+                float* slot = attn_part + (warp * NQ + g4) * S::PAY;
+                if (t4 == 0) { slot[0] = mrun; slot[1] = lrun; }
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                    *reinterpret_cast<float2*>(slot + 4 + t * 8 + t4 * 2) = make_float2(oacc[t][0], oacc[t][1]);
+            }
+        } else {
+            const int sub = lane >> 4, c = lane & 15;
+            float q8[NQ][8], o8[NQ][8], m[NQ], l[NQ];
+    #pragma unroll
             for (int h = 0; h < NQ; ++h) {
-                float mx = sc[h][0];
-#pragma unroll
-                for (int jj = 1; jj < 8; ++jj) mx = fmaxf(mx, sc[h][jj]);
-                const float m_new = fmaxf(m[h], mx);
-                mu[h] = (m_new == -INFINITY) ? 0.f : m_new;
-                const float corr = dsm::exp2_diff(m[h], mu[h]);
-                l[h] *= corr;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o8[h][k] *= corr;
-                m[h] = m_new;
+                m[h] = -INFINITY; l[h] = 0.f;
+    #pragma unroll
+                for (int k = 0; k < 8; ++k) { q8[h][k] = qkv_fin[h * HEAD_DIM + c * 8 + k]; o8[h][k] = 0.f; }
             }
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const int row = 2 * jj + sub;
-                uint4 raw = vt[row * 16 + c];
-                if constexpr (kPaged) {
-                    if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = first_tile(gbase, warp); i < n_kv_tiles; i += CONSUMER_WARPS) {
+                const uint32_t g = gbase + i, s = ring_stage(g);
+                ring_wait_full(full_u32, g);
+                const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+                const uint4* vt = kt + STAGE_BYTES / 32;
+                const int rows_left = row_end - (row_begin + (int)i * ROWS512);
+                float sc[NQ][8];
+    #pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int row = 2 * jj + sub;
+                    float k8[8];
+                    unpack8(kt[row * 16 + c], k8);
+    #pragma unroll
+                    for (int h = 0; h < NQ; ++h) {
+                        float a = 0.f;
+    #pragma unroll
+                        for (int k = 0; k < 8; ++k) a = fmaf(q8[h][k], k8[k], a);
+                        a += __shfl_xor_sync(0xffffffffu, a, 1);
+                        a += __shfl_xor_sync(0xffffffffu, a, 2);
+                        a += __shfl_xor_sync(0xffffffffu, a, 4);
+                        a += __shfl_xor_sync(0xffffffffu, a, 8);
+                        sc[h][jj] = (row < rows_left) ? a : -INFINITY;
+                    }
                 }
-                float v8[8];
-                unpack8(raw, v8);
-#pragma unroll
+                float mu[NQ];
+    #pragma unroll
                 for (int h = 0; h < NQ; ++h) {
-                    const float pr = dsm::fast_exp2(sc[h][jj] - mu[h]);
-                    l[h] += pr;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) o8[h][k] = fmaf(pr, v8[k], o8[h][k]);
+                    float mx = sc[h][0];
+    #pragma unroll
+                    for (int jj = 1; jj < 8; ++jj) mx = fmaxf(mx, sc[h][jj]);
+                    const float m_new = fmaxf(m[h], mx);
+                    mu[h] = (m_new == -INFINITY) ? 0.f : m_new;
+                    const float corr = dsm::exp2_diff(m[h], mu[h]);
+                    l[h] *= corr;
+    #pragma unroll
+                    for (int k = 0; k < 8; ++k) o8[h][k] *= corr;
+                    m[h] = m_new;
+                }
+    #pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int row = 2 * jj + sub;
+                    uint4 raw = vt[row * 16 + c];
+                    if constexpr (kPaged) {
+                        if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
+                    }
+                    float v8[8];
+                    unpack8(raw, v8);
+    #pragma unroll
+                    for (int h = 0; h < NQ; ++h) {
+                        const float pr = dsm::fast_exp2(sc[h][jj] - mu[h]);
+                        l[h] += pr;
+    #pragma unroll
+                        for (int k = 0; k < 8; ++k) o8[h][k] = fmaf(pr, v8[k], o8[h][k]);
+                    }
+                }
+                __syncwarp();
+                issue_tile(g + NSTAGES);
+            }
+            // merge the two half-warps (they saw different rows) in registers
+    #pragma unroll
+            for (int h = 0; h < NQ; ++h) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m[h], 16);
+                const float l2 = __shfl_xor_sync(0xffffffffu, l[h], 16);
+                const float M = fmaxf(m[h], m2);
+                const float w1 = dsm::exp2_diff(m[h], M), w2 = dsm::exp2_diff(m2, M);
+                l[h] = l[h] * w1 + l2 * w2;
+    #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float o2 = __shfl_xor_sync(0xffffffffu, o8[h][k], 16);
+                    o8[h][k] = o8[h][k] * w1 + o2 * w2;
+                }
+                m[h] = M;
+            }
+            // block merge of all NQ heads in one round: every warp writes its NQ states, then thread (h, d) folds the 12
+            // warps (and, on rank 0, the current token) in warp order and publishes the result straight from registers as
+            // (value, epoch) words -- exchange 2, hop A.
+    #pragma unroll
+            for (int h = 0; h < NQ; ++h) {
+                if (sub == 0) {
+                    float* slot = attn_part + (warp * NQ + h) * S::PAY;
+                    if (c == 0) { slot[0] = m[h]; slot[1] = l[h]; }
+                    *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[h][0], o8[h][1], o8[h][2], o8[h][3]);
+                    *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[h][4], o8[h][5], o8[h][6], o8[h][7]);
                 }
             }
-            __syncwarp();
-            issue_tile(g + NSTAGES);
         }
         gbase += n_kv_tiles;
         CF_MARK(5);
-        // merge the two half-warps (they saw different rows) in registers
-#pragma unroll
-        for (int h = 0; h < NQ; ++h) {
-            const float m2 = __shfl_xor_sync(0xffffffffu, m[h], 16);
-            const float l2 = __shfl_xor_sync(0xffffffffu, l[h], 16);
-            const float M = fmaxf(m[h], m2);
-            const float w1 = dsm::exp2_diff(m[h], M), w2 = dsm::exp2_diff(m2, M);
-            l[h] = l[h] * w1 + l2 * w2;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float o2 = __shfl_xor_sync(0xffffffffu, o8[h][k], 16);
-                o8[h][k] = o8[h][k] * w1 + o2 * w2;
-            }
-            m[h] = M;
-        }
-        // block merge of all NQ heads in one round: every warp writes its NQ states, then thread (h, d) folds the 12
-        // warps (and, on rank 0, the current token) in warp order and publishes the result straight from registers as
-        // (value, epoch) words -- exchange 2, hop A.
-#pragma unroll
-        for (int h = 0; h < NQ; ++h) {
-            if (sub == 0) {
-                float* slot = attn_part + (warp * NQ + h) * S::PAY;
-                if (c == 0) { slot[0] = m[h]; slot[1] = l[h]; }
-                *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[h][0], o8[h][1], o8[h][2], o8[h][3]);
-                *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[h][4], o8[h][5], o8[h][6], o8[h][7]);
-            }
-        }
         if (warp < NQ) {                                         // score of the current token against query head `warp`
             float a = 0.f;
 #pragma unroll
@@ -584,7 +690,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 a = fmaf(qkv_fin[warp * HEAD_DIM + lane * 4 + k], qkv_fin[NQ * HEAD_DIM + lane * 4 + k], a);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) red[CONSUMER_WARPS + warp] = a;
+            if (lane == 0) red[CONSUMER_WARPS + warp] = kMma ? a * kScaleLog2 : a;
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
         for (int e = tid; e < NQ * HEAD_DIM; e += CONSUMER_THREADS) {
