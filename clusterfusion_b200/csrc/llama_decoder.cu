@@ -367,8 +367,8 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         return paged ? launch_gqa2<cfb::PAGED>(gp, a->batch, pdl, stream) : launch_gqa2<cfb::SGLANG>(gp, 1, pdl, stream);
     }
     if (gqa) {
-        // first-generation cluster kernel (CF_FLAG_GQA_CLUSTER; kept for A/B measurement).  At most four 16-CTA clusters
-        // are co-resident (1 CTA / SM): use 16 CTAs per cluster only when that covers the whole grid, otherwise 8
+        // first-generation cluster kernel (CF_FLAG_GQA_CLUSTER; kept for A/B measurement).  Only 7 16-CTA clusters are
+        // co-resident at 1 CTA / SM: use 16 CTAs per cluster when there are at most four clusters, otherwise 8
         const int n_clusters = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
         const bool wide = (long long)n_clusters * a->batch <= 4;
         if (paged) return wide ? launch_gqa<cfb::PAGED, 16>(kp, n_clusters, a->batch, pdl, stream)

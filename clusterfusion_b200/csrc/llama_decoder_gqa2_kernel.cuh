@@ -4,9 +4,9 @@
  * Why a second kernel: a B200 SM pulls at most ~64 GB/s through one 192 KB TMA ring (measured), so a
  * layer only reaches the HBM roofline when >= ~110 SMs stream at once.  With grouped-query attention the natural unit
  * of fusion is one KV head + its query heads: Llama-3-8B has 8 of them.  The cluster kernel
- * (llama_decoder_gqa_kernel.cuh) can give a unit 8 CTAs (64 SMs: 48 % of the roofline) -- clusters of 16 with a
- * 225 KB footprint are not co-resident beyond four (tools/cluster_probe.cu, profiles/), and DSMEM does not reach
- * outside a cluster.  Here a unit ("group") is G CTAs, G = 2^k chosen so that groups x G ~ fills the 148 SMs
+ * (llama_decoder_gqa_kernel.cuh) can give a unit 8 CTAs (64 SMs: 48 % of the roofline) -- at a 1-CTA-per-SM footprint
+ * cudaOccupancyMaxActiveClusters answers 15 clusters of 8 and 7 clusters of 16 (tools/cluster_probe.cu,
+ * profiles/r02_cluster_probe.txt), one short of the 16 / 8 it would take, and DSMEM does not reach outside a cluster.  Here a unit ("group") is G CTAs, G = 2^k chosen so that groups x G ~ fills the 148 SMs
  * (8B: 8 x 16 = 128; 70B shards: 8 x 16, 4 x 32, 2 x 64), and the two exchanges the fusion needs go through L2:
  *
  *   exchange 1  q|k|v:  the group's [(NQ+2)*128 x hidden] weight block is cut into 16-row x 256-col tiles, dealt to the
@@ -23,9 +23,12 @@
  * counter, no atomics, nothing to re-zero: one L2 round trip per hop (B300_MICROARCH: L2 hit 234-262 cycles).  The first
  * version used red.global.add + __threadfence + a counter + an acquire spin per exchange and cost 3.4 us + 6.4 us per
  * layer (phase timeline, profiles/); the epoch lives in a 256-byte header at the start of the workspace and is bumped by
- * the launch's last finalising CTA.  The TMA ring keeps landing the next phase's tiles while a CTA waits.
- * Everything else -- the single 24 x 8 KB self-issuing tile stream, fp32 reductions, fp16 rounding points of the eager
- * model, fp32 red + last-arriver finalize of the O projection -- is as in the MHA kernel (llama_decoder_kernel.cuh).
+ * CTA 0 once it has seen every group's output partial.  The TMA ring keeps landing the next phase's tiles while a CTA
+ * waits.  The output partials of the groups are summed the same way (batch 1: ll_finalize_columns, deterministic; for
+ * head-parallel shards the finalising CTAs also push / poll the peers' words over NVLink = the layer's all-reduce).
+ * Attention over contiguous KV runs QK^T and PV on the tensor cores (mma.sync m16n8k16 on 128-byte-swizzled K/V tiles):
+ * with 4 query heads per K/V row the CUDA-core loop is issue-bound.  Everything else -- the single 24 x 8 KB self-issuing
+ * tile stream, fp32 reductions, fp16 rounding points of the eager model -- is as in the MHA kernel.
  * nn.Linear weight layout only (SGLANG / PAGED), NQ = 4 query heads per group; a KV head with 8 query heads (70B) gets
  * two groups.
  *
@@ -43,7 +46,7 @@
 namespace cfb {
 
 constexpr int G2_HIDDEN_MAX = 8192;
-constexpr int G2_RB_LOCAL_MAX = 8;        // 16-row blocks a CTA can touch in the QKV phase (6*8 / G + 1 partial, G >= 8 .. or 4096: G >= 4)
+constexpr int G2_RB_LOCAL_MAX = 8;        // 16-row blocks a CTA can touch in the QKV phase (48 / G whole + 1 partial, G >= 8)
 constexpr int G2_OROWS_MAX = 1024;        // hidden / G
 constexpr int G2_GROUPS_MAX = 16;         // groups per request
 constexpr int G2_G_MAX = 64;              // CTAs per group

@@ -1,11 +1,15 @@
 /*
+ * FIRST-GENERATION grouped-query kernel (selected only with CF_FLAG_GQA_CLUSTER; the default is the group kernel in
+ * llama_decoder_gqa2_kernel.cuh, which is 1.3-2x faster on B200 -- kept for A/B measurement and because it shows the
+ * pure-DSMEM formulation).
  * Grouped-query variant of the fused decoder attention half-layer (Llama-3-8B: 32 Q / 8 KV heads; the
  * Llama-2-70B head-parallel shards: 8 Q heads per KV head).  New capability relative to the reference, whose
  * kernels hard-code MHA (KV row stride = HIDDEN_DIM, /root/reference/include/H100/llama/llama_kernel_dispatch.cu:63-64;
  * SURVEY.md section 8 row a7).  nn.Linear ("sglang") weight layout only -- that is how GQA checkpoints are stored.
  *
  * Mapping: one 8- or 16-CTA cluster per (request, KV head, group of NQ = 4 query heads) -- 16 when at most four
- * clusters exist (only four 16-CTA clusters with 230 KB of shared memory each are co-resident on a B200), else 8.  The 4 query heads share
+ * clusters exist (7 16-CTA / 15 8-CTA clusters are co-resident at this footprint, profiles/r02_cluster_probe.txt), else 8.
+ * The 4 query heads share
  * every K/V tile, so K/V are read from HBM once per KV head (SURVEY.md section 8d bytes model); a KV head with 8
  * query heads (70B) gets two clusters, which recompute the small K/V projection and read the cache twice (the
  * second read hits L2).  Inside the cluster: 16-way K-split of the QKV GEMV, 16-way sequence split of the cache,

@@ -66,3 +66,20 @@ def test_product_never_imports_oracle():
     for p in list((ROOT / "clusterfusion_b200").rglob("*.py")) + list((ROOT / "clusterfusion").rglob("*.py")):
         src = p.read_text()
         assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), p
+
+
+def test_new_argument_errors_without_gpu():
+    """ABI v2 additions fail loudly on misuse (validated before anything touches a device)."""
+    from clusterfusion_b200 import cabi
+    base = dict(variant=1, head_dim=128, hidden=4096, n_q_heads=32, n_kv_heads=8, batch=1, x=16, residual_in=16, residual_out=32,
+                w_qkv=16, w_o=16, rms_w=16, out=16, k_new=16, v_new=16, cos=16, sin=16, workspace=16)
+    # rmsnorm: shape checks
+    lib = cabi.load()
+    assert lib.cf_rmsnorm_launch(16, 16, 16, 4, 100, 1e-6, 0, None) == -3          # hidden not a multiple of 16
+    assert lib.cf_rmsnorm_launch(None, 16, 16, 4, 4096, 1e-6, 0, None) == -1
+    assert lib.cf_tp_exchange_bytes(8192, 8) == 2 * 8 * 8192 * 8
+    assert lib.cf_tp_exchange_bytes(0, 8) == 0
+    # group counts beyond the group kernel's limit
+    with pytest.raises(cabi.CfError) as e:
+        cabi.launch(cabi.CfLlamaArgs(**{**base, "n_q_heads": 96, "n_kv_heads": 24, "hidden": 8192}))
+    assert e.value.code in (-3, -5)
