@@ -284,7 +284,14 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     memset(&kp, 0, sizeof kp);
     const uint64_t H = a->hidden, qd = (uint64_t)a->n_q_heads * 128, kvd = (uint64_t)a->n_kv_heads * 128;
     int rc;
-    if (chat) {
+    // batched paged decode: one cluster per head serves chunks of 4 requests, weights streamed once per chunk
+    const bool batched = paged && !gqa && a->batch >= 2 && a->hidden / CL <= cfb::BK_KS_MAX &&
+                         a->residual_out != a->residual_in && !(a->flags & CF_FLAG_PER_REQUEST);
+    if (batched) {
+        // tensor-core GEMVs: [32 rows x 64 cols] boxes, 128-byte swizzled (two per 8 KB tile)
+        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, 32, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, 32, true))) return rc;
+    } else if (chat) {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, 3 * H, H, 128, cfb::ROWS256))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, qd, H, 128, cfb::ROWS256))) return rc;
     } else {
@@ -376,9 +383,7 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         return wide ? launch_gqa<cfb::SGLANG, 16>(kp, n_clusters, 1, pdl, stream)
                     : launch_gqa<cfb::SGLANG, 8>(kp, n_clusters, 1, pdl, stream);
     }
-    // batched paged decode: one cluster per head serves chunks of 4 requests, weights streamed once per chunk
-    if (paged && a->batch >= 2 && a->hidden / CL <= cfb::BK_KS_MAX && a->residual_out != a->residual_in &&
-        !(a->flags & CF_FLAG_PER_REQUEST))
+    if (batched)
         return launch_kernel<CL>(cfb::llama_decoder_layer_batch_kernel<4>, cfb::SmemB<4>::TOTAL, 11, kp, a->n_q_heads,
                                  (a->batch + 3) / 4, pdl, stream);
     switch (a->variant) {

@@ -14,8 +14,12 @@
  *               would need 24 KB of receive slots;
  *   exchange 2  BC softmax states [m, l, o[128]] per CTA, all-gathered and merged in rank order.
  *
- * QKV tile order: tile g -> row block (g % 12) + 12 * (g / (12*wins)), window (g / 12) % wins, so a warp owns whole row
- * blocks and sums their windows in registers (no per-window slots in shared memory; deterministic).
+ * Both GEMVs run on the tensor cores: with BC activation vectors the product is a skinny GEMM (N = BC <= 8), and on the
+ * CUDA cores it was issue-bound (BC FMAs per weight element: QKV 22.6 us, O 7.2 us per layer at BC = 4).  Weight tiles are
+ * [32 rows x 128 cols] = two 128-byte-swizzled TMA boxes, read with ldmatrix.x4 as the A operand of mma.sync.m16n8k16
+ * (fp16 in, fp32 accumulate); the requests sit on the N dimension (B fragments straight from the fp16 activations in
+ * shared memory, padded row stride -> conflict-free); 16 ldmatrix + 16 mma per 8 KB tile.  QKV tile g = row block g % 12
+ * (owned by warp g % 12, accumulated over its 8 column tiles in registers; deterministic), column tile g / 12.
  * Same decomposition otherwise as llama_decoder_kernel.cuh (K-split QKV, sequence-split KV, N-split O, 24 x 8 KB
  * self-issuing ring, fp32 red + last-arriver finalize per request).  PAGED variant, MHA, hidden <= 4096, page size 1.
  */
@@ -26,6 +30,7 @@
 namespace cfb {
 
 constexpr int BK_KS_MAX = 1024;             // hidden / CLUSTER
+constexpr int BK_XS_STRIDE = BK_KS_MAX + 8; // fp16 activations per request, padded: conflict-free B-fragment loads
 
 template <int BC>
 struct SmemB {
@@ -38,7 +43,7 @@ struct SmemB {
     //   phase QKV : xs fp16 [BC][BK_KS_MAX]            phase ATTN: attn_part fp32 [24][132]
     static constexpr int XS = UNION;
     static constexpr int ATTN_PART = UNION;
-    static constexpr int UNION_BYTES = (BC * BK_KS_MAX * 2 > 24 * PAY * 4) ? BC * BK_KS_MAX * 2 : 24 * PAY * 4;
+    static constexpr int UNION_BYTES = (BC * BK_XS_STRIDE * 2 > 24 * PAY * 4) ? BC * BK_XS_STRIDE * 2 : 24 * PAY * 4;
     // X1: exchange-1 buffers; all dead after RoPE
     static constexpr int X1 = UNION + UNION_BYTES;
     static constexpr int QKV_SRC = X1;                                    // fp32 [BC][384]   this CTA's partial sums
@@ -84,7 +89,6 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
 
     const int hidden = p.hidden;
     const int KS = hidden / CLUSTER;
-    const int wins = KS / 256;
     const int kv_cols = p.n_kv_heads * HEAD_DIM;
 
     const uint32_t full_u32 = smem_base + S::BARS;
@@ -109,7 +113,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
         row_end[b] = min(row_begin[b] + chunk, len);
         kv_tile0[b + 1] = kv_tile0[b] + (row_end[b] - row_begin[b] + ROWS512 - 1) / ROWS512;
     }
-    const uint32_t n_qkv_tiles = (uint32_t)(S::QKV_OUT / ROWS512) * wins;       // 24 row blocks x wins windows
+    const uint32_t n_qkv_tiles = (uint32_t)CONSUMER_WARPS * (KS / 128);          // 12 row blocks of 32 x KS/128 column tiles
     const uint32_t n_kv_tiles = kv_tile0[BC];
     const uint32_t n_o_tiles = (uint32_t)(KS / ROWS256);
     const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
@@ -144,15 +148,16 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
         const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
         if (g < n_qkv_tiles) {
             if (lane == 0) {
-                // warp-owned row blocks: rb = (g % 12) + 12 * (g / (12*wins)), window = (g / 12) % wins
-                const int rb = (int)(g % CONSUMER_WARPS) + CONSUMER_WARPS * (int)(g / (CONSUMER_WARPS * wins));
-                const int win = (int)(g / CONSUMER_WARPS) % wins;
-                const int j = rb / (HEAD_DIM / ROWS512), sub = rb % (HEAD_DIM / ROWS512);
+                // tile g: row block g % 12 (32 of the head's 384 q|k|v rows, owned by warp g % 12), column tile g / 12
+                // (128 input columns) = two [32 rows x 64 cols] boxes, 128-byte swizzled for ldmatrix
+                const int rb = (int)(g % CONSUMER_WARPS), ct = (int)(g / CONSUMER_WARPS);
+                const int j = rb / 4, sub = rb % 4;
                 const int row0 = (j == 0) ? head * HEAD_DIM
                                : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
                                           : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
                 dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                tma_load_2d(dst, &p.tm_wqkv, rank * KS + win * 256, row0 + sub * ROWS512, fb, pol);
+                tma_load_2d(dst, &p.tm_wqkv, rank * KS + ct * 128, row0 + sub * 32, fb, pol);
+                tma_load_2d(dst + 4096, &p.tm_wqkv, rank * KS + ct * 128 + 64, row0 + sub * 32, fb, pol);
             }
         } else if (g < n_qkv_tiles + n_kv_tiles) {
             const uint32_t t = g - n_qkv_tiles;
@@ -181,8 +186,9 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
         } else {
             if (lane == 0) {
                 const uint32_t i = g - n_qkv_tiles - n_kv_tiles;     // Wo [out][in]: 32 output rows x this head's 128 input cols
-                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);          // as two swizzled [32 x 64] boxes
                 tma_load_2d(dst, &p.tm_wo, head * HEAD_DIM, rank * KS + i * ROWS256, fb, pol);
+                tma_load_2d(dst + 4096, &p.tm_wo, head * HEAD_DIM + 64, rank * KS + i * ROWS256, fb, pol);
             }
         }
         const uint32_t g2 = g + NSTAGES;              // the tile that will live in this stage next
@@ -278,7 +284,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
 #pragma unroll
                     for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(0.f);
                 }
-                *reinterpret_cast<uint4*>(xs + b * BK_KS_MAX + e) = *reinterpret_cast<const uint4*>(xn);
+                *reinterpret_cast<uint4*>(xs + b * BK_XS_STRIDE + e) = *reinterpret_cast<const uint4*>(xn);
             }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
@@ -286,76 +292,54 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
 
     CF_MARK(1);
     uint32_t gbase = 0;
-    // ---- phase 1: QKV GEMV, every weight tile against the BC activation vectors --------------------------------
+    // ---- phase 1: QKV GEMV on the tensor cores: D[32 rows][8] += W[32 x 128] * X^T[128 x 8], X = the chunk's BC
+    //      activation vectors (columns BC..7 are zero).  Warp w owns row block w (32 of the head's 384 q|k|v rows) and
+    //      accumulates over its 8 column tiles in registers: 16 ldmatrix.x4 + 16 mma.sync per 8 KB tile. -----------------
     {
-        float acc[BC][2];
+        static_assert(BC <= 8 && BC % 2 == 0, "requests sit on the N = 8 dimension of m16n8k16, two per lane");
+        const int g4 = lane >> 2, t4 = lane & 3;
+        const int lrow = lane & 7, lmat = lane >> 3;
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         for (uint32_t i = warp; i < n_qkv_tiles; i += CONSUMER_WARPS) {        // phase starts at ring index 0
             const uint32_t g = i, s = ring_stage(g);
-            const int k = (int)(i / CONSUMER_WARPS);
-            const int win = k % wins;
-            const int rb = (int)warp + CONSUMER_WARPS * (k / wins);
-            if (win == 0) {
+            const int ct = (int)(i / CONSUMER_WARPS);                           // column tile: input cols ct*128 .. +128
+            // B fragments of this column tile: x[request g4][k], k = ct*128 + ks*16 + 2*t4 (+8)
+            uint32_t xb[8][2];
 #pragma unroll
-                for (int b = 0; b < BC; ++b) { acc[b][0] = 0.f; acc[b][1] = 0.f; }
+            for (int ks = 0; ks < 8; ++ks) {
+                const __half* xp = xs + g4 * BK_XS_STRIDE + ct * 128 + ks * 16 + t4 * 2;
+                xb[ks][0] = g4 < BC ? *reinterpret_cast<const uint32_t*>(xp) : 0u;
+                xb[ks][1] = g4 < BC ? *reinterpret_cast<const uint32_t*>(xp + 8) : 0u;
             }
-            float x8[BC][8];
-#pragma unroll
-            for (int b = 0; b < BC; ++b) unpack8(*reinterpret_cast<const uint4*>(xs + b * BK_KS_MAX + win * 256 + lane * 8), x8[b]);
             ring_wait_full(full_u32, g);
-            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+            const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
 #pragma unroll
-            for (int grp = 0; grp < ROWS512 / 8; ++grp) {
-                float v[BC][8];
+            for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    float w8[8];
-                    unpack8(tile[(grp * 8 + r) * 32 + lane], w8);
-#pragma unroll
-                    for (int b = 0; b < BC; ++b) {
-                        float a = 0.f;
-#pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) a = fmaf(x8[b][kk], w8[kk], a);
-                        v[b][r] = a;
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < BC; ++b) {
-                    // transpose-reduce 8 values over 32 lanes: 4 + 2 + 1 + 1 + 1 shuffles
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const bool hi = lane & 16;
-                        const float send = hi ? v[b][r] : v[b][r + 4];
-                        const float keep = hi ? v[b][r + 4] : v[b][r];
-                        v[b][r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const bool hi = lane & 8;
-                        const float send = hi ? v[b][r] : v[b][r + 2];
-                        const float keep = hi ? v[b][r + 2] : v[b][r];
-                        v[b][r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-                    {
-                        const bool hi = lane & 4;
-                        const float send = hi ? v[b][0] : v[b][1];
-                        const float keep = hi ? v[b][1] : v[b][0];
-                        v[b][0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    v[b][0] += __shfl_xor_sync(0xffffffffu, v[b][0], 2);
-                    v[b][0] += __shfl_xor_sync(0xffffffffu, v[b][0], 1);
-                    acc[b][grp] += v[b][0];            // meaningful on lanes with (lane & 3) == 0: row = lane bits (4,3,2)
-                }
-            }
-            if (win == wins - 1 && (lane & 3) == 0) {
-                const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-#pragma unroll
-                for (int b = 0; b < BC; ++b) {
-                    qkv_src[b * S::QKV_OUT + rb * ROWS512 + r] = acc[b][0];
-                    qkv_src[b * S::QKV_OUT + rb * ROWS512 + 8 + r] = acc[b][1];
+                for (int mb = 0; mb < 2; ++mb) {
+                    const int row = mb * 16 + (lmat & 1) * 8 + lrow, chunk = (ks & 3) * 2 + (lmat >> 1);
+                    const uint32_t addr = st + (ks >> 2) * 4096 + row * 128 + ((chunk ^ (row & 7)) << 4);
+                    uint32_t a0, a1, a2, a3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(acc[mb][0]), "+f"(acc[mb][1]), "+f"(acc[mb][2]), "+f"(acc[mb][3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(xb[ks][0]), "r"(xb[ks][1]));
                 }
             }
             __syncwarp();
             issue_tile(g + NSTAGES);
+        }
+        // C fragment: rows g4 / g4 + 8 of each 16-row block, requests 2*t4 and 2*t4 + 1
+        if (2 * t4 < BC) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                const int row = (int)warp * 32 + mb * 16 + g4;
+                qkv_src[(2 * t4) * S::QKV_OUT + row] = acc[mb][0];
+                qkv_src[(2 * t4 + 1) * S::QKV_OUT + row] = acc[mb][1];
+                qkv_src[(2 * t4) * S::QKV_OUT + row + 8] = acc[mb][2];
+                qkv_src[(2 * t4 + 1) * S::QKV_OUT + row + 8] = acc[mb][3];
+            }
         }
     }
     gbase += n_qkv_tiles;
@@ -547,67 +531,53 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     }
 
     CF_MARK(6);
-    // ---- phase 3: O GEMV for output columns [rank*KS, +KS), every Wo tile against the BC attention outputs ----------
+    // ---- phase 3: O GEMV on the tensor cores: D[32 out rows][8] = Wo tile[32 x 128] * A^T[128 x 8], A = the BC attention
+    //      outputs of this head (fp16-rounded values, exact as fp16) ----------------------------------------------------
     {
-        // tile = 32 output rows x 128 input cols; lane (sub, c): rows sub+2s, input cols c*8..+8
-        const int sub = lane >> 4, c = lane & 15;
-        float a8[BC][8];
+        const int g4 = lane >> 2, t4 = lane & 3;
+        const int lrow = lane & 7, lmat = lane >> 3;
+        uint32_t ob[8][2];
 #pragma unroll
-        for (int b = 0; b < BC; ++b)
+        for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a8[b][k] = attn_out[b * HEAD_DIM + c * 8 + k];
+            for (int hi = 0; hi < 2; ++hi) {
+                const int d = ks * 16 + hi * 8 + t4 * 2;
+                const __half2 h2 = g4 < BC ? __floats2half2_rn(attn_out[g4 * HEAD_DIM + d], attn_out[g4 * HEAD_DIM + d + 1])
+                                           : __floats2half2_rn(0.f, 0.f);
+                ob[ks][hi] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+        }
         for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
             const uint32_t g = gbase + i, s = ring_stage(g);
             ring_wait_full(full_u32, g);
-            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+            const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-            for (int grp = 0; grp < ROWS256 / 16; ++grp) {
-                float v[BC][8];
+            for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int row = 2 * (grp * 8 + r) + sub;
-                    float w8[8];
-                    unpack8(tile[row * 16 + c], w8);
-#pragma unroll
-                    for (int b = 0; b < BC; ++b) {
-                        float a = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) a = fmaf(a8[b][k], w8[k], a);
-                        v[b][r] = a;
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < BC; ++b) {
-                    // transpose-reduce 8 values over the 16 lanes of a half-warp: 4 + 2 + 1 + 1 shuffles
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const bool hi = lane & 8;
-                        const float send = hi ? v[b][r] : v[b][r + 4];
-                        const float keep = hi ? v[b][r + 4] : v[b][r];
-                        v[b][r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const bool hi = lane & 4;
-                        const float send = hi ? v[b][r] : v[b][r + 2];
-                        const float keep = hi ? v[b][r + 2] : v[b][r];
-                        v[b][r] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    {
-                        const bool hi = lane & 2;
-                        const float send = hi ? v[b][0] : v[b][1];
-                        const float keep = hi ? v[b][1] : v[b][0];
-                        v[b][0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                    }
-                    v[b][0] += __shfl_xor_sync(0xffffffffu, v[b][0], 1);
-                    if ((lane & 1) == 0) {
-                        const int r = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        out_part[b * BK_KS_MAX + i * ROWS256 + 2 * (grp * 8 + r) + sub] = v[b][0];
-                    }
+                for (int mb = 0; mb < 2; ++mb) {
+                    const int row = mb * 16 + (lmat & 1) * 8 + lrow, chunk = (ks & 3) * 2 + (lmat >> 1);
+                    const uint32_t addr = st + (ks >> 2) * 4096 + row * 128 + ((chunk ^ (row & 7)) << 4);
+                    uint32_t a0, a1, a2, a3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(acc[mb][0]), "+f"(acc[mb][1]), "+f"(acc[mb][2]), "+f"(acc[mb][3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(ob[ks][0]), "r"(ob[ks][1]));
                 }
             }
             __syncwarp();
             issue_tile(g + NSTAGES);
+            if (2 * t4 < BC) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    const int row = (int)i * ROWS256 + mb * 16 + g4;
+                    out_part[(2 * t4) * BK_KS_MAX + row] = acc[mb][0];
+                    out_part[(2 * t4 + 1) * BK_KS_MAX + row] = acc[mb][1];
+                    out_part[(2 * t4) * BK_KS_MAX + row + 8] = acc[mb][2];
+                    out_part[(2 * t4 + 1) * BK_KS_MAX + row + 8] = acc[mb][3];
+                }
+            }
         }
     }
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
