@@ -147,7 +147,8 @@ def test_paged_form_vs_reference_kernel(ref):
     o, r, k_pool, v_pool = run(clusterfusion.llama_decoder_layer_batch_decode_sglang)
     assert torch.allclose(o.float(), want_o.float(), rtol=1e-3, atol=1e-3)
     assert torch.equal(r, want_r)
-    assert err(k_pool, kp) < 4e-3 and err(v_pool, vp) < 1e-3
+    assert torch.allclose(k_pool.float(), kp.float(), rtol=1e-3, atol=4e-3)
+    assert torch.allclose(v_pool.float(), vp.float(), rtol=1e-3, atol=1e-3)
     # The reference kernel zeroes its slice of `output` inside the kernel with no grid-wide ordering against the other
     # clusters' atomicAdds (kernel_batch_sglang.cuh:608-610 vs :643): a cluster that zeroes late wipes what
     # earlier clusters added.  On B200 its output is wrong on every launch (observed max-abs error 0.19-0.34) and the K/V
