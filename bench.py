@@ -390,9 +390,11 @@ def run_ours(args, rank, world, local_rank):
         ffn_res = run_ffn(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
         batched = run_batched_paged(torch, cabi, dev, timed_replays, peak)
     # ------------------------------------------------------------------ whole-model decode
-    full = None
+    full = full8b = None
     if not args.no_sweep and not args.no_full_model:
         full = run_full_model(torch, dist, dev, world, peak)
+        full8b = run_full_model(torch, dist, dev, world, peak, kv0=8192, n_tok=64, shape_name="llama3-8b",
+                                modes=("fused_attn_fused_ffn", "eager"))
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
     ref_gpu = None
@@ -461,6 +463,8 @@ def run_ours(args, rank, world, local_rank):
         line["reference_gpu_kernel"] = ref_gpu
     if full is not None:
         line["full_model_decode"] = full
+    if full8b is not None:
+        line["full_model_decode_llama3_8b_kv8k"] = full8b
     if ffn_res is not None:
         line["fused_ffn_half_layer"] = ffn_res
     if batched is not None:
@@ -638,14 +642,15 @@ def run_ffn(torch, cabi, dev, timed_replays, peak, pdl=True, hidden=4096, ffn=11
             "kernel": "cfb::llama_ffn_layer_kernel", "launches": reps * nl}
 
 
-def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128):
+def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128, shape_name="llama2-7b", modes=("fused_attn_fused_ffn", "fused", "eager")):
     """Llama-2-7B-shaped whole-model decode (random init): fused attention op + torch FFN / lm_head + device-side
     greedy sampling, one CUDA graph per token (clusterfusion_b200/decode.py).  Also the same loop with eager
     PyTorch attention (the reference's USE_CLUSTER_FUSION=false path on this GPU)."""
-    from clusterfusion_b200.decode import LlamaDecodeEngine, LLAMA2_7B
-    out = {"model": "llama2-7b shapes, random init, fp16", "kv_len_start": kv0, "tokens": n_tok, "replicas": world}
-    for mode in ("fused_attn_fused_ffn", "fused", "eager"):
-        eng = LlamaDecodeEngine(LLAMA2_7B, max_seq=kv0 + 3 * n_tok + 16, device=dev, seed=5,
+    from clusterfusion_b200.decode import LlamaDecodeEngine, LLAMA2_7B, LLAMA3_8B
+    shape = LLAMA3_8B if shape_name == "llama3-8b" else LLAMA2_7B
+    out = {"model": f"{shape_name} shapes, random init, fp16", "kv_len_start": kv0, "tokens": n_tok, "replicas": world}
+    for mode in modes:
+        eng = LlamaDecodeEngine(shape, max_seq=kv0 + 3 * n_tok + 16, device=dev, seed=5,
                                 attn="eager" if mode == "eager" else "fused",
                                 ffn="fused" if mode == "fused_attn_fused_ffn" else "torch")
         eng.set_position(kv0)
@@ -681,8 +686,10 @@ def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128):
             out[mode]["h2d_d2h_bytes_per_token"] = 16
         del eng
         torch.cuda.empty_cache()
-    out["speedup_fused_attention_vs_eager"] = round(out["fused"]["tokens_per_s"] / out["eager"]["tokens_per_s"], 3)
-    out["speedup_fused_attention_and_ffn_vs_eager"] = round(out["fused_attn_fused_ffn"]["tokens_per_s"] / out["eager"]["tokens_per_s"], 3)
+    if "fused" in out and "eager" in out:
+        out["speedup_fused_attention_vs_eager"] = round(out["fused"]["tokens_per_s"] / out["eager"]["tokens_per_s"], 3)
+    if "fused_attn_fused_ffn" in out and "eager" in out:
+        out["speedup_fused_attention_and_ffn_vs_eager"] = round(out["fused_attn_fused_ffn"]["tokens_per_s"] / out["eager"]["tokens_per_s"], 3)
     return out
 
 
