@@ -81,10 +81,6 @@ __device__ __forceinline__ void cluster_wait() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    // bar.sync is the .aligned form: every thread of a warp must execute the SAME barrier instruction together.  A short
-    // divergent region right before it (an `if (lane == 0)` store) does not always reconverge on its own
-    // (compute-sanitizer synccheck flagged one such site), so reconverge explicitly.
-    __syncwarp();
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
