@@ -449,8 +449,8 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int e = tid + u * CONSUMER_THREADS;
-                float v = ll_resolve(qkv_ll + e, w0[u], flag);
-                if (two[u]) v += ll_resolve(qkv_ll + S::R + e, w1[u], flag);
+                float v = ll_resolve(qkv_ll + e, w0[u], flag, p.header + 2);
+                if (two[u]) v += ll_resolve(qkv_ll + S::R + e, w1[u], flag, p.header + 2);
                 qkv_raw[e] = round_h(v);                         // q / k / v leave the projection as fp16 (eager model)
             }
         }
@@ -737,7 +737,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int i = tid + u * CONSUMER_THREADS;
-                if (i < nw) mg[i] = ll_resolve(src[u], w[u], flag);
+                if (i < nw) mg[i] = ll_resolve(src[u], w[u], flag, p.header + 2);
             }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
@@ -765,7 +765,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int e = tid + u * CONSUMER_THREADS;
-                if (e < NA) ag2[e] = ll_resolve(ag_ll + e, w[u], flag);
+                if (e < NA) ag2[e] = ll_resolve(ag_ll + e, w[u], flag, p.header + 2);
             }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);

@@ -169,9 +169,16 @@ __device__ __forceinline__ unsigned long long ll_load(const unsigned long long* 
     asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return w;
 }
-// spin until the word carries this launch's epoch (the first probe `w` was issued by the caller, batched with others)
-__device__ __forceinline__ float ll_resolve(const unsigned long long* p, unsigned long long w, unsigned flag) {
-    while ((unsigned)(w >> 32) != flag) w = ll_load(p);
+// spin until the word carries this launch's epoch (the first probe `w` was issued by the caller, batched with others).
+// The spin is bounded (~1 s of dependent L2 round trips): a publisher that never arrives -- CTAs of a group not
+// co-resident, a workspace shared by two streams -- turns into an error word in the workspace header (`err`, header[2])
+// and a wrong result instead of a hung GPU.
+__device__ __forceinline__ float ll_resolve(const unsigned long long* p, unsigned long long w, unsigned flag, unsigned* err) {
+    unsigned spins = 0;
+    while ((unsigned)(w >> 32) != flag) {
+        w = ll_load(p);
+        if (++spins > (1u << 22)) { *err = 1u; break; }
+    }
     return __uint_as_float((unsigned)w);
 }
 
@@ -239,7 +246,7 @@ __device__ __forceinline__ void ll_finalize_columns(const KParams& p, const unsi
                 for (int j = 0; j < 8; ++j) w[j] = (c + j < c1) ? ll_load(base + (size_t)(c + j) * hidden) : 0ull;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (c + j < c1) acc += ll_resolve(base + (size_t)(c + j) * hidden, w[j], flag);
+                    if (c + j < c1) acc += ll_resolve(base + (size_t)(c + j) * hidden, w[j], flag, p.header + 2);
             }
         }
         // fixed-order combine of the 4 sub-sums: (s0 + s1) + (s2 + s3)

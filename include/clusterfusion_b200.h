@@ -110,7 +110,9 @@ typedef struct CfLlamaArgs {
     void* workspace;  /* cf_llama_workspace_bytes(hidden, workspace_batch) bytes, zero-filled ONCE by the caller and
                          opaque afterwards (a launch epoch, zeroed scratch / counters and stale exchange words
                          live in it).  One workspace per stream that may run concurrently; its internal layout
-                         depends on (hidden, workspace_batch), so keep both fixed for the life of a workspace. */
+                         depends on (hidden, workspace_batch), so keep both fixed for the life of a workspace.
+                         Its first 16 bytes are u32 {launch epoch, -, error, peer-stage launches}: `error` becomes 1 if an
+                         exchange poll inside a kernel ever timed out (~1 s); results of that launch are then invalid. */
     int32_t workspace_batch; /* the batch the workspace was sized for; 0 means `batch`.  Lets one workspace sized for
                                 the largest batch serve smaller launches (batch <= workspace_batch).            */
 

@@ -361,6 +361,7 @@ def test_gqa_group_kernel_repeatability_and_workspace_reset():
     ws = ct.workspace(4096, 1, d["x"].device)
     hdr = ws[:8].view(torch.int32).cpu()
     assert int(hdr[0]) >= 200 and int(hdr[1]) == 0          # one epoch per group-kernel launch on this workspace
+    assert int(ws[8:12].view(torch.int32).item()) == 0      # header[2]: no exchange poll ever timed out
     assert int(ws[256:256 + 4096 * 4 + 32 * 4].count_nonzero()) == 0
     tail = (4096 // 128) * 4096 * 8                          # batch-1 output words live at the end; counters just before
     assert int(ws[-tail - 128 * 4:-tail].count_nonzero()) == 0
