@@ -254,7 +254,7 @@ def test_paged_operator_vs_oracle(lens):
     assert close(out2, want_o)
 
 
-@pytest.mark.parametrize("lens", [[40, 0, 513, 7, 128, 1], [300] * 8, [17, 2]])
+@pytest.mark.parametrize("lens", [[40, 0, 513, 7, 128, 1], [300] * 8, [17, 2], [5000, 17, 3000, 1, 2049]])
 def test_batched_paged_kernel_matches_per_request_kernel_and_oracle(lens):
     """Row f3: the batched kernel (weights streamed once per chunk of 4 requests; chunks of 4 + a ragged tail) against
     the oracle and against the per-request launch (CF_FLAG_PER_REQUEST, the reference's grid shape)."""
@@ -336,6 +336,53 @@ def test_gqa_group_kernel_and_cluster_kernel_agree_with_oracle(shape, kv_len):
         assert close(v, want[3])
         assert close(k, want[2], atol=4e-3)
         assert close(o, want[0])
+
+
+def test_gqa_group_kernel_long_context_32k():
+    """Llama-3-8B shapes at kv 32K: 128 K/V tiles per CTA through the tensor-core attention loop (many online-softmax
+    rescales per warp), against the oracle run in full."""
+    import cabi_torch as ct
+    kv = 32768
+    d = O.make_inputs(S8, kv, seed=32, layout="sglang", theta=500000.0)
+    want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                          d["rms_w"], 1e-5, d["cos"], d["sin"], n_heads=32, n_kv_heads=8, mode="eager")
+    c = cuda(d)
+    o, r, k, v = ct.sglang(c["x"], c["residual"], c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"], c["rms_w"],
+                           1e-5, c["cos"], c["sin"], n_heads=32, n_kv_heads=8)
+    torch.cuda.synchronize()
+    assert close(o, want[0]) and close(v, want[3]) and close(k, want[2], atol=4e-3)
+
+
+def test_gqa_attention_is_a_convex_combination():
+    """Size-independent property of the tensor-core loop: if every cached V row of a KV head is the same vector u and the
+    new token's V row equals u as well, the attention output of all 4 query heads of that KV head is exactly u whatever
+    the scores are (the fp16-rounded probabilities are normalised by their own sum).  Checked through Wo = identity."""
+    import cabi_torch as ct
+    kv, H = 5000, 4096
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, H, generator=g).half(); res = torch.zeros(1, H).half()
+    wq = (torch.randn(32 * 128, H, generator=g) * 0.05).half()
+    wk = (torch.randn(8 * 128, H, generator=g) * 0.05).half()
+    wv = torch.zeros(8 * 128, H).half()                        # new token's V = 0 ...
+    u = torch.zeros(1, 8 * 128).half()                         # ... so u = 0 would be trivial: use V = const instead
+    rms = torch.ones(H).half()
+    kc = torch.randn(kv, 8 * 128, generator=g).half()
+    cvec = torch.randn(8 * 128, generator=g).half()
+    vc = cvec.expand(kv, 8 * 128).contiguous()
+    wo = torch.eye(H).half()                                   # hidden == Hq * 128: out = attention output
+    ang = O.rope_angles(kv, theta=500000.0)
+    o, r, k, v = ct.sglang(x.cuda(), res.cuda(), torch.cat([wq, wk, wv], 0).contiguous().cuda(), wo.cuda(), kc.cuda(), vc.cuda(),
+                           rms.cuda(), 1e-5, ang.cos().cuda(), ang.sin().cuda(), n_heads=32, n_kv_heads=8)
+    torch.cuda.synchronize()
+    # out[head h] = (1 - p_new) * cvec[kv head] + p_new * 0, with p_new = softmax weight of the current token (~1/5001)
+    want = cvec.view(8, 1, 128).expand(8, 4, 128).reshape(1, H).float()
+    got = o.float().cpu()
+    ratio = got / want.clamp_min(1e-3).where(want.abs() > 0.25, torch.ones_like(want))
+    sel = want.abs() > 0.25
+    assert sel.sum() > 1000
+    # every selected element is shrunk by the same factor (1 - p_new) of its head, within fp16 rounding
+    per_head = (got[sel] / want[sel])
+    assert float(per_head.min()) > 0.995 and float(per_head.max()) < 1.002
 
 
 def test_gqa_group_kernel_repeatability_and_workspace_reset():
