@@ -292,12 +292,15 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, 32, true))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, 32, true))) return rc;
     } else if (chat) {
-        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, 3 * H, H, 128, cfb::ROWS256))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, qd, H, 128, cfb::ROWS256))) return rc;
+        // MHA kernels read weight tiles with ldmatrix: [rows x 64 cols] boxes, 128-byte swizzled (2 or 4 per 8 KB tile)
+        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, 3 * H, H, 64, cfb::ROWS256, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, qd, H, 64, cfb::ROWS256, true))) return rc;
+    } else if (!gqa) {
+        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, cfb::ROWS512, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, cfb::ROWS256, true))) return rc;
     } else {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 256, cfb::ROWS512))) return rc;
-        if (gqa) { if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 256, cfb::ROWS512))) return rc; }
-        else     { if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 128, cfb::ROWS256))) return rc; }
+        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 256, cfb::ROWS512))) return rc;
     }
     if (!paged) {
         // kv_len == 0: no tile is ever requested; point the maps at any valid address

@@ -278,6 +278,43 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 }
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core helpers (mma.sync.m16n8k16, fp16 in / fp32 accumulate).  Weight tiles land as 128-byte-swizzled TMA boxes
+// of [rows][64 halves]: the 16-byte chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4), which makes the eight row
+// addresses of every 8x8 ldmatrix hit eight different bank groups.  The GEMVs put the weights on the A operand (M = 16
+// output rows or columns per step) and the activation vector(s) on the N = 8 dimension; at batch 1 only column 0 is
+// real -- the tensor cores are idle anyway and this replaces ~17 LDS/CVT/FFMA per 16 x 8 weight block by one ldmatrix +
+// one mma, which matters where a phase is consumption-bound (O projection: its tiles were prefetched during the softmax
+// exchange) rather than HBM-bound.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragment (m0..m0+15, 16 k) from a swizzled block whose shared-memory rows are the M rows ([m][k], nn.Linear tiles);
+// kchunk0 = first 16-byte chunk of the k-step inside the 64-half row
+__device__ __forceinline__ void ldsm_a_mrows(uint32_t (&a)[4], uint32_t block, int m0, int kchunk0, uint32_t lane) {
+    const int lmat = lane >> 3, row = m0 + (lmat & 1) * 8 + (lane & 7), chunk = kchunk0 + (lmat >> 1);
+    const uint32_t addr = block + row * 128 + ((chunk ^ (row & 7)) << 4);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+}
+// A fragment from a swizzled block whose shared-memory rows are the K rows ([k][m], transposed "chat" tiles): k0 = first
+// k row of the step, mchunk0 = first 16-byte chunk of the 16 output columns inside the 64-half row
+__device__ __forceinline__ void ldsm_a_krows(uint32_t (&a)[4], uint32_t block, int k0, int mchunk0, uint32_t lane) {
+    const int lmat = lane >> 3, row = k0 + (lmat >> 1) * 8 + (lane & 7), chunk = mchunk0 + (lmat & 1);
+    const uint32_t addr = block + row * 128 + ((chunk ^ (row & 7)) << 4);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+}
+// B fragment of a single activation vector on column n = 0: {v[k0 + 2*t4], v[k0 + 2*t4 + 1]} for lanes 0-3, zero elsewhere
+__device__ __forceinline__ uint32_t bfrag_col0(const float* v, int k0, uint32_t lane) {
+    if (lane >= 4) return 0u;
+    const __half2 h2 = __floats2half2_rn(v[k0 + 2 * lane], v[k0 + 2 * lane + 1]);
+    return *reinterpret_cast<const uint32_t*>(&h2);
+}
+
 // Optional phase timeline (build with -DCF_TRACE; tools/trace_timeline.py).  Never compiled into the product.
 #ifdef CF_TRACE
 __device__ unsigned long long* g_cf_trace = nullptr;     // [grid][16] globaltimer ns, set by cf_debug_set_trace
@@ -404,7 +441,13 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                     c1 = row0 + sub * ROWS512;
                 }
                 dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                tma_load_2d(dst, &p.tm_wqkv, c0, c1, fb, pol);
+                if constexpr (kChat) {           // two [32 rows x 64 cols] swizzled boxes
+                    tma_load_2d(dst, &p.tm_wqkv, c0, c1, fb, pol);
+                    tma_load_2d(dst + 4096, &p.tm_wqkv, c0 + 64, c1, fb, pol);
+                } else {                         // four [16 rows x 64 cols] swizzled boxes
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * 2048, &p.tm_wqkv, c0 + q * 64, c1, fb, pol);
+                }
             }
         } else if (g < n_qkv_tiles + n_kv_tiles) {
             const uint32_t i = g - n_qkv_tiles;                 // 16 KV rows: K in the first 4 KB of the stage, V in the second
@@ -441,8 +484,9 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                     c0 = head * HEAD_DIM;
                     c1 = rank * KS + i * ROWS256;
                 }
-                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);           // two [32 rows x 64 cols] swizzled boxes
                 tma_load_2d(dst, &p.tm_wo, c0, c1, fb, pol);
+                tma_load_2d(dst + 4096, &p.tm_wo, c0 + 64, c1, fb, pol);
             }
         }
         if constexpr (kPaged) {
@@ -582,87 +626,62 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         // tile i = 32 input rows (t = i / 3) x 128 output cols of matrix j = i % 3.  The QKV phase starts at
         // ring index 0 and 12 % 3 == 0, so warp w only ever sees matrix j = w % 3: its 8 column sums stay in
         // registers for the whole phase.  lane (sub, c): rows sub + 2s, cols c*8 .. c*8+7.
-        const int sub = lane >> 4, c = lane & 15;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // Tensor cores: D[128 cols][8] += tile^T[128 x 32] * x[32 x 8] (x on column 0): 8 m-blocks x 2 k-steps per tile.
+        const int g4 = lane >> 2, t4 = lane & 3;
+        float acc[8][4];
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb) { acc[mb][0] = 0.f; acc[mb][1] = 0.f; acc[mb][2] = 0.f; acc[mb][3] = 0.f; }
         for (uint32_t i = first_tile(gbase, warp); i < n_qkv_tiles; i += CONSUMER_WARPS) {
             const uint32_t g = gbase + i, s = ring_stage(g);
-            ring_wait_full(full_u32, g);
-            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
             const float* xrow = xs + (i / 3) * ROWS256;
-#pragma unroll 8
-            for (int r = 0; r < ROWS256 / 2; ++r) {
-                const int row = 2 * r + sub;
-                float w8[8];
-                unpack8(tile[row * 16 + c], w8);
-                const float xv = xrow[row];
+            uint32_t xb[2][2];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, w8[k], acc[k]);
+            for (int ks = 0; ks < 2; ++ks) { xb[ks][0] = bfrag_col0(xrow, ks * 16, lane); xb[ks][1] = bfrag_col0(xrow, ks * 16 + 8, lane); }
+            ring_wait_full(full_u32, g);
+            const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
+#pragma unroll
+            for (int mb = 0; mb < 8; ++mb) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    uint32_t af[4];
+                    ldsm_a_krows(af, st + (mb >> 2) * 4096, ks * 16, (mb & 3) * 2, lane);
+                    mma16816(acc[mb], af, xb[ks][0], xb[ks][1]);
+                }
             }
             __syncwarp();
             issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
         }
+        if (t4 == 0) {       // C fragment column 0: rows g4 and g4 + 8 of each 16-column block; write-once slot [warp][128]
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
-        if (sub == 0) {      // write-once slot [warp][128]
-            float4* slot = reinterpret_cast<float4*>(qkv_part + warp * HEAD_DIM + c * 8);
-            slot[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            slot[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            for (int mb = 0; mb < 8; ++mb) {
+                qkv_part[warp * HEAD_DIM + mb * 16 + g4] = acc[mb][0];
+                qkv_part[warp * HEAD_DIM + mb * 16 + g4 + 8] = acc[mb][2];
+            }
         }
     } else {
-        // tile = 16 output rows x 256 input cols; lane owns input cols lane*8..+8 of every row
+        // tile = 16 output rows x 256 input cols as four swizzled [16 x 64] boxes.  Tensor cores: D[16 rows][8] =
+        // tile[16 x 256] * x[256 x 8] (x on column 0): one m-block x 16 k-steps per tile.
         const int wins = KS / 256;
+        const int g4 = lane >> 2, t4 = lane & 3;
         for (uint32_t i = first_tile(gbase, warp); i < n_qkv_tiles; i += CONSUMER_WARPS) {
             const uint32_t g = gbase + i, s = ring_stage(g);
             const int rb = i / wins, win = i % wins;
-            float x8[8];
-            {
-                const float4 a = *reinterpret_cast<const float4*>(xs + win * 256 + lane * 8);
-                const float4 b = *reinterpret_cast<const float4*>(xs + win * 256 + lane * 8 + 4);
-                x8[0] = a.x; x8[1] = a.y; x8[2] = a.z; x8[3] = a.w;
-                x8[4] = b.x; x8[5] = b.y; x8[6] = b.z; x8[7] = b.w;
-            }
+            const float* xw = xs + win * 256;
+            uint32_t xb[16][2];
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) { xb[ks][0] = bfrag_col0(xw, ks * 16, lane); xb[ks][1] = bfrag_col0(xw, ks * 16 + 8, lane); }
             ring_wait_full(full_u32, g);
-            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+            const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int grp = 0; grp < ROWS512 / 8; ++grp) {
-                float v[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    float w8[8];
-                    unpack8(tile[(grp * 8 + r) * 32 + lane], w8);
-                    float a = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) a = fmaf(x8[k], w8[k], a);
-                    v[r] = a;
-                }
-                // transpose-reduce 8 values over 32 lanes: 4 + 2 + 1 + 1 + 1 shuffles
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const bool hi = lane & 16;
-                    const float send = hi ? v[r] : v[r + 4];
-                    const float keep = hi ? v[r + 4] : v[r];
-                    v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const bool hi = lane & 8;
-                    const float send = hi ? v[r] : v[r + 2];
-                    const float keep = hi ? v[r + 2] : v[r];
-                    v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                }
-                {
-                    const bool hi = lane & 4;
-                    const float send = hi ? v[0] : v[1];
-                    const float keep = hi ? v[1] : v[0];
-                    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
-                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-                // lane bits (4,3,2) select the row: row = 4*b4 + 2*b3 + b2
-                if ((lane & 3) == 0) {
-                    const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                    qkv_part[win * S::QKV_OUT + rb * ROWS512 + grp * 8 + r] = v[0];   // write-once slot
-                }
+            for (int ks = 0; ks < 16; ++ks) {
+                uint32_t af[4];
+                ldsm_a_mrows(af, st + (ks >> 2) * 2048, 0, (ks & 3) * 2, lane);
+                mma16816(acc, af, xb[ks][0], xb[ks][1]);
+            }
+            if (t4 == 0) {                                       // write-once slots
+                qkv_part[win * S::QKV_OUT + rb * ROWS512 + g4] = acc[0];
+                qkv_part[win * S::QKV_OUT + rb * ROWS512 + g4 + 8] = acc[2];
             }
             __syncwarp();
             issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
@@ -846,88 +865,69 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     }
 
     CF_MARK(6);   // softmax merge + exchange done
-    // ---- phase 3: O GEMV for output columns [rank*KS, +KS) --------------------------------------------
+    // ---- phase 3: O GEMV for output columns [rank*KS, +KS), on the tensor cores (attention output on column 0) ------
     if constexpr (kChat) {
-        // tile = 32 input rows (a quarter of the head) x 128 output cols; lane (sub, c): rows sub+2s, cols c*8..+8
-        const int sub = lane >> 4, c = lane & 15;
+        // tile = 32 input rows (a quarter of the head) x 128 output cols: D[128][8] = tile^T[128 x 32] * a[32 x 8]
+        const int g4 = lane >> 2, t4 = lane & 3;
         for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
             const uint32_t g = gbase + i, s = ring_stage(g);
-            ring_wait_full(full_u32, g);
-            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
             const int cb = i >> 2, rh = i & 3;
             const float* arow = attn_out + rh * ROWS256;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-            for (int r = 0; r < ROWS256 / 2; ++r) {
-                const int row = 2 * r + sub;
-                float w8[8];
-                unpack8(tile[row * 16 + c], w8);
-                const float av = arow[row];
+            uint32_t ab[2][2];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fmaf(av, w8[k], acc[k]);
+            for (int ks = 0; ks < 2; ++ks) { ab[ks][0] = bfrag_col0(arow, ks * 16, lane); ab[ks][1] = bfrag_col0(arow, ks * 16 + 8, lane); }
+            ring_wait_full(full_u32, g);
+            const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
+            float acc[8][4];
+#pragma unroll
+            for (int mb = 0; mb < 8; ++mb) {
+                acc[mb][0] = 0.f; acc[mb][1] = 0.f; acc[mb][2] = 0.f; acc[mb][3] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    uint32_t af[4];
+                    ldsm_a_krows(af, st + (mb >> 2) * 4096, ks * 16, (mb & 3) * 2, lane);
+                    mma16816(acc[mb], af, ab[ks][0], ab[ks][1]);
+                }
             }
             __syncwarp();
             issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
+            if (t4 == 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
-            if (sub == 0) {
-                float4* dstp = reinterpret_cast<float4*>(out_part + rh * KS + cb * 128 + c * 8);
-                dstp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                dstp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                for (int mb = 0; mb < 8; ++mb) {
+                    out_part[rh * KS + cb * 128 + mb * 16 + g4] = acc[mb][0];
+                    out_part[rh * KS + cb * 128 + mb * 16 + g4 + 8] = acc[mb][2];
+                }
             }
         }
     } else {
-        // tile = 32 output rows x 128 input cols; lane (sub, c): rows sub+2s, input cols c*8..+8
-        const int sub = lane >> 4, c = lane & 15;
-        float a8[8];
+        // tile = 32 output rows x 128 input cols as two swizzled [32 x 64] boxes: D[32][8] = tile[32 x 128] * a[128 x 8]
+        const int g4 = lane >> 2, t4 = lane & 3;
+        uint32_t ab[8][2];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a8[k] = attn_out[c * 8 + k];
+        for (int ks = 0; ks < 8; ++ks) { ab[ks][0] = bfrag_col0(attn_out, ks * 16, lane); ab[ks][1] = bfrag_col0(attn_out, ks * 16 + 8, lane); }
         for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
             const uint32_t g = gbase + i, s = ring_stage(g);
             ring_wait_full(full_u32, g);
-            const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+            const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-            for (int grp = 0; grp < ROWS256 / 16; ++grp) {
-                float v[8];
+            for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int row = 2 * (grp * 8 + r) + sub;
-                    float w8[8];
-                    unpack8(tile[row * 16 + c], w8);
-                    float a = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) a = fmaf(a8[k], w8[k], a);
-                    v[r] = a;
-                }
-                // transpose-reduce 8 values over the 16 lanes of a half-warp: 4 + 2 + 1 + 1 shuffles
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const bool hi = lane & 8;
-                    const float send = hi ? v[r] : v[r + 4];
-                    const float keep = hi ? v[r + 4] : v[r];
-                    v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                }
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const bool hi = lane & 4;
-                    const float send = hi ? v[r] : v[r + 2];
-                    const float keep = hi ? v[r + 2] : v[r];
-                    v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
-                {
-                    const bool hi = lane & 2;
-                    const float send = hi ? v[0] : v[1];
-                    const float keep = hi ? v[1] : v[0];
-                    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                }
-                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-                if ((lane & 1) == 0) {
-                    const int r = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    out_part[i * ROWS256 + 2 * (grp * 8 + r) + sub] = v[0];
+                for (int mb = 0; mb < 2; ++mb) {
+                    uint32_t af[4];
+                    ldsm_a_mrows(af, st + (ks >> 2) * 4096, mb * 16, (ks & 3) * 2, lane);
+                    mma16816(acc[mb], af, ab[ks][0], ab[ks][1]);
                 }
             }
             __syncwarp();
             issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
+            if (t4 == 0) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    out_part[i * ROWS256 + mb * 16 + g4] = acc[mb][0];
+                    out_part[i * ROWS256 + mb * 16 + g4 + 8] = acc[mb][2];
+                }
+            }
         }
     }
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
