@@ -426,8 +426,8 @@ extern "C" int cf_llama_ffn_launch(const CfFfnArgs* a, void* stream_) {
     cfb::FfnParams fp;
     memset(&fp, 0, sizeof fp);
     int rc;
-    if ((rc = get_tensor_map(&fp.tm_w13, a->w_gate_up, 2ull * a->ffn, a->hidden, 64, cfb::FFN_BLOCK, true))) return rc;
-    if ((rc = get_tensor_map(&fp.tm_w2t, a->w_down_t, a->ffn, a->hidden, 64, cfb::FFN_BLOCK, true))) return rc;
+    if ((rc = get_tensor_map(&fp.tm_w13, a->w_gate_up, 2ull * a->ffn, a->hidden, 256, cfb::FFN_BLOCK))) return rc;
+    if ((rc = get_tensor_map(&fp.tm_w2t, a->w_down_t, a->ffn, a->hidden, 256, cfb::FFN_BLOCK))) return rc;
     fp.x = static_cast<const __half*>(a->x);
     fp.residual_in = static_cast<const __half*>(a->residual_in);
     fp.rms_w = static_cast<const __half*>(a->rms_w);

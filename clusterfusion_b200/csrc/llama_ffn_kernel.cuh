@@ -91,16 +91,12 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
         if (g < n_gu_tiles) {
             const int k = g / (2 * wins), r = g % (2 * wins), mat = r / wins, win = r % wins;
             const int blk = cta + k * grid;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)      // four [16 rows x 64 cols] 128-byte-swizzled boxes: ldmatrix-ready
-                tma_load_2d(dst + q * 2048, &p.tm_w13, win * 256 + q * 64, mat * ffn + blk * FFN_BLOCK, fb, pol);
+            tma_load_2d(dst, &p.tm_w13, win * 256, mat * ffn + blk * FFN_BLOCK, fb, pol);
         } else {
             const uint32_t i = g - n_gu_tiles;
             const int k = i / wins, cb = i % wins;
             const int blk = cta + k * grid;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                tma_load_2d(dst + q * 2048, &p.tm_w2t, cb * 256 + q * 64, blk * FFN_BLOCK, fb, pol);
+            tma_load_2d(dst, &p.tm_w2t, cb * 256, blk * FFN_BLOCK, fb, pol);
         }
     };
     if (lane == 0) {
@@ -190,25 +186,52 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
     for (uint32_t g = warp; g < n_gu_tiles; g += CONSUMER_WARPS) {
         const uint32_t s = ring_stage(g);
         const int k = g / (2 * wins), r = g % (2 * wins), mat = r / wins, win = r % wins;
-        // tensor cores: D[16 rows][8] = tile[16 x 256] * x[256 x 8], x on column 0 (see llama_decoder_kernel.cuh)
-        const float* xw = xs + win * 256;
-        uint32_t xb[16][2];
-#pragma unroll
-        for (int ks = 0; ks < 16; ++ks) { xb[ks][0] = bfrag_col0(xw, ks * 16, lane); xb[ks][1] = bfrag_col0(xw, ks * 16 + 8, lane); }
-        ring_wait_full(full_u32, g);
+        float x8[8];
         {
-            const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const float4 a = *reinterpret_cast<const float4*>(xs + win * 256 + lane * 8);
+            const float4 b = *reinterpret_cast<const float4*>(xs + win * 256 + lane * 8 + 4);
+            x8[0] = a.x; x8[1] = a.y; x8[2] = a.z; x8[3] = a.w; x8[4] = b.x; x8[5] = b.y; x8[6] = b.z; x8[7] = b.w;
+        }
+        ring_wait_full(full_u32, g);
+        const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+        float* dst = gu + (k * 2 + mat) * FFN_BLOCK;
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks) {
-                uint32_t af[4];
-                ldsm_a_mrows(af, st + (ks >> 2) * 2048, 0, (ks & 3) * 2, lane);
-                mma16816(acc, af, xb[ks][0], xb[ks][1]);
+        for (int grp = 0; grp < FFN_BLOCK / 8; ++grp) {
+            float v[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                float w8[8];
+                unpack8(tile[(grp * 8 + rr) * 32 + lane], w8);
+                float a = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) a = fmaf(x8[kk], w8[kk], a);
+                v[rr] = a;
             }
-            if ((lane & 3) == 0) {                               // 16 windows of the same row land here
-                float* dst = gu + (k * 2 + mat) * FFN_BLOCK;
-                atomicAdd(dst + (lane >> 2), acc[0]);
-                atomicAdd(dst + (lane >> 2) + 8, acc[2]);
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const bool hi = lane & 16;
+                const float send = hi ? v[rr] : v[rr + 4];
+                const float keep = hi ? v[rr + 4] : v[rr];
+                v[rr] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const bool hi = lane & 8;
+                const float send = hi ? v[rr] : v[rr + 2];
+                const float keep = hi ? v[rr + 2] : v[rr];
+                v[rr] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            {
+                const bool hi = lane & 4;
+                const float send = hi ? v[0] : v[1];
+                const float keep = hi ? v[1] : v[0];
+                v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            if ((lane & 3) == 0) {
+                const int row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                atomicAdd(dst + grp * 8 + row, v[0]);          // 16 windows of the same row land here
             }
         }
         __syncwarp();
@@ -231,28 +254,23 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
     for (uint32_t i = first_tile(n_gu_tiles, warp); i < n_dn_tiles; i += CONSUMER_WARPS) {
         const uint32_t g = n_gu_tiles + i, s = ring_stage(g);
         const int k = i / wins, cb = i % wins;
-        // tensor cores: D[256 cols][8] = tile^T[256 x 16] * act[16 x 8] (act on column 0): 16 m-blocks x 1 k-step
-        const uint32_t ab0 = bfrag_col0(act + k * FFN_BLOCK, 0, lane), ab1 = bfrag_col0(act + k * FFN_BLOCK, 8, lane);
         ring_wait_full(full_u32, g);
-        const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
-        float acc[16][4];
+        const uint4* tile = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+        const float* a16 = act + k * FFN_BLOCK;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int mb = 0; mb < 16; ++mb) {
-            acc[mb][0] = 0.f; acc[mb][1] = 0.f; acc[mb][2] = 0.f; acc[mb][3] = 0.f;
-            uint32_t af[4];
-            ldsm_a_krows(af, st + (mb >> 2) * 2048, 0, (mb & 3) * 2, lane);
-            mma16816(acc[mb], af, ab0, ab1);
+        for (int r = 0; r < FFN_BLOCK; ++r) {
+            float w8[8];
+            unpack8(tile[r * 32 + lane], w8);
+            const float av = a16[r];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) acc[kk] = fmaf(av, w8[kk], acc[kk]);
         }
         __syncwarp();
         issue_tile(g + NSTAGES);
-        if ((lane & 3) == 0) {
-            float* dst = out_acc + cb * 256 + (lane >> 2);
+        float* dst = out_acc + cb * 256 + lane * 8;
 #pragma unroll
-            for (int mb = 0; mb < 16; ++mb) {
-                atomicAdd(dst + mb * 16, acc[mb][0]);
-                atomicAdd(dst + mb * 16 + 8, acc[mb][2]);
-            }
-        }
+        for (int kk = 0; kk < 8; ++kk) atomicAdd(dst + kk, acc[kk]);
     }
     __syncthreads();
 
