@@ -298,9 +298,6 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     } else if (!gqa) {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, cfb::ROWS512, true))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, cfb::ROWS256, true))) return rc;
-    } else if (!(a->flags & CF_FLAG_GQA_CLUSTER)) {      // group kernel: ldmatrix-ready weight tiles, four boxes per tile
-        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, cfb::ROWS512, true))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, cfb::ROWS512, true))) return rc;
     } else {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 256, cfb::ROWS512))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 256, cfb::ROWS512))) return rc;

@@ -228,9 +228,8 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 if (rb < NQ * BPH) row0 = qh0 * HEAD_DIM + rb * ROWS512;
                 else if (rb < NQ * BPH + BPH) row0 = Hq * HEAD_DIM + kvh * HEAD_DIM + (rb - NQ * BPH) * ROWS512;
                 else row0 = (Hq + Hkv) * HEAD_DIM + kvh * HEAD_DIM + (rb - NQ * BPH - BPH) * ROWS512;
-                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);           // four [16 rows x 64 cols] swizzled boxes
-#pragma unroll
-                for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * 2048, &p.tm_wqkv, win * 256 + q * 64, row0, fb, pol);
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wqkv, win * 256, row0, fb, pol);
             }
         } else if (g < n_qkv_tiles + n_kv_tiles) {
             const uint32_t i = g - n_qkv_tiles;
@@ -263,9 +262,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 const uint32_t i = g - n_qkv_tiles - n_kv_tiles;
                 const int rb = i / owins, win = i % owins;       // Wo [out][in]: 16 output rows x 256 of this group's input cols
                 dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    tma_load_2d(dst + q * 2048, &p.tm_wo, qh0 * HEAD_DIM + win * 256 + q * 64, rank * OROWS + rb * ROWS512, fb, pol);
+                tma_load_2d(dst, &p.tm_wo, qh0 * HEAD_DIM + win * 256, rank * OROWS + rb * ROWS512, fb, pol);
             }
         }
         if constexpr (kPaged) {
@@ -395,30 +392,11 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         const uint32_t g = gbase + i, s = ring_stage(g);
         const uint32_t t = t_first + i;
         const int rb = t / wins, win = t % wins;
-        // tensor cores: D[16 rows][8] = tile[16 x 256] * x[256 x 8], x (fp16 in shared memory) on column 0
-        uint32_t xb[16][2];
-#pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {
-            const __half* xp = xs + win * 256 + ks * 16 + 2 * (lane & 3);
-            xb[ks][0] = lane < 4 ? *reinterpret_cast<const uint32_t*>(xp) : 0u;
-            xb[ks][1] = lane < 4 ? *reinterpret_cast<const uint32_t*>(xp + 8) : 0u;
-        }
+        float x8[8];
+        unpack8(*reinterpret_cast<const uint4*>(xs + win * 256 + lane * 8), x8);
         ring_wait_full(full_u32, g);
-        {
-            const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int ks = 0; ks < 16; ++ks) {
-                uint32_t af[4];
-                ldsm_a_mrows(af, st + (ks >> 2) * 2048, 0, (ks & 3) * 2, lane);
-                mma16816(acc, af, xb[ks][0], xb[ks][1]);
-            }
-            if ((lane & 3) == 0) {                               // C fragment column 0: rows lane/4 and lane/4 + 8
-                float* pr = part + (warp * G2_RB_LOCAL_MAX + (rb - rb_first)) * ROWS512;
-                pr[lane >> 2] += acc[0];
-                pr[(lane >> 2) + 8] += acc[2];
-            }
-        }
+        gemv_tile_16x256_acc(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), x8,
+                             part + (warp * G2_RB_LOCAL_MAX + (rb - rb_first)) * ROWS512, lane);
         __syncwarp();
         issue_tile(g + NSTAGES);
     }
@@ -799,28 +777,15 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
             const uint32_t g = gbase + i, s = ring_stage(g);
             const int rb = i / owins, win = i % owins;
-            uint32_t ab[16][2];
-#pragma unroll
-            for (int ks = 0; ks < 16; ++ks) {
-                ab[ks][0] = bfrag_col0(ag2 + win * 256, ks * 16, lane);
-                ab[ks][1] = bfrag_col0(ag2 + win * 256, ks * 16 + 8, lane);
+            float a8[8];
+            {
+                const float4 a = *reinterpret_cast<const float4*>(ag2 + win * 256 + lane * 8);
+                const float4 b = *reinterpret_cast<const float4*>(ag2 + win * 256 + lane * 8 + 4);
+                a8[0] = a.x; a8[1] = a.y; a8[2] = a.z; a8[3] = a.w; a8[4] = b.x; a8[5] = b.y; a8[6] = b.z; a8[7] = b.w;
             }
             ring_wait_full(full_u32, g);
-            {
-                const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int ks = 0; ks < 16; ++ks) {
-                    uint32_t af[4];
-                    ldsm_a_mrows(af, st + (ks >> 2) * 2048, 0, (ks & 3) * 2, lane);
-                    mma16816(acc, af, ab[ks][0], ab[ks][1]);
-                }
-                if ((lane & 3) == 0) {
-                    float* po = out_part + win * G2_OROWS_MAX + rb * ROWS512;
-                    po[lane >> 2] = acc[0];
-                    po[(lane >> 2) + 8] = acc[2];
-                }
-            }
+            gemv_tile_16x256(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), a8,
+                             out_part + win * G2_OROWS_MAX + rb * ROWS512, lane);
             __syncwarp();
             issue_tile(g + NSTAGES);
         }
