@@ -26,6 +26,8 @@ CF_FLAG_PER_REQUEST = 0x10
 
 EXPORTED_SYMBOLS = (
     "cf_abi_version",
+    "cf_sizeof_llama_args",
+    "cf_sizeof_ffn_args",
     "cf_last_error_string",
     "cf_llama_workspace_bytes",
     "cf_rmsnorm_launch",
@@ -116,6 +118,11 @@ def load() -> C.CDLL:
             "(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no CPU fallback.")
     lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
     lib.cf_abi_version.restype = C.c_int
+    lib.cf_sizeof_llama_args.restype = C.c_size_t
+    lib.cf_sizeof_ffn_args.restype = C.c_size_t
+    if lib.cf_sizeof_llama_args() != C.sizeof(CfLlamaArgs) or lib.cf_sizeof_ffn_args() != C.sizeof(CfFfnArgs):
+        raise ImportError(f"clusterfusion_b200.cabi: struct mirror out of date (CfLlamaArgs {C.sizeof(CfLlamaArgs)} vs "
+                          f"{lib.cf_sizeof_llama_args()}, CfFfnArgs {C.sizeof(CfFfnArgs)} vs {lib.cf_sizeof_ffn_args()}): rebuild")
     lib.cf_last_error_string.restype = C.c_char_p
     lib.cf_llama_workspace_bytes.restype = C.c_size_t
     lib.cf_llama_workspace_bytes.argtypes = [C.c_int32, C.c_int32]

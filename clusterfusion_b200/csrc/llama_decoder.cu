@@ -217,6 +217,9 @@ int cf_abi_version(void) { return CF_ABI_VERSION; }
 
 const char* cf_last_error_string(void) { return g_last_error.c_str(); }
 
+size_t cf_sizeof_llama_args(void) { return sizeof(CfLlamaArgs); }
+size_t cf_sizeof_ffn_args(void) { return sizeof(CfFfnArgs); }
+
 size_t cf_llama_workspace_bytes(int32_t hidden, int32_t batch) {
     if (hidden <= 0 || batch <= 0) return 0;
     // header + fp32 scratch [batch][hidden] + counters [batch][32] (any cluster size) + the grouped-query kernel's L2

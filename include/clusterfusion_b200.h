@@ -185,6 +185,10 @@ int cf_test_cluster_reduce(const float* in, float* out, int32_t n, int32_t clust
 
 const char* cf_last_error_string(void);
 int cf_abi_version(void);
+/* sizeof(CfLlamaArgs) / sizeof(CfFfnArgs) as compiled into the library: lets a foreign-language binding (ctypes, cgo, JNI)
+ * verify its mirror of the structs before the first launch. */
+size_t cf_sizeof_llama_args(void);
+size_t cf_sizeof_ffn_args(void);
 
 #ifdef __cplusplus
 }

@@ -83,3 +83,14 @@ def test_new_argument_errors_without_gpu():
     with pytest.raises(cabi.CfError) as e:
         cabi.launch(cabi.CfLlamaArgs(**{**base, "n_q_heads": 96, "n_kv_heads": 24, "hidden": 8192}))
     assert e.value.code in (-3, -5)
+
+
+def test_ctypes_struct_mirrors_match_the_compiled_structs():
+    import ctypes as C
+    from clusterfusion_b200 import cabi
+    lib = cabi.load()
+    assert lib.cf_sizeof_llama_args() == C.sizeof(cabi.CfLlamaArgs)
+    assert lib.cf_sizeof_ffn_args() == C.sizeof(cabi.CfFfnArgs)
+    # spot-check field offsets against the header's declaration order (pointers are 8-byte aligned after 10 x 4 bytes)
+    assert cabi.CfLlamaArgs.x.offset == 40 and cabi.CfLlamaArgs.workspace.offset == 40 + 18 * 8
+    assert cabi.CfLlamaArgs.tp_peer.offset == cabi.CfLlamaArgs.workspace.offset + 8 + 3 * 4 + 4
