@@ -6,7 +6,7 @@
  * Wqkv and Wo (kernel_batch_sglang.cuh:43-664); so did this repo's first paged path (grid (Hq*4, bs) of the MHA
  * kernel).  On B200 a CTA ingests at most ~64 GB/s, so bs requests cost bs layers.  Here one 4-CTA cluster per head
  * serves a chunk of BC = 4 requests: every Wqkv / Wo tile that lands in shared memory is multiplied against the BC
- * activation vectors held in registers (BC x the FMAs per byte -- still under the CUDA-core issue limit at BC = 4), the
+ * activation vectors on the tensor cores (see below), the
  * chunk's K/V pages follow in the same tile stream, and the two cluster exchanges carry all BC requests at once:
  *
  *   exchange 1  BC x (q|k|v) = 6 KB of fp32 partial sums per CTA: reduce-scatter (cluster_scatter, slice r folded in
