@@ -26,6 +26,9 @@
  *    arrival counter per output slice; the last-arriving CTA converts to fp16, writes `out`, and
  *    re-zeroes scratch + counter, so there are no memset launches and no fp16 atomics
  *    (reference: 131 072 fp16 atomicAdd per layer, kernel.cuh:600/:618).
+ *  - the two GEMVs read their 128-byte-swizzled weight tiles with ldmatrix and multiply them with mma.sync.m16n8k16
+ *    (activation vector on column 0 of N = 8): not for tensor throughput -- the layer is HBM-bound -- but because it
+ *    halves the issue slots; the MHA flash-decode loop (one FMA per K/V byte) stays on the CUDA cores.
  *
  * Shapes: head_dim 128; hidden % (CLUSTER*256) == 0, hidden/CLUSTER <= 2048.
  */
