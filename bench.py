@@ -161,7 +161,7 @@ def run_reference(args, rank, world):
         "note": "reference GPU kernels refuse sm_100 (setup.py:5-15); its eager model needs fairscale/fire/flashinfer-CUDA, "
                 "so the CPU path is the oracle's restatement of chat/llama/model.py (torch " + torch.__version__ + ")",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -473,7 +473,7 @@ def run_ours(args, rank, world, local_rank):
         line["llama3_8b_gqa"] = gqa
     if shard70 is not None:
         line["llama2_70b_head_parallel"] = shard70
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -811,7 +811,28 @@ def run_70b_sharded(torch, dist, dev, rank, world, peak):
     return res
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Print the ONE JSON line.  Under torchrun the process's fd 1 was redirected to stderr at start-up (NCCL and other
+    libraries print banners to stdout); the line goes to the saved original stdout."""
+    txt = json.dumps(line) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, txt.encode())
+    else:
+        sys.stdout.write(txt)
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # stdout must carry exactly one JSON line: keep the real stdout aside and send everything else to stderr
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)
