@@ -564,8 +564,8 @@ def run_batched_paged(torch, cabi, dev, timed_replays, peak, kv=1024, nl=8, batc
         bufs = [(torch.empty(bs, HIDDEN, dtype=torch.float16, device=dev), torch.empty(bs, HIDDEN, dtype=torch.float16, device=dev))
                 for _ in range(nl)]
         row = {"batch": bs, "kv_len": kv}
-        for name, fl in (("batched", 0), ("per_request", cabi.CF_FLAG_PER_REQUEST)):
-            if bs == 1 and name == "per_request":
+        for name, fl in (("batched", 0), ("batched_chunks_of_4", cabi.CF_FLAG_BATCH4), ("per_request", cabi.CF_FLAG_PER_REQUEST)):
+            if (bs == 1 and name != "batched") or (bs < 5 and name == "batched_chunks_of_4"):
                 continue
 
             def launch(h, rr, li, st):

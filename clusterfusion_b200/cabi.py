@@ -23,6 +23,7 @@ CF_FLAG_PDL = 0x2
 CF_FLAG_GQA_CLUSTER = 0x4
 CF_FLAG_LL_OUT = 0x8
 CF_FLAG_PER_REQUEST = 0x10
+CF_FLAG_BATCH4 = 0x20
 
 EXPORTED_SYMBOLS = (
     "cf_abi_version",

@@ -15,6 +15,7 @@
 #include "llama_decoder_gqa_kernel.cuh"
 #include "llama_decoder_gqa2_kernel.cuh"
 #include "llama_decoder_batch_kernel.cuh"
+#include "llama_decoder_batch8_kernel.cuh"
 #include "llama_ffn_kernel.cuh"
 #include "rmsnorm_kernel.cuh"
 
@@ -389,6 +390,9 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         return wide ? launch_gqa<cfb::SGLANG, 16>(kp, n_clusters, 1, pdl, stream)
                     : launch_gqa<cfb::SGLANG, 8>(kp, n_clusters, 1, pdl, stream);
     }
+    if (batched && a->batch >= 5 && !(a->flags & CF_FLAG_BATCH4))      // chunks of 8: the whole N dimension of the MMA
+        return launch_kernel<CL>(cfb::llama_decoder_layer_batch8_kernel, cfb::SmemB8::TOTAL, 3, kp, a->n_q_heads,
+                                 (a->batch + 7) / 8, pdl, stream);
     if (batched)
         return launch_kernel<CL>(cfb::llama_decoder_layer_batch_kernel<4>, cfb::SmemB<4>::TOTAL, 11, kp, a->n_q_heads,
                                  (a->batch + 3) / 4, pdl, stream);

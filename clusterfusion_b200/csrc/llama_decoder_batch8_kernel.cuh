@@ -1,0 +1,613 @@
+/*
+ * Batched paged decode, chunks of EIGHT requests per head cluster (second step).
+ *
+ * Same idea as llama_decoder_batch_kernel.cuh (one 4-CTA cluster per head, every Wqkv / Wo tile streamed once per chunk
+ * and multiplied against the chunk's activation vectors with ldmatrix + mma.sync.m16n8k16), but the chunk fills the whole
+ * N = 8 dimension of the MMA, so a batch of 8 streams the weights once instead of twice.  What makes 8 fit into 227 KB
+ * next to the 192 KB tile ring is time-sharing one 19.5 KB region X:
+ *
+ *   QKV phase      X = the 8 activation vectors, fp16 [8][1024 + 8]
+ *   exchange 1     X = reduce-scatter / all-gather buffers for FOUR requests; run twice (requests 0-3, then 4-7: the
+ *                  accumulators of the second half wait in registers), result kept as fp16 q|k|v [8][384] outside X
+ *   attention      two passes of four requests (softmax states in registers), each followed by its own state exchange
+ *                  through X
+ *   O phase        X = a 1 KB staging tile per warp: the [32 rows x 8 requests] C fragments are transposed through it
+ *                  and leave as red.global.add.v4 straight away (no 32 KB out_part; the reds overlap the stream)
+ *
+ * X is written by peer CTAs (st.async) in the exchange phases, so every change of its role is fenced by a cluster barrier
+ * (arrive as soon as this CTA is done with the old role, wait right before the first remote write of the new one): B1
+ * after the QKV loop, B2 after the second RoPE, B3 after the first softmax merge.  PAGED variant, MHA, hidden <= 4096.
+ */
+#pragma once
+
+#include "llama_decoder_batch_kernel.cuh"
+
+namespace cfb {
+
+struct SmemB8 {
+    static constexpr int BC = 8, HB = 4, CL = 4;                          // chunk, half chunk, cluster
+    static constexpr int QKV_OUT = 3 * HEAD_DIM;                          // 384
+    static constexpr int SLICE1 = HB * QKV_OUT / CL;                      // 384 floats per CTA slice in exchange 1
+    static constexpr int PAY = HEAD_DIM + 4;
+    static constexpr int RING = 0;
+    static constexpr int ATTN_PART = RING + NSTAGES * STAGE_BYTES;        // fp32 [12 warps][132]
+    static constexpr int X = ATTN_PART + CONSUMER_WARPS * PAY * 4;
+    // role 1: activations
+    static constexpr int XS = X;                                          // fp16 [8][BK_XS_STRIDE]
+    // role 2: exchange 1 of one half chunk
+    static constexpr int QKV_SRC = X;                                     // fp32 [4][384]
+    static constexpr int RED1 = QKV_SRC + HB * QKV_OUT * 4;               // fp32 [384]
+    static constexpr int AG_RECV = RED1 + SLICE1 * 4;                     // fp32 [4][384]
+    static constexpr int RS_RECV = AG_RECV + CL * SLICE1 * 4;             // fp32 [4][384]
+    static constexpr int X_BYTES = RS_RECV + CL * SLICE1 * 4 - X;         // 19968
+    static_assert(BC * BK_XS_STRIDE * 2 <= X_BYTES, "activations must fit into X");
+    // role 3: exchange 2 of one half chunk
+    static constexpr int ATTN_SRC = X;                                    // fp32 [4][132]
+    static constexpr int ATTN_RECV = ATTN_SRC + HB * PAY * 4;             // fp32 [4 ranks][4][132]
+    static_assert((1 + CL) * HB * PAY * 4 <= X_BYTES, "exchange-2 buffers must fit into X");
+    // role 4: O-phase staging
+    static constexpr int OSTAGE = X;                                      // fp32 [12 warps][8][32]
+    static_assert(CONSUMER_WARPS * BC * 32 * 4 <= X_BYTES, "staging must fit into X");
+    static constexpr int QKV_FIN = X + X_BYTES;                           // fp16 [8][384]  roped q (unscaled) | k | v
+    static constexpr int ATTN_OUT = QKV_FIN + BC * QKV_OUT * 2;           // fp16 [8][128]
+    static constexpr int RED = ATTN_OUT + BC * HEAD_DIM * 2;              // fp32 [12][8] + [8]
+    static constexpr int META = RED + (CONSUMER_WARPS + 1) * BC * 4;      // int [8][4]: kv_base, row_begin, row_end, new_slot; u32 [9] tile0
+    static constexpr int BARS = META + (BC * 4 + BC + 1 + 3) / 4 * 16;    // u64 full[NSTAGES], xbar[6]
+    static constexpr int FLAGS = BARS + (NSTAGES + 6) * 8;                // u32 [8]
+    static constexpr int TOTAL = FLAGS + BC * 4;
+    static_assert(BARS % 8 == 0, "mbarrier alignment");
+    static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
+};
+
+__global__ void __launch_bounds__(BLOCK_THREADS, 1)
+llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
+{
+    using S = SmemB8;
+    constexpr int BC = S::BC, HB = S::HB, CLUSTER = S::CL;
+    constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t smem_base = dsm::smem_u32(smem);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t lane = tid & 31;
+    const uint32_t rank = dsm::cluster_ctarank();
+    const uint32_t head = blockIdx.x / CLUSTER;
+    const int b0 = blockIdx.y * BC;
+    const int nb = min(BC, p.batch - b0);
+
+    const int hidden = p.hidden;
+    const int KS = hidden / CLUSTER;
+    const int kv_cols = p.n_kv_heads * HEAD_DIM;
+
+    const uint32_t full_u32 = smem_base + S::BARS;
+    const uint32_t xbar_u32 = full_u32 + NSTAGES * 8;
+
+    __half* xs = reinterpret_cast<__half*>(smem + S::XS);
+    float* attn_part = reinterpret_cast<float*>(smem + S::ATTN_PART);
+    float* qkv_src = reinterpret_cast<float*>(smem + S::QKV_SRC);
+    float* rs_recv = reinterpret_cast<float*>(smem + S::RS_RECV);
+    float* red1 = reinterpret_cast<float*>(smem + S::RED1);
+    float* ag_recv = reinterpret_cast<float*>(smem + S::AG_RECV);
+    __half* qkv_fin = reinterpret_cast<__half*>(smem + S::QKV_FIN);
+    float* attn_src = reinterpret_cast<float*>(smem + S::ATTN_SRC);
+    float* attn_recv = reinterpret_cast<float*>(smem + S::ATTN_RECV);
+    __half* attn_out = reinterpret_cast<__half*>(smem + S::ATTN_OUT);
+    float* ostage = reinterpret_cast<float*>(smem + S::OSTAGE);
+    float* red = reinterpret_cast<float*>(smem + S::RED);
+    int* meta = reinterpret_cast<int*>(smem + S::META);                       // [b][4]
+    uint32_t* tile0 = reinterpret_cast<uint32_t*>(smem + S::META) + BC * 4;   // [9]
+    uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
+
+    // ---- per-request KV ranges -> shared memory (8 requests x 5 words would not stay in registers) ----------------
+    if (tid == 0) {
+        uint32_t acc = 0;
+        tile0[0] = 0;
+        for (int b = 0; b < BC; ++b) {
+            int len = 0, kb = 0, ns = 0;
+            if (b < nb) {
+                kb = p.indptr[b0 + b];
+                const int end = p.indptr[b0 + b + 1] - 1;
+                len = end - kb;
+                ns = p.indices[end];
+            }
+            const int chunk = (((len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);
+            const int rb = min((int)rank * chunk, len), re = min(rb + chunk, len);
+            meta[b * 4 + 0] = kb; meta[b * 4 + 1] = rb; meta[b * 4 + 2] = re; meta[b * 4 + 3] = ns;
+            acc += (re - rb + ROWS512 - 1) / ROWS512;
+            tile0[b + 1] = acc;
+        }
+    }
+    if (lane == 0) {
+        dsm::mbar_init(full_u32 + 8 * warp, 1);
+        dsm::mbar_init(full_u32 + 8 * (warp + CONSUMER_WARPS), 1);
+        if (tid == 0) {
+            prefetch_tmap(&p.tm_wqkv);
+            prefetch_tmap(&p.tm_wo);
+            cluster_reduce_arm<CLUSTER>(xbar_u32, S::SLICE1 * 4);            // scatter, half 0
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::SLICE1 * 4);        // scatter, half 1
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 16, S::SLICE1 * 4);       // gather, half 0
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 24, S::SLICE1 * 4);       // gather, half 1
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 32, HB * S::PAY * 4);     // softmax states, half 0
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 40, HB * S::PAY * 4);     // softmax states, half 1
+        }
+        dsm::mbar_fence_init();
+    }
+    __syncthreads();                                                          // meta visible to every warp
+
+    const uint32_t n_qkv_tiles = (uint32_t)CONSUMER_WARPS * (KS / 128);
+    const uint32_t n_kv_tiles = tile0[BC];
+    const uint32_t n_o_tiles = (uint32_t)(KS / ROWS256);
+    const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
+
+    CF_MARK(0);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    const uint64_t pol = policy_evict_first();
+    const __half* kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
+    const __half* vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
+
+    auto request_of = [&](uint32_t t) -> int {            // which request KV tile t (phase-local index) belongs to
+        int b = 0;
+#pragma unroll
+        for (int q = 1; q < BC; ++q) b += (t >= tile0[q]) ? 1 : 0;
+        return b;
+    };
+    int pre_slot0 = 0, pre_slot1 = 0;
+    uint32_t pre_g0 = 0xffffffffu, pre_g1 = 0xffffffffu;
+    auto page_of = [&](uint32_t g) -> int {               // page index of this lane's row of KV tile g
+        const uint32_t t = g - n_qkv_tiles;
+        const int b = request_of(t);
+        const int r = meta[b * 4 + 1] + (int)(t - tile0[b]) * ROWS512 + (int)(lane & 15);
+        return (r < meta[b * 4 + 2]) ? p.indices[meta[b * 4 + 0] + r] : 0;
+    };
+    auto issue_tile = [&](uint32_t g) {
+        if (g >= total_tiles) return;
+        const uint32_t s = ring_stage(g);
+        const uint32_t fb = full_u32 + 8 * s;
+        const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
+        if (g < n_qkv_tiles) {
+            if (lane == 0) {
+                const int rb = (int)(g % CONSUMER_WARPS), ct = (int)(g / CONSUMER_WARPS);
+                const int j = rb / 4, sub = rb % 4;
+                const int row0 = (j == 0) ? head * HEAD_DIM
+                               : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
+                                          : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wqkv, rank * KS + ct * 128, row0 + sub * 32, fb, pol);
+                tma_load_2d(dst + 4096, &p.tm_wqkv, rank * KS + ct * 128 + 64, row0 + sub * 32, fb, pol);
+            }
+        } else if (g < n_qkv_tiles + n_kv_tiles) {
+            const uint32_t t = g - n_qkv_tiles;
+            const int b = request_of(t);
+            const int rbeg = meta[b * 4 + 1], rend = meta[b * 4 + 2];
+            const int i = (int)(t - tile0[b]);
+            const int r = rbeg + i * ROWS512 + (lane & 15);
+            const bool valid = r < rend;
+            const bool odd = (g / CONSUMER_WARPS) & 1u;
+            const long long slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
+            const int nvalid = min(ROWS512, rend - (rbeg + i * ROWS512));
+            if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
+            __syncwarp();
+            if (valid) {
+                const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
+                if (lane < 16) bulk_load_1d(d, kpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                else bulk_load_1d(d + STAGE_BYTES / 2, vpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+            }
+        } else {
+            if (lane == 0) {
+                const uint32_t i = g - n_qkv_tiles - n_kv_tiles;
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(dst, &p.tm_wo, head * HEAD_DIM, rank * KS + i * ROWS256, fb, pol);
+                tma_load_2d(dst + 4096, &p.tm_wo, head * HEAD_DIM + 64, rank * KS + i * ROWS256, fb, pol);
+            }
+        }
+        const uint32_t g2 = g + NSTAGES;
+        if (g2 >= n_qkv_tiles && g2 < n_qkv_tiles + n_kv_tiles) {
+            const int pg = page_of(g2);
+            if ((g / CONSUMER_WARPS) & 1u) { pre_slot1 = pg; pre_g1 = g2; } else { pre_slot0 = pg; pre_g0 = g2; }
+        }
+    };
+
+    CF_MARK(12);
+    issue_tile(warp);
+    issue_tile(warp + CONSUMER_WARPS);
+    dsm::cluster_arrive();                                                    // B0: barriers armed
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // ---- phase 0: fused residual add + RMSNorm for the 8 requests ---------------------------------------------------
+    {
+        float ss[BC];
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
+            ss[b] = 0.f;
+            if (b < nb) {
+                const __half* xg = p.x + (size_t)(b0 + b) * hidden;
+                const __half* rg = p.residual_in + (size_t)(b0 + b) * hidden;
+                for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
+                    float f[8], r8[8];
+                    unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
+                    unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { const float h = round_h(f[k] + r8[k]); ss[b] = fmaf(h, h, ss[b]); }
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
+            if (lane == 0) red[warp * BC + b] = ss[b];
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w * BC + b];
+            const float rstd = rsqrtf(tot / (float)hidden + p.eps);
+            for (int e = tid * 8; e < KS; e += CONSUMER_THREADS * 8) {
+                __align__(16) __half xn[8];
+                if (b < nb) {
+                    const int ge = rank * KS + e;
+                    const __half* xg = p.x + (size_t)(b0 + b) * hidden;
+                    const __half* rg = p.residual_in + (size_t)(b0 + b) * hidden;
+                    float f[8], w8[8], r8[8];
+                    unpack8(*reinterpret_cast<const uint4*>(xg + ge), f);
+                    unpack8(*reinterpret_cast<const uint4*>(p.rms_w + ge), w8);
+                    unpack8(*reinterpret_cast<const uint4*>(rg + ge), r8);
+                    __align__(16) __half hs[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { hs[k] = __float2half_rn(f[k] + r8[k]); f[k] = __half2float(hs[k]); }
+                    if (head == 0)
+                        *reinterpret_cast<uint4*>(p.residual_out + (size_t)(b0 + b) * hidden + ge) = *reinterpret_cast<const uint4*>(hs);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(round_h(f[k] * rstd) * w8[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(0.f);
+                }
+                *reinterpret_cast<uint4*>(xs + b * BK_XS_STRIDE + e) = *reinterpret_cast<const uint4*>(xn);
+            }
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+    CF_MARK(1);
+
+    uint32_t gbase = 0;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    // ---- phase 1: QKV GEMV on the tensor cores, all 8 requests on the N dimension ------------------------------------
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (uint32_t i = warp; i < n_qkv_tiles; i += CONSUMER_WARPS) {
+        const uint32_t g = i, s = ring_stage(g);
+        const int ct = (int)(i / CONSUMER_WARPS);
+        uint32_t xb[8][2];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const __half* xp = xs + g4 * BK_XS_STRIDE + ct * 128 + ks * 16 + t4 * 2;
+            xb[ks][0] = *reinterpret_cast<const uint32_t*>(xp);
+            xb[ks][1] = *reinterpret_cast<const uint32_t*>(xp + 8);
+        }
+        ring_wait_full(full_u32, g);
+        const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                uint32_t af[4];
+                ldsm_a_mrows(af, st + (ks >> 2) * 4096, mb * 16, (ks & 3) * 2, lane);
+                mma16816(acc[mb], af, xb[ks][0], xb[ks][1]);
+            }
+        }
+        __syncwarp();
+        issue_tile(g + NSTAGES);
+    }
+    gbase += n_qkv_tiles;
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);       // every warp is done reading xs
+    CF_MARK(2);
+    dsm::cluster_wait();                                        // B0
+    dsm::cluster_arrive();                                      // B1: this CTA no longer reads xs (X changes role)
+    dsm::cluster_wait();
+
+    // ---- exchange 1 + RoPE, one half chunk at a time --------------------------------------------------------------
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        // this half's accumulators -> qkv_src [4][384]: C fragment = rows g4 / g4 + 8, requests 2*t4 and 2*t4 + 1
+        if ((t4 >> 1) == h) {
+            const int n0 = (2 * t4) & 3;
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                const int row = (int)warp * 32 + mb * 16 + g4;
+                qkv_src[n0 * S::QKV_OUT + row] = acc[mb][0];
+                qkv_src[(n0 + 1) * S::QKV_OUT + row] = acc[mb][1];
+                qkv_src[n0 * S::QKV_OUT + row + 8] = acc[mb][2];
+                qkv_src[(n0 + 1) * S::QKV_OUT + row + 8] = acc[mb][3];
+            }
+        }
+        uint32_t ph_s = 0, ph_g = 0;
+        cluster_scatter<CLUSTER, CONSUMER_THREADS, CONSUMER_BAR>(S::SLICE1 * 4, tid, rank, smem_base + S::RS_RECV,
+                                                                 xbar_u32 + 8 * h, ph_s, qkv_src, rs_recv);
+        for (int e = tid; e < S::SLICE1; e += CONSUMER_THREADS) {
+            float a = 0.f;
+#pragma unroll
+            for (int r = 0; r < CLUSTER; ++r) a += rs_recv[r * S::SLICE1 + e];
+            red1[e] = round_h(a);                                // q / k / v leave the projection as fp16 (eager model)
+        }
+        cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
+            S::SLICE1 * 4, tid, S::SLICE1, rank, smem_base + S::RED1, smem_base + S::AG_RECV, xbar_u32 + 16 + 8 * h, ph_g,
+            red1, ag_recv);
+        // RoPE (NeoX) for the half's 4 requests; new K / V rows into the pool; q stays unscaled fp16
+        for (int f = tid; f < HB * S::QKV_OUT; f += CONSUMER_THREADS) {
+            const int bb = f / S::QKV_OUT, e = f % S::QKV_OUT, b = h * HB + bb;
+            const int which = e >> 7, d = e & 127;
+            const float a = ag_recv[f];
+            __half outv = __float2half_rn(a);
+            if (b < nb) {
+                if (which < 2) {
+                    const float* cosp = p.cos + p.positions[b0 + b] * HEAD_DIM;
+                    const float* sinp = cosp + HEAD_DIM / 2;
+                    const float bbv = ag_recv[f ^ 64];
+                    const int i = d & 63;
+                    const float rot = (d & 64) ? fmaf(a, cosp[i], bbv * sinp[i]) : fmaf(a, cosp[i], -bbv * sinp[i]);
+                    outv = __float2half_rn(rot);
+                    if (which == 1 && rank == 0) {
+                        __half* kp = reinterpret_cast<__half*>(p.k_pool_ptrs[p.layer_id]);
+                        kp[(size_t)meta[b * 4 + 3] * kv_cols + head * HEAD_DIM + d] = outv;
+                    }
+                } else if (rank == 0) {
+                    __half* vp = reinterpret_cast<__half*>(p.v_pool_ptrs[p.layer_id]);
+                    vp[(size_t)meta[b * 4 + 3] * kv_cols + head * HEAD_DIM + d] = outv;
+                }
+            }
+            qkv_fin[b * S::QKV_OUT + e] = outv;
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    }
+    CF_MARK(4);
+    dsm::cluster_arrive();                                      // B2: done reading ag_recv (X changes role again)
+
+    // ---- phase 2: flash-decode + softmax-state exchange, one half chunk at a time -------------------------------------
+    {
+        const int sub = lane >> 4, c = lane & 15;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float m[HB], l[HB], o8[HB][8];
+#pragma unroll
+            for (int bb = 0; bb < HB; ++bb) {
+                const int b = h * HB + bb;
+                m[bb] = -INFINITY; l[bb] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o8[bb][k] = 0.f;
+                float q8[8];
+                unpack8(*reinterpret_cast<const uint4*>(qkv_fin + b * S::QKV_OUT + c * 8), q8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) q8[k] *= kScaleLog2;
+                const uint32_t nt = tile0[b + 1] - tile0[b];
+                const uint32_t gb = gbase + tile0[b];
+                const int rbeg = meta[b * 4 + 1], rend = meta[b * 4 + 2];
+                for (uint32_t i = first_tile(gb, warp); i < nt; i += CONSUMER_WARPS) {
+                    const uint32_t g = gb + i, s = ring_stage(g);
+                    ring_wait_full(full_u32, g);
+                    const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+                    const uint4* vt = kt + STAGE_BYTES / 32;
+                    const int rows_left = rend - (rbeg + (int)i * ROWS512);
+                    float sc[ROWS512 / 2];
+#pragma unroll
+                    for (int jj = 0; jj < ROWS512 / 2; ++jj) {
+                        const int row = 2 * jj + sub;
+                        float k8[8];
+                        unpack8(kt[row * 16 + c], k8);
+                        float a = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) a = fmaf(q8[k], k8[k], a);
+                        a += __shfl_xor_sync(0xffffffffu, a, 1);
+                        a += __shfl_xor_sync(0xffffffffu, a, 2);
+                        a += __shfl_xor_sync(0xffffffffu, a, 4);
+                        a += __shfl_xor_sync(0xffffffffu, a, 8);
+                        sc[jj] = (row < rows_left) ? a : -INFINITY;
+                    }
+                    float mx = sc[0];
+#pragma unroll
+                    for (int jj = 1; jj < ROWS512 / 2; ++jj) mx = fmaxf(mx, sc[jj]);
+                    const float m_new = fmaxf(m[bb], mx);
+                    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                    const float corr = dsm::exp2_diff(m[bb], m_use);
+                    l[bb] *= corr;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o8[bb][k] *= corr;
+#pragma unroll
+                    for (int jj = 0; jj < ROWS512 / 2; ++jj) {
+                        const int row = 2 * jj + sub;
+                        const float pr = dsm::fast_exp2(sc[jj] - m_use);
+                        l[bb] += pr;
+                        uint4 raw = vt[row * 16 + c];
+                        if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
+                        float v8[8];
+                        unpack8(raw, v8);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o8[bb][k] = fmaf(pr, v8[k], o8[bb][k]);
+                    }
+                    m[bb] = m_new;
+                    __syncwarp();
+                    issue_tile(g + NSTAGES);
+                }
+            }
+            // merge the two half-warps in registers, then block merge one request per round through [12][132]
+#pragma unroll
+            for (int bb = 0; bb < HB; ++bb) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m[bb], 16);
+                const float l2 = __shfl_xor_sync(0xffffffffu, l[bb], 16);
+                const float M = fmaxf(m[bb], m2);
+                const float w1 = dsm::exp2_diff(m[bb], M), w2 = dsm::exp2_diff(m2, M);
+                l[bb] = l[bb] * w1 + l2 * w2;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float o2 = __shfl_xor_sync(0xffffffffu, o8[bb][k], 16);
+                    o8[bb][k] = o8[bb][k] * w1 + o2 * w2;
+                }
+                m[bb] = M;
+            }
+            if (h == 0) dsm::cluster_wait();                    // B2: every peer is past its RoPE, X may take exchange-2 data
+            else dsm::cluster_wait();                           // B3: every peer has merged the first half out of attn_recv
+#pragma unroll
+            for (int bb = 0; bb < HB; ++bb) {
+                const int b = h * HB + bb;
+                if (sub == 0) {
+                    float* slot = attn_part + warp * S::PAY;
+                    if (c == 0) { slot[0] = m[bb]; slot[1] = l[bb]; }
+                    *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[bb][0], o8[bb][1], o8[bb][2], o8[bb][3]);
+                    *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[bb][4], o8[bb][5], o8[bb][6], o8[bb][7]);
+                }
+                if (warp == 0) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        a = fmaf(__half2float(qkv_fin[b * S::QKV_OUT + lane * 4 + k]),
+                                 __half2float(qkv_fin[b * S::QKV_OUT + HEAD_DIM + lane * 4 + k]), a);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    if (lane == 0) red[CONSUMER_WARPS * BC + b] = a * kScaleLog2;
+                }
+                dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+                if (tid < HEAD_DIM) {
+                    const bool with_new = (rank == 0);
+                    const float s_new = red[CONSUMER_WARPS * BC + b];
+                    float M = with_new ? s_new : -INFINITY;
+#pragma unroll
+                    for (int gI = 0; gI < CONSUMER_WARPS; ++gI) M = fmaxf(M, attn_part[gI * S::PAY]);
+                    float L = 0.f, Ov = 0.f;
+#pragma unroll
+                    for (int gI = 0; gI < CONSUMER_WARPS; ++gI) {
+                        const float w = dsm::exp2_diff(attn_part[gI * S::PAY], M);
+                        L = fmaf(attn_part[gI * S::PAY + 1], w, L);
+                        Ov = fmaf(attn_part[gI * S::PAY + 4 + tid], w, Ov);
+                    }
+                    if (with_new) {
+                        const float w = dsm::exp2_diff(s_new, M);
+                        L += w;
+                        Ov = fmaf(__half2float(qkv_fin[b * S::QKV_OUT + 2 * HEAD_DIM + tid]), w, Ov);
+                    }
+                    float* stp = attn_src + bb * S::PAY;
+                    stp[4 + tid] = Ov;
+                    if (tid == 0) { stp[0] = M; stp[1] = L; stp[2] = 0.f; stp[3] = 0.f; }
+                }
+                dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            }
+            uint32_t ph_a = 0;
+            cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
+                HB * S::PAY * 4, tid, HB * S::PAY, rank, smem_base + S::ATTN_SRC, smem_base + S::ATTN_RECV,
+                xbar_u32 + 32 + 8 * h, ph_a, attn_src, attn_recv);
+            for (int f = tid; f < HB * HEAD_DIM; f += CONSUMER_THREADS) {
+                const int bb = f >> 7, d = f & 127, b = h * HB + bb;
+                float M = -INFINITY;
+#pragma unroll
+                for (int r = 0; r < CLUSTER; ++r) M = fmaxf(M, attn_recv[(r * HB + bb) * S::PAY]);
+                float L = 0.f, Ov = 0.f;
+#pragma unroll
+                for (int r = 0; r < CLUSTER; ++r) {
+                    const float* stp = attn_recv + (r * HB + bb) * S::PAY;
+                    const float w = dsm::exp2_diff(stp[0], M);
+                    L = fmaf(stp[1], w, L);
+                    Ov = fmaf(stp[4 + d], w, Ov);
+                }
+                attn_out[b * HEAD_DIM + d] = __float2half_rn((b < nb) ? Ov / L : 0.f);   // fp16, as the eager model
+            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            if (h == 0) dsm::cluster_arrive();                  // B3: done reading attn_recv of the first half
+        }
+        gbase += n_kv_tiles;
+    }
+    CF_MARK(6);
+
+    // ---- phase 3: O GEMV on the tensor cores, C fragments leave through a per-warp staging tile as red.v4 -------------
+    {
+        uint32_t ob[8][2];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const __half* ap = attn_out + g4 * HEAD_DIM + ks * 16 + t4 * 2;
+            ob[ks][0] = *reinterpret_cast<const uint32_t*>(ap);
+            ob[ks][1] = *reinterpret_cast<const uint32_t*>(ap + 8);
+        }
+        float* stg = ostage + warp * (BC * 32);
+        for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            ring_wait_full(full_u32, g);
+            const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
+            float oc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    uint32_t af[4];
+                    ldsm_a_mrows(af, st + (ks >> 2) * 4096, mb * 16, (ks & 3) * 2, lane);
+                    mma16816(oc[mb], af, ob[ks][0], ob[ks][1]);
+                }
+            }
+            __syncwarp();
+            issue_tile(g + NSTAGES);
+            // transpose through the staging tile: stg[request][row]
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                stg[(2 * t4) * 32 + mb * 16 + g4] = oc[mb][0];
+                stg[(2 * t4 + 1) * 32 + mb * 16 + g4] = oc[mb][1];
+                stg[(2 * t4) * 32 + mb * 16 + g4 + 8] = oc[mb][2];
+                stg[(2 * t4 + 1) * 32 + mb * 16 + g4 + 8] = oc[mb][3];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int f = lane + 32 * j, n = f >> 3, r4 = f & 7;           // request n, rows r4*4 .. +4
+                if (n < nb)
+                    red_add_v4(p.scratch + (size_t)(b0 + n) * hidden + rank * KS + i * ROWS256 + r4 * 4,
+                               *reinterpret_cast<const float4*>(stg + n * 32 + r4 * 4));
+            }
+            __syncwarp();
+        }
+    }
+    CF_MARK(7);
+
+    // ---- last arriver of each (request, slice) finalises ----------------------------------------------------------------
+    __threadfence();
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    if (tid < (uint32_t)nb) {
+        unsigned* counters = p.counters + (size_t)(b0 + tid) * (CLUSTER + 1);
+        const unsigned prev = atomicAdd(&counters[rank], 1u);
+        sflags[tid] = (prev == (unsigned)p.n_heads - 1u);
+    }
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    CF_MARK(8);
+    {
+        __threadfence();
+        const bool fp32_out = p.flags & 1u;
+        const int e = tid * 4;                                // KS <= 1024: one float4 per thread
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float4 v[HB];
+#pragma unroll
+            for (int bb = 0; bb < HB; ++bb) {
+                const int b = half * HB + bb;
+                if (b < nb && sflags[b] && e < KS) v[bb] = ld_cg_v4(p.scratch + (size_t)(b0 + b) * hidden + rank * KS + e);
+            }
+#pragma unroll
+            for (int bb = 0; bb < HB; ++bb) {
+                const int b = half * HB + bb;
+                if (b < nb && sflags[b] && e < KS) {
+                    const size_t off = (size_t)(b0 + b) * hidden + rank * KS + e;
+                    *reinterpret_cast<float4*>(p.scratch + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (fp32_out) {
+                        *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v[bb];
+                    } else {
+                        __align__(8) __half h4[4] = {__float2half_rn(v[bb].x), __float2half_rn(v[bb].y),
+                                                     __float2half_rn(v[bb].z), __float2half_rn(v[bb].w)};
+                        *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
+                    }
+                }
+                if (b < nb && sflags[b] && tid == 0) p.counters[(size_t)(b0 + b) * (CLUSTER + 1) + rank] = 0u;
+            }
+        }
+    }
+    CF_MARK(9);
+}
+
+}  // namespace cfb

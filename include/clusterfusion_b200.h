@@ -71,6 +71,8 @@ enum {
                                      (weights re-streamed per request) instead of the batched kernel that streams every
                                      weight tile once per chunk of 4 requests (measurement / A-B)                          */
 
+#define CF_FLAG_BATCH4 0x20u /* PAGED, batch >= 5, MHA: keep chunks of 4 requests per head cluster instead of 8 (A/B)          */
+
 typedef struct CfLlamaArgs {
     int32_t variant;    /* CF_VARIANT_*                                                             */
     uint32_t flags;     /* CF_FLAG_*                                                                */

@@ -254,7 +254,8 @@ def test_paged_operator_vs_oracle(lens):
     assert close(out2, want_o)
 
 
-@pytest.mark.parametrize("lens", [[40, 0, 513, 7, 128, 1], [300] * 8, [17, 2], [5000, 17, 3000, 1, 2049]])
+@pytest.mark.parametrize("lens", [[40, 0, 513, 7, 128, 1], [300] * 8, [17, 2], [5000, 17, 3000, 1, 2049],
+                                  [64, 0, 1, 900, 33, 16, 15, 17, 700, 2, 31]])
 def test_batched_paged_kernel_matches_per_request_kernel_and_oracle(lens):
     """Row f3: the batched kernel (weights streamed once per chunk of 4 requests; chunks of 4 + a ragged tail) against
     the oracle and against the per-request launch (CF_FLAG_PER_REQUEST, the reference's grid shape)."""
@@ -275,7 +276,7 @@ def test_batched_paged_kernel_matches_per_request_kernel_and_oracle(lens):
                                    d["rms_w"], 1e-5, positions, cos_sin, n_heads=32, mode="eager")
     c = cuda(d)
     res = {}
-    for name, flags in (("batched", 0), ("per_request", cabi.CF_FLAG_PER_REQUEST)):
+    for name, flags in (("batched", 0), ("batched4", cabi.CF_FLAG_BATCH4), ("per_request", cabi.CF_FLAG_PER_REQUEST)):
         kpool, vpool = c["k_cache"].clone(), c["v_cache"].clone()
         kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
         vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
@@ -289,7 +290,7 @@ def test_batched_paged_kernel_matches_per_request_kernel_and_oracle(lens):
         assert close(out, want_o), name
         assert close(kpool, kp, atol=4e-3) and close(vpool, vp), name
         res[name] = out
-    assert close(res["batched"], res["per_request"])
+    assert close(res["batched"], res["per_request"]) and close(res["batched4"], res["per_request"])
 
 
 # ---------------------------------------------------------------------------------------------------
