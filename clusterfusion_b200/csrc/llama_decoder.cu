@@ -98,7 +98,11 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
     CUtensorMap m;
     const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+#ifdef CF_EXPERIMENT_L2_PROMO_128      /* tools/sweep_build.sh experiment, never defined in the product build */
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+#else
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+#endif
     if (r != CUDA_SUCCESS) return fail((int)r, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu",
                                        (int)r, (unsigned long long)rows, (unsigned long long)cols);
     {

@@ -145,7 +145,11 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
+#ifdef CF_EXPERIMENT_EVICT_NORMAL      /* tools/sweep_build.sh experiment, never defined in the product build */
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+#else
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#endif
     return p;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {

@@ -12,7 +12,7 @@ for path in sys.argv[1:]:
     lib.cf_llama_workspace_bytes.restype = C.c_size_t
     lib.cf_llama_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     ws = torch.zeros(lib.cf_llama_workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
-    for kv in (1024, 4096):
+    for kv in (1024, 16384):
         L = [dict(w_qkv=r(3 * H, H, sc=0.02), w_o=r(H, H, sc=0.02), k=r(kv + 1, H), v=r(kv + 1, H), rms=r(H) * 0.1 + 1,
                   o=torch.empty(1, H, dtype=torch.float16, device=dev), ro=torch.empty(1, H, dtype=torch.float16, device=dev),
                   kn=torch.empty(H, dtype=torch.float16, device=dev), vn=torch.empty(H, dtype=torch.float16, device=dev)) for _ in range(nl)]
