@@ -1,6 +1,6 @@
 """GPU probe: time the MHA kernel variants (chat / sglang / paged, batch 1) of two builds of the C-ABI library.
     python tools/lib_ab.py gpurun_out/libcf_premma.so clusterfusion_b200/libclusterfusion_b200.so"""
-import ctypes as C, sys, torch
+import ctypes as C, os, sys, torch
 sys.path.insert(0, ".")
 from clusterfusion_b200 import cabi
 dev = torch.device("cuda", 0)
@@ -19,7 +19,7 @@ for path in sys.argv[1:]:
         x = r(1, H); res = r(1, H); cos = torch.rand(1, D, device=dev); sin = torch.rand(1, D, device=dev)
         kptrs = torch.tensor([l["k"].data_ptr() for l in L], dtype=torch.uint64).to(dev)
         vptrs = torch.tensor([l["v"].data_ptr() for l in L], dtype=torch.uint64).to(dev)
-        indptr = torch.tensor([0, kv + 1], dtype=torch.int32, device=dev); indices = torch.randperm(kv + 1).int().to(dev)
+        indptr = torch.tensor([0, kv + 1], dtype=torch.int32, device=dev); indices = (torch.arange(kv + 1) if os.environ.get('CF_SEQ_PAGES') == '1' else torch.randperm(kv + 1)).int().to(dev)
         positions = torch.tensor([kv], dtype=torch.int64, device=dev); cos_sin = torch.rand(kv + 1, D, device=dev)
         for variant in (0, 1, 2):
             def launch(h, rr, li, st):
