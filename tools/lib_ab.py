@@ -6,6 +6,7 @@ from clusterfusion_b200 import cabi
 dev = torch.device("cuda", 0)
 H, D, nl = 4096, 128, 8
 r = lambda *s, sc=1.0: (torch.randn(*s, device=dev) * sc).half()
+outs = {}
 for path in sys.argv[1:]:
     lib = C.CDLL(path)
     lib.cf_llama_decoder_layer_launch.argtypes = [C.POINTER(cabi.CfLlamaArgs), C.c_void_p]
@@ -13,6 +14,7 @@ for path in sys.argv[1:]:
     lib.cf_llama_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     ws = torch.zeros(lib.cf_llama_workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
     for kv in (1024, 16384):
+        torch.manual_seed(kv)
         L = [dict(w_qkv=r(3 * H, H, sc=0.02), w_o=r(H, H, sc=0.02), k=r(kv + 1, H), v=r(kv + 1, H), rms=r(H) * 0.1 + 1,
                   o=torch.empty(1, H, dtype=torch.float16, device=dev), ro=torch.empty(1, H, dtype=torch.float16, device=dev),
                   kn=torch.empty(H, dtype=torch.float16, device=dev), vn=torch.empty(H, dtype=torch.float16, device=dev)) for _ in range(nl)]
@@ -53,4 +55,7 @@ for path in sys.argv[1:]:
                 e1.record(); torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1) * 1e3 / (100 * nl))
             print(f"{path.split('/')[-1]:32s} kv={kv:5d} variant={('chat','sglang','paged')[variant]:6s} us/layer={best:6.2f}", flush=True)
+            key = (kv, variant); o_last = L[-1]['o'].float().clone()
+            if key in outs: print('   max |diff| vs first lib:', float((outs[key] - o_last).abs().max()), 'finite', bool(torch.isfinite(o_last).all()), flush=True)
+            else: outs[key] = o_last
         del L
