@@ -383,8 +383,9 @@ def run_ours(args, rank, world, local_rank):
             del Ls, g2
             torch.cuda.empty_cache()
     # ------------------------------------------------------------------ BASELINE config 4: Llama-3-8B GQA (32 Q / 8 KV), kv 8K
-    gqa = ffn_res = batched = None
+    gqa = ffn_res = batched = deepseek = None
     if not args.no_sweep:
+        deepseek = run_deepseek(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
         gqa = run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl, kvs=(1024, 8192))
         gqa += run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl, cluster_kernel=True)
         ffn_res = run_ffn(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
@@ -471,6 +472,8 @@ def run_ours(args, rank, world, local_rank):
         line["batched_paged_decode"] = batched
     if gqa is not None:
         line["llama3_8b_gqa"] = gqa
+    if deepseek is not None:
+        line["deepseek_mla_half_layer"] = deepseek
     if shard70 is not None:
         line["llama2_70b_head_parallel"] = shard70
     emit(line)
@@ -640,6 +643,51 @@ def run_ffn(torch, cabi, dev, timed_replays, peak, pdl=True, hidden=4096, ffn=11
     return {"hidden": hidden, "ffn": ffn, "us_per_layer": round(us, 3), "bytes": B, "achieved_gbs": round(a, 1),
             "frac_of_measured_peak": round(a / peak, 4), "frac_of_8tbs": round(a / 8000.0, 4),
             "kernel": "cfb::llama_ffn_layer_kernel", "launches": reps * nl}
+
+
+def run_deepseek(torch, cabi, dev, timed_replays, peak, pdl=True, seq_lens=(4096, 16384), nl=16):
+    """DeepSeek-MLA half-layer (row f4; the reference's config.h shapes): CUDA graph of `nl` distinct layers chained through
+    x, through the C ABI.  Three kernels per call."""
+    g = torch.Generator(device=dev).manual_seed(31)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * sc).half()
+    ws = torch.zeros(cabi.load().cf_deepseek_workspace_bytes(), dtype=torch.uint8, device=dev)
+    out = []
+    for S in seq_lens:
+        L = [dict(wqn=r(2048, 2048, sc=0.022), wqp=r(2048, 1024, sc=0.022), wuk=r(128, 8192, sc=0.088), wkv=r(2048, 512, sc=0.022),
+                  wkp=r(2048, 64, sc=0.022), wuv=r(512, 2048, sc=0.1), wo=r(2048, 2048, sc=0.05), cache=r(S, 576),
+                  r1=(1 + 0.1 * r(2048).float()).half(), r2=(1 + 0.1 * r(512).float()).half(),
+                  o=torch.empty(1, 2048, dtype=torch.float16, device=dev)) for _ in range(nl)]
+        x = r(1, 2048); cos = torch.rand(64, generator=g, device=dev); sin = torch.rand(64, generator=g, device=dev)
+
+        def launch(h, lay, st):
+            a = cabi.CfDeepseekArgs(flags=cabi.CF_FLAG_PDL if pdl else 0, hidden=2048, n_heads=16, seq_len=S, eps=1e-6, x=h.data_ptr(),
+                                    w_q_nope=lay["wqn"].data_ptr(), w_q_pe=lay["wqp"].data_ptr(), w_uk=lay["wuk"].data_ptr(),
+                                    w_kv_nope=lay["wkv"].data_ptr(), w_k_pe=lay["wkp"].data_ptr(), w_uv=lay["wuv"].data_ptr(),
+                                    w_o=lay["wo"].data_ptr(), ckv_cache=lay["cache"].data_ptr(), rms_input_w=lay["r1"].data_ptr(),
+                                    rms_ckv_w=lay["r2"].data_ptr(), cos=cos.data_ptr(), sin=sin.data_ptr(), out=lay["o"].data_ptr(),
+                                    workspace=ws.data_ptr())
+            cabi.launch_deepseek(a, st)
+        s_ = torch.cuda.Stream()
+        with torch.cuda.stream(s_):
+            launch(x, L[0], s_.cuda_stream)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            st = torch.cuda.current_stream().cuda_stream
+            h = x
+            for lay in L:
+                launch(h, lay, st)
+                h = lay["o"]
+        B = 2 * (2048 * 2048 + 2048 * 1024 + 128 * 8192 + 2048 * 512 + 2048 * 64 + 512 * 2048 + 2048 * 2048) + (S - 1) * 1152
+        ms = timed_replays(gr, 40, 5)
+        us = ms * 1e3 / (40 * nl)
+        a = B / (us * 1e-6) / 1e9
+        out.append({"seq_len": S, "us_per_layer": round(us, 3), "bytes": B, "achieved_gbs": round(a, 1),
+                    "frac_of_measured_peak": round(a / peak, 4), "kernels_per_call": 3, "launches": 40 * nl * 3,
+                    "shapes": "hidden 2048, 16 heads, nope 128, rope 64, kv_lora 512 (reference config.h)"})
+        del gr, L
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128, shape_name="llama2-7b", modes=("fused_attn_fused_ffn", "fused", "eager")):

@@ -24,6 +24,7 @@ CF_FLAG_GQA_CLUSTER = 0x4
 CF_FLAG_LL_OUT = 0x8
 CF_FLAG_PER_REQUEST = 0x10
 CF_FLAG_BATCH4 = 0x20
+CF_DS_FLAG_ROPE_SCORES = 0x100
 
 EXPORTED_SYMBOLS = (
     "cf_abi_version",
@@ -40,6 +41,9 @@ EXPORTED_SYMBOLS = (
     "cf_llama_algorithmic_bytes",
     "cf_llama_decoder_layer_launch",
     "cf_llama_ffn_launch",
+    "cf_deepseek_workspace_bytes",
+    "cf_deepseek_decoder_layer_launch",
+    "cf_sizeof_deepseek_args",
     "cf_test_cluster_reduce",
 )
 
@@ -99,6 +103,33 @@ class CfFfnArgs(C.Structure):
     ]
 
 
+class CfDeepseekArgs(C.Structure):
+    _fields_ = [
+        ("flags", C.c_uint32),
+        ("hidden", C.c_int32),
+        ("n_heads", C.c_int32),
+        ("seq_len", C.c_int32),
+        ("eps", C.c_float),
+        ("x", C.c_void_p),
+        ("w_q_nope", C.c_void_p),
+        ("w_q_pe", C.c_void_p),
+        ("w_uk", C.c_void_p),
+        ("w_kv_nope", C.c_void_p),
+        ("w_k_pe", C.c_void_p),
+        ("w_uv", C.c_void_p),
+        ("w_o", C.c_void_p),
+        ("ckv_cache", C.c_void_p),
+        ("rms_input_w", C.c_void_p),
+        ("rms_ckv_w", C.c_void_p),
+        ("cos", C.c_void_p),
+        ("sin", C.c_void_p),
+        ("out", C.c_void_p),
+        ("ckv_new", C.c_void_p),
+        ("k_pe_new", C.c_void_p),
+        ("workspace", C.c_void_p),
+    ]
+
+
 class CfError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"clusterfusion_b200 C ABI error {code}: {msg}")
@@ -124,6 +155,13 @@ def load() -> C.CDLL:
     if lib.cf_sizeof_llama_args() != C.sizeof(CfLlamaArgs) or lib.cf_sizeof_ffn_args() != C.sizeof(CfFfnArgs):
         raise ImportError(f"clusterfusion_b200.cabi: struct mirror out of date (CfLlamaArgs {C.sizeof(CfLlamaArgs)} vs "
                           f"{lib.cf_sizeof_llama_args()}, CfFfnArgs {C.sizeof(CfFfnArgs)} vs {lib.cf_sizeof_ffn_args()}): rebuild")
+    lib.cf_sizeof_deepseek_args.restype = C.c_size_t
+    if lib.cf_sizeof_deepseek_args() != C.sizeof(CfDeepseekArgs):
+        raise ImportError(f"clusterfusion_b200.cabi: CfDeepseekArgs mirror out of date ({C.sizeof(CfDeepseekArgs)} vs "
+                          f"{lib.cf_sizeof_deepseek_args()}): rebuild")
+    lib.cf_deepseek_workspace_bytes.restype = C.c_size_t
+    lib.cf_deepseek_decoder_layer_launch.restype = C.c_int
+    lib.cf_deepseek_decoder_layer_launch.argtypes = [C.POINTER(CfDeepseekArgs), C.c_void_p]
     lib.cf_last_error_string.restype = C.c_char_p
     lib.cf_llama_workspace_bytes.restype = C.c_size_t
     lib.cf_llama_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
@@ -172,6 +210,11 @@ def algorithmic_bytes(args: CfLlamaArgs, total_kv_rows: int) -> int:
 def launch(args: CfLlamaArgs, stream: int = 0) -> None:
     """One fused-kernel launch on CUDA stream handle `stream` (0 = legacy default stream)."""
     check(load().cf_llama_decoder_layer_launch(C.byref(args), C.c_void_p(stream)))
+
+
+def launch_deepseek(args: CfDeepseekArgs, stream: int = 0) -> None:
+    """cf_deepseek_decoder_layer_launch; raises CfError on a non-zero return code."""
+    check(load().cf_deepseek_decoder_layer_launch(C.byref(args), C.c_void_p(stream)))
 
 
 def launch_ffn(args: CfFfnArgs, stream: int = 0) -> None:

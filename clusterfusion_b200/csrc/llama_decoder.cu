@@ -18,6 +18,7 @@
 #include "llama_decoder_batch8_kernel.cuh"
 #include "llama_ffn_kernel.cuh"
 #include "rmsnorm_kernel.cuh"
+#include "deepseek_mla_kernel.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -541,6 +542,122 @@ extern "C" int cf_rmsnorm_launch(const void* x, const void* weight, void* out, i
                                              static_cast<const __half*>(weight), static_cast<__half*>(out), (int)hidden, eps);
     if (e != cudaSuccess) return fail((int)e, "rmsnorm kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+// ---- DeepSeek-MLA half-layer: three kernels back to back on the caller's stream (deepseek_mla_kernel.cuh) ----
+namespace {
+constexpr size_t DS_WS_CKV = 0;                                                  // 576 floats
+constexpr size_t DS_WS_OUT = 2560;                                               // 2048 floats
+constexpr size_t DS_WS_CNT = DS_WS_OUT + cfb::DS_HIDDEN * 4;                     // 8 counters
+constexpr size_t DS_WS_ZERO_END = DS_WS_CNT + 256;                               // everything below must start zeroed
+constexpr size_t DS_WS_Q = DS_WS_ZERO_END;                                       // 16 x 576 halves
+constexpr size_t DS_WS_ML = DS_WS_Q + cfb::DS_HEADS * cfb::DS_MLA * 2;           // 129 x 16 x 2 floats
+constexpr size_t DS_WS_O = (DS_WS_ML + cfb::DS_STATES * cfb::DS_HEADS * 2 * 4 + 255) / 256 * 256;
+constexpr size_t DS_WS_TOTAL = DS_WS_O + (size_t)cfb::DS_STATES * cfb::DS_HEADS * cfb::DS_LORA * 4;
+
+template <typename Kern>
+int ds_launch(Kern kern, int slot, int smem_max, int smem_bytes, int cluster, const cfb::DsParams& dp, bool pdl, cudaStream_t stream) {
+    static std::once_flag once[3][16];
+    static cudaError_t attr_err[3][16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::call_once(once[slot][dev & 15], [&] {
+        attr_err[slot][dev & 15] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    });
+    if (attr_err[slot][dev & 15] != cudaSuccess)
+        return fail((int)attr_err[slot][dev & 15], "cudaFuncSetAttribute(deepseek %d): %s", slot, cudaGetErrorString(attr_err[slot][dev & 15]));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cfb::DS_SPLITS, 1, 1);                // 16 heads x 8 CTAs == 128 cache slices
+    cfg.blockDim = dim3(cfb::DS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, dp);
+    if (e != cudaSuccess) return fail((int)e, "deepseek kernel %d launch failed: %s", slot, cudaGetErrorString(e));
+    return 0;
+}
+}  // namespace
+
+extern "C" size_t cf_deepseek_workspace_bytes(void) { return DS_WS_TOTAL; }
+extern "C" size_t cf_sizeof_deepseek_args(void) { return sizeof(CfDeepseekArgs); }
+
+extern "C" int cf_deepseek_decoder_layer_launch(const CfDeepseekArgs* a, void* stream_) {
+    static_assert(cfb::DS_HEADS * cfb::DS_CLUSTER == cfb::DS_SPLITS, "all three kernels use one grid size");
+    static_assert(CF_DS_FLAG_ROPE_SCORES == cfb::DS_FLAG_ROPE_SCORES, "flag mirror");
+    if (!a) return fail(CF_ERR_NULL_ARG, "args is NULL");
+    if (a->hidden != cfb::DS_HIDDEN || a->n_heads != cfb::DS_HEADS)
+        return fail(CF_ERR_BAD_SHAPE, "deepseek: hidden must be %d and n_heads %d (got %d, %d)", cfb::DS_HIDDEN, cfb::DS_HEADS,
+                    a->hidden, a->n_heads);
+    if (a->seq_len < 1 || a->seq_len > (1 << 24)) return fail(CF_ERR_BAD_SHAPE, "deepseek: seq_len must be in [1, 2^24] (got %d)", a->seq_len);
+    const void* need[] = {a->x, a->w_q_nope, a->w_q_pe, a->w_uk, a->w_kv_nope, a->w_k_pe, a->w_uv, a->w_o, a->rms_input_w,
+                          a->rms_ckv_w, a->cos, a->sin, a->out, a->workspace};
+    for (const void* q : need)
+        if (!q) return fail(CF_ERR_NULL_ARG, "deepseek: x / weights / rms weights / cos / sin / out / workspace must be non-NULL");
+    if (a->seq_len > 1 && !a->ckv_cache) return fail(CF_ERR_NULL_ARG, "deepseek: ckv_cache must be non-NULL when seq_len > 1");
+    const void* al[] = {a->x, a->w_q_nope, a->w_q_pe, a->w_uk, a->w_kv_nope, a->w_k_pe, a->w_uv, a->w_o, a->ckv_cache,
+                        a->rms_input_w, a->rms_ckv_w, a->out, a->ckv_new, a->k_pe_new, a->workspace};
+    for (const void* q : al)
+        if (q && !aligned16(q)) return fail(CF_ERR_BAD_ALIGNMENT, "all tensors must be 16-byte aligned (%p)", q);
+    if (!device_is_sm100()) return fail(CF_ERR_NO_DEVICE, "current CUDA device is not compute capability 10.x");
+
+    cfb::DsParams dp;
+    memset(&dp, 0, sizeof dp);
+    const int H = cfb::DS_HIDDEN, NH = cfb::DS_HEADS;
+    const int n_rows = a->seq_len - 1;
+    int rc;
+    if ((rc = get_tensor_map(&dp.tm_wq_nope, a->w_q_nope, H, (uint64_t)NH * cfb::DS_NOPE, cfb::DS_NOPE, cfb::DS_KSLICE))) return rc;
+    if ((rc = get_tensor_map(&dp.tm_wq_pe, a->w_q_pe, H, (uint64_t)NH * cfb::DS_ROPE, cfb::DS_ROPE, cfb::DS_KSLICE))) return rc;
+    if ((rc = get_tensor_map(&dp.tm_wuk, a->w_uk, cfb::DS_NOPE, (uint64_t)NH * cfb::DS_LORA, 64, cfb::DS_NOPE))) return rc;
+    if ((rc = get_tensor_map(&dp.tm_wkv, a->w_kv_nope, H, cfb::DS_LORA, 256, cfb::DS_KV_ROWS))) return rc;
+    if ((rc = get_tensor_map(&dp.tm_wk_pe, a->w_k_pe, H, cfb::DS_ROPE, cfb::DS_ROPE, cfb::DS_KV_ROWS))) return rc;
+    if ((rc = get_tensor_map(&dp.tm_wuv, a->w_uv, cfb::DS_LORA, (uint64_t)NH * cfb::DS_NOPE, cfb::DS_NOPE, 64))) return rc;
+    if ((rc = get_tensor_map(&dp.tm_wo, a->w_o, (uint64_t)NH * cfb::DS_NOPE, H, 256, cfb::DS_NOPE))) return rc;
+    if (n_rows > 0 && (rc = get_tensor_map(&dp.tm_cache, a->ckv_cache, n_rows, cfb::DS_MLA, 64, cfb::DS_TILE_ROWS, true))) return rc;
+    char* ws = static_cast<char*>(a->workspace);
+    dp.x = static_cast<const __half*>(a->x);
+    dp.rms_in_w = static_cast<const __half*>(a->rms_input_w);
+    dp.rms_ckv_w = static_cast<const __half*>(a->rms_ckv_w);
+    dp.cos = a->cos;
+    dp.sin = a->sin;
+    dp.out = static_cast<__half*>(a->out);
+    dp.ckv_new = static_cast<__half*>(a->ckv_new);
+    dp.k_pe_new = static_cast<__half*>(a->k_pe_new);
+    dp.ckv_acc = reinterpret_cast<float*>(ws + DS_WS_CKV);
+    dp.out_acc = reinterpret_cast<float*>(ws + DS_WS_OUT);
+    dp.counters = reinterpret_cast<unsigned*>(ws + DS_WS_CNT);
+    dp.q = reinterpret_cast<__half*>(ws + DS_WS_Q);
+    dp.part_ml = reinterpret_cast<float*>(ws + DS_WS_ML);
+    dp.part_o = reinterpret_cast<float*>(ws + DS_WS_O);
+    dp.n_rows = n_rows;
+    const int per = (n_rows + cfb::DS_SPLITS - 1) / cfb::DS_SPLITS;
+    dp.rows_per_split = per <= cfb::DS_TILE_ROWS ? cfb::DS_TILE_ROWS : (per + cfb::DS_TILE_ROWS - 1) / cfb::DS_TILE_ROWS * cfb::DS_TILE_ROWS;
+    dp.n_stages = dp.rows_per_split <= cfb::DS_TILE_ROWS ? 1 : cfb::DS_STAGES;
+    dp.eps = a->eps;
+    dp.scale_log2 = 1.4426950408889634f / sqrtf((float)(cfb::DS_NOPE + cfb::DS_ROPE));
+    dp.flags = a->flags;
+
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
+    if ((rc = ds_launch(cfb::ds_proj_kernel, 0, cfb::SmemDsProj::TOTAL, cfb::SmemDsProj::TOTAL, cfb::DS_CLUSTER, dp, pdl, stream))) return rc;
+    // the two inner launches always overlap their prologues with the kernel before them; CF_FLAG_PDL decides only
+    // whether the FIRST kernel may start before the caller's previous kernel on the stream has finished
+    if ((rc = ds_launch(cfb::ds_attn_kernel, 1, cfb::SmemDsAttn::total(cfb::DS_STAGES), cfb::SmemDsAttn::total(dp.n_stages), 1, dp, true, stream))) return rc;
+    return ds_launch(cfb::ds_out_kernel, 2, cfb::SmemDsOut::TOTAL, cfb::SmemDsOut::TOTAL, cfb::DS_CLUSTER, dp, true, stream);
 }
 
 #ifdef CF_TRACE

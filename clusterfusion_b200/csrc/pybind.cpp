@@ -279,6 +279,103 @@ Tensor rmsnorm(Tensor input, Tensor weight) {
     return out;
 }
 
+// deepseek_decoder_layer(input, weight_q_nope, weight_q_pe, weight_uk, weight_kv_nope, weight_k_pe, weight_uv, weight_o,
+//                        ckv_cache, rms_input_weight, rms_ckv_weight, cos, sin) -> fp16 [1, hidden]
+// (/root/reference/include/pybind.cpp:45-59, :113; deepseek_kernel_dispatch.cu:4-18).  seq_len = ckv_cache.size(0).
+Tensor deepseek_workspace_for(const Tensor& like, cudaStream_t stream) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, void*>, Tensor> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple((int)like.get_device(), (void*)stream);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    Tensor w = torch::zeros({(int64_t)cf_deepseek_workspace_bytes()}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device()));
+    cache[key] = w;
+    return w;
+}
+
+Tensor deepseek_run(Tensor input, Tensor weight_q_nope, Tensor weight_q_pe, Tensor weight_uk, Tensor weight_kv_nope,
+                    Tensor weight_k_pe, Tensor weight_uv, Tensor weight_o, Tensor ckv_cache, Tensor rms_input_weight,
+                    Tensor rms_ckv_weight, Tensor cos, Tensor sin, bool rope_scores, Tensor* ckv_new, Tensor* k_pe_new)
+{
+    const std::pair<const Tensor*, const char*> halves[] = {
+        {&input, "input"}, {&weight_q_nope, "weight_q_nope"}, {&weight_q_pe, "weight_q_pe"}, {&weight_uk, "weight_uk"},
+        {&weight_kv_nope, "weight_kv_nope"}, {&weight_k_pe, "weight_k_pe"}, {&weight_uv, "weight_uv"}, {&weight_o, "weight_o"},
+        {&ckv_cache, "ckv_cache"}, {&rms_input_weight, "rms_input_weight"}, {&rms_ckv_weight, "rms_ckv_weight"}};
+    for (const auto& t : halves) check_cuda_contig(*t.first, t.second, torch::kHalf);
+    check_cuda_contig(cos, "cos", torch::kFloat);
+    check_cuda_contig(sin, "sin", torch::kFloat);
+    const int64_t hidden = input.size(-1);
+    TORCH_CHECK(input.numel() == hidden, "deepseek_decoder_layer: input must be [1, hidden]");
+    TORCH_CHECK(weight_q_nope.dim() == 2 && weight_q_nope.size(0) == hidden && weight_q_nope.size(1) % 128 == 0,
+                "weight_q_nope must be [hidden, n_heads*128]");
+    const int64_t nh = weight_q_nope.size(1) / 128;
+    TORCH_CHECK(weight_q_pe.dim() == 2 && weight_q_pe.size(0) == hidden && weight_q_pe.size(1) == nh * 64, "weight_q_pe must be [hidden, n_heads*64]");
+    TORCH_CHECK(weight_uk.dim() == 2 && weight_uk.size(0) == 128 && weight_uk.size(1) == nh * 512, "weight_uk must be [128, n_heads*512]");
+    TORCH_CHECK(weight_kv_nope.dim() == 2 && weight_kv_nope.size(0) == hidden && weight_kv_nope.size(1) == 512, "weight_kv_nope must be [hidden, 512]");
+    TORCH_CHECK(weight_k_pe.dim() == 2 && weight_k_pe.size(0) == hidden && weight_k_pe.size(1) == 64, "weight_k_pe must be [hidden, 64]");
+    TORCH_CHECK(weight_uv.dim() == 2 && weight_uv.size(0) == 512 && weight_uv.size(1) == nh * 128, "weight_uv must be [512, n_heads*128]");
+    TORCH_CHECK(weight_o.dim() == 2 && weight_o.size(0) == nh * 128 && weight_o.size(1) == hidden, "weight_o must be [n_heads*128, hidden]");
+    TORCH_CHECK(ckv_cache.dim() == 2 && ckv_cache.size(0) >= 1 && ckv_cache.size(1) == 576, "ckv_cache must be [seq_len >= 1, 576]");
+    TORCH_CHECK(rms_input_weight.numel() == hidden && rms_ckv_weight.numel() == 512, "rms weights must be [hidden] and [512]");
+    TORCH_CHECK(cos.numel() >= 64 && sin.numel() >= 64, "cos / sin must hold 64 floats");
+    const c10::cuda::CUDAGuard guard(input.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
+    Tensor ws = deepseek_workspace_for(input, stream);
+    Tensor out = torch::empty({1, hidden}, input.options());
+    CfDeepseekArgs a;
+    memset(&a, 0, sizeof a);
+    a.flags = (g_pdl ? CF_FLAG_PDL : 0u) | (rope_scores ? CF_DS_FLAG_ROPE_SCORES : 0u);
+    a.hidden = (int32_t)hidden;
+    a.n_heads = (int32_t)nh;
+    a.seq_len = (int32_t)ckv_cache.size(0);
+    a.eps = 1e-6f;                              // compiled into the reference kernel (kernel.cuh:46)
+    a.x = input.data_ptr();
+    a.w_q_nope = weight_q_nope.data_ptr();
+    a.w_q_pe = weight_q_pe.data_ptr();
+    a.w_uk = weight_uk.data_ptr();
+    a.w_kv_nope = weight_kv_nope.data_ptr();
+    a.w_k_pe = weight_k_pe.data_ptr();
+    a.w_uv = weight_uv.data_ptr();
+    a.w_o = weight_o.data_ptr();
+    a.ckv_cache = ckv_cache.data_ptr();
+    a.rms_input_w = rms_input_weight.data_ptr();
+    a.rms_ckv_w = rms_ckv_weight.data_ptr();
+    a.cos = cos.data_ptr<float>();
+    a.sin = sin.data_ptr<float>();
+    a.out = out.data_ptr();
+    if (ckv_new) {
+        *ckv_new = torch::empty({512}, input.options());
+        *k_pe_new = torch::empty({64}, input.options());
+        a.ckv_new = ckv_new->data_ptr();
+        a.k_pe_new = k_pe_new->data_ptr();
+    }
+    a.workspace = ws.data_ptr();
+    const int rc = cf_deepseek_decoder_layer_launch(&a, stream);
+    TORCH_CHECK(rc == 0, "clusterfusion_b200: deepseek launch failed (", rc, "): ", cf_last_error_string());
+    return out;
+}
+
+Tensor deepseek_decoder_layer(Tensor input, Tensor weight_q_nope, Tensor weight_q_pe, Tensor weight_uk, Tensor weight_kv_nope,
+                              Tensor weight_k_pe, Tensor weight_uv, Tensor weight_o, Tensor ckv_cache, Tensor rms_input_weight,
+                              Tensor rms_ckv_weight, Tensor cos, Tensor sin)
+{
+    return deepseek_run(input, weight_q_nope, weight_q_pe, weight_uk, weight_kv_nope, weight_k_pe, weight_uv, weight_o, ckv_cache,
+                        rms_input_weight, rms_ckv_weight, cos, sin, false, nullptr, nullptr);
+}
+
+// extended form: (out, ckv_new [512], k_pe_new [64]); rope_scores adds the q_pe . k_pe term the reference kernel leaves out
+std::tuple<Tensor, Tensor, Tensor> deepseek_decoder_layer_ex(Tensor input, Tensor weight_q_nope, Tensor weight_q_pe, Tensor weight_uk,
+                                                             Tensor weight_kv_nope, Tensor weight_k_pe, Tensor weight_uv, Tensor weight_o,
+                                                             Tensor ckv_cache, Tensor rms_input_weight, Tensor rms_ckv_weight, Tensor cos,
+                                                             Tensor sin, bool rope_scores)
+{
+    Tensor ckv_new, k_pe_new;
+    Tensor out = deepseek_run(input, weight_q_nope, weight_q_pe, weight_uk, weight_kv_nope, weight_k_pe, weight_uv, weight_o, ckv_cache,
+                              rms_input_weight, rms_ckv_weight, cos, sin, rope_scores, &ckv_new, &k_pe_new);
+    return std::make_tuple(out, ckv_new, k_pe_new);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -292,6 +389,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("llama_ffn_layer", &llama_ffn_layer, "");
     m.def("llama_ffn_layer_out", &llama_ffn_layer_out, "");
     m.def("rmsnorm", &rmsnorm, "");
+    m.def("deepseek_decoder_layer", &deepseek_decoder_layer, "");
+    m.def("deepseek_decoder_layer_ex", &deepseek_decoder_layer_ex, "");
     m.def("set_pdl", [](bool on) { g_pdl = on; }, "enable / disable programmatic dependent launch for all ops of this module");
     m.def("get_pdl", []() { return g_pdl; });
     m.def("abi_version", []() { return cf_abi_version(); });

@@ -177,6 +177,46 @@ int cf_llama_ffn_launch(const CfFfnArgs* args, void* stream);
 int cf_rmsnorm_launch(const void* x, const void* weight, void* out, int32_t batch, int32_t hidden, float eps,
                       uint32_t flags, void* stream);
 
+/* ---- fused DeepSeek-MLA decoder attention half-layer -- replaces the reference op
+ * `deepseek_decoder_layer(input, weight_q_nope, weight_q_pe, weight_uk, weight_kv_nope, weight_k_pe, weight_uv, weight_o,
+ * ckv_cache, rms_input_weight, rms_ckv_weight, cos, sin) -> [1, hidden]`
+ * (/root/reference/include/H100/deepseek/deepseek_kernel_dispatch.cu:4-242, kernel.cuh:9-697, pybind.cpp:45-59, :113):
+ * RMSNorm -> q_nope / q_pe / ckv / k_pe projections -> RoPE on q_pe, k_pe -> RMSNorm(ckv) -> q_nope . W_uk -> decode
+ * attention of all heads over the latent cache rows [0, seq_len-1) ++ the current token -> W_uv -> W_o.  No residual.
+ * Weight layouts are the reference's ([in, out] row-major).  Shapes are the reference's compile-time ones (config.h:1-8:
+ * hidden 2048, 16 heads, nope 128, rope 64, kv_lora_rank 512) except seq_len, which is a run-time argument here
+ * (the reference binary is fixed at 4096).  As in the reference kernel the scores use the 512 latent columns only;
+ * CF_DS_FLAG_ROPE_SCORES adds the decoupled-RoPE term q_pe . k_pe (cache columns 512..575).  The cache is not written:
+ * the current token's row is returned through ckv_new / k_pe_new when those are non-NULL. */
+#define CF_DS_FLAG_ROPE_SCORES 0x100u
+typedef struct CfDeepseekArgs {
+    uint32_t flags;          /* CF_FLAG_PDL, CF_DS_FLAG_ROPE_SCORES                                          */
+    int32_t hidden;          /* 2048                                                                         */
+    int32_t n_heads;         /* 16                                                                           */
+    int32_t seq_len;         /* rows of ckv_cache, >= 1; row seq_len-1 is replaced by the current token      */
+    float eps;               /* 1e-6 in the reference (kernel.cuh:46)                                        */
+    const void* x;           /* fp16 [hidden]                                                                */
+    const void* w_q_nope;    /* fp16 [hidden, n_heads*128]                                                   */
+    const void* w_q_pe;      /* fp16 [hidden, n_heads*64]                                                    */
+    const void* w_uk;        /* fp16 [128, n_heads*512]                                                      */
+    const void* w_kv_nope;   /* fp16 [hidden, 512]                                                           */
+    const void* w_k_pe;      /* fp16 [hidden, 64]                                                            */
+    const void* w_uv;        /* fp16 [512, n_heads*128]                                                      */
+    const void* w_o;         /* fp16 [n_heads*128, hidden]                                                   */
+    const void* ckv_cache;   /* fp16 [seq_len, 576]                                                          */
+    const void* rms_input_w; /* fp16 [hidden]                                                                */
+    const void* rms_ckv_w;   /* fp16 [512]                                                                   */
+    const float* cos;        /* fp32 [64]                                                                    */
+    const float* sin;        /* fp32 [64]                                                                    */
+    void* out;               /* fp16 [hidden]                                                                */
+    void* ckv_new;           /* optional fp16 [512]: normalised latent of the current token                  */
+    void* k_pe_new;          /* optional fp16 [64]: rotated k_pe of the current token                        */
+    void* workspace;         /* cf_deepseek_workspace_bytes() bytes, zeroed once; one call at a time         */
+} CfDeepseekArgs;
+size_t cf_deepseek_workspace_bytes(void);
+int cf_deepseek_decoder_layer_launch(const CfDeepseekArgs* args, void* stream);
+size_t cf_sizeof_deepseek_args(void);
+
 /* Unit-test hook for the device primitive in include/dsm.cuh:
  * launches n_clusters clusters of `cluster_size` CTAs; CTA r of cluster c contributes
  * in[(c*cluster_size + r)*n .. +n) (float); stage 0 = LINEAR (sum), 1 = ATTN (softmax-state merge of

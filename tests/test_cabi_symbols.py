@@ -94,3 +94,26 @@ def test_ctypes_struct_mirrors_match_the_compiled_structs():
     # spot-check field offsets against the header's declaration order (pointers are 8-byte aligned after 10 x 4 bytes)
     assert cabi.CfLlamaArgs.x.offset == 40 and cabi.CfLlamaArgs.workspace.offset == 40 + 18 * 8
     assert cabi.CfLlamaArgs.tp_peer.offset == cabi.CfLlamaArgs.workspace.offset + 8 + 3 * 4 + 4
+
+
+def test_deepseek_boundary_without_gpu():
+    """DeepSeek-MLA entry points: struct mirror, workspace size, shape / NULL validation before any device work, and the
+    reference's operator name on the pybind module."""
+    import ctypes as C
+    import clusterfusion
+    from clusterfusion_b200 import cabi
+    lib = cabi.load()
+    assert lib.cf_sizeof_deepseek_args() == C.sizeof(cabi.CfDeepseekArgs)
+    assert cabi.CfDeepseekArgs.x.offset == 24 and cabi.CfDeepseekArgs.workspace.offset == 24 + 16 * 8
+    # 129 flash-decode states of [16][512] floats dominate the workspace
+    assert lib.cf_deepseek_workspace_bytes() >= 129 * 16 * 512 * 4 + 129 * 16 * 8 + 16 * 576 * 2 + (576 + 2048 + 8) * 4
+    ptrs = {k: 16 for k in ("x", "w_q_nope", "w_q_pe", "w_uk", "w_kv_nope", "w_k_pe", "w_uv", "w_o", "ckv_cache", "rms_input_w",
+                            "rms_ckv_w", "cos", "sin", "out", "workspace")}
+    for bad, code in ((dict(hidden=4096), -3), (dict(n_heads=32), -3), (dict(seq_len=0), -3), (dict(x=None), -1),
+                      (dict(ckv_cache=None), -1), (dict(out=24), -4)):
+        with pytest.raises(cabi.CfError) as e:
+            cabi.launch_deepseek(cabi.CfDeepseekArgs(**{**dict(hidden=2048, n_heads=16, seq_len=4096, eps=1e-6), **ptrs, **bad}))
+        assert e.value.code == code, (bad, str(e.value))
+    assert callable(clusterfusion.deepseek_decoder_layer)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        clusterfusion.deepseek_decoder_layer(*[torch.zeros(1) for _ in range(13)])

@@ -174,3 +174,25 @@ def test_rmsnorm_vs_reference_kernel(ref):
     torch.cuda.synchronize()
     print(f"rmsnorm: |ours-oracle|={err(o, want):.2e} |ref-oracle|={err(r, want):.2e} |ours-ref|={err(o, r):.2e}")
     assert err(o, want) < 4e-3 and err(r, want) < 4e-3 and err(o, r) < 4e-3        # values up to ~16: 1 fp16 ulp = 7.8e-3 / 2
+
+
+def test_reference_deepseek_kernel_vs_oracle(ref):
+    """The reference's DeepSeek-MLA kernel (fixed at hidden 2048 / 16 heads / SEQ_LEN 4096, no test of its own upstream) next to
+    ours and to the oracle on the same inputs.  On B200 its output is not reproducible from launch to launch and is far from
+    the oracle (tools/deepseek_probe.py measured |diff| ~ 33 on outputs of magnitude 2), so the oracle stays UNPINNED for this
+    op: only our kernel is asserted, the reference's numbers are printed for the record."""
+    import clusterfusion
+    from oracle import deepseek_oracle as D
+    d = D.make_inputs(4096, seed=4096, out_gain=2.4)
+    keys = ("x", "w_q_nope", "w_q_pe", "w_uk", "w_kv", "w_k_pe", "w_uv", "w_o", "ckv_cache", "rms_in_w", "rms_ckv_w", "cos", "sin")
+    c = [d[k].cuda() for k in keys]
+    want, _, _ = D.deepseek_layer(**d)
+    ours = clusterfusion.deepseek_decoder_layer(*c)
+    torch.cuda.synchronize()
+    assert torch.allclose(ours.float().cpu(), want.float(), rtol=1e-3, atol=1e-3)
+    errs = []
+    for _ in range(4):
+        o = ref.deepseek_decoder_layer(*c)
+        torch.cuda.synchronize()
+        errs.append(err(o, want))
+    print(f"reference DeepSeek kernel vs oracle: {errs}; ours vs oracle: {err(ours, want)}")

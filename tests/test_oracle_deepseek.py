@@ -1,0 +1,65 @@
+"""CPU checks of the DeepSeek-MLA oracle (oracle/deepseek_oracle.py).  The reference holds no fixture for this op (the
+oracle's header says "parity unpinned"), so what can be checked on the CPU is internal: closed forms at seq_len 1, the
+rounding noise of the fp16 flavour against float64, and the algebraic properties the GPU tests rely on."""
+import math
+
+import torch
+
+from oracle import deepseek_oracle as D
+
+
+def test_seq_len_1_closed_form():
+    """With no cache rows the softmax has one term: out = W_o (W_uv ckv_n), independent of q, RoPE and the flag."""
+    d = D.make_inputs(1, seed=5, out_gain=0.75)
+    out, ckv_n, k_pe = D.deepseek_layer(**d, mode="exact")
+    x = d["x"].double().view(-1)
+    xn = x * torch.rsqrt((x * x).mean() + D.EPS) * d["rms_in_w"].double()
+    ckv = xn @ d["w_kv"].double()
+    want_ckv = ckv * torch.rsqrt((ckv * ckv).mean() + D.EPS) * d["rms_ckv_w"].double()
+    assert torch.allclose(ckv_n.double(), want_ckv, atol=2e-3)
+    attn = torch.einsum("k,khn->hn", want_ckv, d["w_uv"].double().view(D.LORA, D.N_HEADS, D.NOPE))
+    want = attn.reshape(1, -1) @ d["w_o"].double()
+    assert torch.allclose(out.double(), want, rtol=1e-3, atol=1e-3)
+    out_r, _, _ = D.deepseek_layer(**d, mode="exact", rope_scores=True)
+    assert torch.equal(out, out_r)
+
+
+def test_eager_flavour_is_rounding_close_to_float64():
+    for S, gain in ((2, 0.75), (300, 1.5), (4096, 2.4)):
+        d = D.make_inputs(S, seed=S, out_gain=gain)
+        for rope in (False, True):
+            o, c, k = D.deepseek_layer(**d, rope_scores=rope)
+            oe, ce, ke = D.deepseek_layer(**d, rope_scores=rope, mode="exact")
+            assert float(o.float().abs().max()) > 0.5                       # the comparison is not vacuous
+            assert torch.allclose(o.float(), oe.float(), rtol=2e-3, atol=2e-3), (S, rope)
+            assert torch.allclose(c.float(), ce.float(), rtol=2e-3, atol=2e-3)
+            assert torch.allclose(k.float(), ke.float(), rtol=2e-3, atol=2e-3)
+
+
+def test_rope_term_and_row_permutation():
+    d = D.make_inputs(200, seed=9, out_gain=1.5)
+    o, _, _ = D.deepseek_layer(**d)
+    o_r, _, _ = D.deepseek_layer(**d, rope_scores=True)
+    assert float((o.float() - o_r.float()).abs().max()) > 0.05              # the flag changes the scores
+    # the reference kernel's scores never see cache columns 512..575 (kernel.cuh:400-470 loads latent columns only)
+    d2 = dict(d, ckv_cache=d["ckv_cache"].clone())
+    d2["ckv_cache"][:, D.LORA:] = 7.0
+    assert torch.equal(D.deepseek_layer(**d2)[0], o)
+    # the cache's last row is replaced by the current token (kernel.cuh:469-470)
+    d2["ckv_cache"][-1] = -3.0
+    assert torch.equal(D.deepseek_layer(**d2)[0], o)
+    # attention is a set function of the cache rows
+    perm = torch.randperm(199, generator=torch.Generator().manual_seed(1))
+    d3 = dict(d, ckv_cache=torch.cat([d["ckv_cache"][:199][perm], d["ckv_cache"][199:]]))
+    assert torch.allclose(D.deepseek_layer(**d3, rope_scores=True)[0].float(), o_r.float(), rtol=1e-3, atol=1e-3)
+
+
+def test_rope_matches_complex_rotation():
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(3, D.ROPE, generator=g)
+    ang = torch.rand(D.ROPE // 2, generator=g) * 6
+    cos, sin = torch.cat([ang.cos(), ang.cos()]), torch.cat([ang.sin(), ang.sin()])
+    got = D._rope(v, cos, sin)
+    z = torch.complex(v[:, : D.ROPE // 2], v[:, D.ROPE // 2:]) * torch.polar(torch.ones_like(ang), ang)
+    assert torch.allclose(got, torch.cat([z.real, z.imag], dim=-1), atol=1e-5)
+    assert math.isclose(float(got.norm()), float(v.norm()), rel_tol=1e-5)

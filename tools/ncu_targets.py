@@ -1,6 +1,7 @@
 """Plain (graph-free) launch loops for ncu captures of the kernels bench.py's headline arm does not launch:
     python tools/ncu_targets.py gqa 8192     # group kernel, Llama-3-8B shapes
     python tools/ncu_targets.py ffn          # fused FFN half-layer, Llama-2-7B shapes
+    python tools/ncu_targets.py deepseek 4096  # DeepSeek-MLA half-layer (3 kernels per call), through the C ABI
 8 distinct layer sets, 3 passes (24 launches); capture with  ncu --set full -k regex:<kernel> -s 8 -c 3 ..."""
 import sys, torch
 sys.path.insert(0, ".")
@@ -27,6 +28,22 @@ if what == "gqa":
                                  k_new=lay["kn"].data_ptr(), v_new=lay["vn"].data_ptr(), k_cache=lay["k"].data_ptr(), v_cache=lay["v"].data_ptr(),
                                  cos=cos.data_ptr(), sin=sin.data_ptr(), workspace=ws.data_ptr())
             cabi.launch(a, st)
+elif what == "deepseek":
+    S = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    ws = torch.zeros(cabi.load().cf_deepseek_workspace_bytes(), dtype=torch.uint8, device=dev)
+    L = [dict(wqn=r(2048, 2048, sc=0.02), wqp=r(2048, 1024, sc=0.02), wuk=r(128, 8192, sc=0.09), wkv=r(2048, 512, sc=0.02),
+              wkp=r(2048, 64, sc=0.02), wuv=r(512, 2048, sc=0.05), wo=r(2048, 2048, sc=0.03), cache=r(S, 576),
+              r1=(1 + 0.1 * r(2048).float()).half(), r2=(1 + 0.1 * r(512).float()).half(),
+              o=torch.empty(1, 2048, dtype=torch.float16, device=dev)) for _ in range(8)]
+    x = r(1, 2048); cos = torch.rand(64, device=dev); sin = torch.rand(64, device=dev)
+    for _ in range(3):
+        for lay in L:
+            a = cabi.CfDeepseekArgs(flags=0, hidden=2048, n_heads=16, seq_len=S, eps=1e-6, x=x.data_ptr(), w_q_nope=lay["wqn"].data_ptr(),
+                                    w_q_pe=lay["wqp"].data_ptr(), w_uk=lay["wuk"].data_ptr(), w_kv_nope=lay["wkv"].data_ptr(),
+                                    w_k_pe=lay["wkp"].data_ptr(), w_uv=lay["wuv"].data_ptr(), w_o=lay["wo"].data_ptr(),
+                                    ckv_cache=lay["cache"].data_ptr(), rms_input_w=lay["r1"].data_ptr(), rms_ckv_w=lay["r2"].data_ptr(),
+                                    cos=cos.data_ptr(), sin=sin.data_ptr(), out=lay["o"].data_ptr(), workspace=ws.data_ptr())
+            cabi.launch_deepseek(a, st)
 else:
     H, F = 4096, 11008
     ws = torch.zeros(cabi.workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
