@@ -22,7 +22,7 @@
  *  2. ds_attn_kernel   128 CTAs, CTA = a contiguous slice of cache rows, ALL 16 heads at once: the heads are the M = 16
  *     rows of `mma.sync.m16n8k16`, so the cache is read once (not once per head) and QK^T / PV run on the tensor cores
  *     from 128-byte-swizzled TMA boxes (ldmatrix conflict-free).  Each CTA leaves an un-normalised flash-decode state
- *     (m, l, o[16][512]) in the workspace; CTA 0 also finishes the current token (fp16 ckv -> RMSNorm, RoPE on k_pe), which
+ *     (m, l, o[16][512]) in the workspace; a 129th CTA finishes the current token (fp16 ckv -> RMSNorm, RoPE on k_pe), which
  *     enters the merge as one more state.
  *  3. ds_out_kernel    16 clusters of 8, cluster = head.  CTA (h, r) merges the 129 states for latent columns
  *     [64r, 64r+64) of head h, multiplies by its 64 rows of W_uv[head], the 8 partial head outputs are summed with
@@ -78,7 +78,7 @@ struct DsParams {
     float* ckv_acc;           // ws [576]  fp32 sums of the shared projection, zero between calls
     __half* q;                // ws [16][576] fp16: q_lat ++ rotated q_pe (zeros unless DS_FLAG_ROPE_SCORES)
     float* part_ml;           // ws [129][16][2]  (m in the log2 domain, l)
-    float* part_o;            // ws [129][16][512]
+    float* part_o;            // ws [128][16][512] ++ [512] (the current token's latent, shared by the heads)
     float* out_acc;           // ws [2048], zero between calls
     unsigned* counters;       // ws [8], zero between calls
     int n_rows;               // cache rows that take part: seq_len - 1
@@ -99,18 +99,24 @@ __device__ __forceinline__ float ds_rope(const float* v, const float* cos, const
 // 1. projections
 // ------------------------------------------------------------------------------------------------------------------
 struct SmemDsProj {
+    // 134 KB, so that a CTA of this kernel fits on an SM NEXT TO a CTA of the previous call's output kernel (89 KB): with
+    // CF_FLAG_PDL its weight tiles stream in while that kernel is still running.  The W_kv / W_k_pe tiles are consumed first;
+    // their 18 KB are then reused for the cross-thread scratch and the cluster exchange (peers are held back by the cluster
+    // barrier, which this CTA arrives at only after its last read of the tiles).
     static constexpr int WQ = 0;                                   // [256][128] halves
     static constexpr int WQPE = WQ + DS_KSLICE * DS_NOPE * 2;      // [256][64]
     static constexpr int WKV = WQPE + DS_KSLICE * DS_ROPE * 2;     // [2 boxes][16][256]
     static constexpr int WKPE = WKV + DS_KV_ROWS * DS_LORA * 2;    // [16][64]
     static constexpr int WUK = WKPE + DS_KV_ROWS * DS_ROPE * 2;    // [128][64]
     static constexpr int XN = WUK + DS_NOPE * 64 * 2;              // [2048] halves
-    static constexpr int RED = XN + DS_HIDDEN * 2;                 // 2048 floats of cross-thread scratch
-    static constexpr int SRC = RED + 2048 * 4;                     // 192 floats
-    static constexpr int RECV = SRC + 192 * 4;                     // 2 * 8 * 192 floats
-    static constexpr int MISC = RECV + 2 * DS_CLUSTER * 192 * 4;   // warp sums
+    static constexpr int MISC = XN + DS_HIDDEN * 2;                // warp sums
     static constexpr int BARS = MISC + 64;                         // 4 mbarriers
     static constexpr int TOTAL = BARS + 64;
+    // aliases inside [WKV, WUK)
+    static constexpr int RED = WKV;                                // 2048 floats of cross-thread scratch
+    static constexpr int RECV = RED + 2048 * 4;                    // 8 x 192 floats: one exchange, phase 0 only
+    static constexpr int SRC = RECV + DS_CLUSTER * 192 * 4;        // 192 floats
+    static_assert(SRC + 192 * 4 <= WUK, "scratch must fit in the consumed W_kv / W_k_pe tiles");
 };
 
 __global__ void __launch_bounds__(DS_THREADS, 1)
@@ -155,7 +161,6 @@ ds_proj_kernel(const __grid_constant__ DsParams p)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     float w8[8];
     unpack8(*reinterpret_cast<const uint4*>(p.rms_in_w + tid * 8), w8);
-    dsm::cluster_arrive();                       // peers may push into this CTA only after its exchange barrier is armed
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---- RMSNorm of the whole input row (4 KB; every CTA needs all of it) ----
@@ -196,6 +201,8 @@ ds_proj_kernel(const __grid_constant__ DsParams p)
         }
         red_add_v4(p.ckv_acc + tid * 4, make_float4(a0, a1, a2, a3));
     }
+    __syncthreads();                             // the W_kv / W_k_pe tiles are dead: their bytes become red / recv / src
+    dsm::cluster_arrive();                       // peers may push into this CTA from here on (exchange barrier armed at the top)
 
     // ---- q_nope / q_pe partials over this CTA's 256 hidden rows ----
     dsm::mbar_wait(bar_q, 0);
@@ -344,8 +351,9 @@ ds_attn_kernel(const __grid_constant__ DsParams p)
         *reinterpret_cast<uint4*>(qs + h * DS_Q_STRIDE + c * 8) = *reinterpret_cast<const uint4*>(p.q + h * DS_MLA + c * 8);
     }
 
-    // ---- CTA 0: finish the current token and publish it as state number DS_SPLITS ----
-    if (split == 0) {
+    // ---- CTA number DS_SPLITS (one more than there are cache slices; it owns no rows and runs on an SM of its own):
+    //      finish the current token and publish it as state number DS_SPLITS ----
+    if (split == DS_SPLITS) {
         float ss = 0.f;
         float v[2];
 #pragma unroll
@@ -390,8 +398,9 @@ ds_attn_kernel(const __grid_constant__ DsParams p)
                 p.part_ml[(DS_SPLITS * DS_HEADS + h) * 2 + 1] = 1.f;
             }
         }
-        for (int i = tid; i < DS_HEADS * DS_LORA; i += DS_THREADS)
-            p.part_o[(size_t)DS_SPLITS * DS_HEADS * DS_LORA + i] = tok[i & (DS_LORA - 1)];
+        // its o is the token's latent, the same for every head: stored once
+        for (int i = tid; i < DS_LORA; i += DS_THREADS) p.part_o[(size_t)DS_SPLITS * DS_HEADS * DS_LORA + i] = tok[i];
+        return;
     }
     __syncthreads();
 
@@ -518,16 +527,18 @@ ds_attn_kernel(const __grid_constant__ DsParams p)
 // 3. state merge, W_uv, W_o
 // ------------------------------------------------------------------------------------------------------------------
 struct SmemDsOut {
+    // 89 KB: see SmemDsProj.  The exchange buffer of the cluster reduction reuses the cross-thread scratch.
     static constexpr int WUV = 0;                                  // [64][128] halves
     static constexpr int WO = WUV + 64 * DS_NOPE * 2;              // [128][256] halves
     static constexpr int RED = WO + DS_NOPE * 256 * 2;             // 2048 floats
+    static constexpr int RECV = RED;                               // 8 x 128 floats: one exchange, phase 0 only
     static constexpr int SRC = RED + 2048 * 4;                     // 128 floats
-    static constexpr int RECV = SRC + DS_NOPE * 4;                 // 2 * 8 * 128 floats
-    static constexpr int OLAT = RECV + 2 * DS_CLUSTER * DS_NOPE * 4;   // 64 floats
+    static constexpr int OLAT = SRC + DS_NOPE * 4;                 // 64 floats
     static constexpr int WGT = OLAT + 64 * 4;                      // 132 floats: merge weights of the states (+ pad)
     static constexpr int MISC = WGT + 132 * 4;
     static constexpr int BARS = MISC + 64;
     static constexpr int TOTAL = BARS + 64;
+    static_assert(SmemDsProj::TOTAL + TOTAL + 2048 <= 228 * 1024, "a projection CTA and an output CTA must fit on one SM");
 };
 
 __global__ void __launch_bounds__(DS_THREADS, 1)
@@ -561,7 +572,6 @@ ds_out_kernel(const __grid_constant__ DsParams p)
         tma_load_2d(sb + SmemDsOut::WO, &p.tm_wo, rank * 256, head * DS_NOPE, bar_o, pol);
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    dsm::cluster_arrive();
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // the shared projection has been consumed by the attention kernel: clear it for the next call
@@ -579,7 +589,9 @@ ds_out_kernel(const __grid_constant__ DsParams p)
 #pragma unroll
         for (int i = 0; i < NPER; ++i) {
             const int s = g + 4 * i;
-            v[i] = s < DS_STATES ? po[(size_t)s * DS_HEADS * DS_LORA] : 0.f;
+            // state DS_SPLITS (the current token) keeps one [512] row for all heads
+            v[i] = s < DS_SPLITS ? po[(size_t)s * DS_HEADS * DS_LORA]
+                 : s == DS_SPLITS ? p.part_o[(size_t)DS_SPLITS * DS_HEADS * DS_LORA + rank * 64 + j] : 0.f;
         }
         float m = -INFINITY, l = 0.f;
         if (tid < DS_STATES) {
@@ -639,6 +651,8 @@ ds_out_kernel(const __grid_constant__ DsParams p)
         for (int g = 0; g < 16; ++g) t += red[g * DS_NOPE + tid];
         src[tid] = t;
     }
+    __syncthreads();                             // last read of `red`, which now becomes the exchange buffer
+    dsm::cluster_arrive();
     dsm::cluster_wait();
     uint32_t phase = 0;
     cluster_reduce<DS_CLUSTER, Stage::ATTN_DEEPSEEK>(DS_NOPE * 4, tid, DS_NOPE, rank, dsm::smem_u32(src), dsm::smem_u32(recv),

@@ -556,7 +556,7 @@ constexpr size_t DS_WS_O = (DS_WS_ML + cfb::DS_STATES * cfb::DS_HEADS * 2 * 4 + 
 constexpr size_t DS_WS_TOTAL = DS_WS_O + (size_t)cfb::DS_STATES * cfb::DS_HEADS * cfb::DS_LORA * 4;
 
 template <typename Kern>
-int ds_launch(Kern kern, int slot, int smem_max, int smem_bytes, int cluster, const cfb::DsParams& dp, bool pdl, cudaStream_t stream) {
+int ds_launch(Kern kern, int slot, int grid, int smem_max, int smem_bytes, int cluster, const cfb::DsParams& dp, bool pdl, cudaStream_t stream) {
     static std::once_flag once[3][16];
     static cudaError_t attr_err[3][16];
     int dev = 0;
@@ -567,7 +567,7 @@ int ds_launch(Kern kern, int slot, int smem_max, int smem_bytes, int cluster, co
     if (attr_err[slot][dev & 15] != cudaSuccess)
         return fail((int)attr_err[slot][dev & 15], "cudaFuncSetAttribute(deepseek %d): %s", slot, cudaGetErrorString(attr_err[slot][dev & 15]));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(cfb::DS_SPLITS, 1, 1);                // 16 heads x 8 CTAs == 128 cache slices
+    cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(cfb::DS_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
@@ -597,7 +597,6 @@ extern "C" size_t cf_deepseek_workspace_bytes(void) { return DS_WS_TOTAL; }
 extern "C" size_t cf_sizeof_deepseek_args(void) { return sizeof(CfDeepseekArgs); }
 
 extern "C" int cf_deepseek_decoder_layer_launch(const CfDeepseekArgs* a, void* stream_) {
-    static_assert(cfb::DS_HEADS * cfb::DS_CLUSTER == cfb::DS_SPLITS, "all three kernels use one grid size");
     static_assert(CF_DS_FLAG_ROPE_SCORES == cfb::DS_FLAG_ROPE_SCORES, "flag mirror");
     if (!a) return fail(CF_ERR_NULL_ARG, "args is NULL");
     if (a->hidden != cfb::DS_HIDDEN || a->n_heads != cfb::DS_HEADS)
@@ -653,11 +652,11 @@ extern "C" int cf_deepseek_decoder_layer_launch(const CfDeepseekArgs* a, void* s
 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
-    if ((rc = ds_launch(cfb::ds_proj_kernel, 0, cfb::SmemDsProj::TOTAL, cfb::SmemDsProj::TOTAL, cfb::DS_CLUSTER, dp, pdl, stream))) return rc;
+    if ((rc = ds_launch(cfb::ds_proj_kernel, 0, cfb::DS_HEADS * cfb::DS_CLUSTER, cfb::SmemDsProj::TOTAL, cfb::SmemDsProj::TOTAL, cfb::DS_CLUSTER, dp, pdl, stream))) return rc;
     // the two inner launches always overlap their prologues with the kernel before them; CF_FLAG_PDL decides only
     // whether the FIRST kernel may start before the caller's previous kernel on the stream has finished
-    if ((rc = ds_launch(cfb::ds_attn_kernel, 1, cfb::SmemDsAttn::total(cfb::DS_STAGES), cfb::SmemDsAttn::total(dp.n_stages), 1, dp, true, stream))) return rc;
-    return ds_launch(cfb::ds_out_kernel, 2, cfb::SmemDsOut::TOTAL, cfb::SmemDsOut::TOTAL, cfb::DS_CLUSTER, dp, true, stream);
+    if ((rc = ds_launch(cfb::ds_attn_kernel, 1, cfb::DS_SPLITS + 1, cfb::SmemDsAttn::total(cfb::DS_STAGES), cfb::SmemDsAttn::total(dp.n_stages), 1, dp, true, stream))) return rc;
+    return ds_launch(cfb::ds_out_kernel, 2, cfb::DS_HEADS * cfb::DS_CLUSTER, cfb::SmemDsOut::TOTAL, cfb::SmemDsOut::TOTAL, cfb::DS_CLUSTER, dp, true, stream);
 }
 
 #ifdef CF_TRACE
