@@ -93,16 +93,21 @@ def test_layer_chain_with_pdl_matches_plain_chain():
         torch.cuda.synchronize()
         return x
 
+    def rel(u, v):
+        return float((u.float().cpu() - v.float().cpu()).norm() / v.float().cpu().norm())
+
     a, b = chain(False), chain(True)
     assert torch.isfinite(a.float()).all()
-    assert torch.allclose(a.float(), b.float(), rtol=2e-2, atol=2e-2)         # 8 layers deep: last-bit differences amplify
+    # 8 layers deep, last-bit differences (fp32 atomics order) amplify: compare in the relative L2 norm, which a broken
+    # dependency (garbage from a kernel that started too early) would put near 1
+    assert rel(a, b) < 1e-2
     # and against the oracle, layer by layer on the CPU
     x = L[0]["x"].cpu()
     for i in range(8):
         d = {k: v.cpu() for k, v in L[i % 4].items()}
         d["x"] = x
         x, _, _ = D.deepseek_layer(**d, rope_scores=True)
-    assert torch.allclose(a.float().cpu(), x.float(), rtol=3e-2, atol=3e-2)
+    assert rel(a, x) < 2e-2
 
 
 def test_properties_at_long_cache():

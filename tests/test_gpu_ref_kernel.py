@@ -190,9 +190,13 @@ def test_reference_deepseek_kernel_vs_oracle(ref):
     ours = clusterfusion.deepseek_decoder_layer(*c)
     torch.cuda.synchronize()
     assert torch.allclose(ours.float().cpu(), want.float(), rtol=1e-3, atol=1e-3)
-    errs = []
-    for _ in range(4):
-        o = ref.deepseek_decoder_layer(*c)
-        torch.cuda.synchronize()
-        errs.append(err(o, want))
-    print(f"reference DeepSeek kernel vs oracle: {errs}; ours vs oracle: {err(ours, want)}")
+    ours_err = err(ours, want)
+    try:                                                  # nothing of the reference kernel's behaviour on B200 is relied upon
+        errs = []
+        for _ in range(4):
+            o = ref.deepseek_decoder_layer(*c)
+            torch.cuda.synchronize()
+            errs.append(err(o, want))
+        print(f"reference DeepSeek kernel vs oracle: {errs}; ours vs oracle: {ours_err}")
+    except Exception as e:                                # noqa: BLE001 -- recorded, not asserted
+        print(f"reference DeepSeek kernel failed on this GPU: {e!r}; ours vs oracle: {ours_err}")
