@@ -10,6 +10,14 @@ every public name of its native module; ``include/pybind.cpp:108-123`` defines t
                                weight_o, paged_kv_indptr, paged_kv_indices, k_cache_ptrs,
                                v_cache_ptrs, layer_id, rms_w, eps, positions, cos_sin) -> None
 
+and, from the reference's sm90 module (``include/pybind.cpp:45-64``, ``:113-114``):
+
+    deepseek_decoder_layer(input, weight_q_nope, weight_q_pe, weight_uk, weight_kv_nope, weight_k_pe,
+                           weight_uv, weight_o, ckv_cache, rms_input_weight, rms_ckv_weight, cos, sin) -> o
+    rmsnorm(input, weight) -> out
+
+plus operators the reference does not have (``llama_ffn_layer``, ``deepseek_decoder_layer_ex``, ``set_pdl``).
+
 Everything is native: a torch-free C-ABI library (``libclusterfusion_b200.so``, the CUDA kernels) and a
 thin PyTorch C++ extension (``_clusterfusion``).  There is no Python or CPU fallback -- importing
 this package without the built extension raises ImportError, exactly like the reference package.
