@@ -7,6 +7,8 @@ import torch
 
 from oracle import deepseek_oracle as D
 
+ORACLE_DIGEST = "4c25e94b816e3f847d4f8b2e02c23396b014706553f3031930a4d47aacf8e822"
+
 
 def test_seq_len_1_closed_form():
     """With no cache rows the softmax has one term: out = W_o (W_uv ckv_n), independent of q, RoPE and the flag."""
@@ -63,3 +65,40 @@ def test_rope_matches_complex_rotation():
     z = torch.complex(v[:, : D.ROPE // 2], v[:, D.ROPE // 2:]) * torch.polar(torch.ones_like(ang), ang)
     assert torch.allclose(got, torch.cat([z.real, z.imag], dim=-1), atol=1e-5)
     assert math.isclose(float(got.norm()), float(v.norm()), rel_tol=1e-5)
+
+
+def test_absorbed_form_equals_explicit_per_head_attention():
+    """The kernel (and the oracle) work in the latent space: q_lat = q_nope W_uk scores the 512-wide cache rows directly and
+    W_uv is applied after the softmax.  The textbook form materialises per-head keys and values,
+    k[h, t] = W_uk[h] row_t (128 dims), v[h, t] = row_t W_uv[h], and attends over those.  Both must agree (float64)."""
+    S = 50
+    d = D.make_inputs(S, seed=13, out_gain=1.0)
+    out, ckv_n, k_pe = D.deepseek_layer(**d, rope_scores=True, mode="exact")
+    f = lambda t: t.double()
+    x = f(d["x"]).view(-1)
+    xn = x * torch.rsqrt((x * x).mean() + D.EPS) * f(d["rms_in_w"])
+    q_nope = (xn @ f(d["w_q_nope"])).view(D.N_HEADS, D.NOPE)
+    q_pe = D._rope((xn @ f(d["w_q_pe"])).view(D.N_HEADS, D.ROPE), f(d["cos"]), f(d["sin"]))
+    rows = torch.cat([f(d["ckv_cache"][: S - 1, : D.LORA]), f(ckv_n)[None]], 0)                    # [S, 512]
+    pes = torch.cat([f(d["ckv_cache"][: S - 1, D.LORA:]), f(k_pe)[None]], 0)                       # [S, 64]
+    w_uk = f(d["w_uk"]).view(D.NOPE, D.N_HEADS, D.LORA)
+    w_uv = f(d["w_uv"]).view(D.LORA, D.N_HEADS, D.NOPE)
+    k = torch.einsum("tc,dhc->htd", rows, w_uk)                                                    # [heads, S, 128]
+    v = torch.einsum("tc,chn->htn", rows, w_uv)                                                    # [heads, S, 128]
+    scores = (torch.einsum("hd,htd->ht", q_nope, k) + q_pe @ pes.T) / math.sqrt(D.NOPE + D.ROPE)
+    attn = torch.einsum("ht,htn->hn", torch.softmax(scores, -1), v)
+    want = attn.reshape(1, -1) @ f(d["w_o"])
+    # the oracle's outputs (out, ckv_n, k_pe) are fp16 tensors: one rounding of the inputs to this check and one of the result
+    assert torch.allclose(out.double(), want, rtol=2e-3, atol=2e-3)
+
+
+def test_oracle_digest_is_stable():
+    """Drift guard for the oracle itself (NOT a pin to the reference, which has nothing to pin to): SHA-256 of the float64
+    flavour's fp16 outputs on seeded inputs, as committed when the CUDA path was validated against it on B200."""
+    import hashlib
+    h = hashlib.sha256()
+    for S, rope in ((1, False), (37, False), (37, True), (300, True)):
+        d = D.make_inputs(S, seed=1000 + S, out_gain=1.0)
+        for t in D.deepseek_layer(**d, rope_scores=rope, mode="exact"):
+            h.update(t.contiguous().view(torch.uint8).numpy().tobytes())
+    assert h.hexdigest() == ORACLE_DIGEST, h.hexdigest()
