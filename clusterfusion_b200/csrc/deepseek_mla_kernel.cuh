@@ -300,7 +300,7 @@ ds_proj_kernel(const __grid_constant__ DsParams p)
 struct SmemDsAttn {
     // [n_stages x 36864 tile ring, 1024-aligned][q][current token][misc][barriers].  The ring has ONE stage when every
     // CTA has at most one tile (seq_len <= 4097): 56 KB per CTA, so the CTAs of this kernel become resident NEXT TO the
-    // projection kernel's (159 KB) and their cache tile is in flight while that kernel still runs; otherwise DS_STAGES.
+    // projection kernel's (137 KB) and their cache tile is in flight while that kernel still runs; otherwise DS_STAGES.
     static constexpr int Q_BYTES = DS_HEADS * DS_Q_STRIDE * 2;               // [16][DS_Q_STRIDE] halves
     static constexpr int TOK_BYTES = DS_MLA * 4;                             // the current token's row (CTA 0)
     static constexpr int TAIL = Q_BYTES + TOK_BYTES + 64 + 64;
