@@ -449,13 +449,18 @@ def run_ours(args, rank, world, local_rank):
             "frac": k16["frac_of_measured_peak"], "frac_of_8tbs": k16["frac_of_8tbs"],
             "us_per_layer": k16["us_per_layer"], "algorithmic_bytes_per_launch": k16["bytes"]},
         "kv_sweep": sweep,
-        "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 2,
+        # headline e2e = the call the reference README shows (README.md:55-75): one operator call per layer does the whole
+        # attention half-layer including KV append and residual; the 8-argument chat form, where the caller appends K/V and
+        # adds the residual with three more torch ops per layer (chat/llama/model.py:358-374, :488-492), is reported next to it
+        "e2e": {"value": e2e_paged_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 2,
                 "d2h_bytes_per_step": out_host.numel() * 2, "steps": e2e_steps,
-                "api": "clusterfusion.llama_decoder_layer (pybind) + caller-side KV append and residual add, no CUDA graph"},
-        "e2e_paged_form": {"value": e2e_paged_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 2,
-                           "d2h_bytes_per_step": out_host.numel() * 2, "steps": e2e_steps,
-                           "api": "clusterfusion.llama_decoder_layer, 15-argument paged form of the reference README "
-                                  "(KV append + residual fused in the kernel), 32 calls per step, no CUDA graph"},
+                "api": "clusterfusion.llama_decoder_layer, 15-argument paged form of the reference README "
+                       "(KV append + residual fused in the kernel), 32 pybind calls per step from pinned host input to "
+                       "pinned host output, no CUDA graph"},
+        "e2e_chat_form": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": x_host.numel() * 2,
+                          "d2h_bytes_per_step": out_host.numel() * 2, "steps": e2e_steps,
+                          "api": "clusterfusion.llama_decoder_layer, 8-argument chat form + caller-side KV append and residual "
+                                 "add (3 extra torch ops per layer), no CUDA graph"},
         "gpu_launches": args.steps * LAYERS,
         "clocks": clocks,
         "cpu_baseline": cpu,
