@@ -96,4 +96,26 @@ if sos:
     print(json.dumps(dict(reference_kernel=True, ref_vs_oracle=[err(o, want) for o in outs], ours_vs_oracle=err(ours, want),
                           ours_vs_exact=err(ours, exact), ref_vs_exact=err(outs[-1], exact), ref_vs_ours=err(outs[-1], ours),
                           out_absmax=float(want.float().abs().max()))), flush=True)
+    # how long the reference's kernel takes on this GPU: CUDA events around its operator (3 device syncs and 9 tensor-map
+    # encodes per call, deepseek_kernel_dispatch.cu:40-241) and the kernel alone from CUPTI
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ref.deepseek_decoder_layer(*c)
+    e1.record()
+    torch.cuda.synchronize()
+    us_call, us_kernel = e0.elapsed_time(e1) * 1e3 / 20, None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(10):
+                ref.deepseek_decoder_layer(*c)
+            torch.cuda.synchronize()
+        ks = [e for e in prof.events() if "DeepSeekDecoderLayerKernel" in e.name]
+        if ks:
+            us_kernel = sum(e.device_time for e in ks) / len(ks)
+    except Exception as ex:                      # noqa: BLE001
+        print("profiler unavailable:", repr(ex))
+    print(json.dumps(dict(reference_kernel_time=True, seq_len=4096, us_per_call=round(us_call, 2),
+                          us_kernel=None if us_kernel is None else round(us_kernel, 2))), flush=True)
 
