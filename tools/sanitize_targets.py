@@ -31,5 +31,10 @@ for shape, dd, bs in ((S7, d, 1), (S7, d, 5), (S8, g, 2)):
 w13 = (torch.randn(2 * 1024, 4096, device=dev) * 0.02).half(); w2t = (torch.randn(1024, 4096, device=dev) * 0.02).half()
 clusterfusion.llama_ffn_layer(d["x"], d["residual"], w13, w2t, d["rms_w"], 1e-5)
 clusterfusion.rmsnorm(torch.randn(5, 4096, device=dev).half(), d["rms_w"])
+from oracle import deepseek_oracle as DS
+for seq_len in (70, 5000):                  # one-stage ring and the 4-stage ring of the attention kernel
+    z = DS.make_inputs(seq_len, seed=4)
+    clusterfusion.deepseek_decoder_layer_ex(*[z[k].to(dev) for k in ("x", "w_q_nope", "w_q_pe", "w_uk", "w_kv", "w_k_pe", "w_uv", "w_o",
+                                                                     "ckv_cache", "rms_in_w", "rms_ckv_w", "cos", "sin")], True)
 torch.cuda.synchronize()
 print("sanitize targets done")
