@@ -406,9 +406,10 @@ def run_ours(args, rank, world, local_rank):
     # ------------------------------------------------------------------ whole-model decode
     full = full8b = None
     if not args.no_sweep and not args.no_full_model:
-        full = run_full_model(torch, dist, dev, world, peak)
-        full8b = run_full_model(torch, dist, dev, world, peak, kv0=8192, n_tok=64, shape_name="llama3-8b",
-                                modes=("fused_attn_fused_ffn", "eager"))
+        full = guarded(run_full_model, torch, dist, dev, world, peak)
+        torch.cuda.empty_cache()
+        full8b = guarded(run_full_model, torch, dist, dev, world, peak, kv0=8192, n_tok=64, shape_name="llama3-8b",
+                         modes=("fused_attn_fused_ffn", "eager"))
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
     ref_gpu = None
