@@ -19,17 +19,17 @@ and, from the reference's sm90 module (``include/pybind.cpp:45-64``, ``:113-114`
 plus operators the reference does not have (``llama_ffn_layer``, ``deepseek_decoder_layer_ex``, ``set_pdl``).
 
 Everything is native: a torch-free C-ABI library (``libclusterfusion_b200.so``, the CUDA kernels) and a
-thin PyTorch C++ extension (``_clusterfusion``).  There is no Python or CPU fallback -- importing
+thin PyTorch C++ extension (``clusterfusion._clusterfusion``, the reference's module name).  There is no Python or CPU fallback -- importing
 this package without the built extension raises ImportError, exactly like the reference package.
 """
 import importlib as _importlib
 
 try:
-    _ext = _importlib.import_module("._clusterfusion", __package__)
+    _ext = _importlib.import_module("clusterfusion._clusterfusion")
 except ImportError as e:  # same behaviour as /root/reference/clusterfusion/__init__.py:6-12
     raise ImportError(
-        "Failed to import clusterfusion_b200 native extension. Build it in-tree with "
-        "`python -m clusterfusion_b200.build` (needs nvcc for sm_100a); there is no fallback path."
+        "Failed to import the clusterfusion native extension. Build it in-tree with "
+        "`python clusterfusion_b200/build.py` (needs nvcc for sm_100a) or `pip install .`; there is no fallback path."
     ) from e
 
 for _attr in dir(_ext):

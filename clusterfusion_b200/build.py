@@ -1,7 +1,12 @@
-"""In-tree build of the two native artefacts (both land next to this file):
+"""In-tree build of the two native artefacts:
 
-  libclusterfusion_b200.so   torch-free C ABI + sm_100a kernels   (nvcc, ~10 s)
-  _clusterfusion*.so         PyTorch C++ extension over the C ABI  (g++, ~1 min: torch headers)
+  clusterfusion_b200/libclusterfusion_b200.so   torch-free C ABI + sm_100a kernels   (nvcc, ~1 min)
+  clusterfusion/_clusterfusion*.so              PyTorch C++ extension over the C ABI  (g++, ~1 min: torch headers)
+
+The extension lands where the reference's setup.py puts its own (`clusterfusion._clusterfusion`,
+/root/reference/setup.py:48) so `from clusterfusion import llama_decoder_layer` resolves the same way; it finds the
+kernel library through an $ORIGIN-relative rpath, in the source tree and in an installed copy alike (setup.py at the
+repo root installs both packages side by side).
 
 The reference builds one CUDAExtension whose every .cu includes torch/extension.h
 (/root/reference/setup.py:40-63, ~3.5 min per translation unit) and refuses any GPU but SM 9.0 /
@@ -25,7 +30,7 @@ GENCODE = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def _ext_path() -> Path:
-    return HERE / ("_clusterfusion" + sysconfig.get_config_var("EXT_SUFFIX"))
+    return ROOT / "clusterfusion" / ("_clusterfusion" + sysconfig.get_config_var("EXT_SUFFIX"))
 
 
 def _newer(target: Path, sources) -> bool:
@@ -66,7 +71,7 @@ def build_ext(force: bool = False, verbose: bool = True) -> Path:
     cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_clusterfusion",
            "-DTORCH_API_INCLUDE_EXTENSION_H", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
            *inc, CSRC / "pybind.cpp", "-o", out,
-           f"-L{HERE}", "-lclusterfusion_b200", "-Wl,-rpath,$ORIGIN",
+           f"-L{HERE}", "-lclusterfusion_b200", "-Wl,-rpath,$ORIGIN/../clusterfusion_b200",
            *[f"-L{d}" for d in libdirs], *[f"-Wl,-rpath,{d}" for d in libdirs],
            "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart"]
     _run(cmd, verbose)

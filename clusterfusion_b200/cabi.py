@@ -20,10 +20,8 @@ LIB_PATH = Path(os.environ["CF_LIB_PATH"]) if os.environ.get("CF_LIB_PATH") else
 CF_VARIANT_CHAT, CF_VARIANT_SGLANG, CF_VARIANT_PAGED = 0, 1, 2
 CF_FLAG_OUT_FP32_PARTIAL = 0x1
 CF_FLAG_PDL = 0x2
-CF_FLAG_GQA_CLUSTER = 0x4
 CF_FLAG_LL_OUT = 0x8
 CF_FLAG_PER_REQUEST = 0x10
-CF_FLAG_BATCH4 = 0x20
 CF_DS_FLAG_ROPE_SCORES = 0x100
 
 EXPORTED_SYMBOLS = (
@@ -45,6 +43,9 @@ EXPORTED_SYMBOLS = (
     "cf_deepseek_decoder_layer_launch",
     "cf_sizeof_deepseek_args",
     "cf_test_cluster_reduce",
+    "cf_workspace_status",
+    "cf_workspace_clear_status",
+    "cf_debug_tensor_map_encodes",
 )
 
 
@@ -100,6 +101,7 @@ class CfFfnArgs(C.Structure):
         ("out", C.c_void_p),
         ("residual_out", C.c_void_p),
         ("workspace", C.c_void_p),
+        ("workspace_batch", C.c_int32),
     ]
 
 
@@ -186,6 +188,11 @@ def load() -> C.CDLL:
     lib.cf_test_cluster_reduce.restype = C.c_int
     lib.cf_test_cluster_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_int32, C.c_void_p]
+    lib.cf_workspace_status.restype = C.c_int
+    lib.cf_workspace_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+    lib.cf_workspace_clear_status.restype = C.c_int
+    lib.cf_workspace_clear_status.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cf_debug_tensor_map_encodes.restype = C.c_uint64
     _lib = lib
     return lib
 
@@ -205,6 +212,23 @@ def workspace_bytes(hidden: int, batch: int = 1) -> int:
 
 def algorithmic_bytes(args: CfLlamaArgs, total_kv_rows: int) -> int:
     return int(load().cf_llama_algorithmic_bytes(C.byref(args), total_kv_rows))
+
+
+def workspace_status(workspace_ptr: int, stream: int = 0) -> int:
+    """Sticky error word of a workspace (0 = ok; non-zero = an in-kernel exchange poll timed out since the last clear).
+    Synchronises `stream`."""
+    st = C.c_uint32(0)
+    check(load().cf_workspace_status(C.c_void_p(workspace_ptr), C.c_void_p(stream), C.byref(st)))
+    return int(st.value)
+
+
+def workspace_clear_status(workspace_ptr: int, stream: int = 0) -> None:
+    check(load().cf_workspace_clear_status(C.c_void_p(workspace_ptr), C.c_void_p(stream)))
+
+
+def tensor_map_encodes() -> int:
+    """cuTensorMapEncodeTiled calls made by the library so far in this process."""
+    return int(load().cf_debug_tensor_map_encodes())
 
 
 def launch(args: CfLlamaArgs, stream: int = 0) -> None:

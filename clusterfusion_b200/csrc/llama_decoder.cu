@@ -12,7 +12,6 @@
  */
 #include "../../include/clusterfusion_b200.h"
 #include "llama_decoder_kernel.cuh"
-#include "llama_decoder_gqa_kernel.cuh"
 #include "llama_decoder_gqa2_kernel.cuh"
 #include "llama_decoder_batch_kernel.cuh"
 #include "llama_decoder_batch8_kernel.cuh"
@@ -23,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -79,16 +79,30 @@ struct MapKeyHash {
 };
 
 std::mutex g_map_mutex;
+// Two caches.  `g_map_cache`: maps whose key does not change while a model decodes -- weights, KV caches / pools mapped from
+// their base pointer with a fixed (huge) row extent.  Never flushed: a serving process holds a few hundred of them.
+// `g_kv_len_cache`: maps whose row extent is the CURRENT kv_len (only the grouped-query kernel's swizzled K/V boxes, whose
+// ragged last tile relies on TMA zero fill); one entry per base pointer, overwritten in place when kv_len moves on, so a
+// growing cache can neither evict the weight maps nor grow the table.
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+struct KvLenEntry { MapKey key; CUtensorMap map; };
+std::unordered_map<const void*, KvLenEntry> g_kv_len_cache;
+std::atomic<uint64_t> g_encode_calls{0};
 
 // 2-D fp16 row-major tensor [rows][cols], box {box_c, box_r}; OOB rows/cols read as zero.
+// by_base: key the map on the base pointer alone in the per-kv_len cache (see above).
 int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_c,
-                   uint32_t box_r, bool swizzle128 = false) {
+                   uint32_t box_r, bool swizzle128 = false, bool per_kv_len = false) {
     const MapKey key{ptr, rows, cols, box_c, box_r | (swizzle128 ? 0x80000000u : 0u)};
     {
         std::lock_guard<std::mutex> lk(g_map_mutex);
-        auto it = g_map_cache.find(key);
-        if (it != g_map_cache.end()) { *out = it->second; return 0; }
+        if (per_kv_len) {
+            auto it = g_kv_len_cache.find(ptr);
+            if (it != g_kv_len_cache.end() && it->second.key == key) { *out = it->second.map; return 0; }
+        } else {
+            auto it = g_map_cache.find(key);
+            if (it != g_map_cache.end()) { *out = it->second; return 0; }
+        }
     }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(CF_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
@@ -97,6 +111,7 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
     const cuuint32_t box[2] = {box_c, box_r};
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
+    g_encode_calls.fetch_add(1, std::memory_order_relaxed);
     const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
 #ifdef CF_EXPERIMENT_L2_PROMO_128      /* tools/sweep_build.sh experiment, never defined in the product build */
@@ -108,11 +123,26 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
                                        (int)r, (unsigned long long)rows, (unsigned long long)cols);
     {
         std::lock_guard<std::mutex> lk(g_map_mutex);
-        if (g_map_cache.size() > 4096) g_map_cache.clear();   // bounded; KV maps churn with kv_len
-        g_map_cache.emplace(key, m);
+        if (per_kv_len) {
+            if (g_kv_len_cache.size() > 8192) g_kv_len_cache.clear();   // one entry per live cache tensor; bounded anyway
+            g_kv_len_cache[ptr] = KvLenEntry{key, m};
+        } else {
+            // bounded as a safety net only (a process that keeps allocating new weights): weights are re-encoded on demand
+            if (g_map_cache.size() > (1u << 16)) g_map_cache.clear();
+            g_map_cache.emplace(key, m);
+        }
     }
     *out = m;
     return 0;
+}
+
+// Row extent of the base-pointer-keyed K/V maps: a power of two >= 2^24 that covers kv_len.  The extent says nothing about
+// the allocation -- the kernel only ever requests rows < kv_len through these maps (full tiles; a ragged last tile is
+// fetched row by row), so nothing beyond the caller's tensor is touched.
+uint64_t kv_map_rows(uint64_t kv_len) {
+    uint64_t r = 1ull << 24;
+    while (r < kv_len) r <<= 1;
+    return r;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -155,12 +185,6 @@ template <int VARIANT, int CLUSTER>
 int launch(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cudaStream_t stream) {
     return launch_kernel<CLUSTER>(cfb::llama_decoder_layer_kernel<VARIANT, CLUSTER>, cfb::Smem<CLUSTER>::TOTAL, VARIANT,
                                   kp, n_clusters, batch, pdl, stream);
-}
-
-template <int VARIANT, int CLUSTER>
-int launch_gqa(const cfb::KParams& kp, int n_clusters, int batch, bool pdl, cudaStream_t stream) {
-    return launch_kernel<CLUSTER>(cfb::llama_decoder_layer_gqa_kernel<VARIANT, CLUSTER, 4>, cfb::SmemGqa<CLUSTER, 4>::TOTAL,
-                                  (CLUSTER == 16 ? 3 : 5) + VARIANT, kp, n_clusters, batch, pdl, stream);
 }
 
 // second-generation grouped-query kernel: G plain CTAs per (KV head, 4 query heads) group, exchanges through L2
@@ -223,6 +247,25 @@ int cf_abi_version(void) { return CF_ABI_VERSION; }
 
 const char* cf_last_error_string(void) { return g_last_error.c_str(); }
 
+uint64_t cf_debug_tensor_map_encodes(void) { return g_encode_calls.load(std::memory_order_relaxed); }
+
+int cf_workspace_status(const void* workspace, void* stream_, uint32_t* status) {
+    if (!workspace || !status) return fail(CF_ERR_NULL_ARG, "cf_workspace_status: NULL argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    uint32_t word = 0;
+    cudaError_t e = cudaMemcpyAsync(&word, static_cast<const uint32_t*>(workspace) + 2, sizeof word, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return fail((int)e, "cf_workspace_status: %s", cudaGetErrorString(e));
+    *status = word;
+    return 0;
+}
+
+int cf_workspace_clear_status(void* workspace, void* stream_) {
+    if (!workspace) return fail(CF_ERR_NULL_ARG, "cf_workspace_clear_status: NULL argument");
+    const cudaError_t e = cudaMemsetAsync(static_cast<uint32_t*>(workspace) + 2, 0, sizeof(uint32_t), static_cast<cudaStream_t>(stream_));
+    return e == cudaSuccess ? 0 : fail((int)e, "cf_workspace_clear_status: %s", cudaGetErrorString(e));
+}
+
 size_t cf_sizeof_llama_args(void) { return sizeof(CfLlamaArgs); }
 size_t cf_sizeof_ffn_args(void) { return sizeof(CfFfnArgs); }
 
@@ -267,8 +310,8 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         if ((a->n_q_heads / a->n_kv_heads) % 4 != 0)
             return fail(CF_ERR_BAD_SHAPE, "grouped-query attention needs a multiple of 4 query heads per KV head (q=%d, kv=%d)",
                         a->n_q_heads, a->n_kv_heads);
-        if (a->hidden <= 0 || a->hidden % (16 * 256) != 0 || a->hidden / 8 > cfb::GQA_KS_MAX)
-            return fail(CF_ERR_BAD_SHAPE, "GQA: hidden must be a multiple of 4096 and <= %d (got %d)", 8 * cfb::GQA_KS_MAX, a->hidden);
+        if (a->hidden <= 0 || a->hidden % (16 * 256) != 0 || a->hidden > cfb::G2_HIDDEN_MAX)
+            return fail(CF_ERR_BAD_SHAPE, "GQA: hidden must be a multiple of 4096 and <= %d (got %d)", cfb::G2_HIDDEN_MAX, a->hidden);
     }
     if (a->batch < 1 || (!paged && a->batch != 1))
         return fail(CF_ERR_BAD_SHAPE, "batch must be 1 for CHAT/SGLANG and >= 1 for PAGED (got %d)", a->batch);
@@ -311,14 +354,33 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 256, cfb::ROWS512))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 256, cfb::ROWS512))) return rc;
     }
+    const bool group_kernel = gqa;
     if (!paged) {
         // kv_len == 0: no tile is ever requested; point the maps at any valid address
         const void* kc = a->kv_len ? a->k_cache : a->x;
         const void* vc = a->kv_len ? a->v_cache : a->x;
-        // group kernel (tensor-core attention): 64-dim half rows, 128-byte swizzled, so ldmatrix is conflict-free
-        const bool mma_kv = gqa && !(a->flags & CF_FLAG_GQA_CLUSTER);
-        if ((rc = get_tensor_map(&kp.tm_k, kc, a->kv_len, kvd, mma_kv ? 64 : 128, cfb::ROWS512, mma_kv))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_v, vc, a->kv_len, kvd, mma_kv ? 64 : 128, cfb::ROWS512, mma_kv))) return rc;
+        if (group_kernel) {
+            // group kernel (tensor-core attention): 64-dim half rows, 128-byte swizzled, so ldmatrix is conflict-free; its
+            // ragged last tile relies on TMA zero fill, so these two maps carry the current kv_len (one cache entry per tensor)
+            if ((rc = get_tensor_map(&kp.tm_k, kc, a->kv_len, kvd, 64, cfb::ROWS512, true, true))) return rc;
+            if ((rc = get_tensor_map(&kp.tm_v, vc, a->kv_len, kvd, 64, cfb::ROWS512, true, true))) return rc;
+        } else {
+            if ((rc = get_tensor_map(&kp.tm_k, kc, kv_map_rows(a->kv_len), kvd, 128, cfb::ROWS512))) return rc;
+            if ((rc = get_tensor_map(&kp.tm_v, vc, kv_map_rows(a->kv_len), kvd, 128, cfb::ROWS512))) return rc;
+        }
+        kp.k_base = static_cast<const __half*>(kc);
+        kp.v_base = static_cast<const __half*>(vc);
+    } else if (!gqa && !batched && a->k_cache && a->v_cache) {
+        // optional fast paths of the paged form: the caller knows the pool addresses of this layer on the host (k_cache /
+        // v_cache = its copy of k_pool_ptrs[layer_id] / v_pool_ptrs[layer_id]).  Tiles whose 16 rows sit in consecutive
+        // slots are fetched with one tiled TMA load per tensor, all other full tiles with tile::gather4 requests (four
+        // arbitrary rows each).  The pool's slot count is not part of the interface: the maps cover 2^24 slots.
+        if ((rc = get_tensor_map(&kp.tm_k, a->k_cache, 1ull << 24, kvd, 128, cfb::ROWS512))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_v, a->v_cache, 1ull << 24, kvd, 128, cfb::ROWS512))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_kg, a->k_cache, 1ull << 24, kvd, 128, 1))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_vg, a->v_cache, 1ull << 24, kvd, 128, 1))) return rc;
+        kp.k_base = static_cast<const __half*>(a->k_cache);
+        kp.v_base = static_cast<const __half*>(a->v_cache);
     }
     kp.x = static_cast<const __half*>(a->x);
     kp.residual_in = static_cast<const __half*>(a->residual_in);
@@ -354,7 +416,7 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     if (a->tp_world > 1) {
         if (a->tp_world > 8 || a->tp_rank < 0 || a->tp_rank >= a->tp_world)
             return fail(CF_ERR_BAD_SHAPE, "tp_world must be in [2, 8] and 0 <= tp_rank < tp_world (got rank %d of %d)", a->tp_rank, a->tp_world);
-        if (!gqa || a->batch != 1 || (a->flags & CF_FLAG_GQA_CLUSTER))
+        if (!gqa || a->batch != 1)
             return fail(CF_ERR_BAD_SHAPE, "the fused all-reduce needs a grouped-query shape, batch 1 and the group kernel");
         for (int r = 0; r < a->tp_world; ++r) {
             if (!a->tp_peer[r] || !aligned16(a->tp_peer[r])) return fail(CF_ERR_NULL_ARG, "tp_peer[%d] must be a 16-byte aligned device pointer", r);
@@ -365,7 +427,7 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     }
 
     const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
-    if (gqa && !(a->flags & CF_FLAG_GQA_CLUSTER)) {
+    if (gqa) {
         // group kernel: G CTAs per group, G = largest power of two in [8, 64] with groups * G * batch <= #SMs
         const int n_groups = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
         if (n_groups > cfb::G2_GROUPS_MAX)
@@ -385,17 +447,7 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         gp.n_groups = n_groups;
         return paged ? launch_gqa2<cfb::PAGED>(gp, a->batch, pdl, stream) : launch_gqa2<cfb::SGLANG>(gp, 1, pdl, stream);
     }
-    if (gqa) {
-        // first-generation cluster kernel (CF_FLAG_GQA_CLUSTER; kept for A/B measurement).  Only 7 16-CTA clusters are
-        // co-resident at 1 CTA / SM: use 16 CTAs per cluster when there are at most four clusters, otherwise 8
-        const int n_clusters = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
-        const bool wide = (long long)n_clusters * a->batch <= 4;
-        if (paged) return wide ? launch_gqa<cfb::PAGED, 16>(kp, n_clusters, a->batch, pdl, stream)
-                               : launch_gqa<cfb::PAGED, 8>(kp, n_clusters, a->batch, pdl, stream);
-        return wide ? launch_gqa<cfb::SGLANG, 16>(kp, n_clusters, 1, pdl, stream)
-                    : launch_gqa<cfb::SGLANG, 8>(kp, n_clusters, 1, pdl, stream);
-    }
-    if (batched && a->batch >= 5 && !(a->flags & CF_FLAG_BATCH4))      // chunks of 8: the whole N dimension of the MMA
+    if (batched && a->batch >= 5)      // chunks of 8: the whole N dimension of the MMA
         return launch_kernel<CL>(cfb::llama_decoder_layer_batch8_kernel, cfb::SmemB8::TOTAL, 3, kp, a->n_q_heads,
                                  (a->batch + 7) / 8, pdl, stream);
     if (batched)
@@ -443,7 +495,7 @@ extern "C" int cf_llama_ffn_launch(const CfFfnArgs* a, void* stream_) {
     fp.out = a->out;
     fp.residual_out = static_cast<__half*>(a->residual_out);
     fp.scratch = reinterpret_cast<float*>(static_cast<char*>(a->workspace) + ws_off_scratch());
-    fp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + ws_off_counters(a->hidden, 1));
+    fp.counters = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + ws_off_counters(a->hidden, a->workspace_batch > 0 ? a->workspace_batch : 1));
     fp.eps = a->eps;
     fp.hidden = a->hidden;
     fp.ffn = a->ffn;

@@ -3,8 +3,8 @@
  *
  * Why a second kernel: a B200 SM pulls at most ~64 GB/s through one 192 KB TMA ring (measured), so a
  * layer only reaches the HBM roofline when >= ~110 SMs stream at once.  With grouped-query attention the natural unit
- * of fusion is one KV head + its query heads: Llama-3-8B has 8 of them.  The cluster kernel
- * (llama_decoder_gqa_kernel.cuh) can give a unit 8 CTAs (64 SMs: 48 % of the roofline) -- at a 1-CTA-per-SM footprint
+ * of fusion is one KV head + its query heads: Llama-3-8B has 8 of them.  A thread-block cluster per unit (the first
+ * generation of this kernel, removed in round 2) can give a unit 8 CTAs (64 SMs: 48 % of the roofline) -- at a 1-CTA-per-SM footprint
  * cudaOccupancyMaxActiveClusters answers 15 clusters of 8 and 7 clusters of 16 (tools/cluster_probe.cu,
  * profiles/r02_cluster_probe.txt), one short of the 16 / 8 it would take, and DSMEM does not reach outside a cluster.  Here a unit ("group") is G CTAs, G = 2^k chosen so that groups x G ~ fills the 148 SMs
  * (8B: 8 x 16 = 128; 70B shards: 8 x 16, 4 x 32, 2 x 64), and the two exchanges the fusion needs go through L2:
@@ -41,7 +41,7 @@
  */
 #pragma once
 
-#include "llama_decoder_gqa_kernel.cuh"
+#include "llama_decoder_kernel.cuh"
 
 namespace cfb {
 
@@ -93,6 +93,50 @@ struct G2Params {
     int G;                 // CTAs per group (power of two)
     int n_groups;          // groups per request
 };
+
+// 16 output rows x 256 input columns of an [out,in] weight tile against 8 activations per lane;
+// writes the 16 row sums to out[0..16).  (CUDA-core loop: 8 FMA per lane per row, then a 9-shuffle transpose-reduce.)
+__device__ __forceinline__ void gemv_tile_16x256(const uint4* tile, const float (&x8)[8], float* out, uint32_t lane) {
+#pragma unroll
+    for (int grp = 0; grp < ROWS512 / 8; ++grp) {
+        float v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float w8[8];
+            unpack8(tile[(grp * 8 + r) * 32 + lane], w8);
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a = fmaf(x8[k], w8[k], a);
+            v[r] = a;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const bool hi = lane & 16;
+            const float send = hi ? v[r] : v[r + 4];
+            const float keep = hi ? v[r + 4] : v[r];
+            v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const bool hi = lane & 8;
+            const float send = hi ? v[r] : v[r + 2];
+            const float keep = hi ? v[r + 2] : v[r];
+            v[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const bool hi = lane & 4;
+            const float send = hi ? v[0] : v[1];
+            const float keep = hi ? v[1] : v[0];
+            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        if ((lane & 3) == 0) {
+            const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            out[grp * 8 + r] = v[0];
+        }
+    }
+}
 
 // 16 output rows x 256 input columns; ACCUMULATES the 16 row sums into acc[0..16) (owned by the calling warp)
 __device__ __forceinline__ void gemv_tile_16x256_acc(const uint4* tile, const float (&x8)[8], float* acc, uint32_t lane) {

@@ -61,8 +61,10 @@ static_assert(CONSUMER_WARPS % 3 == 0 && CONSUMER_THREADS >= 3 * HEAD_DIM, "chat
 struct alignas(64) KParams {
     CUtensorMap tm_wqkv;   // CHAT: [3*hidden][hidden] box {128,64}; else [(Hq+2Hkv)*128][hidden] box {256,32}
     CUtensorMap tm_wo;     // CHAT: [Hq*128][hidden] box {128,64};  else [hidden][Hq*128] box {128,64}
-    CUtensorMap tm_k;      // CHAT/SGLANG: [kv_len][Hkv*128] box {128,32}
+    CUtensorMap tm_k;      // CHAT/SGLANG: [>= 2^24][Hkv*128] from k_cache, box {128,16}; PAGED (k_base given): the same over the pool
     CUtensorMap tm_v;
+    CUtensorMap tm_kg;     // PAGED (k_base given): the pool again with box {128,1} for tile::gather4 requests
+    CUtensorMap tm_vg;
     const __half* x;
     const __half* residual_in;
     const __half* rms_w;
@@ -76,6 +78,11 @@ struct alignas(64) KParams {
     const int* indices;
     const unsigned long long* k_pool_ptrs;
     const unsigned long long* v_pool_ptrs;
+    // CHAT / SGLANG: k_cache / v_cache (tm_k / tm_v then map [2^24+ rows][kv_cols] from the same base: the maps depend on
+    // the base pointer only, so a growing cache never re-encodes them; a ragged last tile is fetched row by row).
+    // PAGED, optional: the host's copy of k_pool_ptrs[layer_id] / v_pool_ptrs[layer_id]; tm_k / tm_v then map the pools.
+    const __half* k_base;
+    const __half* v_base;
     const long long* positions;
     float* scratch;          // fp32 [batch][hidden], zero between launches
     unsigned* counters;      // [batch][CLUSTER + 1], zero between launches
@@ -142,6 +149,16 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1], %2, [%3], %4;"
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+// Four ARBITRARY rows of a 2-D tensor with one TMA request (sm_100 tile::gather4): the map's box is {cols, 1}, the four
+// rows land back to back in shared memory.  This is what a page-size-1 KV gather wants: 8 requests per 8 KB stage instead
+// of 32 row-sized bulk copies.
+__device__ __forceinline__ void tma_gather4_2d(uint32_t dst, const CUtensorMap* tm, int c0, int r0, int r1, int r2, int r3,
+                                               uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar), "l"(policy) : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
@@ -406,12 +423,16 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     // ---- tile stream ----------------------------------------------------------------------------------
     const uint64_t pol = policy_evict_first();
     const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
-    const __half* kpool = nullptr;
-    const __half* vpool = nullptr;
+    const __half* kpool = p.k_base;      // contiguous forms: the cache itself
+    const __half* vpool = p.v_base;
     if constexpr (kPaged) {
         kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
         vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
     }
+    // Paged: the host may pass its own copy of the two pool addresses together with tensor maps over the pools.  They are
+    // used only if they agree with what the device-side pointer table says NOW (a stale host copy just disables the fast
+    // paths: correctness never depends on it).
+    const bool pool_maps = !kPaged || (p.k_base != nullptr && kpool == p.k_base && vpool == p.v_base);
     // Paged KV: the page index of this lane's row of KV tile g.  A warp fetches it one ring cycle ahead (when it issues
     // tile g - 24 into the same stage), so the index load is never on the path between consuming a tile and refilling
     // its stage (the reference gathers with an index load per row on the critical path, kernel_batch_sglang.cuh:356-371;
@@ -458,23 +479,45 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             }
         } else if (g < n_qkv_tiles + n_kv_tiles) {
             const uint32_t i = g - n_qkv_tiles;                 // 16 KV rows: K in the first 4 KB of the stage, V in the second
-            if constexpr (!kPaged) {
+            const int r0 = row_begin + (int)i * ROWS512;
+            const int nvalid = min(ROWS512, row_end - r0);
+            // Three ways to fill the stage, all with the same shared-memory layout:
+            //   tiled   one {128 x 16} TMA box per tensor -- 16 rows in consecutive slots (contiguous cache: always; paged: a
+            //           sequence that grew without competition), 2 requests per stage;
+            //   gather4 four arbitrary pool rows per request (sm_100 tile::gather4), 8 requests per stage;
+            //   rows    one 256-byte bulk copy per row per tensor, 32 requests per stage -- ragged last tile of a request,
+            //           and paged launches whose caller did not pass the pool addresses on the host (no tensor map).
+            long long slot = r0 + (int)(lane & 15);             // contiguous cache: the row index itself
+            bool tiled = (nvalid == ROWS512), gather = false;
+            if constexpr (kPaged) {
+                const bool odd = (g / CONSUMER_WARPS) & 1u;
+                slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
+                const long long slot0 = __shfl_sync(0xffffffffu, slot, 0);
+                const bool run = __all_sync(0xffffffffu, slot == slot0 + (long long)(lane & 15));
+                gather = pool_maps && tiled && !run;
+                tiled = pool_maps && tiled && run;
+            }
+            if (tiled) {
                 if (lane == 0) {
-                    const int r0 = row_begin + i * ROWS512;
+                    const int s0 = (int)slot;
                     dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                    tma_load_2d(dst, &p.tm_k, head * HEAD_DIM, r0, fb, pol);
-                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, head * HEAD_DIM, r0, fb, pol);
+                    tma_load_2d(dst, &p.tm_k, head * HEAD_DIM, s0, fb, pol);
+                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, head * HEAD_DIM, s0, fb, pol);
+                }
+            } else if (gather) {
+                const int s1 = (int)__shfl_down_sync(0xffffffffu, slot, 1);
+                const int s2 = (int)__shfl_down_sync(0xffffffffu, slot, 2);
+                const int s3 = (int)__shfl_down_sync(0xffffffffu, slot, 3);
+                if (lane == 0) dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                __syncwarp();
+                if ((lane & 3) == 0) {                          // lanes 0,4,8,12: K rows 4q..4q+3; lanes 16,..,28: V rows
+                    const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2) + (lane < 16 ? 0 : STAGE_BYTES / 2);
+                    tma_gather4_2d(d, lane < 16 ? &p.tm_kg : &p.tm_vg, head * HEAD_DIM, (int)slot, s1, s2, s3, fb, pol);
                 }
             } else {
-                // paged KV, page size 1: one 256-byte bulk copy per row per tensor; lanes 0-15 fetch K rows, 16-31 V rows
-                const int r = row_begin + i * ROWS512 + (lane & 15);
-                const bool valid = r < row_end;
-                const bool odd = (g / CONSUMER_WARPS) & 1u;
-                const long long slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
-                const int nvalid = min(ROWS512, row_end - (row_begin + (int)i * ROWS512));
                 if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
                 __syncwarp();
-                if (valid) {
+                if ((int)(lane & 15) < nvalid) {
                     const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
                     if (lane < 16) bulk_load_1d(d, kpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
                     else bulk_load_1d(d + STAGE_BYTES / 2, vpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
@@ -515,7 +558,10 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         if (tid == 0) {
             prefetch_tmap(&p.tm_wqkv);
             prefetch_tmap(&p.tm_wo);
-            if constexpr (!kPaged) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); }
+            if (pool_maps) {
+                prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v);
+                if constexpr (kPaged) { prefetch_tmap(&p.tm_kg); prefetch_tmap(&p.tm_vg); }
+            }
             cluster_reduce_arm<CLUSTER>(xbar_u32, S::QKV_OUT * 4);
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::ATTN_PAYLOAD * 4);
         }
@@ -812,9 +858,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                 const float pr = dsm::fast_exp2(sc[jj] - m_use);       // -inf -> 0
                 l += pr;
                 uint4 raw = vt[row * 16 + c];
-                if constexpr (kPaged) {                                   // rows past the end were never copied
-                    if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
-                }
+                if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);       // rows past the end were never copied (stale smem)
                 float v8[8];
                 unpack8(raw, v8);
 #pragma unroll

@@ -23,9 +23,12 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <utility>
+#include <vector>
 
 #include "../../include/clusterfusion_b200.h"
 
@@ -42,29 +45,90 @@ void check_cuda_contig(const Tensor& t, const char* name, c10::ScalarType dtype)
 // One zero-initialised workspace per (device, stream, hidden): memset exactly once, opaque afterwards.  Its layout depends
 // on the batch it was sized for, so that batch is remembered and passed as CfLlamaArgs::workspace_batch; a larger batch gets
 // a fresh (zeroed) workspace sized for it, which then also serves the smaller ones.
+// A first call that happens INSIDE a stream capture must not record the allocation's memset into the graph (every replay
+// would re-zero the workspace, and a buffer from the graph's private pool would die with the graph): in that case the
+// workspace comes from a plain cudaMalloc + synchronous cudaMemset issued in relaxed capture mode, outside the graph.
 struct Workspace { Tensor buf; int batch; };
+std::mutex g_ws_mu;
+std::map<std::tuple<int, void*, int>, Workspace> g_ws_cache;
+std::map<std::tuple<int, void*>, Tensor> g_ds_ws_cache;
+
+Tensor zeroed_bytes(const Tensor& like, size_t need, cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+    if (!capturing)
+        return torch::zeros({(int64_t)need}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device()));
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, need);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    TORCH_CHECK(e == cudaSuccess, "clusterfusion_b200: workspace allocation during stream capture failed: ", cudaGetErrorString(e));
+    return torch::from_blob(p, {(int64_t)need}, [](void* q) { cudaFree(q); },
+                            torch::TensorOptions().dtype(torch::kUInt8).device(like.device()));
+}
+
 Workspace workspace_for(const Tensor& like, int hidden, int batch, cudaStream_t stream) {
-    static std::mutex mu;
-    static std::map<std::tuple<int, void*, int>, Workspace> cache;
-    std::lock_guard<std::mutex> lk(mu);
+    std::lock_guard<std::mutex> lk(g_ws_mu);
     auto key = std::make_tuple((int)like.get_device(), (void*)stream, hidden);
-    auto it = cache.find(key);
-    if (it == cache.end() || it->second.batch < batch) {
-        const size_t need = cf_llama_workspace_bytes(hidden, batch);
-        Workspace w{torch::zeros({(int64_t)need}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device())), batch};
-        cache[key] = w;
+    auto it = g_ws_cache.find(key);
+    if (it == g_ws_cache.end() || it->second.batch < batch) {
+        Workspace w{zeroed_bytes(like, cf_llama_workspace_bytes(hidden, batch), stream), batch};
+        g_ws_cache[key] = w;
         return w;
     }
     return it->second;
 }
 
-// Programmatic dependent launch for every op issued through this module (off by default).  Contract: see CF_FLAG_PDL in
-// include/clusterfusion_b200.h -- weights / KV pools / page tables of a call are not written by kernels still in flight.
-bool g_pdl = false;
+// Programmatic dependent launch for every op issued through this module (off by default; process-wide switch -- set it once
+// at start-up, not per call from several threads).  Contract: see CF_FLAG_PDL in include/clusterfusion_b200.h -- the weights,
+// KV cache / pools, page tables (indptr / indices), positions and pool-pointer tables of a call are not written by kernels
+// still in flight on the stream: the kernel reads them BEFORE it waits for the previous kernel.
+std::atomic<bool> g_pdl{false};
+// debug mode: after every launch, read the workspace's sticky error word back (synchronises) and raise if an in-kernel
+// exchange poll timed out -- see cf_workspace_status in the C ABI header
+std::atomic<bool> g_check_status{false};
+
+// [a, a+na) and [b, b+nb) overlap?
+bool overlaps(const Tensor& a, const Tensor& b) {
+    const char* pa = static_cast<const char*>(a.data_ptr());
+    const char* pb = static_cast<const char*>(b.data_ptr());
+    return pa < pb + b.nbytes() && pb < pa + a.nbytes();
+}
+
+// Host copies of the device pointer tables of the paged form, fetched once per table (one blocking copy of 8 bytes per layer,
+// never during stream capture).  They only enable the tiled / gather4 KV fast paths: the kernel re-checks the address against
+// the device table, so a stale copy costs speed, not correctness.
+const std::vector<uint64_t>* host_ptr_table(const Tensor& t, cudaStream_t stream) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int64_t>, std::vector<uint64_t>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_pair((const void*)t.data_ptr(), (int64_t)t.numel());
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+    std::vector<uint64_t> h((size_t)t.numel());
+    if (cudaMemcpyAsync(h.data(), t.data_ptr(), 8 * (size_t)t.numel(), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return &(cache[key] = std::move(h));
+}
 
 void run(const CfLlamaArgs& a, cudaStream_t stream) {
     const int rc = cf_llama_decoder_layer_launch(&a, stream);
     TORCH_CHECK(rc == 0, "clusterfusion_b200: launch failed (", rc, "): ", cf_last_error_string());
+    if (g_check_status.load(std::memory_order_relaxed)) {
+        uint32_t st = 0;
+        const int rs = cf_workspace_status(a.workspace, stream, &st);
+        TORCH_CHECK(rs == 0, "clusterfusion_b200: cf_workspace_status failed (", rs, "): ", cf_last_error_string());
+        TORCH_CHECK(st == 0, "clusterfusion_b200: an exchange poll inside the kernel timed out (CTAs of a group not co-resident, "
+                             "a stalled peer rank, or one workspace shared by two streams); the results of this launch are invalid");
+    }
 }
 
 std::tuple<Tensor, Tensor, Tensor> llama_decoder_layer(
@@ -110,7 +174,7 @@ std::tuple<Tensor, Tensor, Tensor> llama_decoder_layer(
     a.k_cache = k_cache.data_ptr(); a.v_cache = v_cache.data_ptr();
     a.cos = cos.data_ptr<float>(); a.sin = sin.data_ptr<float>();
     a.workspace = ws.buf.data_ptr(); a.workspace_batch = ws.batch;
-    if (g_pdl) a.flags |= CF_FLAG_PDL;
+    if (g_pdl.load(std::memory_order_relaxed)) a.flags |= CF_FLAG_PDL;
     run(a, stream);
     return std::make_tuple(o, k, v);
 }
@@ -140,6 +204,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> llama_decoder_layer_sglang(
     TORCH_CHECK(v_cache.sizes() == k_cache.sizes(), "v_cache must match k_cache");
     TORCH_CHECK(rms_input_weight.numel() == hidden, "rms_input_weight must be [hidden]");
     TORCH_CHECK(cos.numel() >= 64 && sin.numel() >= 64, "cos / sin must hold at least head_dim/2 = 64 floats");
+    TORCH_CHECK(!overlaps(input, residual), "input and residual must not overlap (residual is updated in place)");
 
     const c10::cuda::CUDAGuard guard(input.device());
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
@@ -161,7 +226,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> llama_decoder_layer_sglang(
     a.k_cache = k_cache.data_ptr(); a.v_cache = v_cache.data_ptr();
     a.cos = cos.data_ptr<float>(); a.sin = sin.data_ptr<float>();
     a.workspace = ws.buf.data_ptr(); a.workspace_batch = ws.batch;
-    if (g_pdl) a.flags |= CF_FLAG_PDL;
+    if (g_pdl.load(std::memory_order_relaxed)) a.flags |= CF_FLAG_PDL;
     run(a, stream);
     return std::make_tuple(o, residual, k, v);
 }
@@ -199,6 +264,12 @@ void llama_decoder_layer_batch_decode_sglang(
     TORCH_CHECK(positions.numel() == bs, "positions must be [batch]");
     TORCH_CHECK(layer_id >= 0 && layer_id < k_cache_ptrs.numel() && layer_id < v_cache_ptrs.numel(), "layer_id out of range");
     TORCH_CHECK(cos_sin.dim() == 2 && cos_sin.size(1) == 128, "cos_sin must be [max_pos, 128] = [cos(64) | sin(64)]");
+    // the epilogues write `output` / `residual_output` while other CTAs may still be reading `input` / `residual`: the only
+    // supported aliasing is residual_output == residual exactly (in place; written by the request's very last CTA)
+    TORCH_CHECK(!overlaps(output, input) && !overlaps(output, residual) && !overlaps(output, residual_output) &&
+                !overlaps(residual_output, input), "output / residual_output must not overlap input / residual / each other");
+    TORCH_CHECK(residual_output.data_ptr() == residual.data_ptr() || !overlaps(residual_output, residual),
+                "residual_output may alias residual only exactly (same tensor, in place)");
 
     const c10::cuda::CUDAGuard guard(input.device());
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
@@ -219,7 +290,15 @@ void llama_decoder_layer_batch_decode_sglang(
     a.positions = positions.data_ptr<int64_t>();
     a.cos = cos_sin.data_ptr<float>();
     a.workspace = ws.buf.data_ptr(); a.workspace_batch = ws.batch;
-    if (g_pdl) a.flags |= CF_FLAG_PDL;
+    if (const auto* hk = host_ptr_table(k_cache_ptrs, stream))
+        if (const auto* hv = host_ptr_table(v_cache_ptrs, stream)) {
+            const uint64_t kb = (*hk)[(size_t)layer_id], vb = (*hv)[(size_t)layer_id];
+            if (kb && vb && kb % 16 == 0 && vb % 16 == 0) {
+                a.k_cache = reinterpret_cast<const void*>(kb);
+                a.v_cache = reinterpret_cast<const void*>(vb);
+            }
+        }
+    if (g_pdl.load(std::memory_order_relaxed)) a.flags |= CF_FLAG_PDL;
     run(a, stream);
 }
 
@@ -241,15 +320,20 @@ void llama_ffn_layer_out(Tensor output, Tensor residual_output, Tensor input, Te
     TORCH_CHECK(weight_gate_up.dim() == 2 && weight_gate_up.size(0) == 2 * ffn && weight_gate_up.size(1) == hidden,
                 "weight_gate_up must be [2*ffn, hidden] = [W1; W3]");
     TORCH_CHECK(rms_weight.numel() == hidden, "rms_weight must be [hidden]");
+    TORCH_CHECK(!overlaps(output, input) && !overlaps(output, residual) && !overlaps(output, residual_output) &&
+                !overlaps(residual_output, input), "output / residual_output must not overlap input / residual / each other");
+    TORCH_CHECK(residual_output.data_ptr() == residual.data_ptr() || !overlaps(residual_output, residual),
+                "residual_output may alias residual only exactly (same tensor, in place)");
     const c10::cuda::CUDAGuard guard(input.device());
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
     Workspace ws = workspace_for(input, (int)hidden, 1, stream);
     CfFfnArgs a{};
-    a.flags = g_pdl ? CF_FLAG_PDL : 0u;
+    a.flags = g_pdl.load(std::memory_order_relaxed) ? CF_FLAG_PDL : 0u;
     a.hidden = (int)hidden; a.ffn = (int)ffn; a.eps = (float)eps;
     a.x = input.data_ptr(); a.residual_in = residual.data_ptr();
     a.w_gate_up = weight_gate_up.data_ptr(); a.w_down_t = weight_down_t.data_ptr(); a.rms_w = rms_weight.data_ptr();
     a.out = output.data_ptr(); a.residual_out = residual_output.data_ptr(); a.workspace = ws.buf.data_ptr();
+    a.workspace_batch = ws.batch;
     const int rc = cf_llama_ffn_launch(&a, stream);
     TORCH_CHECK(rc == 0, "clusterfusion_b200: ffn launch failed (", rc, "): ", cf_last_error_string());
 }
@@ -274,7 +358,7 @@ Tensor rmsnorm(Tensor input, Tensor weight) {
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
     Tensor out = torch::empty_like(input);
     const int rc = cf_rmsnorm_launch(input.data_ptr(), weight.data_ptr(), out.data_ptr(), (int)input.size(0), (int)input.size(1),
-                                     1e-6f, g_pdl ? CF_FLAG_PDL : 0u, stream);
+                                     1e-6f, g_pdl.load(std::memory_order_relaxed) ? CF_FLAG_PDL : 0u, stream);
     TORCH_CHECK(rc == 0, "clusterfusion_b200: rmsnorm launch failed (", rc, "): ", cf_last_error_string());
     return out;
 }
@@ -283,14 +367,12 @@ Tensor rmsnorm(Tensor input, Tensor weight) {
 //                        ckv_cache, rms_input_weight, rms_ckv_weight, cos, sin) -> fp16 [1, hidden]
 // (/root/reference/include/pybind.cpp:45-59, :113; deepseek_kernel_dispatch.cu:4-18).  seq_len = ckv_cache.size(0).
 Tensor deepseek_workspace_for(const Tensor& like, cudaStream_t stream) {
-    static std::mutex mu;
-    static std::map<std::tuple<int, void*>, Tensor> cache;
-    std::lock_guard<std::mutex> lk(mu);
+    std::lock_guard<std::mutex> lk(g_ws_mu);
     auto key = std::make_tuple((int)like.get_device(), (void*)stream);
-    auto it = cache.find(key);
-    if (it != cache.end()) return it->second;
-    Tensor w = torch::zeros({(int64_t)cf_deepseek_workspace_bytes()}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device()));
-    cache[key] = w;
+    auto it = g_ds_ws_cache.find(key);
+    if (it != g_ds_ws_cache.end()) return it->second;
+    Tensor w = zeroed_bytes(like, cf_deepseek_workspace_bytes(), stream);
+    g_ds_ws_cache[key] = w;
     return w;
 }
 
@@ -325,7 +407,7 @@ Tensor deepseek_run(Tensor input, Tensor weight_q_nope, Tensor weight_q_pe, Tens
     Tensor out = torch::empty({1, hidden}, input.options());
     CfDeepseekArgs a;
     memset(&a, 0, sizeof a);
-    a.flags = (g_pdl ? CF_FLAG_PDL : 0u) | (rope_scores ? CF_DS_FLAG_ROPE_SCORES : 0u);
+    a.flags = (g_pdl.load(std::memory_order_relaxed) ? CF_FLAG_PDL : 0u) | (rope_scores ? CF_DS_FLAG_ROPE_SCORES : 0u);
     a.hidden = (int32_t)hidden;
     a.n_heads = (int32_t)nh;
     a.seq_len = (int32_t)ckv_cache.size(0);
@@ -391,8 +473,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rmsnorm", &rmsnorm, "");
     m.def("deepseek_decoder_layer", &deepseek_decoder_layer, "");
     m.def("deepseek_decoder_layer_ex", &deepseek_decoder_layer_ex, "");
-    m.def("set_pdl", [](bool on) { g_pdl = on; }, "enable / disable programmatic dependent launch for all ops of this module");
-    m.def("get_pdl", []() { return g_pdl; });
+    m.def("set_pdl", [](bool on) { g_pdl.store(on); },
+          "enable / disable programmatic dependent launch for all ops of this module (process-wide; contract: weights, KV "
+          "caches / pools, page tables and positions of a call are not written by kernels still in flight on the stream)");
+    m.def("get_pdl", []() { return g_pdl.load(); });
+    m.def("set_check_status", [](bool on) { g_check_status.store(on); },
+          "debug mode: after every launch read the workspace's sticky error word back (synchronises) and raise on an "
+          "in-kernel exchange time-out");
+    m.def("tensor_map_encodes", []() { return cf_debug_tensor_map_encodes(); },
+          "cuTensorMapEncodeTiled calls made by the library so far (0 per token in a steady-state decode loop)");
+    // called from an atexit hook of the Python package: CUDA tensors must not be destroyed by static destructors after the
+    // CUDA context is gone
+    m.def("_release_workspaces", []() {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        g_ws_cache.clear();
+        g_ds_ws_cache.clear();
+    });
     m.def("abi_version", []() { return cf_abi_version(); });
     m.def("workspace_bytes", [](int hidden, int batch) { return cf_llama_workspace_bytes(hidden, batch); });
 }

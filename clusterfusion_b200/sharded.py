@@ -116,7 +116,32 @@ class ShardedDecoderLayer:
         self.out = torch.empty(1, hidden, dtype=torch.float16, device=dev)
         self.tp = TpExchange(hidden, rank, world, group) if (fused_allreduce and world > 1) else None
 
-    def forward(self, x, residual, k_cache, v_cache, cos, sin, pdl: bool = False):
+    def status(self) -> int:
+        """Sticky error word of this layer's workspace (cf_workspace_status; synchronises the current stream): non-zero
+        means an exchange poll inside a kernel timed out -- a peer rank stalled or died, or the group's CTAs were not
+        co-resident -- and the outputs of that launch (NaN in the peer stage) must be discarded."""
+        return cabi.workspace_status(self.ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    def check(self) -> None:
+        if self.status() != 0:
+            raise RuntimeError("clusterfusion_b200.sharded: an exchange poll inside the fused kernel timed out "
+                               "(stalled peer rank or CTAs not co-resident); the layer's outputs are invalid")
+
+    def forward(self, x, residual, k_cache, v_cache, cos, sin, pdl: bool = False, fp16_out: bool = False, check: bool = False):
+        """check=True reads the workspace's error word back after the launch (synchronises; debug mode).
+        fp16_out (world == 1 only): let the kernel write the final fp16 result itself instead of the fp32 partial."""
+        if self.tp is None and self.world == 1 and fp16_out:
+            a = cabi.CfLlamaArgs(
+                variant=cabi.CF_VARIANT_SGLANG, flags=(cabi.CF_FLAG_PDL if pdl else 0), hidden=self.hidden, n_q_heads=self.nq,
+                n_kv_heads=self.nkv, head_dim=HEAD_DIM, batch=1, kv_len=k_cache.shape[0], eps=self.eps, x=x.data_ptr(),
+                residual_in=residual.data_ptr(), residual_out=self.residual_out.data_ptr(), w_qkv=self.wqkv.data_ptr(),
+                w_o=self.wo.data_ptr(), rms_w=self.rms_w.data_ptr(), out=self.out.data_ptr(),
+                k_new=self.k_new.data_ptr(), v_new=self.v_new.data_ptr(), k_cache=k_cache.data_ptr(),
+                v_cache=v_cache.data_ptr(), cos=cos.data_ptr(), sin=sin.data_ptr(), workspace=self.ws.data_ptr())
+            cabi.launch(a, torch.cuda.current_stream().cuda_stream)
+            if check:
+                self.check()
+            return self.out, self.residual_out, self.k_new, self.v_new
         if self.tp is not None:
             # all-reduce fused into the kernel: `out` is the rank-identical fp16 result, nothing else is launched
             a = cabi.CfLlamaArgs(
@@ -128,6 +153,8 @@ class ShardedDecoderLayer:
                 v_cache=v_cache.data_ptr(), cos=cos.data_ptr(), sin=sin.data_ptr(), workspace=self.ws.data_ptr())
             self.tp.fill(a)
             cabi.launch(a, torch.cuda.current_stream().cuda_stream)
+            if check:
+                self.check()
             return self.out, self.residual_out, self.k_new, self.v_new
         flags = cabi.CF_FLAG_OUT_FP32_PARTIAL | (cabi.CF_FLAG_PDL if pdl else 0)
         a = cabi.CfLlamaArgs(
@@ -138,6 +165,8 @@ class ShardedDecoderLayer:
             k_new=self.k_new.data_ptr(), v_new=self.v_new.data_ptr(), k_cache=k_cache.data_ptr(),
             v_cache=v_cache.data_ptr(), cos=cos.data_ptr(), sin=sin.data_ptr(), workspace=self.ws.data_ptr())
         cabi.launch(a, torch.cuda.current_stream().cuda_stream)
+        if check:
+            self.check()
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.partial, op=dist.ReduceOp.SUM, group=self.group)     # the ONE collective of the layer

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 2
+#define CF_ABI_VERSION 3
 
 enum {
     CF_VARIANT_CHAT = 0,   /* W^T weights, GPT-J interleaved RoPE, eps fixed by caller (1e-6), no residual   */
@@ -59,8 +59,7 @@ enum {
                             in flight in the stream (true for a decoder stack: layer l+1's weights and cache are
                             not produced by layer l).                                                           */
 
-#define CF_FLAG_GQA_CLUSTER 0x4u /* grouped-query shapes: use the first-generation 8/16-CTA cluster kernel instead of the
-                                    group kernel (measurement / A-B only; slower on B200)              */
+/* 0x4u was CF_FLAG_GQA_CLUSTER (first-generation grouped-query cluster kernel, removed in ABI 3) */
 
 #define CF_FLAG_LL_OUT 0x8u /* batch-1 MHA launches: reduce the O projection across clusters through flag-in-data words summed
                                in head order (bitwise reproducible output, no atomics) instead of fp32 red.global.add + a
@@ -71,7 +70,7 @@ enum {
                                      (weights re-streamed per request) instead of the batched kernel that streams every
                                      weight tile once per chunk of 4 requests (measurement / A-B)                          */
 
-#define CF_FLAG_BATCH4 0x20u /* PAGED, batch >= 5, MHA: keep chunks of 4 requests per head cluster instead of 8 (A/B)          */
+/* 0x20u was CF_FLAG_BATCH4 (chunks of 4 requests at batch >= 5, removed in ABI 3) */
 
 typedef struct CfLlamaArgs {
     int32_t variant;    /* CF_VARIANT_*                                                             */
@@ -97,7 +96,13 @@ typedef struct CfLlamaArgs {
     void* k_new;        /* fp16 [n_kv*128]  post-RoPE K of the new token (CHAT / SGLANG)            */
     void* v_new;        /* fp16 [n_kv*128]                                                          */
 
-    const void* k_cache; /* CHAT / SGLANG: fp16 [kv_len, n_kv*128]                                  */
+    const void* k_cache; /* CHAT / SGLANG: fp16 [kv_len, n_kv*128].  The TMA descriptors are keyed on this base pointer, not on
+                            kv_len: a cache that grows in place (chat/llama/model.py:355-372) never re-encodes them.
+                            PAGED (optional; may be NULL): the HOST's copy of k_pool_ptrs[layer_id] / v_pool_ptrs[layer_id].
+                            With it, full 16-row KV tiles are fetched by tiled TMA (16 consecutive slots) or tile::gather4
+                            requests (any slots) instead of 32 row-sized bulk copies.  The kernel compares the copy with the
+                            device table and ignores it if they differ (stale copy = slower, never wrong).  Pools of up to
+                            2^24 slots.                                                                                    */
     const void* v_cache;
 
     const int32_t* indptr;       /* PAGED: int32 [batch+1]                                          */
@@ -146,6 +151,19 @@ int cf_ipc_open(const unsigned char handle[64], void** dev_ptr);
 int cf_ipc_close(void* dev_ptr);
 int cf_ipc_free(void* dev_ptr);
 
+/* ---- workspace status.  The cross-CTA / cross-GPU exchanges inside the kernels poll with a bound (about one second); a
+ * publisher that never arrives (peer rank stalled or crashed, CTAs of a group not co-resident because another kernel holds
+ * SMs, one workspace shared by two streams) sets the workspace's sticky error word instead of hanging the GPU, and the
+ * results of that launch are invalid (the peer stage also writes NaN).  cf_workspace_status: copy the word to the host
+ * (synchronises `stream`; not capturable): *status = 0 ok, non-zero = some launch on this workspace since the last clear
+ * timed out.  cf_workspace_clear_status: reset it (asynchronous on `stream`).  Both return 0 or a cudaError_t.          */
+int cf_workspace_status(const void* workspace, void* stream, uint32_t* status);
+int cf_workspace_clear_status(void* workspace, void* stream);
+
+/* Number of cuTensorMapEncodeTiled calls this process has made through the library (tests: a decode loop in steady state
+ * must not encode anything). */
+uint64_t cf_debug_tensor_map_encodes(void);
+
 /* Algorithmic HBM bytes of one call (SURVEY.md section 8d formula) -- used by bench / tests. */
 uint64_t cf_llama_algorithmic_bytes(const CfLlamaArgs* args, uint64_t total_kv_rows);
 
@@ -164,8 +182,9 @@ typedef struct CfFfnArgs {
     const void* rms_w;       /* fp16 [hidden]                                                               */
     void* out;               /* fp16 [hidden] (float with CF_FLAG_OUT_FP32_PARTIAL)                         */
     void* residual_out;      /* fp16 [hidden]; may alias residual_in                                        */
-    void* workspace;         /* cf_llama_workspace_bytes(hidden, 1) bytes, zeroed once; may be shared with the
-                                attention op on the same stream                                            */
+    void* workspace;         /* cf_llama_workspace_bytes(hidden, workspace_batch) bytes, zeroed once; may be shared
+                                with the attention op on the same stream                                   */
+    int32_t workspace_batch; /* the batch the workspace was sized for (its layout depends on it); 0 means 1  */
 } CfFfnArgs;
 
 int cf_llama_ffn_launch(const CfFfnArgs* args, void* stream);

@@ -23,7 +23,7 @@ def test_header_symbols_all_exported():
     assert set(syms) == set(cabi.EXPORTED_SYMBOLS), syms
     for s in syms:
         assert getattr(lib, s) is not None
-    assert lib.cf_abi_version() == 2
+    assert lib.cf_abi_version() == 3
 
 
 def test_workspace_and_bytes_model():

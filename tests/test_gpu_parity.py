@@ -32,6 +32,30 @@ def close(a, b, rtol=RTOL, atol=ATOL):
     return ok
 
 
+def _ordered_fp16(t):
+    """fp16 bit patterns mapped to integers that are monotone in the value (so |a - b| = distance in fp16 ulps)."""
+    i = t.contiguous().view(torch.int16).to(torch.int32)
+    return torch.where(i < 0, -(i & 0x7FFF), i)
+
+
+def close_k(got, want, name="k"):
+    """K rows after RoPE: |k| reaches ~4-8, where ONE fp16 ulp is 3.9e-3 - 7.8e-3, i.e. already outside atol = rtol = 1e-3.
+    north_star's bar (rtol = atol = 1e-3) is therefore applied where it can hold, and the rest is stated in ulps: every
+    element is either inside the 1e-3 tolerance or at most 2 fp16 ulps from the oracle, and at most 0.1 % of the elements
+    are more than 1 ulp off (a 1-ulp flip = the two sides rounded a value sitting on a rounding boundary differently;
+    2 ulps = both inputs of a RoPE pair flipped).  Counts are printed."""
+    g16 = got.detach().to("cpu", torch.float16).reshape(-1)
+    w16 = want.detach().to("cpu", torch.float16).reshape(-1)
+    g, w = g16.float(), w16.float()
+    in_tol = (g - w).abs() <= ATOL + RTOL * w.abs()
+    ulps = (_ordered_fp16(g16) - _ordered_fp16(w16)).abs()
+    n = g.numel()
+    n_out, n_gt1, n_gt2 = int((~in_tol).sum()), int((~in_tol & (ulps > 1)).sum()), int((~in_tol & (ulps > 2)).sum())
+    print(f"{name}: {n} elements, {n_out} outside rtol=atol=1e-3 (all <= {int(ulps[~in_tol].max()) if n_out else 0} ulp), "
+          f"{n_gt1} of them > 1 ulp, {n_gt2} > 2 ulp")
+    return n_gt2 == 0 and n_gt1 <= max(1, n // 1000) and bool(torch.isfinite(g).all())
+
+
 # ---------------------------------------------------------------------------------------------------
 # device primitive (include/dsm.cuh) in isolation
 # ---------------------------------------------------------------------------------------------------
@@ -109,7 +133,7 @@ def test_chat_operator_vs_oracle(kv_len):
     assert o.shape == (1, 4096) and k.shape == (1, 32, 128) and v.shape == (1, 32, 128)
     assert o.dtype == k.dtype == v.dtype == torch.float16
     assert close(v, want_v)
-    assert close(k, want_k, atol=4e-3)          # |k| ~ 4 after RoPE: 1 fp16 ulp = 3.9e-3
+    assert close_k(k, want_k)
     assert close(o, want_o)
 
 
@@ -126,7 +150,7 @@ def test_sglang_cabi_vs_oracle(kv_len):
     torch.cuda.synchronize()
     assert torch.equal(r.cpu(), want[1])
     assert close(v, want[3])
-    assert close(k, want[2], atol=4e-3)
+    assert close_k(k, want[2])
     assert close(o, want[0])
     assert torch.equal(c["residual"].cpu(), d["residual"])     # out-of-place form leaves the input alone
 
@@ -146,7 +170,7 @@ def test_sglang_operator_updates_residual_in_place():
         torch.cuda.synchronize()
         assert r.data_ptr() == res.data_ptr()
         assert torch.equal(res.cpu(), want[1])
-        assert close(o, want[0]) and close(k, want[2], atol=4e-3) and close(v, want[3])
+        assert close(o, want[0]) and close_k(k, want[2]) and close(v, want[3])
 
 
 @pytest.mark.parametrize("name", sorted(p.name for p in GOLDEN.glob("sglang_*w0.02.npz")))
@@ -192,7 +216,7 @@ def test_chat_operator_vs_reference_golden(name):
     tol = 1e-3 if kv >= 37 else 2.5e-3
     assert close(o, torch.from_numpy(z["out"]), rtol=tol, atol=tol)
     if str(z["dtype"]) == "float16":     # the reference ran natively in fp16: same rounding points as the kernel
-        assert close(k, torch.from_numpy(z["k"]), atol=4e-3)
+        assert close_k(k, torch.from_numpy(z["k"]))
         assert close(v, torch.from_numpy(z["v"]))
     else:                                # fp32 run of the reference: see the note in the sglang golden test
         assert close(k, torch.from_numpy(z["k"]), rtol=2e-3, atol=6e-3)
@@ -238,7 +262,7 @@ def test_paged_operator_vs_oracle(lens):
     torch.cuda.synchronize()
     assert torch.equal(rout.cpu(), want_r)
     assert close(out, want_o)
-    assert close(kpools[layer_id], kp, atol=4e-3)       # appended K rows (post-RoPE), everything else untouched
+    assert close_k(kpools[layer_id], kp)                # appended K rows (post-RoPE), everything else untouched
     assert close(vpools[layer_id], vp)
     touched = {int(indices[indptr[b + 1] - 1]) for b in range(bs)}
     keep = [i for i in range(nslots) if i not in touched]
@@ -257,7 +281,7 @@ def test_paged_operator_vs_oracle(lens):
 @pytest.mark.parametrize("lens", [[40, 0, 513, 7, 128, 1], [300] * 8, [17, 2], [5000, 17, 3000, 1, 2049],
                                   [64, 0, 1, 900, 33, 16, 15, 17, 700, 2, 31]])
 def test_batched_paged_kernel_matches_per_request_kernel_and_oracle(lens):
-    """Row f3: the batched kernel (weights streamed once per chunk of 4 requests; chunks of 4 + a ragged tail) against
+    """Row f3: the batched kernels (weights streamed once per chunk of 4 requests up to batch 4, of 8 from batch 5; ragged tail) against
     the oracle and against the per-request launch (CF_FLAG_PER_REQUEST, the reference's grid shape)."""
     import cabi_torch as ct
     from clusterfusion_b200 import cabi
@@ -276,7 +300,7 @@ def test_batched_paged_kernel_matches_per_request_kernel_and_oracle(lens):
                                    d["rms_w"], 1e-5, positions, cos_sin, n_heads=32, mode="eager")
     c = cuda(d)
     res = {}
-    for name, flags in (("batched", 0), ("batched4", cabi.CF_FLAG_BATCH4), ("per_request", cabi.CF_FLAG_PER_REQUEST)):
+    for name, flags in (("batched", 0), ("per_request", cabi.CF_FLAG_PER_REQUEST)):
         kpool, vpool = c["k_cache"].clone(), c["v_cache"].clone()
         kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
         vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
@@ -288,9 +312,9 @@ def test_batched_paged_kernel_matches_per_request_kernel_and_oracle(lens):
         torch.cuda.synchronize()
         assert torch.equal(rout.cpu(), want_r), name
         assert close(out, want_o), name
-        assert close(kpool, kp, atol=4e-3) and close(vpool, vp), name
+        assert close_k(kpool, kp) and close(vpool, vp), name
         res[name] = out
-    assert close(res["batched"], res["per_request"]) and close(res["batched4"], res["per_request"])
+    assert close(res["batched"], res["per_request"])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -314,28 +338,28 @@ def test_gqa_llama3_8b_operator_vs_oracle(kv_len):
     assert k.shape == (1, 8, 128) and v.shape == (1, 8, 128)
     assert torch.equal(r.cpu(), want[1])
     assert close(v, want[3])
-    assert close(k, want[2], atol=4e-3)
+    assert close_k(k, want[2])
     assert close(o, want[0])
 
 
 @pytest.mark.parametrize("shape,kv_len", [(S8, 8192), (S8, 17), (S70, 64), (O.LayerShape(8192, 16, 2), 3000),
                                           (O.LayerShape(8192, 8, 1), 1000), (O.LayerShape(4096, 8, 2), 555)])
-def test_gqa_group_kernel_and_cluster_kernel_agree_with_oracle(shape, kv_len):
-    """Both grouped-query kernels (default: G CTAs per group with L2 exchanges, G = 8 / 16 / 32 / 64 depending on the
-    shape; CF_FLAG_GQA_CLUSTER: the first-generation 8/16-CTA cluster kernel) against the oracle on the same inputs."""
+def test_gqa_group_kernel_shapes_vs_oracle(shape, kv_len):
+    """The grouped-query kernel (G CTAs per group with L2 exchanges, G = 8 / 16 / 32 / 64 depending on the shape) against the
+    oracle: Llama-3-8B, the full Llama-2-70B layer and its 1/4 and 1/8 head shards, and a small 8/2 shape."""
     import cabi_torch as ct
     from clusterfusion_b200 import cabi
     d = O.make_inputs(shape, kv_len, seed=kv_len + shape.n_heads, layout="sglang")
     want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
                           d["rms_w"], 1e-5, d["cos"], d["sin"], n_heads=shape.n_heads, n_kv_heads=shape.n_kv_heads, mode="eager")
     c = cuda(d)
-    for flags in (0, cabi.CF_FLAG_GQA_CLUSTER):
+    for flags in (0,):
         o, r, k, v = ct.sglang(c["x"], c["residual"], c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"], c["rms_w"],
                                1e-5, c["cos"], c["sin"], n_heads=shape.n_heads, n_kv_heads=shape.n_kv_heads, flags=flags)
         torch.cuda.synchronize()
         assert torch.equal(r.cpu(), want[1])
         assert close(v, want[3])
-        assert close(k, want[2], atol=4e-3)
+        assert close_k(k, want[2])
         assert close(o, want[0])
 
 
@@ -351,7 +375,7 @@ def test_gqa_group_kernel_long_context_32k():
     o, r, k, v = ct.sglang(c["x"], c["residual"], c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"], c["rms_w"],
                            1e-5, c["cos"], c["sin"], n_heads=32, n_kv_heads=8)
     torch.cuda.synchronize()
-    assert close(o, want[0]) and close(v, want[3]) and close(k, want[2], atol=4e-3)
+    assert close(o, want[0]) and close(v, want[3]) and close_k(k, want[2])
 
 
 def test_gqa_attention_is_a_convex_combination():
@@ -476,17 +500,18 @@ def test_gqa_paged_operator_vs_oracle():
     torch.cuda.synchronize()
     assert torch.equal(rout.cpu(), want_r)
     assert close(out, want_o)
-    assert close(kpool, kp, atol=4e-3) and close(vpool, vp)
+    assert close_k(kpool, kp) and close(vpool, vp)
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_llama2_70b_head_parallel_shards_sum_to_full_layer(world):
+@pytest.mark.parametrize("world,kv", [(2, 777), (4, 777), (8, 777), (2, 1024), (8, 1024), (4, 16384), (8, 16384)])
+def test_llama2_70b_head_parallel_shards_sum_to_full_layer(world, kv):
     """Every rank's kernel emits its fp32 O-projection partial (CF_FLAG_OUT_FP32_PARTIAL); the sum over ranks
-    (what the one NCCL all-reduce per layer computes) must equal the full 64/8-head layer.  Ranks emulated in turn."""
+    (what the one all-reduce per layer computes) must equal the full 64/8-head layer of the oracle -- at a ragged kv and at
+    the two kv lengths bench.py times the sharded layer at (1024, 16384).  Ranks emulated in turn on one GPU, so this runs on
+    the driver's 1-GPU box; the real 2-GPU exchange is tests/test_gpu_multi.py and bench.py's parity_ok."""
     from clusterfusion_b200 import cabi
     from clusterfusion_b200 import sharded
     import cabi_torch as ct
-    kv = 777
     d = O.make_inputs(S70, kv, seed=70, layout="sglang")
     want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
                           d["rms_w"], 1e-5, d["cos"], d["sin"], n_heads=64, n_kv_heads=8, mode="eager")
@@ -513,7 +538,7 @@ def test_llama2_70b_head_parallel_shards_sum_to_full_layer(world):
         k_all.append(kn); v_all.append(vn)
         assert torch.equal(ro.cpu(), want[1])
     assert close(total.half(), want[0])
-    assert close(torch.cat(k_all), want[2], atol=4e-3)
+    assert close_k(torch.cat(k_all), want[2])
     assert close(torch.cat(v_all), want[3])
 
 
@@ -776,3 +801,192 @@ def test_errors_are_loud():
     with pytest.raises(cabi.CfError) as e:
         cabi.launch(a)
     assert e.value.code == -2
+
+
+# ---------------------------------------------------------------------------------------------------
+# long context (BASELINE configs 2-3: kv 16K / 64K) against the oracle run in full
+# ---------------------------------------------------------------------------------------------------
+def _paged_case(lens, seed, table="random", nslots_extra=37):
+    """Inputs + oracle result of a 15-argument call.  table: random = a permutation of the pool; sequential = one run of
+    consecutive slots per request; runs = runs of 48/16/5/31/64/1/17 slots with gaps and backward jumps."""
+    bs = len(lens)
+    nslots = sum(lens) + bs + nslots_extra
+    d = O.make_inputs(S7, nslots, seed=seed, layout="sglang", bs=bs)
+    need = sum(lens) + bs
+    if table == "random":
+        slots = torch.randperm(nslots, generator=torch.Generator().manual_seed(seed)).tolist()
+    elif table == "sequential":
+        slots = list(range(nslots_extra // 2, nslots_extra // 2 + need))
+    else:
+        slots, s0, free = [], 0, list(range(nslots))
+        runs = (48, 16, 5, 31, 64, 1, 17)
+        chunks = []
+        while s0 < nslots:
+            for r in runs:
+                chunks.append(free[s0:s0 + r]); s0 += r
+        order = torch.randperm(len(chunks), generator=torch.Generator().manual_seed(seed)).tolist()
+        for ci in order:
+            slots += chunks[ci]
+    indptr, indices, off = [0], [], 0
+    for L in lens:
+        indices += slots[off:off + L + 1]; off += L + 1; indptr.append(len(indices))
+    assert len(set(indices)) == len(indices)
+    indptr = torch.tensor(indptr, dtype=torch.int32); indices = torch.tensor(indices, dtype=torch.int32)
+    positions = torch.tensor(lens, dtype=torch.int64)
+    pos_tab = torch.arange(max(lens) + 1, dtype=torch.float32)[:, None] * O.rope_angles(1)[None, :]
+    cos_sin = torch.cat([pos_tab.cos(), pos_tab.sin()], 1).contiguous()
+    kp, vp = d["k_cache"].clone(), d["v_cache"].clone()
+    want_o, want_r = O.paged_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], indptr, indices, kp, vp,
+                                   d["rms_w"], 1e-5, positions, cos_sin, n_heads=32, mode="eager")
+    return d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r
+
+
+def _run_paged_cabi(d, indptr, indices, positions, cos_sin, flags=0, host_pool_copy="right"):
+    """One 15-argument launch through the C ABI.  host_pool_copy: right = pass the host's copy of the pool addresses
+    (tiled / gather4 KV fast paths), none = NULL (row-by-row gather), stale = a WRONG copy (the kernel must notice)."""
+    import cabi_torch as CT
+    from clusterfusion_b200 import cabi
+    c = cuda(d)
+    bs = d["x"].shape[0]
+    kpool, vpool = c["k_cache"].clone(), c["v_cache"].clone()
+    decoy_k, decoy_v = torch.zeros_like(kpool), torch.zeros_like(vpool)
+    kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
+    vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
+    out = torch.full((bs, 4096), float("nan"), dtype=torch.float16, device="cuda")
+    rout = torch.full((bs, 4096), float("nan"), dtype=torch.float16, device="cuda")
+    dev_t = (indptr.cuda(), indices.cuda(), positions.cuda(), cos_sin.cuda())
+    hk = {"right": kpool, "stale": decoy_k, "none": None}[host_pool_copy]
+    hv = {"right": vpool, "stale": decoy_v, "none": None}[host_pool_copy]
+    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=flags, hidden=4096, n_q_heads=32, n_kv_heads=32, head_dim=128,
+                         batch=bs, layer_id=0, eps=1e-5, x=c["x"].data_ptr(), residual_in=c["residual"].data_ptr(),
+                         residual_out=rout.data_ptr(), w_qkv=c["weight_qkv"].data_ptr(), w_o=c["weight_o"].data_ptr(),
+                         rms_w=c["rms_w"].data_ptr(), out=out.data_ptr(), indptr=dev_t[0].data_ptr(), indices=dev_t[1].data_ptr(),
+                         k_pool_ptrs=kptrs.data_ptr(), v_pool_ptrs=vptrs.data_ptr(), positions=dev_t[2].data_ptr(),
+                         cos=dev_t[3].data_ptr(), k_cache=None if hk is None else hk.data_ptr(),
+                         v_cache=None if hv is None else hv.data_ptr(), workspace=CT.workspace(4096, bs, c["x"].device).data_ptr())
+    cabi.launch(a, CT.stream_handle())
+    torch.cuda.synchronize()
+    assert torch.equal(decoy_k.cpu(), torch.zeros_like(d["k_cache"]))
+    return out, rout, kpool, vpool
+
+
+@pytest.mark.parametrize("table", ["random", "sequential", "runs"])
+@pytest.mark.parametrize("host_pool_copy", ["right", "none", "stale"])
+def test_paged_kv_fetch_paths_agree_with_oracle(table, host_pool_copy):
+    """The three ways the per-request paged kernel fills a KV stage -- tiled TMA over 16 consecutive slots, tile::gather4 over
+    arbitrary slots, row-by-row bulk copies (ragged tail; no / stale host copy of the pool addresses) -- against the oracle, on
+    a random table, a sequential one and one made of runs of 48/16/5/31/64/1/17 slots."""
+    from clusterfusion_b200 import cabi
+    d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r = _paged_case([1000], seed=321, table=table)
+    out, rout, kpool, vpool = _run_paged_cabi(d, indptr, indices, positions, cos_sin, host_pool_copy=host_pool_copy)
+    assert torch.equal(rout.cpu(), want_r)
+    assert close(out, want_o)
+    assert close_k(kpool, kp) and close(vpool, vp)
+
+
+@pytest.mark.parametrize("table", ["random", "sequential"])
+def test_paged_form_kv16384_bs1_vs_oracle(table):
+    """north_star's form at north_star's size: 15-argument paged call, batch 1, kv_len 16384 (Llama-2-7B), through the public
+    operator (which passes the host copy of the pool addresses, so the tiled / gather4 paths run), oracle run in full."""
+    import clusterfusion
+    d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r = _paged_case([16384], seed=1616, table=table)
+    c = cuda(d)
+    kpool, vpool = c["k_cache"].clone(), c["v_cache"].clone()
+    kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
+    vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
+    out = torch.full((1, 4096), float("nan"), dtype=torch.float16, device="cuda"); rout = torch.empty_like(out)
+    clusterfusion.llama_decoder_layer(out, rout, c["x"], c["residual"], c["weight_qkv"], c["weight_o"], indptr.cuda(),
+                                      indices.cuda(), kptrs, vptrs, 0, c["rms_w"], 1e-5, positions.cuda(), cos_sin.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(rout.cpu(), want_r)
+    assert close(out, want_o)
+    assert close_k(kpool, kp) and close(vpool, vp)
+
+
+@pytest.mark.parametrize("per_request", [False, True])
+def test_paged_form_ragged_bs4_long_context_vs_oracle(per_request):
+    """Ragged batch of 4 with two requests at kv 16384: the batched kernel (weights once per chunk) and the one-cluster-per-
+    (request, head) launch of the reference's grid shape, both against the oracle."""
+    from clusterfusion_b200 import cabi
+    lens = [16384, 5000, 16384, 1]
+    d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r = _paged_case(lens, seed=44, table="random")
+    out, rout, kpool, vpool = _run_paged_cabi(d, indptr, indices, positions, cos_sin,
+                                              flags=cabi.CF_FLAG_PER_REQUEST if per_request else 0)
+    assert torch.equal(rout.cpu(), want_r)
+    assert close(out, want_o)
+    assert close_k(kpool, kp) and close(vpool, vp)
+
+
+def test_chat_operator_kv65536_vs_oracle():
+    """8-argument form at the top of BASELINE config 3's sweep (kv 65536: 1 GB of K/V, 1024 tiles per CTA), oracle run in full."""
+    import clusterfusion
+    kv = 65536
+    d = O.make_inputs(S7, kv, seed=65, layout="chat")
+    want_o, want_k, want_v = O.chat_layer(d["x"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"],
+                                          d["rms_w"], d["cos"], d["sin"], n_heads=32, eps=1e-6, mode="eager")
+    c = cuda(d)
+    o, k, v = clusterfusion.llama_decoder_layer(c["x"], c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"],
+                                                c["rms_w"], c["cos"], c["sin"])
+    torch.cuda.synchronize()
+    assert close(o, want_o) and close(v, want_v) and close_k(k, want_k)
+
+
+def test_chat_form_growing_cache_64_tokens_like_the_reference_chat_loop():
+    """The 8-argument form driven the way /root/reference/chat/llama/model.py:355-374 drives it: `k_cache` / `v_cache` are
+    views `[:start_pos]` of larger per-layer buffers, kv_len grows by one every token, the caller appends the returned k / v.
+    64 tokens x 2 layers against the oracle fed with the same growing cache; and the host path must be in steady state after
+    the first token: ZERO cuTensorMapEncodeTiled calls for tokens 2..64 (maps are keyed on the base pointer, not kv_len)."""
+    import clusterfusion
+    n_layers, start, n_tok, max_seq = 2, 200, 64, 512
+    g = torch.Generator().manual_seed(2024)
+    layers = []
+    for li in range(n_layers):
+        d = O.make_inputs(S7, start, seed=900 + li, layout="chat")
+        ck = torch.zeros(max_seq, 4096, dtype=torch.float16); cv = torch.zeros_like(ck)
+        ck[:start] = d["k_cache"]; cv[:start] = d["v_cache"]
+        layers.append(dict(w_qkv=d["weight_qkv"], w_o=d["weight_o"], rms=d["rms_w"], ck=ck, cv=cv))
+    dev = [{k: v.cuda() for k, v in l.items()} for l in layers]
+    x0 = torch.randn(1, 1, 4096, generator=g).half()
+    h_ref, h_dev = x0.clone(), x0.cuda()
+    worst = 0.0
+    enc_after_first = None
+    for t in range(n_tok):
+        pos = start + t
+        ang = O.rope_angles(pos)
+        cos = torch.repeat_interleave(ang.cos(), 2).view(1, 128).contiguous()
+        sin = torch.repeat_interleave(ang.sin(), 2).view(1, 128).contiguous()
+        cos_d, sin_d = cos.cuda(), sin.cuda()
+        for l, ld in zip(layers, dev):
+            # oracle, fed with what the DEVICE path consumed (so a 1-ulp difference in token t cannot drift into token t+1)
+            want_o, want_k, want_v = O.chat_layer(h_dev.cpu().view(1, 4096), l["w_qkv"], l["w_o"], ld["ck"][:pos].cpu(), ld["cv"][:pos].cpu(),
+                                                  l["rms"], cos, sin, n_heads=32, eps=1e-6, mode="eager")
+            o, xk, xv = clusterfusion.llama_decoder_layer(h_dev, ld["w_qkv"], ld["w_o"], ld["ck"][:pos], ld["cv"][:pos],
+                                                          ld["rms"], cos_d, sin_d)
+            ld["ck"][pos:pos + 1] = xk.view(1, 4096)          # model.py:371-372
+            ld["cv"][pos:pos + 1] = xv.view(1, 4096)
+            assert close(o, want_o) and close(xv, want_v) and close_k(xk, want_k, name=f"k[t={t}]")
+            worst = max(worst, float((o.float().cpu() - want_o.float()).abs().max()))
+            h_dev = (h_dev + o.view(1, 1, 4096)) * 0.5          # keep activations O(1) over 128 layer calls
+        if t == 0:
+            torch.cuda.synchronize()
+            enc_after_first = clusterfusion.tensor_map_encodes()
+    torch.cuda.synchronize()
+    print(f"growing cache: {n_tok} tokens x {n_layers} layers, worst |o - oracle| = {worst:.2e}, "
+          f"tensor-map encodes after token 1: {clusterfusion.tensor_map_encodes() - enc_after_first}")
+    assert clusterfusion.tensor_map_encodes() == enc_after_first
+
+
+def test_workspace_status_word_round_trip():
+    """cf_workspace_status / cf_workspace_clear_status (C ABI): the sticky error word of a workspace reads 0 after normal
+    launches, reads back a planted value, and clears."""
+    import cabi_torch as CT
+    from clusterfusion_b200 import cabi
+    d = O.make_inputs(S7, 64, seed=5, layout="chat")
+    c = cuda(d)
+    CT.chat(c["x"], c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"], c["rms_w"], c["cos"], c["sin"])
+    ws = CT.workspace(4096, 1, c["x"].device)
+    assert cabi.workspace_status(ws.data_ptr(), CT.stream_handle()) == 0
+    ws.view(torch.int32)[2] = 1
+    assert cabi.workspace_status(ws.data_ptr(), CT.stream_handle()) == 1
+    cabi.workspace_clear_status(ws.data_ptr(), CT.stream_handle())
+    assert cabi.workspace_status(ws.data_ptr(), CT.stream_handle()) == 0
