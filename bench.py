@@ -317,15 +317,16 @@ def run_ours(args, rank, world, local_rank):
         return world * n * 1e3 / t_ms
 
     # 8-argument chat form, driven as chat/llama/model.py:355-374 drives it: cache views, caller-side KV append, residual add
-    kviews = [(lay["k"][:kv], lay["v"][:kv], lay["k"][kv:kv + 1], lay["v"][kv:kv + 1]) for lay in layers]
+    kviews = [(lay["k"][:kv], lay["v"][:kv], lay["k"][kv:kv + 1].view(1, HEADS, D), lay["v"][kv:kv + 1].view(1, HEADS, D))
+              for lay in layers]
 
     def e2e_step():
         h = x_host.to(dev, non_blocking=True)                                   # H2D: this token's input
         for lay, (kc, vc, kdst, vdst) in zip(layers, kviews):
             o, k_new, v_new = clusterfusion.llama_decoder_layer(h, lay["w_qkv"], lay["w_o"], kc, vc, lay["rms"], cos, sin)
-            kdst.copy_(k_new.view(1, HIDDEN))                                   # caller-side KV append (model.py:371-372)
-            vdst.copy_(v_new.view(1, HIDDEN))
-            h = h + o.view(1, 1, HIDDEN)                                        # caller-side residual (model.py:488-492)
+            kdst.copy_(k_new)                                                   # caller-side KV append (model.py:371-372)
+            vdst.copy_(v_new)
+            h = h + o                                                           # caller-side residual (model.py:488-492)
         out_host.copy_(h, non_blocking=True)                                    # D2H: the step's result
         torch.cuda.current_stream().synchronize()
 

@@ -79,34 +79,24 @@ struct MapKeyHash {
 };
 
 std::mutex g_map_mutex;
-// Two caches.  `g_map_cache`: maps whose key does not change while a model decodes -- weights, KV caches / pools mapped from
-// their base pointer with a fixed (huge) row extent.  Never flushed: a serving process holds a few hundred of them.
-// `g_kv_len_cache`: maps whose row extent is the CURRENT kv_len (only the grouped-query kernel's swizzled K/V boxes, whose
-// ragged last tile relies on TMA zero fill); one entry per base pointer, overwritten in place when kv_len moves on, so a
-// growing cache can neither evict the weight maps nor grow the table.
+// Every map is keyed on (base pointer, extent, box): weights, and KV caches / pools mapped from their base pointer with a
+// fixed (huge) row extent -- nothing in the key moves while a model decodes, so the steady state of a decode loop is zero
+// encodes per token.  Never flushed in normal operation: a serving process holds a few hundred entries.
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
-struct KvLenEntry { MapKey key; CUtensorMap map; };
-std::unordered_map<const void*, KvLenEntry> g_kv_len_cache;
 std::atomic<uint64_t> g_encode_calls{0};
 
 // 2-D fp16 row-major tensor [rows][cols], box {box_c, box_r}; OOB rows/cols read as zero.
-// by_base: key the map on the base pointer alone in the per-kv_len cache (see above).
 int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_c,
-                   uint32_t box_r, bool swizzle128 = false, bool per_kv_len = false) {
+                   uint32_t box_r, bool swizzle128 = false) {
     const MapKey key{ptr, rows, cols, box_c, box_r | (swizzle128 ? 0x80000000u : 0u)};
     {
         std::lock_guard<std::mutex> lk(g_map_mutex);
-        if (per_kv_len) {
-            auto it = g_kv_len_cache.find(ptr);
-            if (it != g_kv_len_cache.end() && it->second.key == key) { *out = it->second.map; return 0; }
-        } else {
-            auto it = g_map_cache.find(key);
-            if (it != g_map_cache.end()) { *out = it->second; return 0; }
-        }
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) { *out = it->second; return 0; }
     }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(CF_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
-    const cuuint64_t dims[2] = {cols, rows ? rows : 1};      // a zero-row cache still needs a valid map
+    const cuuint64_t dims[2] = {cols, rows ? rows : 1};
     const cuuint64_t strides[1] = {cols * sizeof(__half)};
     const cuuint32_t box[2] = {box_c, box_r};
     const cuuint32_t estr[2] = {1, 1};
@@ -123,14 +113,9 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
                                        (int)r, (unsigned long long)rows, (unsigned long long)cols);
     {
         std::lock_guard<std::mutex> lk(g_map_mutex);
-        if (per_kv_len) {
-            if (g_kv_len_cache.size() > 8192) g_kv_len_cache.clear();   // one entry per live cache tensor; bounded anyway
-            g_kv_len_cache[ptr] = KvLenEntry{key, m};
-        } else {
-            // bounded as a safety net only (a process that keeps allocating new weights): weights are re-encoded on demand
-            if (g_map_cache.size() > (1u << 16)) g_map_cache.clear();
-            g_map_cache.emplace(key, m);
-        }
+        // bounded as a safety net only (a process that keeps allocating new tensors): maps are re-encoded on demand
+        if (g_map_cache.size() > (1u << 16)) g_map_cache.clear();
+        g_map_cache.emplace(key, m);
     }
     *out = m;
     return 0;
@@ -351,8 +336,9 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, cfb::ROWS512, true))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, cfb::ROWS256, true))) return rc;
     } else {
+        // group kernel: CUDA-core QKV GEMV over unswizzled [16 x 256] tiles, tensor-core O GEMV over swizzled [32 x 64] boxes
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 256, cfb::ROWS512))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 256, cfb::ROWS512))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, cfb::ROWS256, true))) return rc;
     }
     const bool group_kernel = gqa;
     if (!paged) {
@@ -360,16 +346,27 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         const void* kc = a->kv_len ? a->k_cache : a->x;
         const void* vc = a->kv_len ? a->v_cache : a->x;
         if (group_kernel) {
-            // group kernel (tensor-core attention): 64-dim half rows, 128-byte swizzled, so ldmatrix is conflict-free; its
-            // ragged last tile relies on TMA zero fill, so these two maps carry the current kv_len (one cache entry per tensor)
-            if ((rc = get_tensor_map(&kp.tm_k, kc, a->kv_len, kvd, 64, cfb::ROWS512, true, true))) return rc;
-            if ((rc = get_tensor_map(&kp.tm_v, vc, a->kv_len, kvd, 64, cfb::ROWS512, true, true))) return rc;
+            // group kernel (tensor-core attention): 64-dim half rows, 128-byte swizzled, so ldmatrix is conflict-free.  Full
+            // tiles come through the {64 x 16} boxes, a ragged last tile through tile::gather4 over the {64 x 1} maps (rows
+            // clamped to kv_len - 1), so nothing depends on kv_len here either
+            if ((rc = get_tensor_map(&kp.tm_k, kc, kv_map_rows(a->kv_len), kvd, 64, cfb::ROWS512, true))) return rc;
+            if ((rc = get_tensor_map(&kp.tm_v, vc, kv_map_rows(a->kv_len), kvd, 64, cfb::ROWS512, true))) return rc;
+            if ((rc = get_tensor_map(&kp.tm_kg, kc, kv_map_rows(a->kv_len), kvd, 64, 1, true))) return rc;
+            if ((rc = get_tensor_map(&kp.tm_vg, vc, kv_map_rows(a->kv_len), kvd, 64, 1, true))) return rc;
         } else {
             if ((rc = get_tensor_map(&kp.tm_k, kc, kv_map_rows(a->kv_len), kvd, 128, cfb::ROWS512))) return rc;
             if ((rc = get_tensor_map(&kp.tm_v, vc, kv_map_rows(a->kv_len), kvd, 128, cfb::ROWS512))) return rc;
         }
         kp.k_base = static_cast<const __half*>(kc);
         kp.v_base = static_cast<const __half*>(vc);
+    } else if (gqa && a->k_cache && a->v_cache) {
+        // paged group kernel with the pool addresses known on the host: swizzled maps over the pools, tensor-core attention
+        if ((rc = get_tensor_map(&kp.tm_k, a->k_cache, 1ull << 24, kvd, 64, cfb::ROWS512, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_v, a->v_cache, 1ull << 24, kvd, 64, cfb::ROWS512, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_kg, a->k_cache, 1ull << 24, kvd, 64, 1, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_vg, a->v_cache, 1ull << 24, kvd, 64, 1, true))) return rc;
+        kp.k_base = static_cast<const __half*>(a->k_cache);
+        kp.v_base = static_cast<const __half*>(a->v_cache);
     } else if (!gqa && !batched && a->k_cache && a->v_cache) {
         // optional fast paths of the paged form: the caller knows the pool addresses of this layer on the host (k_cache /
         // v_cache = its copy of k_pool_ptrs[layer_id] / v_pool_ptrs[layer_id]).  Tiles whose 16 rows sit in consecutive
@@ -432,9 +429,32 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         const int n_groups = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
         if (n_groups > cfb::G2_GROUPS_MAX)
             return fail(CF_ERR_BAD_SHAPE, "GQA: at most %d (KV head, 4 query heads) groups per call (got %d)", cfb::G2_GROUPS_MAX, n_groups);
-        const int n_sm = sm_count_of_current_device();
+        if (n_groups * 4 > a->hidden / 128)
+            return fail(CF_ERR_BAD_SHAPE, "GQA: at most hidden/128 = %d query heads per call (got %d)", a->hidden / 128, n_groups * 4);
+        // The CTAs of a group spin on each other through L2, so a group must be co-resident (for batch 1: the whole grid,
+        // because the output columns are summed across groups the same way).  Capacity = what the occupancy calculator says
+        // this kernel can keep resident on this device (1 CTA / SM at its shared-memory footprint) -- G is the largest power
+        // of two that fits.  For batch > 1 the grid exceeds it by design: requests are the slow grid dimension and a group's
+        // CTAs are contiguous in blockIdx.x, so a group only ever waits for CTAs that are dispatched as earlier groups drain.
+        // Anything that breaks those assumptions (another kernel holding SMs, MPS partitions) ends in the bounded poll's
+        // error word, not a hang: see cf_workspace_status.
+        static int capacity[16] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (capacity[dev & 15] == 0) {
+            int occ = 0;
+            cudaFuncSetAttribute(cfb::llama_decoder_layer_gqa2_kernel<cfb::SGLANG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 cfb::SmemGqa2<4>::TOTAL);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cfb::llama_decoder_layer_gqa2_kernel<cfb::SGLANG, 4>,
+                                                              cfb::BLOCK_THREADS, cfb::SmemGqa2<4>::TOTAL) != cudaSuccess || occ < 1)
+                occ = 1;
+            capacity[dev & 15] = occ * sm_count_of_current_device();
+        }
+        const int n_sm = capacity[dev & 15];
         int G = cfb::G2_G_MAX;
         while (G > 8 && (long long)n_groups * G * a->batch > n_sm) G >>= 1;
+        if (a->batch == 1 && n_groups * G > n_sm)
+            return fail(CF_ERR_BAD_SHAPE, "GQA: %d groups x %d CTAs cannot be co-resident on this device (%d CTAs fit)", n_groups, G, n_sm);
         cfb::G2Params gp;
         memset(&gp, 0, sizeof gp);
         gp.k = kp;

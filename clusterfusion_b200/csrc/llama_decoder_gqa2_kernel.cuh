@@ -14,9 +14,11 @@
  *               CTA publishes its row sums, every CTA reads all 768 back, adds the (at most two) parts in a fixed order
  *               and applies RoPE itself.
  *   exchange 2  softmax state: CTA r streams KV rows [r*chunk, ...) for all NQ query heads and publishes its
- *               NQ x [m, l, o[128]]; CTA j merges dims [j*512/G, ...) over all G states in rank order and publishes the
- *               normalised fp16-rounded result; every CTA reads the 512 merged values (reduce-scatter + all-gather: an
- *               all-to-all of full states would be 67-270 KB per CTA through a ~64 GB/s SM port).
+ *               NQ x [m, l, o[128]].  For the O projection CTA r owns ONE query head (r % NQ) and hidden*NQ/G output rows,
+ *               so it needs the merged state of that head only: it gathers [m, l, o[128]] of its head from all G ranks
+ *               (G x 130 words: 17 KB at G = 16, 68 KB at G = 64), merges them in a fixed order and normalises -- ONE
+ *               hop.  (Round 1 split the O projection by output rows over all NQ*128 input columns, which needs the whole
+ *               merged attention output in every CTA: reduce-scatter + all-gather, two hops, 4.9 us per layer.)
  *
  * Both exchanges use a flag-in-data protocol (what NCCL calls LL): every 64-bit word carries a float and the launch's
  * epoch, written with one st.relaxed.gpu.b64 and polled with ld.relaxed.gpu.b64 until the epoch matches.  No fence, no
@@ -47,7 +49,7 @@ namespace cfb {
 
 constexpr int G2_HIDDEN_MAX = 8192;
 constexpr int G2_RB_LOCAL_MAX = 8;        // 16-row blocks a CTA can touch in the QKV phase (48 / G whole + 1 partial, G >= 8)
-constexpr int G2_OROWS_MAX = 1024;        // hidden / G
+constexpr int G2_OROWS_MAX = 4096;        // output rows per CTA in the O phase: hidden * NQ / G (G >= 8, hidden <= 8192)
 constexpr int G2_GROUPS_MAX = 16;         // groups per request
 constexpr int G2_G_MAX = 64;              // CTAs per group
 constexpr int G2_SLOTS = 160;             // softmax-state slots per request (groups x G <= 148 whenever batch == 1)
@@ -61,21 +63,22 @@ struct SmemGqa2 {
     static constexpr int RING = 0;
     static constexpr int UNION = RING + NSTAGES * STAGE_BYTES;
     //   phase QKV : xs fp16[hidden <= 8192] | part fp32[12 warps][G2_RB_LOCAL_MAX][16]
-    //   phase ATTN: attn_part fp32[12][NQ][132] | mg fp32[640]
-    //   phase O   : out_part fp32[NQ*128/256][G2_OROWS_MAX]
+    //   phase ATTN: attn_part fp32[12][NQ][132] | ml fp32[G_MAX][2] | opart fp32[3][128]
+    //   phase O   : out_part fp32[G2_OROWS_MAX]
     static constexpr int XS = UNION;
     static constexpr int PART = UNION + G2_HIDDEN_MAX * 2;
     static constexpr int QKV_BYTES = G2_HIDDEN_MAX * 2 + CONSUMER_WARPS * G2_RB_LOCAL_MAX * ROWS512 * 4;
     static constexpr int ATTN_PART = UNION;                                // fp32 [12 warps][NQ][132]
-    static constexpr int MG = UNION + CONSUMER_WARPS * NQ * PAY * 4;       // fp32 [G][S2 + 2] <= 640 floats
-    static constexpr int ATTN_BYTES = CONSUMER_WARPS * NQ * PAY * 4 + 640 * 4;
+    static constexpr int ML = UNION + CONSUMER_WARPS * NQ * PAY * 4;       // fp32 [G2_G_MAX][2]: (m, l) of this CTA's head, per rank
+    static constexpr int OPART = ML + G2_G_MAX * 2 * 4;                    // fp32 [3][128]: partial merges of three rank ranges
+    static constexpr int ATTN_BYTES = CONSUMER_WARPS * NQ * PAY * 4 + G2_G_MAX * 2 * 4 + 3 * HEAD_DIM * 4;
     static constexpr int OUT_PART = UNION;
-    static constexpr int OUT_BYTES = (NQ * HEAD_DIM / 256) * G2_OROWS_MAX * 4;
+    static constexpr int OUT_BYTES = G2_OROWS_MAX * 4;
     static constexpr int UNION_SIZE = QKV_BYTES > ATTN_BYTES ? (QKV_BYTES > OUT_BYTES ? QKV_BYTES : OUT_BYTES)
                                                              : (ATTN_BYTES > OUT_BYTES ? ATTN_BYTES : OUT_BYTES);
     static constexpr int QKV_FIN = UNION + UNION_SIZE;                     // fp32[R] roped q*scale | k | v
-    static constexpr int AG2 = QKV_FIN + R * 4;                            // fp32[NQ*128] attention output
-    static constexpr int RED = AG2 + NQ * HEAD_DIM * 4;                    // fp32[32]
+    static constexpr int ATTN_OUT = QKV_FIN + R * 4;                       // fp32[128] merged attention output of this CTA's head
+    static constexpr int RED = ATTN_OUT + HEAD_DIM * 4;                    // fp32[32]
     static constexpr int BARS = RED + 32 * 4;                              // u64 full[NSTAGES]
     static constexpr int FLAGS = BARS + NSTAGES * 8;
     static constexpr int TOTAL = FLAGS + 16;
@@ -191,10 +194,11 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     using S = SmemGqa2<NQ>;
     static_assert(VARIANT != CHAT, "GQA uses the nn.Linear weight layout");
     constexpr bool kPaged = (VARIANT == PAGED);
-    // contiguous KV arrives through TMA and can be laid out 128-byte-swizzled, which makes ldmatrix conflict-free: that
-    // variant runs QK^T and PV on the tensor cores (mma.sync m16n8k16).  Page-size-1 KV lands as linear 256-byte rows
-    // (bulk copies cannot swizzle) and keeps the CUDA-core loop.
-    constexpr bool kMma = !kPaged;
+    // KV that arrives through tensor maps (tiled boxes over consecutive rows, tile::gather4 over arbitrary pool rows) is laid
+    // out 128-byte-swizzled, which makes ldmatrix conflict-free: QK^T and PV then run on the tensor cores (mma.sync
+    // m16n8k16).  That is every contiguous-cache launch, and every paged launch whose caller passed the pool addresses on
+    // the host (see `pool_maps`).  Paged launches without them gather linear 256-byte rows with bulk copies (which cannot
+    // swizzle) and keep the CUDA-core loop.
     constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;      // 1/sqrt(128) * log2(e)
     const KParams& p = gp.k;
 
@@ -214,7 +218,9 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     const int kvh = gid / qsplit;
     const int qh0 = kvh * (Hq / Hkv) + (gid % qsplit) * NQ;     // first query head of this group
     const bool writes_kv = (gid % qsplit) == 0;
-    const int OROWS = hidden / G;                        // this CTA's slice of the O output dim
+    // O projection: CTA `rank` owns query head ho of the group and output rows [rq*OROWS, +OROWS)
+    const int ho = rank % NQ, rq = rank / NQ;
+    const int OROWS = hidden / (G / NQ);
     const int kv_cols = Hkv * HEAD_DIM;
     const int wins = hidden / 256;
 
@@ -236,8 +242,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     const uint32_t t_first = rank * n_qkv_tiles;                                 // group-level index of this CTA's first tile
     const int rb_first = t_first / wins;
     const uint32_t n_kv_tiles = (row_end - row_begin + ROWS512 - 1) / ROWS512;
-    constexpr int owins = NQ * HEAD_DIM / 256;
-    const uint32_t n_o_tiles = (OROWS / ROWS512) * owins;
+    const uint32_t n_o_tiles = OROWS / ROWS256;          // [32 output rows x this head's 128 input cols] per tile
 
     CF_MARK(0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -245,18 +250,23 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     // ---- tile stream: every warp requests, consumes and re-requests its own tiles (see llama_decoder_kernel.cuh) ----
     const uint64_t pol = policy_evict_first();
     const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
-    const __half* kpool = nullptr;
-    const __half* vpool = nullptr;
+    const __half* kpool = p.k_base;
+    const __half* vpool = p.v_base;
     if constexpr (kPaged) {
         kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
         vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
     }
-    // paged KV: page index of this lane's row of KV tile g, fetched one ring cycle ahead (see llama_decoder_kernel.cuh)
+    // the host's copy of the pool addresses is used only if it agrees with the device table (see llama_decoder_kernel.cuh)
+    const bool pool_maps = !kPaged || (p.k_base != nullptr && kpool == p.k_base && vpool == p.v_base);
+    const bool use_mma = pool_maps;                      // uniform over the launch
+    // paged KV: page index of this lane's row of KV tile g, fetched one ring cycle ahead (see llama_decoder_kernel.cuh).
+    // Rows past the end of the chunk repeat its last row: tile::gather4 needs four valid rows, the scores mask them.
     int pre_slot0 = 0, pre_slot1 = 0;
     uint32_t pre_g0 = 0xffffffffu, pre_g1 = 0xffffffffu;
     auto page_of = [&](uint32_t g) -> int {
-        const int r = row_begin + (int)(g - n_qkv_tiles) * ROWS512 + (int)(lane & 15);
-        return (r < row_end) ? p.indices[kv_base + r] : 0;
+        const int r = min(row_begin + (int)(g - n_qkv_tiles) * ROWS512 + (int)(lane & 15), row_end - 1);
+        if constexpr (kPaged) return p.indices[kv_base + r];
+        else return r;
     };
     auto issue_tile = [&](uint32_t g) {
         if (g >= total_tiles) return;
@@ -277,36 +287,59 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             }
         } else if (g < n_qkv_tiles + n_kv_tiles) {
             const uint32_t i = g - n_qkv_tiles;
-            if constexpr (!kPaged) {
-                if (lane == 0) {
-                    const int r0 = row_begin + i * ROWS512;
-                    dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                    // stage = K dims 0-63 | K dims 64-127 | V dims 0-63 | V dims 64-127, each [16 rows][128 B] swizzled
-                    tma_load_2d(dst, &p.tm_k, kvh * HEAD_DIM, r0, fb, pol);
-                    tma_load_2d(dst + 2048, &p.tm_k, kvh * HEAD_DIM + 64, r0, fb, pol);
-                    tma_load_2d(dst + 4096, &p.tm_v, kvh * HEAD_DIM, r0, fb, pol);
-                    tma_load_2d(dst + 6144, &p.tm_v, kvh * HEAD_DIM + 64, r0, fb, pol);
+            const int r0 = row_begin + (int)i * ROWS512;
+            const int nvalid = min(ROWS512, row_end - r0);
+            int slot;
+            if constexpr (kPaged) {
+                const bool odd = (g / CONSUMER_WARPS) & 1u;
+                slot = (odd ? pre_g1 : pre_g0) == g ? (odd ? pre_slot1 : pre_slot0) : page_of(g);
+            } else {
+                slot = min(r0 + (int)(lane & 15), row_end - 1);
+            }
+            if (use_mma) {
+                // stage = K dims 0-63 | K dims 64-127 | V dims 0-63 | V dims 64-127, each [16 rows][128 B] 128-byte swizzled
+                const int slot0 = __shfl_sync(0xffffffffu, slot, 0);
+                const bool run = nvalid == ROWS512 && __all_sync(0xffffffffu, slot == slot0 + (int)(lane & 15));
+                if (run) {                                  // 16 consecutive rows: one tiled box per quarter
+                    if (lane == 0) {
+                        dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                        tma_load_2d(dst, &p.tm_k, kvh * HEAD_DIM, slot0, fb, pol);
+                        tma_load_2d(dst + 2048, &p.tm_k, kvh * HEAD_DIM + 64, slot0, fb, pol);
+                        tma_load_2d(dst + 4096, &p.tm_v, kvh * HEAD_DIM, slot0, fb, pol);
+                        tma_load_2d(dst + 6144, &p.tm_v, kvh * HEAD_DIM + 64, slot0, fb, pol);
+                    }
+                } else {                                    // arbitrary rows (or a ragged last tile): tile::gather4, 4 rows x 128 B
+                    const int s1 = __shfl_down_sync(0xffffffffu, slot, 1);
+                    const int s2 = __shfl_down_sync(0xffffffffu, slot, 2);
+                    const int s3 = __shfl_down_sync(0xffffffffu, slot, 3);
+                    if (lane == 0) dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                    __syncwarp();
+                    if ((lane & 3) == 0) {                  // lanes 0,4,8,12: K rows 4q..4q+3; lanes 16,..,28: V rows
+                        const uint32_t d = dst + (lane < 16 ? 0 : 4096) + ((lane & 15) >> 2) * 512;
+                        const CUtensorMap* tm = lane < 16 ? &p.tm_kg : &p.tm_vg;
+                        tma_gather4_2d(d, tm, kvh * HEAD_DIM, slot, s1, s2, s3, fb, pol);
+                        tma_gather4_2d(d + 2048, tm, kvh * HEAD_DIM + 64, slot, s1, s2, s3, fb, pol);
+                    }
                 }
             } else {
-                const int r = row_begin + i * ROWS512 + (lane & 15);
-                const bool valid = r < row_end;
-                const bool odd = (g / CONSUMER_WARPS) & 1u;
-                const long long slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
-                const int nvalid = min(ROWS512, row_end - (row_begin + (int)i * ROWS512));
-                if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
-                __syncwarp();
-                if (valid) {
-                    const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
-                    if (lane < 16) bulk_load_1d(d, kpool + slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2, fb, pol);
-                    else bulk_load_1d(d + STAGE_BYTES / 2, vpool + slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                if constexpr (kPaged) {                     // no tensor map over the pool: linear 256-byte rows, CUDA-core loop
+                    if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
+                    __syncwarp();
+                    if ((int)(lane & 15) < nvalid) {
+                        const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
+                        if (lane < 16) bulk_load_1d(d, kpool + (long long)slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                        else bulk_load_1d(d + STAGE_BYTES / 2, vpool + (long long)slot * kv_cols + kvh * HEAD_DIM, HEAD_DIM * 2, fb, pol);
+                    }
                 }
             }
         } else {
             if (lane == 0) {
                 const uint32_t i = g - n_qkv_tiles - n_kv_tiles;
-                const int rb = i / owins, win = i % owins;       // Wo [out][in]: 16 output rows x 256 of this group's input cols
+                // Wo [out][in]: 32 output rows x the 128 input cols of head qh0 + ho, as two swizzled [32 x 64] boxes
+                const int c0 = (qh0 + ho) * HEAD_DIM, r0 = rq * OROWS + (int)i * ROWS256;
                 dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                tma_load_2d(dst, &p.tm_wo, qh0 * HEAD_DIM + win * 256, rank * OROWS + rb * ROWS512, fb, pol);
+                tma_load_2d(dst, &p.tm_wo, c0, r0, fb, pol);
+                tma_load_2d(dst + 4096, &p.tm_wo, c0 + 64, r0, fb, pol);
             }
         }
         if constexpr (kPaged) {
@@ -324,7 +357,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         if (tid == 0) {
             prefetch_tmap(&p.tm_wqkv);
             prefetch_tmap(&p.tm_wo);
-            if constexpr (!kPaged) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); }
+            if (pool_maps) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); prefetch_tmap(&p.tm_kg); prefetch_tmap(&p.tm_vg); }
         }
         dsm::mbar_fence_init();
     }
@@ -336,10 +369,11 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     __half* xs = reinterpret_cast<__half*>(smem + S::XS);
     float* part = reinterpret_cast<float*>(smem + S::PART);
     float* attn_part = reinterpret_cast<float*>(smem + S::ATTN_PART);
-    float* mg = reinterpret_cast<float*>(smem + S::MG);
+    float* ml = reinterpret_cast<float*>(smem + S::ML);
+    float* opart = reinterpret_cast<float*>(smem + S::OPART);
     float* out_part = reinterpret_cast<float*>(smem + S::OUT_PART);
     float* qkv_fin = reinterpret_cast<float*>(smem + S::QKV_FIN);
-    float* ag2 = reinterpret_cast<float*>(smem + S::AG2);
+    float* attn_out = reinterpret_cast<float*>(smem + S::ATTN_OUT);
     float* red = reinterpret_cast<float*>(smem + S::RED);
     uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
 
@@ -349,7 +383,6 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     const bool residual_inplace = (static_cast<const void*>(rout) == static_cast<const void*>(rg));
     unsigned long long* qkv_ll = gp.qkv_ll + ((size_t)batch * G2_GROUPS_MAX + gid) * (2 * S::R);
     unsigned long long* attn_ll = gp.attn_ll + ((size_t)batch * G2_SLOTS + (size_t)gid * G) * (NQ * S::PAY);
-    unsigned long long* ag_ll = gp.ag_ll + ((size_t)batch * G2_GROUPS_MAX + gid) * (NQ * HEAD_DIM);
     unsigned* gcnt = gp.gcounters + (size_t)batch * G2_COUNTERS;
 
     // zero this warp's accumulation slots (smem only: legal before griddepcontrol.wait)
@@ -389,7 +422,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 rr[it] = make_uint4(0, 0, 0, 0);
             }
         }
-        const int own_lo = rank * OROWS, own_hi = own_lo + OROWS;       // residual_out slice written by group 0
+        const int own_lo = rank * (hidden / G), own_hi = own_lo + hidden / G;       // residual_out slice written by group 0
 #pragma unroll
         for (int it = 0; it < P0_ITERS; ++it) {
             const int e = (it * CONSUMER_THREADS + tid) * 8;
@@ -509,7 +542,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 const float rot = (d & 64) ? fmaf(a, cosp[i], b * sinp[i]) : fmaf(a, cosp[i], -b * sinp[i]);
                 const __half rh = __float2half_rn(rot);
                 // CUDA-core loop: q pre-scaled in fp32; mma loop: q must stay an exact fp16 value, the scale goes onto S
-                qkv_fin[e] = (hd < NQ && !kMma) ? __half2float(rh) * kScaleLog2 : __half2float(rh);
+                qkv_fin[e] = (hd < NQ && !use_mma) ? __half2float(rh) * kScaleLog2 : __half2float(rh);
                 if (hd == NQ && rank == 0 && writes_kv) {
                     if constexpr (kPaged) {
                         __half* kp = reinterpret_cast<__half*>(p.k_pool_ptrs[p.layer_id]);
@@ -537,7 +570,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 
     // ---- phase 2: flash-decode, NQ query heads share each K/V tile -------------------------------------
     {
-        if constexpr (kMma) {
+        if (use_mma) {
             // ---- tensor-core loop.  Per 16-key tile and warp: S[head][key] = Q K^T (M = 16 rows of which NQ = 4 are real
             // heads, N = 2 x 8 keys, K = 128 dims: 16 mma), online softmax on the C fragments (a head's 16 scores sit in one
             // quad), then O[head][dim] += P V (P's C fragments are the A fragments of the second product: 16 mma).  ~150
@@ -633,7 +666,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 for (int t = 0; t < 16; ++t)
                     *reinterpret_cast<float2*>(slot + 4 + t * 8 + t4 * 2) = make_float2(oacc[t][0], oacc[t][1]);
             }
-        } else {
+        } else if constexpr (kPaged) {
             const int sub = lane >> 4, c = lane & 15;
             float q8[NQ][8], o8[NQ][8], m[NQ], l[NQ];
     #pragma unroll
@@ -684,9 +717,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 for (int jj = 0; jj < 8; ++jj) {
                     const int row = 2 * jj + sub;
                     uint4 raw = vt[row * 16 + c];
-                    if constexpr (kPaged) {
-                        if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
-                    }
+                    if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
                     float v8[8];
                     unpack8(raw, v8);
     #pragma unroll
@@ -737,7 +768,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 a = fmaf(qkv_fin[warp * HEAD_DIM + lane * 4 + k], qkv_fin[NQ * HEAD_DIM + lane * 4 + k], a);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) red[CONSUMER_WARPS + warp] = kMma ? a * kScaleLog2 : a;
+            if (lane == 0) red[CONSUMER_WARPS + warp] = use_mma ? a * kScaleLog2 : a;
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
         for (int e = tid; e < NQ * HEAD_DIM; e += CONSUMER_THREADS) {
@@ -764,97 +795,97 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             ll_store(st + 4 + d, O, flag);
             if (d == 0) { ll_store(st, M, flag); ll_store(st + 1, L, flag); }
         }
-        // this CTA owns merged dims [rank*S2, +S2) of the group's NQ*128: gather [m, l, o[S2]] of every rank ...
-        const int S2 = NQ * HEAD_DIM / G;                        // 64 / 32 / 16 / 8 for G = 8 / 16 / 32 / 64
-        const int hh = (rank * S2) >> 7, d0 = (rank * S2) & 127;
+        // ---- exchange 2, the ONE hop: this CTA needs the merged state of query head `ho` only (its O-projection tiles are
+        //      that head's 128 input columns).  Gather [m, l] and o[128] of head ho from all G ranks: thread (part, d) =
+        //      (tid / 128, tid % 128) probes dim d of ranks [part*R3, ...), R3 = ceil(G / 3), all probes of a thread back to
+        //      back (one L2 round trip for up to 22 words per thread); threads 0 .. 2G-1 also fetch the (m, l) words. ----
         {
-            const int nw = G * (S2 + 2);                         // <= 640 words: at most two per thread
-            const unsigned long long* src[2];
-            unsigned long long w[2];
+            constexpr int RMAX = (G2_G_MAX + 2) / 3;                   // 22
+            const int R3 = (G + 2) / 3;
+            const int part = tid >> 7, d = tid & 127;
+            const int rlo = part * R3, rhi = min(G, rlo + R3);
+            const unsigned long long* obase = attn_ll + ho * S::PAY + 4 + d;
+            unsigned long long w[RMAX];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int i = tid + u * CONSUMER_THREADS;
-                const int r = i / (S2 + 2), j = i % (S2 + 2);
-                src[u] = attn_ll + (size_t)r * (NQ * S::PAY) + hh * S::PAY + (j < 2 ? j : 4 + d0 + (j - 2));
-                w[u] = i < nw ? ll_load(src[u]) : 0ull;
-            }
+            for (int j = 0; j < RMAX; ++j)
+                w[j] = (rlo + j < rhi) ? ll_load(obase + (size_t)(rlo + j) * (NQ * S::PAY)) : 0ull;
+            const unsigned long long* mlsrc = attn_ll + (size_t)(tid >> 1) * (NQ * S::PAY) + ho * S::PAY + (tid & 1);
+            unsigned long long wml = ((int)tid < 2 * G) ? ll_load(mlsrc) : 0ull;
+            if ((int)tid < 2 * G) ml[tid] = ll_resolve(mlsrc, wml, flag, p.header + 2);
+            float ov[RMAX];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int i = tid + u * CONSUMER_THREADS;
-                if (i < nw) mg[i] = ll_resolve(src[u], w[u], flag, p.header + 2);
-            }
-        }
-        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-        // ... merge them in rank order (deterministic) and publish the normalised, fp16-rounded slice (hop B)
-        if ((int)tid < S2) {
+            for (int j = 0; j < RMAX; ++j)
+                ov[j] = (rlo + j < rhi) ? ll_resolve(obase + (size_t)(rlo + j) * (NQ * S::PAY), w[j], flag, p.header + 2) : 0.f;
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            // merge in a fixed order (deterministic): every thread derives the same M and L from shared memory
             float M = -INFINITY;
-            for (int r = 0; r < G; ++r) M = fmaxf(M, mg[r * (S2 + 2)]);
-            float L = 0.f, O = 0.f;
-            for (int r = 0; r < G; ++r) {
-                const float w = dsm::exp2_diff(mg[r * (S2 + 2)], M);
-                L = fmaf(mg[r * (S2 + 2) + 1], w, L);
-                O = fmaf(mg[r * (S2 + 2) + 2 + tid], w, O);
-            }
-            ll_store(ag_ll + rank * S2 + tid, round_h(O / L), flag);   // attention output leaves as fp16 (eager model)
-        }
-        // every CTA reads the whole merged attention output of the group
-        {
-            constexpr int NA = NQ * HEAD_DIM;                    // 512 words: at most two per thread
-            unsigned long long w[2];
+            for (int r = 0; r < G; ++r) M = fmaxf(M, ml[2 * r]);
+            float O = 0.f;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int e = tid + u * CONSUMER_THREADS;
-                w[u] = e < NA ? ll_load(ag_ll + e) : 0ull;
+            for (int j = 0; j < RMAX; ++j)
+                if (rlo + j < rhi) O = fmaf(ov[j], dsm::exp2_diff(ml[2 * (rlo + j)], M), O);
+            opart[part * HEAD_DIM + d] = O;
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            if (tid < HEAD_DIM) {
+                float L = 0.f;
+                for (int r = 0; r < G; ++r) L = fmaf(ml[2 * r + 1], dsm::exp2_diff(ml[2 * r], M), L);
+                const float Osum = (opart[d] + opart[HEAD_DIM + d]) + opart[2 * HEAD_DIM + d];
+                attn_out[d] = round_h(Osum / L);                       // attention output leaves as fp16 (eager model)
             }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int e = tid + u * CONSUMER_THREADS;
-                if (e < NA) ag2[e] = ll_resolve(ag_ll + e, w[u], flag, p.header + 2);
-            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
         }
-        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
     CF_MARK(6);
 
-    // ---- phase 3: O GEMV for output rows [rank*OROWS, +OROWS) over this group's NQ*128 input columns --------
+    // ---- phase 3: O GEMV, output rows [rq*OROWS, +OROWS) x the 128 input columns of head qh0 + ho, on the tensor cores
+    //      (attention output on column 0 of N = 8; same loop as the MHA kernel's nn.Linear O phase) ----
     {
+        const int g4 = lane >> 2, t4 = lane & 3;
+        uint32_t ab[8][2];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) { ab[ks][0] = bfrag_col0(attn_out, ks * 16, lane); ab[ks][1] = bfrag_col0(attn_out, ks * 16 + 8, lane); }
         for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
-            const uint32_t g = gbase + i, s = ring_stage(g);
-            const int rb = i / owins, win = i % owins;
-            float a8[8];
-            {
-                const float4 a = *reinterpret_cast<const float4*>(ag2 + win * 256 + lane * 8);
-                const float4 b = *reinterpret_cast<const float4*>(ag2 + win * 256 + lane * 8 + 4);
-                a8[0] = a.x; a8[1] = a.y; a8[2] = a.z; a8[3] = a.w; a8[4] = b.x; a8[5] = b.y; a8[6] = b.z; a8[7] = b.w;
-            }
+            const uint32_t g = gbase + i, s_ = ring_stage(g);
             ring_wait_full(full_u32, g);
-            gemv_tile_16x256(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), a8,
-                             out_part + win * G2_OROWS_MAX + rb * ROWS512, lane);
+            const uint32_t st = smem_base + S::RING + s_ * STAGE_BYTES;
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    uint32_t af[4];
+                    ldsm_a_mrows(af, st + (ks >> 2) * 4096, mb * 16, (ks & 3) * 2, lane);
+                    mma16816(acc[mb], af, ab[ks][0], ab[ks][1]);
+                }
+            }
             __syncwarp();
             issue_tile(g + NSTAGES);
+            if (t4 == 0) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    out_part[i * ROWS256 + mb * 16 + g4] = acc[mb][0];
+                    out_part[i * ROWS256 + mb * 16 + g4 + 8] = acc[mb][2];
+                }
+            }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
     CF_MARK(7);
 
+    const int ncl = gp.n_groups * NQ;                    // partials per output column: one per (group, query head)
+    const int cid = gid * NQ + ho;                       // this CTA's index among the ncl CTAs that share row slice rq
     if (gridDim.y == 1 && p.out_ll != nullptr) {
-        // ---- cross-group reduction, batch == 1: publish the fp32 partial of this rank's output slice as (value, epoch)
-        //      words; the n_groups CTAs that share the slice each sum 1/n_groups of its columns over all groups in group
-        //      order (deterministic; see ll_finalize_columns in llama_decoder_kernel.cuh) ----
-        unsigned long long* mine = p.out_ll + (size_t)gid * hidden + rank * OROWS;
+        // ---- cross-head reduction, batch == 1: publish the fp32 partial of this CTA's row slice as (value, epoch) words; the
+        //      ncl CTAs that share the slice (one per group and query head) each sum 1/ncl of its columns over all of them
+        //      in (group, head) order (deterministic; see ll_finalize_columns in llama_decoder_kernel.cuh) ----
+        unsigned long long* mine = p.out_ll + (size_t)cid * hidden + rq * OROWS;
         for (int e = tid * 2; e < OROWS; e += CONSUMER_THREADS * 2) {
-            float2 v = *reinterpret_cast<const float2*>(out_part + e);
-#pragma unroll
-            for (int w = 1; w < owins; ++w) {
-                const float2 u = *reinterpret_cast<const float2*>(out_part + w * G2_OROWS_MAX + e);
-                v.x += u.x; v.y += u.y;
-            }
+            const float2 v = *reinterpret_cast<const float2*>(out_part + e);
             ll_store2(mine + e, v.x, v.y, flag);
         }
         CF_MARK(8);
-        const int ng = gp.n_groups;
-        const int lo = (int)((long long)gid * OROWS / ng), hi = (int)((long long)(gid + 1) * OROWS / ng);
-        ll_finalize_columns(p, p.out_ll, hidden, ng, rank * OROWS, lo, hi, flag, tp_flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
+        const int lo = (int)((long long)cid * OROWS / ncl), hi = (int)((long long)(cid + 1) * OROWS / ncl);
+        ll_finalize_columns(p, p.out_ll, hidden, ncl, rq * OROWS, lo, hi, flag, tp_flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
         // a CTA that got here has seen every group's partial of its slice, and a group only gets past its exchanges once
         // all of its CTAs are past phase 0: CTA 0 may bump the epoch and (in-place form) overwrite `residual`
         if (blockIdx.x == 0) {
@@ -878,21 +909,14 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         return;
     }
     // ---- cross-group reduction, batch > 1: fp32 red into scratch, last arriver of the slice finalises ----------------
-    float* scratch = p.scratch + (size_t)batch * hidden + rank * OROWS;
-    for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4) {
-        float4 v = *reinterpret_cast<const float4*>(out_part + e);
-#pragma unroll
-        for (int w = 1; w < owins; ++w) {
-            const float4 u = *reinterpret_cast<const float4*>(out_part + w * G2_OROWS_MAX + e);
-            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-        }
-        red_add_v4(scratch + e, v);
-    }
+    float* scratch = p.scratch + (size_t)batch * hidden + rq * OROWS;
+    for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4)
+        red_add_v4(scratch + e, *reinterpret_cast<const float4*>(out_part + e));
     __threadfence();
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     if (tid == 0) {
-        const unsigned prev = atomicAdd(&gcnt[rank], 1u);
-        sflags[0] = (prev == (unsigned)gp.n_groups - 1u);
+        const unsigned prev = atomicAdd(&gcnt[rq], 1u);
+        sflags[0] = (prev == (unsigned)ncl - 1u);
     }
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     CF_MARK(8);
@@ -902,13 +926,13 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             // a slice is finalised only after every group reached the end, so when the launch's last slice is, no CTA
             // will read another flag-in-data word: bump the workspace epoch for the next launch
             const unsigned prevf = atomicAdd(p.header + 1, 1u);
-            if (prevf == gridDim.y * (unsigned)G - 1u) { p.header[1] = 0u; p.header[0] = epoch + 1u; }
+            if (prevf == gridDim.y * (unsigned)(G / NQ) - 1u) { p.header[1] = 0u; p.header[0] = epoch + 1u; }
         }
         const bool fp32_out = p.flags & 1u;
         for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4) {
             const float4 v = ld_cg_v4(scratch + e);
             *reinterpret_cast<float4*>(scratch + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-            const size_t off = (size_t)batch * hidden + rank * OROWS + e;
+            const size_t off = (size_t)batch * hidden + rq * OROWS + e;
             if (fp32_out) {
                 *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
             } else {
@@ -917,13 +941,13 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
             }
         }
-        if (tid == 0) gcnt[rank] = 0u;
+        if (tid == 0) gcnt[rq] = 0u;
         if (residual_inplace) {
             __threadfence();
             dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
             if (tid == 0) {
                 const unsigned prev = atomicAdd(&gcnt[64], 1u);
-                sflags[1] = (prev == (unsigned)G - 1u);
+                sflags[1] = (prev == (unsigned)(G / NQ) - 1u);
                 if (sflags[1]) gcnt[64] = 0u;
             }
             dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);

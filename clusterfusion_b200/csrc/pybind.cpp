@@ -58,12 +58,17 @@ Tensor zeroed_bytes(const Tensor& like, size_t need, cudaStream_t stream) {
     const bool capturing = cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
     if (!capturing)
         return torch::zeros({(int64_t)need}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device()));
+    // relaxed mode: this thread may call cudaMalloc etc. while its stream is capturing.  The memset runs on a private
+    // NON-BLOCKING stream (the legacy stream would implicitly join the capturing stream and invalidate the capture).
     cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
     cudaThreadExchangeStreamCaptureMode(&mode);
     void* p = nullptr;
+    cudaStream_t side = nullptr;
     cudaError_t e = cudaMalloc(&p, need);
-    if (e == cudaSuccess) e = cudaMemset(p, 0, need);
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, need, side);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(side);
+    if (side) cudaStreamDestroy(side);
     cudaThreadExchangeStreamCaptureMode(&mode);
     TORCH_CHECK(e == cudaSuccess, "clusterfusion_b200: workspace allocation during stream capture failed: ", cudaGetErrorString(e));
     return torch::from_blob(p, {(int64_t)need}, [](void* q) { cudaFree(q); },

@@ -32,27 +32,27 @@ def close(a, b, rtol=RTOL, atol=ATOL):
     return ok
 
 
-def _ordered_fp16(t):
-    """fp16 bit patterns mapped to integers that are monotone in the value (so |a - b| = distance in fp16 ulps)."""
-    i = t.contiguous().view(torch.int16).to(torch.int32)
-    return torch.where(i < 0, -(i & 0x7FFF), i)
-
-
-def close_k(got, want, name="k"):
-    """K rows after RoPE: |k| reaches ~4-8, where ONE fp16 ulp is 3.9e-3 - 7.8e-3, i.e. already outside atol = rtol = 1e-3.
-    north_star's bar (rtol = atol = 1e-3) is therefore applied where it can hold, and the rest is stated in ulps: every
-    element is either inside the 1e-3 tolerance or at most 2 fp16 ulps from the oracle, and at most 0.1 % of the elements
-    are more than 1 ulp off (a 1-ulp flip = the two sides rounded a value sitting on a rounding boundary differently;
-    2 ulps = both inputs of a RoPE pair flipped).  Counts are printed."""
-    g16 = got.detach().to("cpu", torch.float16).reshape(-1)
-    w16 = want.detach().to("cpu", torch.float16).reshape(-1)
-    g, w = g16.float(), w16.float()
-    in_tol = (g - w).abs() <= ATOL + RTOL * w.abs()
-    ulps = (_ordered_fp16(g16) - _ordered_fp16(w16)).abs()
+def close_k(got, want, name="k", pairing="neox"):
+    """K rows after RoPE.  k = a cos - b sin mixes two fp16-rounded projections (a, b) of magnitude up to r = |(a, b)| =
+    |(k_i, k_pair(i))| ~ 4-8: ONE rounding flip of an input (the kernel and the oracle sum the 4096 products in different
+    orders, so a value sitting on a rounding boundary can land on either side) moves the output by ulp_fp16(r) = 3.9e-3 -
+    7.8e-3 however small the output itself came out -- already outside atol = rtol = 1e-3.  north_star's bar is therefore
+    applied where it can hold and the rest is stated in ulps of the pair magnitude: every element is inside the 1e-3
+    tolerance or within 2 ulp_fp16(r) of the oracle, and at most 0.1 % of the elements are more than 1 ulp_fp16(r) off.
+    Counts are printed.  pairing: neox = (i, i+64) (sglang / paged forms), gptj = (2i, 2i+1) (chat form)."""
+    g = got.detach().to("cpu", torch.float32).reshape(-1, 128)
+    w = want.detach().to("cpu", torch.float32).reshape(-1, 128)
+    if pairing == "neox":
+        r = torch.hypot(w[:, :64], w[:, 64:]).repeat(1, 2)
+    else:
+        r = torch.hypot(w[:, 0::2], w[:, 1::2]).repeat_interleave(2, dim=1)
+    ulp = torch.exp2(torch.floor(torch.log2(r.clamp_min(2.0 ** -14))) - 10)
+    err = (g - w).abs()
+    in_tol = err <= ATOL + RTOL * w.abs()
     n = g.numel()
-    n_out, n_gt1, n_gt2 = int((~in_tol).sum()), int((~in_tol & (ulps > 1)).sum()), int((~in_tol & (ulps > 2)).sum())
-    print(f"{name}: {n} elements, {n_out} outside rtol=atol=1e-3 (all <= {int(ulps[~in_tol].max()) if n_out else 0} ulp), "
-          f"{n_gt1} of them > 1 ulp, {n_gt2} > 2 ulp")
+    n_out, n_gt1, n_gt2 = int((~in_tol).sum()), int((~in_tol & (err > 1.001 * ulp)).sum()), int((~in_tol & (err > 2.001 * ulp)).sum())
+    print(f"{name}: {n} elements, {n_out} outside rtol=atol=1e-3, {n_gt1} of them > 1 ulp of the RoPE pair magnitude, {n_gt2} > 2 ulp"
+          + (f" (worst {float((err / ulp)[~in_tol].max()):.2f} ulp)" if n_out else ""))
     return n_gt2 == 0 and n_gt1 <= max(1, n // 1000) and bool(torch.isfinite(g).all())
 
 
@@ -133,7 +133,7 @@ def test_chat_operator_vs_oracle(kv_len):
     assert o.shape == (1, 4096) and k.shape == (1, 32, 128) and v.shape == (1, 32, 128)
     assert o.dtype == k.dtype == v.dtype == torch.float16
     assert close(v, want_v)
-    assert close_k(k, want_k)
+    assert close_k(k, want_k, pairing="gptj")
     assert close(o, want_o)
 
 
@@ -806,12 +806,13 @@ def test_errors_are_loud():
 # ---------------------------------------------------------------------------------------------------
 # long context (BASELINE configs 2-3: kv 16K / 64K) against the oracle run in full
 # ---------------------------------------------------------------------------------------------------
-def _paged_case(lens, seed, table="random", nslots_extra=37):
+def _paged_case(lens, seed, table="random", nslots_extra=37, shape=None):
     """Inputs + oracle result of a 15-argument call.  table: random = a permutation of the pool; sequential = one run of
     consecutive slots per request; runs = runs of 48/16/5/31/64/1/17 slots with gaps and backward jumps."""
+    shape = shape or S7
     bs = len(lens)
     nslots = sum(lens) + bs + nslots_extra
-    d = O.make_inputs(S7, nslots, seed=seed, layout="sglang", bs=bs)
+    d = O.make_inputs(shape, nslots, seed=seed, layout="sglang", bs=bs)
     need = sum(lens) + bs
     if table == "random":
         slots = torch.randperm(nslots, generator=torch.Generator().manual_seed(seed)).tolist()
@@ -837,33 +838,35 @@ def _paged_case(lens, seed, table="random", nslots_extra=37):
     cos_sin = torch.cat([pos_tab.cos(), pos_tab.sin()], 1).contiguous()
     kp, vp = d["k_cache"].clone(), d["v_cache"].clone()
     want_o, want_r = O.paged_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], indptr, indices, kp, vp,
-                                   d["rms_w"], 1e-5, positions, cos_sin, n_heads=32, mode="eager")
+                                   d["rms_w"], 1e-5, positions, cos_sin, n_heads=shape.n_heads, n_kv_heads=shape.n_kv_heads, mode="eager")
     return d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r
 
 
-def _run_paged_cabi(d, indptr, indices, positions, cos_sin, flags=0, host_pool_copy="right"):
+def _run_paged_cabi(d, indptr, indices, positions, cos_sin, flags=0, host_pool_copy="right", shape=None):
     """One 15-argument launch through the C ABI.  host_pool_copy: right = pass the host's copy of the pool addresses
     (tiled / gather4 KV fast paths), none = NULL (row-by-row gather), stale = a WRONG copy (the kernel must notice)."""
     import cabi_torch as CT
     from clusterfusion_b200 import cabi
+    shape = shape or S7
+    H = shape.hidden
     c = cuda(d)
     bs = d["x"].shape[0]
     kpool, vpool = c["k_cache"].clone(), c["v_cache"].clone()
     decoy_k, decoy_v = torch.zeros_like(kpool), torch.zeros_like(vpool)
     kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
     vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
-    out = torch.full((bs, 4096), float("nan"), dtype=torch.float16, device="cuda")
-    rout = torch.full((bs, 4096), float("nan"), dtype=torch.float16, device="cuda")
+    out = torch.full((bs, H), float("nan"), dtype=torch.float16, device="cuda")
+    rout = torch.full((bs, H), float("nan"), dtype=torch.float16, device="cuda")
     dev_t = (indptr.cuda(), indices.cuda(), positions.cuda(), cos_sin.cuda())
     hk = {"right": kpool, "stale": decoy_k, "none": None}[host_pool_copy]
     hv = {"right": vpool, "stale": decoy_v, "none": None}[host_pool_copy]
-    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=flags, hidden=4096, n_q_heads=32, n_kv_heads=32, head_dim=128,
-                         batch=bs, layer_id=0, eps=1e-5, x=c["x"].data_ptr(), residual_in=c["residual"].data_ptr(),
+    a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=flags, hidden=H, n_q_heads=shape.n_heads, n_kv_heads=shape.n_kv_heads,
+                         head_dim=128, batch=bs, layer_id=0, eps=1e-5, x=c["x"].data_ptr(), residual_in=c["residual"].data_ptr(),
                          residual_out=rout.data_ptr(), w_qkv=c["weight_qkv"].data_ptr(), w_o=c["weight_o"].data_ptr(),
                          rms_w=c["rms_w"].data_ptr(), out=out.data_ptr(), indptr=dev_t[0].data_ptr(), indices=dev_t[1].data_ptr(),
                          k_pool_ptrs=kptrs.data_ptr(), v_pool_ptrs=vptrs.data_ptr(), positions=dev_t[2].data_ptr(),
                          cos=dev_t[3].data_ptr(), k_cache=None if hk is None else hk.data_ptr(),
-                         v_cache=None if hv is None else hv.data_ptr(), workspace=CT.workspace(4096, bs, c["x"].device).data_ptr())
+                         v_cache=None if hv is None else hv.data_ptr(), workspace=CT.workspace(H, bs, c["x"].device).data_ptr())
     cabi.launch(a, CT.stream_handle())
     torch.cuda.synchronize()
     assert torch.equal(decoy_k.cpu(), torch.zeros_like(d["k_cache"]))
@@ -879,6 +882,21 @@ def test_paged_kv_fetch_paths_agree_with_oracle(table, host_pool_copy):
     from clusterfusion_b200 import cabi
     d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r = _paged_case([1000], seed=321, table=table)
     out, rout, kpool, vpool = _run_paged_cabi(d, indptr, indices, positions, cos_sin, host_pool_copy=host_pool_copy)
+    assert torch.equal(rout.cpu(), want_r)
+    assert close(out, want_o)
+    assert close_k(kpool, kp) and close(vpool, vp)
+
+
+@pytest.mark.parametrize("table", ["random", "sequential", "runs"])
+@pytest.mark.parametrize("host_pool_copy", ["right", "none", "stale"])
+@pytest.mark.parametrize("lens", [[1000], [333, 0, 2100]])
+def test_gqa_paged_kv_fetch_paths_agree_with_oracle(table, host_pool_copy, lens):
+    """Group kernel, paged form (Llama-3-8B shapes): with the host's copy of the pool addresses K/V arrive 128-byte swizzled
+    through tiled boxes (runs of 16 consecutive slots) or tile::gather4 (anything else, ragged last tiles included) and the
+    attention runs on the tensor cores; without it (or with a stale copy) the linear row gather + CUDA-core loop runs.
+    All against the oracle, batch 1 and a ragged batch of 3."""
+    d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r = _paged_case(lens, seed=808, table=table, shape=S8)
+    out, rout, kpool, vpool = _run_paged_cabi(d, indptr, indices, positions, cos_sin, host_pool_copy=host_pool_copy, shape=S8)
     assert torch.equal(rout.cpu(), want_r)
     assert close(out, want_o)
     assert close_k(kpool, kp) and close(vpool, vp)
@@ -928,7 +946,7 @@ def test_chat_operator_kv65536_vs_oracle():
     o, k, v = clusterfusion.llama_decoder_layer(c["x"], c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"],
                                                 c["rms_w"], c["cos"], c["sin"])
     torch.cuda.synchronize()
-    assert close(o, want_o) and close(v, want_v) and close_k(k, want_k)
+    assert close(o, want_o) and close(v, want_v) and close_k(k, want_k, pairing="gptj")
 
 
 def test_chat_form_growing_cache_64_tokens_like_the_reference_chat_loop():
@@ -964,7 +982,7 @@ def test_chat_form_growing_cache_64_tokens_like_the_reference_chat_loop():
                                                           ld["rms"], cos_d, sin_d)
             ld["ck"][pos:pos + 1] = xk.view(1, 4096)          # model.py:371-372
             ld["cv"][pos:pos + 1] = xv.view(1, 4096)
-            assert close(o, want_o) and close(xv, want_v) and close_k(xk, want_k, name=f"k[t={t}]")
+            assert close(o, want_o) and close(xv, want_v) and close_k(xk, want_k, name=f"k[t={t}]", pairing="gptj")
             worst = max(worst, float((o.float().cpu() - want_o.float()).abs().max()))
             h_dev = (h_dev + o.view(1, 1, 4096)) * 0.5          # keep activations O(1) over 128 layer calls
         if t == 0:

@@ -5,12 +5,15 @@ from pathlib import Path
 import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-lib_path = ROOT / "gpurun_out" / "libcf_trace.so"
-lib_path.parent.mkdir(exist_ok=True)
-extra = os.environ.get("CF_EXTRA_FLAGS", "").split()
-subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DCF_TRACE", *extra,
-                       "-Xcompiler", "-fPIC", "-shared", "-o", str(lib_path),
-                       str(ROOT / "clusterfusion_b200/csrc/llama_decoder.cu"), "-lcudart"])
+if os.environ.get("CF_TRACE_LIB"):          # a prebuilt -DCF_TRACE library (A/B of two kernel versions on one box)
+    lib_path = Path(os.environ["CF_TRACE_LIB"]).resolve()
+else:
+    lib_path = ROOT / "gpurun_out" / "libcf_trace.so"
+    lib_path.parent.mkdir(exist_ok=True)
+    extra = os.environ.get("CF_EXTRA_FLAGS", "").split()
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DCF_TRACE", *extra,
+                           "-Xcompiler", "-fPIC", "-shared", "-o", str(lib_path),
+                           str(ROOT / "clusterfusion_b200/csrc/llama_decoder.cu"), "-lcudart"])
 from clusterfusion_b200 import cabi
 lib = C.CDLL(str(lib_path))
 lib.cf_llama_decoder_layer_launch.argtypes = [C.POINTER(cabi.CfLlamaArgs), C.c_void_p]
@@ -31,7 +34,9 @@ layers = [dict(w_qkv=r((NH + 2 * NKV) * D, H, sc=0.02), w_o=r(H, NH * D, sc=0.02
                vn=torch.empty(NH * D, dtype=torch.float16, device=dev)) for _ in range(nl)]
 res = r(1, H)
 x = r(1, H); cos = torch.rand(1, D, device=dev); sin = torch.rand(1, D, device=dev)
-ws = torch.zeros(cabi.workspace_bytes(H, BS), dtype=torch.uint8, device=dev)
+lib.cf_llama_workspace_bytes.restype = C.c_size_t
+lib.cf_llama_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+ws = torch.zeros(lib.cf_llama_workspace_bytes(H, BS), dtype=torch.uint8, device=dev)
 if variant == 2:
     x = r(BS, H); res = r(BS, H)
     for lay in layers:
