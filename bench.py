@@ -725,7 +725,8 @@ def run_batched_paged(torch, cabi, dev, timed_replays, peak, kv=1024, nl=8, batc
                                      residual_out=bufs[li][1].data_ptr(), w_qkv=L[li]["w_qkv"].data_ptr(), w_o=L[li]["w_o"].data_ptr(),
                                      rms_w=L[li]["rms"].data_ptr(), out=bufs[li][0].data_ptr(), indptr=indptr.data_ptr(),
                                      indices=indices.data_ptr(), k_pool_ptrs=kptrs.data_ptr(), v_pool_ptrs=vptrs.data_ptr(),
-                                     positions=positions.data_ptr(), cos=cos_sin.data_ptr(), workspace=ws.data_ptr())
+                                     positions=positions.data_ptr(), cos=cos_sin.data_ptr(), workspace=ws.data_ptr(),
+                                     k_cache=pools[li][0].data_ptr(), v_cache=pools[li][1].data_ptr())   # host copy of the pool addresses, as the pybind shim passes
                 cabi.launch(a, st)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())

@@ -154,7 +154,9 @@ def load() -> C.CDLL:
     lib.cf_abi_version.restype = C.c_int
     lib.cf_sizeof_llama_args.restype = C.c_size_t
     lib.cf_sizeof_ffn_args.restype = C.c_size_t
-    if lib.cf_sizeof_llama_args() != C.sizeof(CfLlamaArgs) or lib.cf_sizeof_ffn_args() != C.sizeof(CfFfnArgs):
+    # CF_LIB_PATH experiments (tools/) may load an older build whose FFN / DeepSeek structs differ; the product never sets it
+    experiment = bool(os.environ.get("CF_LIB_PATH")) and os.environ.get("CF_SKIP_ABI_CHECK") == "1"
+    if not experiment and (lib.cf_sizeof_llama_args() != C.sizeof(CfLlamaArgs) or lib.cf_sizeof_ffn_args() != C.sizeof(CfFfnArgs)):
         raise ImportError(f"clusterfusion_b200.cabi: struct mirror out of date (CfLlamaArgs {C.sizeof(CfLlamaArgs)} vs "
                           f"{lib.cf_sizeof_llama_args()}, CfFfnArgs {C.sizeof(CfFfnArgs)} vs {lib.cf_sizeof_ffn_args()}): rebuild")
     lib.cf_sizeof_deepseek_args.restype = C.c_size_t
@@ -188,11 +190,12 @@ def load() -> C.CDLL:
     lib.cf_test_cluster_reduce.restype = C.c_int
     lib.cf_test_cluster_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_int32, C.c_void_p]
-    lib.cf_workspace_status.restype = C.c_int
-    lib.cf_workspace_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
-    lib.cf_workspace_clear_status.restype = C.c_int
-    lib.cf_workspace_clear_status.argtypes = [C.c_void_p, C.c_void_p]
-    lib.cf_debug_tensor_map_encodes.restype = C.c_uint64
+    if not experiment:
+        lib.cf_workspace_status.restype = C.c_int
+        lib.cf_workspace_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        lib.cf_workspace_clear_status.restype = C.c_int
+        lib.cf_workspace_clear_status.argtypes = [C.c_void_p, C.c_void_p]
+        lib.cf_debug_tensor_map_encodes.restype = C.c_uint64
     _lib = lib
     return lib
 

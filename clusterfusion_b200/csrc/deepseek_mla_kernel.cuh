@@ -12,19 +12,20 @@
  * with programmatic dependent launch so that each kernel's weight tiles are already in shared memory when the data it
  * depends on arrives; every byte of weights and cache leaves HBM once:
  *
- *  1. ds_proj_kernel   16 clusters of 8 CTAs, cluster = head.  CTA (h, r) takes hidden rows [256r, 256r+256) of the
- *     head's W_q_nope / W_q_pe columns and hidden rows [16c, 16c+16) (c = 8h + r) of the shared W_kv / W_k_pe, so the
- *     ckv / k_pe projection is computed ONCE, split 128 ways (fp32 `red.global.add.v4` into the workspace).  The 8
- *     partial q vectors are summed with cluster_reduce<8, LINEAR> over distributed shared memory (include/dsm.cuh);
- *     then CTA r computes latent columns [64r, 64r+64) of q_lat = q_nope . W_uk[head] and writes them to the
- *     workspace (the "all-gather" of the reference, :391-398, becomes a plain store because the next kernel is not
- *     organised by head).
+ *  1. ds_proj_kernel   16 clusters of 8 CTAs, cluster = head, 108 KB of shared memory so that all 16 clusters are resident at
+ *     once (at one CTA per SM a B200 holds only 15 clusters of 8: ncu launch__cluster_max_active).  CTA (h, r) takes hidden
+ *     rows [256r, 256r+256) of the head's W_q_nope / W_q_pe columns.  The 8 partial q vectors are summed with
+ *     cluster_reduce<8, LINEAR> over distributed shared memory (include/dsm.cuh); then CTA r computes latent columns
+ *     [64r, 64r+64) of q_lat = q_nope . W_uk[head] (tile fetched into the consumed W_q_nope bytes during the exchange) and
+ *     writes them to the workspace (the "all-gather" of the reference, :391-398, becomes a plain store because the next
+ *     kernel is not organised by head).
  *  2. ds_attn_kernel   128 CTAs, CTA = a contiguous slice of cache rows, ALL 16 heads at once: the heads are the M = 16
  *     rows of `mma.sync.m16n8k16`, so the cache is read once (not once per head) and QK^T / PV run on the tensor cores
  *     from 128-byte-swizzled TMA boxes (ldmatrix conflict-free).  Each CTA leaves an un-normalised flash-decode state
- *     (m, l, o[16][512]) in the workspace; a 129th CTA finishes the current token (fp16 ckv -> RMSNorm, RoPE on k_pe), which
- *     enters the merge as one more state.
- *  3. ds_out_kernel    16 clusters of 8, cluster = head.  CTA (h, r) merges the 129 states for latent columns
+ *     (m, l, o[16][512]) in the workspace.  The same CTA c also multiplies hidden rows [16c, 16c+16) into the shared W_kv /
+ *     W_k_pe columns, so the ckv / k_pe projection is computed ONCE per call, split 128 ways (fp32 `red.global.add.v4`).
+ *  3. ds_out_kernel    16 clusters of 8, cluster = head.  Every CTA finishes the current token from the complete sums (fp16
+ *     ckv -> RMSNorm, RoPE on k_pe, its head's score): one more flash-decode state.  CTA (h, r) merges the 129 states for latent columns
  *     [64r, 64r+64) of head h, multiplies by its 64 rows of W_uv[head], the 8 partial head outputs are summed with
  *     cluster_reduce<8, LINEAR>, then every CTA multiplies the head output by W_o[128h..128h+128, 256r..256r+256) and adds
  *     its fp32 partial to the workspace; the last of the 16 heads to arrive on a column slice rounds it to fp16.
@@ -95,44 +96,65 @@ __device__ __forceinline__ float ds_rope(const float* v, const float* cos, const
                            : v[i] * cos[i] + v[i - DS_ROPE / 2] * sin[i - DS_ROPE / 2];
 }
 
+// RMSNorm of the whole 2048-wide input row by one 256-thread CTA: xn = fp16(x * rsqrt(mean(x^2) + eps) * w), w8 = this
+// thread's 8 weights.  Ends without a barrier: the caller synchronises before reading xn.
+__device__ __forceinline__ void ds_rmsnorm_row(const __half* x, const float (&w8)[8], float eps, __half* xn, float* misc,
+                                               uint32_t tid, uint32_t lane, uint32_t warp) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + tid * 8), f);
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ss = fmaf(f[k], f[k], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) misc[warp] = ss;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < DS_THREADS / 32; ++i) t += misc[i];
+    const float rstd = rsqrtf(t / (float)DS_HIDDEN + eps);
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = __float2half_rn(f[k] * rstd * w8[k]);
+    *reinterpret_cast<uint4*>(xn + tid * 8) = *reinterpret_cast<const uint4*>(h);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // 1. projections
 // ------------------------------------------------------------------------------------------------------------------
 struct SmemDsProj {
-    // 134 KB, so that a CTA of this kernel fits on an SM NEXT TO a CTA of the previous call's output kernel (89 KB): with
-    // CF_FLAG_PDL its weight tiles stream in while that kernel is still running.  The W_kv / W_k_pe tiles are consumed first;
-    // their 18 KB are then reused for the cross-thread scratch and the cluster exchange (peers are held back by the cluster
-    // barrier, which this CTA arrives at only after its last read of the tiles).
+    // 108 KB: two CTAs of this kernel -- or one of this and one of the previous call's output kernel -- fit on an SM.  That
+    // matters twice: at one CTA per SM only 15 clusters of 8 are co-resident on a B200 (GPC sizes), so the 16 head clusters
+    // would run in TWO waves; and with CF_FLAG_PDL the weight tiles stream in while the previous kernel is still running.
+    // The W_q_nope tile is consumed first; its bytes then hold the W_uk tile (fetched while the q_pe product and the cluster
+    // exchange run), the exchange buffer and the exchange source.  Peers are held back by the cluster barrier, which this CTA
+    // arrives at only after its last read of the tile.
     static constexpr int WQ = 0;                                   // [256][128] halves
     static constexpr int WQPE = WQ + DS_KSLICE * DS_NOPE * 2;      // [256][64]
-    static constexpr int WKV = WQPE + DS_KSLICE * DS_ROPE * 2;     // [2 boxes][16][256]
-    static constexpr int WKPE = WKV + DS_KV_ROWS * DS_LORA * 2;    // [16][64]
-    static constexpr int WUK = WKPE + DS_KV_ROWS * DS_ROPE * 2;    // [128][64]
-    static constexpr int XN = WUK + DS_NOPE * 64 * 2;              // [2048] halves
-    static constexpr int MISC = XN + DS_HIDDEN * 2;                // warp sums
-    static constexpr int BARS = MISC + 64;                         // 4 mbarriers
+    static constexpr int XN = WQPE + DS_KSLICE * DS_ROPE * 2;      // [2048] halves
+    static constexpr int RED = XN + DS_HIDDEN * 2;                 // 2048 floats of cross-thread scratch
+    static constexpr int MISC = RED + 2048 * 4;                    // warp sums
+    static constexpr int BARS = MISC + 64;                         // 3 mbarriers
     static constexpr int TOTAL = BARS + 64;
-    // aliases inside [WKV, WUK)
-    static constexpr int RED = WKV;                                // 2048 floats of cross-thread scratch
-    static constexpr int RECV = RED + 2048 * 4;                    // 8 x 192 floats: one exchange, phase 0 only
+    // aliases inside the consumed W_q_nope tile
+    static constexpr int WUK = WQ;                                 // [128][64] halves
+    static constexpr int RECV = WUK + DS_NOPE * 64 * 2;            // 8 x 192 floats: one exchange, phase 0 only
     static constexpr int SRC = RECV + DS_CLUSTER * 192 * 4;        // 192 floats
-    static_assert(SRC + 192 * 4 <= WUK, "scratch must fit in the consumed W_kv / W_k_pe tiles");
+    static_assert(SRC + 192 * 4 <= WQPE, "aliases must fit in the W_q_nope tile");
+    static_assert(2 * (TOTAL + 1024) <= 228 * 1024, "two CTAs per SM");
 };
 
-__global__ void __launch_bounds__(DS_THREADS, 1)
+__global__ void __launch_bounds__(DS_THREADS, 2)
 ds_proj_kernel(const __grid_constant__ DsParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = dsm::cluster_ctarank();
     const uint32_t head = blockIdx.x / DS_CLUSTER;
-    const uint32_t cta = blockIdx.x;
     const uint32_t sb = dsm::smem_u32(smem);
-    const uint32_t bar_q = sb + SmemDsProj::BARS, bar_kv = bar_q + 8, bar_uk = bar_q + 16, bar_x = bar_q + 24;
+    const uint32_t bar_q = sb + SmemDsProj::BARS, bar_uk = bar_q + 8, bar_x = bar_q + 16;
     const __half* wq = reinterpret_cast<const __half*>(smem + SmemDsProj::WQ);
     const __half* wqpe = reinterpret_cast<const __half*>(smem + SmemDsProj::WQPE);
-    const __half* wkv = reinterpret_cast<const __half*>(smem + SmemDsProj::WKV);
-    const __half* wkpe = reinterpret_cast<const __half*>(smem + SmemDsProj::WKPE);
     const __half* wuk = reinterpret_cast<const __half*>(smem + SmemDsProj::WUK);
     __half* xn = reinterpret_cast<__half*>(smem + SmemDsProj::XN);
     float* red = reinterpret_cast<float*>(smem + SmemDsProj::RED);
@@ -142,21 +164,14 @@ ds_proj_kernel(const __grid_constant__ DsParams p)
 
     if (tid == 0) {
         dsm::mbar_init(bar_q, 1);
-        dsm::mbar_init(bar_kv, 1);
         dsm::mbar_init(bar_uk, 1);
         cluster_reduce_arm<DS_CLUSTER>(bar_x, 192 * 4);
         dsm::mbar_fence_init();
-        // weights do not depend on the previous kernel: fetch all of this CTA's tiles now
+        // weights do not depend on the previous kernel: fetch this CTA's q tiles now
         const uint64_t pol = policy_evict_first();
-        dsm::mbar_arrive_expect_tx(bar_kv, DS_KV_ROWS * DS_MLA * 2);
-        tma_load_2d(sb + SmemDsProj::WKV, &p.tm_wkv, 0, cta * DS_KV_ROWS, bar_kv, pol);
-        tma_load_2d(sb + SmemDsProj::WKV + DS_KV_ROWS * 256 * 2, &p.tm_wkv, 256, cta * DS_KV_ROWS, bar_kv, pol);
-        tma_load_2d(sb + SmemDsProj::WKPE, &p.tm_wk_pe, 0, cta * DS_KV_ROWS, bar_kv, pol);
         dsm::mbar_arrive_expect_tx(bar_q, DS_KSLICE * (DS_NOPE + DS_ROPE) * 2);
         tma_load_2d(sb + SmemDsProj::WQ, &p.tm_wq_nope, head * DS_NOPE, rank * DS_KSLICE, bar_q, pol);
         tma_load_2d(sb + SmemDsProj::WQPE, &p.tm_wq_pe, head * DS_ROPE, rank * DS_KSLICE, bar_q, pol);
-        dsm::mbar_arrive_expect_tx(bar_uk, DS_NOPE * 64 * 2);
-        tma_load_2d(sb + SmemDsProj::WUK, &p.tm_wuk, head * DS_LORA + rank * 64, 0, bar_uk, pol);
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     float w8[8];
@@ -164,50 +179,12 @@ ds_proj_kernel(const __grid_constant__ DsParams p)
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---- RMSNorm of the whole input row (4 KB; every CTA needs all of it) ----
-    {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(p.x + tid * 8), f);
-        float ss = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ss = fmaf(f[k], f[k], ss);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) misc[warp] = ss;
-        __syncthreads();
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < DS_THREADS / 32; ++i) t += misc[i];
-        const float rstd = rsqrtf(t / (float)DS_HIDDEN + p.eps);
-        __align__(16) __half h[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) h[k] = __float2half_rn(f[k] * rstd * w8[k]);
-        *reinterpret_cast<uint4*>(xn + tid * 8) = *reinterpret_cast<const uint4*>(h);
-    }
+    ds_rmsnorm_row(p.x, w8, p.eps, xn, misc, tid, lane, warp);
     __syncthreads();
 
-    // ---- shared ckv / k_pe projection: hidden rows [16 cta, 16 cta + 16), all 576 columns, fp32 partial -> workspace ----
-    dsm::mbar_wait(bar_kv, 0);
-    if (tid < DS_MLA / 4) {
-        const __half* base = tid < 128 ? wkv + (tid >> 6) * (DS_KV_ROWS * 256) + (tid & 63) * 4 : wkpe + (tid - 128) * 4;
-        const int stride = tid < 128 ? 256 : DS_ROPE;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < DS_KV_ROWS; ++i) {
-            const float xk = __half2float(xn[cta * DS_KV_ROWS + i]);
-            const uint2 u = *reinterpret_cast<const uint2*>(base + i * stride);
-            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-            a0 = fmaf(xk, lo.x, a0); a1 = fmaf(xk, lo.y, a1); a2 = fmaf(xk, hi.x, a2); a3 = fmaf(xk, hi.y, a3);
-        }
-        red_add_v4(p.ckv_acc + tid * 4, make_float4(a0, a1, a2, a3));
-    }
-    __syncthreads();                             // the W_kv / W_k_pe tiles are dead: their bytes become red / recv / src
-    dsm::cluster_arrive();                       // peers may push into this CTA from here on (exchange barrier armed at the top)
-
-    // ---- q_nope / q_pe partials over this CTA's 256 hidden rows ----
+    // ---- q_nope partial over this CTA's 256 hidden rows: 16 column groups of 8 x 16 row groups of 16 ----
     dsm::mbar_wait(bar_q, 0);
     {
-        // nope: 16 column groups of 8 x 16 row groups of 16
         const int cg = tid & 15, kg = tid >> 4;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
@@ -222,7 +199,13 @@ ds_proj_kernel(const __grid_constant__ DsParams p)
 #pragma unroll
         for (int j = 0; j < 8; ++j) red[kg * DS_NOPE + cg * 8 + j] = acc[j];
     }
-    __syncthreads();
+    __syncthreads();                             // the W_q_nope tile is dead: its bytes become W_uk / recv / src
+    if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the tile before the async-proxy write
+        dsm::mbar_arrive_expect_tx(bar_uk, DS_NOPE * 64 * 2);
+        tma_load_2d(sb + SmemDsProj::WUK, &p.tm_wuk, head * DS_LORA + rank * 64, 0, bar_uk, policy_evict_first());
+    }
+    dsm::cluster_arrive();                       // peers may push into this CTA from here on (exchange barrier armed at the top)
     if (tid < DS_NOPE) {
         float t = 0.f;
 #pragma unroll
@@ -231,7 +214,7 @@ ds_proj_kernel(const __grid_constant__ DsParams p)
     }
     __syncthreads();
     {
-        // pe: 8 column groups of 8 x 32 row groups of 8
+        // q_pe partial: 8 column groups of 8 x 32 row groups of 8
         const int cg = tid & 7, kg = tid >> 3;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
@@ -298,14 +281,16 @@ ds_proj_kernel(const __grid_constant__ DsParams p)
 // 2. attention over the latent cache: all heads per CTA on the tensor cores
 // ------------------------------------------------------------------------------------------------------------------
 struct SmemDsAttn {
-    // [n_stages x 36864 tile ring, 1024-aligned][q][current token][misc][barriers].  The ring has ONE stage when every
-    // CTA has at most one tile (seq_len <= 4097): 56 KB per CTA, so the CTAs of this kernel become resident NEXT TO the
-    // projection kernel's (137 KB) and their cache tile is in flight while that kernel still runs; otherwise DS_STAGES.
+    // [n_stages x 36864 tile ring, 1024-aligned][q][W_kv / W_k_pe rows][xn][misc][barriers].  The ring has ONE stage when every
+    // CTA has at most one tile (seq_len <= 4097): 78 KB per CTA, so the CTAs of this kernel become resident NEXT TO the
+    // projection kernel's (108 KB) and their tiles are in flight while that kernel still runs; otherwise DS_STAGES.
     static constexpr int Q_BYTES = DS_HEADS * DS_Q_STRIDE * 2;               // [16][DS_Q_STRIDE] halves
-    static constexpr int TOK_BYTES = DS_MLA * 4;                             // the current token's row (CTA 0)
-    static constexpr int TAIL = Q_BYTES + TOK_BYTES + 64 + 64;
+    static constexpr int WKV_BYTES = DS_KV_ROWS * DS_MLA * 2;                // [2 boxes][16][256] ++ [16][64] halves
+    static constexpr int XN_BYTES = DS_HIDDEN * 2;
+    static constexpr int TAIL = Q_BYTES + WKV_BYTES + XN_BYTES + 64 + 64;
     static constexpr int MERGE_STRIDE = DS_HEADS * 128 + 2 * DS_HEADS;       // floats per (column block) slot of the warp-pair merge
     static_assert(4 * MERGE_STRIDE * 4 <= DS_TILE_BYTES, "merge scratch reuses the first stage of the tile ring");
+    static_assert(DS_STAGES + 1 <= 8, "barriers: one per stage + one for the projection rows");
     __host__ __device__ static constexpr int total(int n_stages) { return n_stages * DS_TILE_BYTES + TAIL; }
 };
 
@@ -323,10 +308,15 @@ ds_attn_kernel(const __grid_constant__ DsParams p)
     const uint32_t sb = dsm::smem_u32(smem);
     const int n_stages = p.n_stages;
     const int q_off = n_stages * DS_TILE_BYTES;
+    const int wkv_off = q_off + SmemDsAttn::Q_BYTES;
+    const int xn_off = wkv_off + SmemDsAttn::WKV_BYTES;
     __half* qs = reinterpret_cast<__half*>(smem + q_off);
-    float* tok = reinterpret_cast<float*>(smem + q_off + SmemDsAttn::Q_BYTES);
-    float* misc = tok + DS_MLA;
-    const uint32_t bars = sb + q_off + SmemDsAttn::Q_BYTES + SmemDsAttn::TOK_BYTES + 64;
+    const __half* wkv = reinterpret_cast<const __half*>(smem + wkv_off);
+    const __half* wkpe = wkv + DS_KV_ROWS * DS_LORA;
+    __half* xn = reinterpret_cast<__half*>(smem + xn_off);
+    float* misc = reinterpret_cast<float*>(smem + xn_off + SmemDsAttn::XN_BYTES);
+    const uint32_t bars = sb + xn_off + SmemDsAttn::XN_BYTES + 64;
+    const uint32_t bar_kv = bars + 8 * DS_STAGES;
     const int split = blockIdx.x;
     const int row0 = split * p.rows_per_split;
     const int row1 = min(row0 + p.rows_per_split, p.n_rows);
@@ -334,75 +324,50 @@ ds_attn_kernel(const __grid_constant__ DsParams p)
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) dsm::mbar_init(bars + 8 * s, 1);
+        dsm::mbar_init(bar_kv, 1);
         dsm::mbar_fence_init();
-        // The cache is an input of the CALL, not a product of the projection kernel: its tiles may be fetched before the
-        // dependency resolves.  (Without CF_FLAG_PDL the projection kernel -- and so this one -- starts only after everything
-        // earlier on the stream has finished; with it the caller promises that no kernel in flight writes the cache.)
+        // The cache and the weights are inputs of the CALL, not products of the projection kernel: their tiles may be fetched
+        // before the dependency resolves.  (Without CF_FLAG_PDL the projection kernel -- and so this one -- starts only after
+        // everything earlier on the stream has finished; with it the caller promises that no kernel in flight writes the cache.)
         const uint64_t pol = policy_evict_first();
         for (int t = 0; t < min(ntiles, n_stages); ++t)
             ds_issue_tile(p, sb + t * DS_TILE_BYTES, bars + 8 * t, row0 + t * DS_TILE_ROWS, pol);
+        dsm::mbar_arrive_expect_tx(bar_kv, SmemDsAttn::WKV_BYTES);
+        tma_load_2d(sb + wkv_off, &p.tm_wkv, 0, split * DS_KV_ROWS, bar_kv, pol);
+        tma_load_2d(sb + wkv_off + DS_KV_ROWS * 256 * 2, &p.tm_wkv, 256, split * DS_KV_ROWS, bar_kv, pol);
+        tma_load_2d(sb + wkv_off + DS_KV_ROWS * DS_LORA * 2, &p.tm_wk_pe, 0, split * DS_KV_ROWS, bar_kv, pol);
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    float w8[8];
+    unpack8(*reinterpret_cast<const uint4*>(p.rms_in_w + tid * 8), w8);
     __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");           // q and the shared projection come from the projection kernel
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // q comes from the projection kernel, x from whatever preceded the call
     // q of all heads -> padded rows in shared memory (72 16-byte chunks per head)
     for (int i = tid; i < DS_HEADS * (DS_MLA / 8); i += DS_THREADS) {
         const int h = i / (DS_MLA / 8), c = i - h * (DS_MLA / 8);
         *reinterpret_cast<uint4*>(qs + h * DS_Q_STRIDE + c * 8) = *reinterpret_cast<const uint4*>(p.q + h * DS_MLA + c * 8);
     }
 
-    // ---- CTA number DS_SPLITS (one more than there are cache slices; it owns no rows and runs on an SM of its own):
-    //      finish the current token and publish it as state number DS_SPLITS ----
-    if (split == DS_SPLITS) {
-        float ss = 0.f;
-        float v[2];
+    // ---- shared ckv / k_pe projection, computed ONCE per call and split 128 ways: this CTA multiplies hidden rows
+    //      [16 split, 16 split + 16) into all 576 columns and adds its fp32 partial to the workspace.  It lives here rather than
+    //      in the projection kernel to keep that kernel at two CTAs per SM; the sums are complete when this kernel is. ----
+    ds_rmsnorm_row(p.x, w8, p.eps, xn, misc, tid, lane, warp);
+    __syncthreads();                                             // xn and qs visible
+    dsm::mbar_wait(bar_kv, 0);
+    if (tid < DS_MLA / 4) {
+        const __half* base = tid < 128 ? wkv + (tid >> 6) * (DS_KV_ROWS * 256) + (tid & 63) * 4 : wkpe + (tid - 128) * 4;
+        const int stride = tid < 128 ? 256 : DS_ROPE;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            v[k] = round_h(p.ckv_acc[tid + k * DS_THREADS]);
-            ss = fmaf(v[k], v[k], ss);
+        for (int i = 0; i < DS_KV_ROWS; ++i) {
+            const float xk = __half2float(xn[split * DS_KV_ROWS + i]);
+            const uint2 u = *reinterpret_cast<const uint2*>(base + i * stride);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+            a0 = fmaf(xk, lo.x, a0); a1 = fmaf(xk, lo.y, a1); a2 = fmaf(xk, hi.x, a2); a3 = fmaf(xk, hi.y, a3);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) misc[warp] = ss;
-        if (tid < DS_ROPE) tok[DS_LORA + tid] = round_h(p.ckv_acc[DS_LORA + tid]);       // un-rotated k_pe, staged
-        __syncthreads();
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < DS_THREADS / 32; ++i) t += misc[i];
-        const float rstd = rsqrtf(t / (float)DS_LORA + p.eps);
-        float kr = 0.f;
-        if (tid < DS_ROPE) kr = round_h(ds_rope(tok + DS_LORA, p.cos, p.sin, tid));
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int c = tid + k * DS_THREADS;
-            const float n = round_h(v[k] * rstd * __half2float(p.rms_ckv_w[c]));
-            tok[c] = n;
-            if (p.ckv_new) p.ckv_new[c] = __float2half_rn(n);
-        }
-        __syncthreads();                                   // every thread has read the un-rotated k_pe
-        if (tid < DS_ROPE) {
-            tok[DS_LORA + tid] = kr;
-            if (p.k_pe_new) p.k_pe_new[tid] = __float2half_rn(kr);
-        }
-        __syncthreads();
-        // scores of the 16 heads against the current token: warp w takes heads 2w, 2w+1
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int h = warp * 2 + hh;
-            float a = 0.f;
-            for (int c = lane; c < DS_MLA; c += 32) a = fmaf(__half2float(qs[h * DS_Q_STRIDE + c]), tok[c], a);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) {
-                p.part_ml[(DS_SPLITS * DS_HEADS + h) * 2] = a * p.scale_log2;
-                p.part_ml[(DS_SPLITS * DS_HEADS + h) * 2 + 1] = 1.f;
-            }
-        }
-        // its o is the token's latent, the same for every head: stored once
-        for (int i = tid; i < DS_LORA; i += DS_THREADS) p.part_o[(size_t)DS_SPLITS * DS_HEADS * DS_LORA + i] = tok[i];
-        return;
+        red_add_v4(p.ckv_acc + tid * 4, make_float4(a0, a1, a2, a3));
     }
-    __syncthreads();
 
     // ---- flash-decode over this CTA's rows.  Warp (rg, cb): rows rg*16..rg*16+15 of each tile, output columns cb*128.. ----
     const int rg = warp & 1, cb = warp >> 1;
@@ -535,7 +500,8 @@ struct SmemDsOut {
     static constexpr int SRC = RED + 2048 * 4;                     // 128 floats
     static constexpr int OLAT = SRC + DS_NOPE * 4;                 // 64 floats
     static constexpr int WGT = OLAT + 64 * 4;                      // 132 floats: merge weights of the states (+ pad)
-    static constexpr int MISC = WGT + 132 * 4;
+    static constexpr int TOK = WGT + 132 * 4;                      // 576 floats: the current token's cache row
+    static constexpr int MISC = TOK + DS_MLA * 4;
     static constexpr int BARS = MISC + 64;
     static constexpr int TOTAL = BARS + 64;
     static_assert(SmemDsProj::TOTAL + TOTAL + 2048 <= 228 * 1024, "a projection CTA and an output CTA must fit on one SM");
@@ -557,8 +523,9 @@ ds_out_kernel(const __grid_constant__ DsParams p)
     float* recv = reinterpret_cast<float*>(smem + SmemDsOut::RECV);
     float* olat = reinterpret_cast<float*>(smem + SmemDsOut::OLAT);
     float* wgt = reinterpret_cast<float*>(smem + SmemDsOut::WGT);
+    float* tok = reinterpret_cast<float*>(smem + SmemDsOut::TOK);
     float* misc = reinterpret_cast<float*>(smem + SmemDsOut::MISC);
-    __shared__ unsigned s_last;
+    __shared__ unsigned s_last, s_zero;
 
     if (tid == 0) {
         dsm::mbar_init(bar_uv, 1);
@@ -574,42 +541,83 @@ ds_out_kernel(const __grid_constant__ DsParams p)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // the shared projection has been consumed by the attention kernel: clear it for the next call
-    if (blockIdx.x == 0)
-        for (int i = tid; i < DS_MLA; i += DS_THREADS) p.ckv_acc[i] = 0.f;
-
-    // ---- merge the 129 flash-decode states of this head for latent columns [64 rank, 64 rank + 64) ----
+    // ---- merge the flash-decode states of this head for latent columns [64 rank, 64 rank + 64): 128 cache slices from the
+    //      attention kernel + the current token, which every CTA finishes for itself from the (now complete) fp32 sums of the
+    //      shared projection: fp16 ckv -> RMSNorm, RoPE on k_pe, the head's score ----
     {
         // thread (j, g) folds states g, g+4, ... of column j: their loads are issued first, so that they are in flight
-        // while the block works out the merge weights from the (m, l) pairs
+        // while the block works out the current token and the merge weights
         const int j = tid & 63, g = tid >> 6;
         const float* po = p.part_o + (size_t)head * DS_LORA + rank * 64 + j;
-        constexpr int NPER = (DS_STATES + 3) / 4;               // 33
+        constexpr int NPER = (DS_STATES + 3) / 4;               // 33; the last one of group 0 is the current token
         float v[NPER];
 #pragma unroll
         for (int i = 0; i < NPER; ++i) {
             const int s = g + 4 * i;
-            // state DS_SPLITS (the current token) keeps one [512] row for all heads
-            v[i] = s < DS_SPLITS ? po[(size_t)s * DS_HEADS * DS_LORA]
-                 : s == DS_SPLITS ? p.part_o[(size_t)DS_SPLITS * DS_HEADS * DS_LORA + rank * 64 + j] : 0.f;
+            v[i] = s < DS_SPLITS ? po[(size_t)s * DS_HEADS * DS_LORA] : 0.f;
         }
         float m = -INFINITY, l = 0.f;
-        if (tid < DS_STATES) {
+        if (tid < DS_SPLITS) {
             const float2 ml = *reinterpret_cast<const float2*>(p.part_ml + (tid * DS_HEADS + head) * 2);
             m = ml.x; l = ml.y;
         }
-        float mx = m;
+        const float c0 = round_h(p.ckv_acc[tid]), c1 = round_h(p.ckv_acc[tid + DS_THREADS]);
+        const float kraw = tid < DS_ROPE ? round_h(p.ckv_acc[DS_LORA + tid]) : 0.f;
+        const __half* qh = p.q + head * DS_MLA;
+        const float q0 = __half2float(qh[tid]), q1 = __half2float(qh[tid + DS_THREADS]);
+        const float q2 = tid < DS_ROPE ? __half2float(qh[DS_LORA + tid]) : 0.f;
+        const float g0 = __half2float(p.rms_ckv_w[tid]), g1 = __half2float(p.rms_ckv_w[tid + DS_THREADS]);
+        if (tid < DS_ROPE) tok[DS_LORA + tid] = kraw;                       // un-rotated k_pe, staged
+        float ss = fmaf(c0, c0, c1 * c1), mx = m;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) misc[warp] = mx;
+        for (int o = 16; o > 0; o >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) { misc[warp] = ss; misc[8 + warp] = mx; }
         __syncthreads();
-        float M = misc[0];
+        // every thread of this CTA has consumed its words of the shared projection: count the CTA as done with it.  The
+        // last CTA of the grid to get here clears the sums for the next call (nobody reads them after its own count).
+        if (tid == 0) {
+            __threadfence();
+            s_zero = atomicAdd(p.counters + DS_CLUSTER, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        float t = 0.f, Mst = -INFINITY;
 #pragma unroll
-        for (int i = 1; i < DS_THREADS / 32; ++i) M = fmaxf(M, misc[i]);
-        // the current token's state is always finite, so M is
-        const float w = tid < DS_STATES ? dsm::exp2_diff(m, M) : 0.f;
+        for (int i = 0; i < DS_THREADS / 32; ++i) { t += misc[i]; Mst = fmaxf(Mst, misc[8 + i]); }
+        const float rstd = rsqrtf(t / (float)DS_LORA + p.eps);
+        const float n0 = round_h(c0 * rstd * g0), n1 = round_h(c1 * rstd * g1);
+        const float kr = tid < DS_ROPE ? round_h(ds_rope(tok + DS_LORA, p.cos, p.sin, tid)) : 0.f;
+        tok[tid] = n0;
+        tok[tid + DS_THREADS] = n1;
+        if (blockIdx.x == 0 && p.ckv_new) {
+            p.ckv_new[tid] = __float2half_rn(n0);
+            p.ckv_new[tid + DS_THREADS] = __float2half_rn(n1);
+        }
+        __syncthreads();                                   // every thread has read the un-rotated k_pe and the warp results
+        if (tid < DS_ROPE) {
+            tok[DS_LORA + tid] = kr;
+            if (blockIdx.x == 0 && p.k_pe_new) p.k_pe_new[tid] = __float2half_rn(kr);
+        }
+        if (s_zero) {
+            for (int i = tid; i < DS_MLA; i += DS_THREADS) p.ckv_acc[i] = 0.f;
+            if (tid == 0) p.counters[DS_CLUSTER] = 0u;
+        }
+        // the head's score against the current token (q_pe is zero without DS_FLAG_ROPE_SCORES)
+        float sc = fmaf(q0, n0, q1 * n1) + q2 * kr;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        if (lane == 0) misc[warp] = sc;
+        __syncthreads();                                   // tok complete, score partials written
+        float score = 0.f;
+#pragma unroll
+        for (int i = 0; i < DS_THREADS / 32; ++i) score += misc[i];
+        const float m_new = score * p.scale_log2;
+        const float M = fmaxf(Mst, m_new);                 // finite: the current token always takes part
+        if (g == 0) v[NPER - 1] = tok[rank * 64 + j];      // state DS_SPLITS: o = the token's latent, l = 1
+        const float w = tid < DS_SPLITS ? dsm::exp2_diff(m, M) : tid == DS_SPLITS ? dsm::exp2_diff(m_new, M) : 0.f;
         if (tid < 132) wgt[tid] = w;
-        float wl = w * l;
+        float wl = w * (tid == DS_SPLITS ? 1.f : l);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wl += __shfl_xor_sync(0xffffffffu, wl, o);
         __syncthreads();                                   // misc read by everyone, wgt written

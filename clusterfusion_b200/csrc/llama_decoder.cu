@@ -336,9 +336,9 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, cfb::ROWS512, true))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, cfb::ROWS256, true))) return rc;
     } else {
-        // group kernel: CUDA-core QKV GEMV over unswizzled [16 x 256] tiles, tensor-core O GEMV over swizzled [32 x 64] boxes
+        // group kernel: CUDA-core GEMVs over unswizzled [16 x 256] tiles (512-byte row segments)
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 256, cfb::ROWS512))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, cfb::ROWS256, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 256, cfb::ROWS512))) return rc;
     }
     const bool group_kernel = gqa;
     if (!paged) {
@@ -367,7 +367,7 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         if ((rc = get_tensor_map(&kp.tm_vg, a->v_cache, 1ull << 24, kvd, 64, 1, true))) return rc;
         kp.k_base = static_cast<const __half*>(a->k_cache);
         kp.v_base = static_cast<const __half*>(a->v_cache);
-    } else if (!gqa && !batched && a->k_cache && a->v_cache) {
+    } else if (!gqa && a->k_cache && a->v_cache) {
         // optional fast paths of the paged form: the caller knows the pool addresses of this layer on the host (k_cache /
         // v_cache = its copy of k_pool_ptrs[layer_id] / v_pool_ptrs[layer_id]).  Tiles whose 16 rows sit in consecutive
         // slots are fetched with one tiled TMA load per tensor, all other full tiles with tile::gather4 requests (four
@@ -429,8 +429,6 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         const int n_groups = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
         if (n_groups > cfb::G2_GROUPS_MAX)
             return fail(CF_ERR_BAD_SHAPE, "GQA: at most %d (KV head, 4 query heads) groups per call (got %d)", cfb::G2_GROUPS_MAX, n_groups);
-        if (n_groups * 4 > a->hidden / 128)
-            return fail(CF_ERR_BAD_SHAPE, "GQA: at most hidden/128 = %d query heads per call (got %d)", a->hidden / 128, n_groups * 4);
         // The CTAs of a group spin on each other through L2, so a group must be co-resident (for batch 1: the whole grid,
         // because the output columns are summed across groups the same way).  Capacity = what the occupancy calculator says
         // this kernel can keep resident on this device (1 CTA / SM at its shared-memory footprint) -- G is the largest power
@@ -727,7 +725,7 @@ extern "C" int cf_deepseek_decoder_layer_launch(const CfDeepseekArgs* a, void* s
     if ((rc = ds_launch(cfb::ds_proj_kernel, 0, cfb::DS_HEADS * cfb::DS_CLUSTER, cfb::SmemDsProj::TOTAL, cfb::SmemDsProj::TOTAL, cfb::DS_CLUSTER, dp, pdl, stream))) return rc;
     // the two inner launches always overlap their prologues with the kernel before them; CF_FLAG_PDL decides only
     // whether the FIRST kernel may start before the caller's previous kernel on the stream has finished
-    if ((rc = ds_launch(cfb::ds_attn_kernel, 1, cfb::DS_SPLITS + 1, cfb::SmemDsAttn::total(cfb::DS_STAGES), cfb::SmemDsAttn::total(dp.n_stages), 1, dp, true, stream))) return rc;
+    if ((rc = ds_launch(cfb::ds_attn_kernel, 1, cfb::DS_SPLITS, cfb::SmemDsAttn::total(cfb::DS_STAGES), cfb::SmemDsAttn::total(dp.n_stages), 1, dp, true, stream))) return rc;
     return ds_launch(cfb::ds_out_kernel, 2, cfb::DS_HEADS * cfb::DS_CLUSTER, cfb::SmemDsOut::TOTAL, cfb::SmemDsOut::TOTAL, cfb::DS_CLUSTER, dp, true, stream);
 }
 

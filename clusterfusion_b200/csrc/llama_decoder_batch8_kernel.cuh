@@ -146,6 +146,9 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
     const uint64_t pol = policy_evict_first();
     const __half* kpool = reinterpret_cast<const __half*>(p.k_pool_ptrs[p.layer_id]);
     const __half* vpool = reinterpret_cast<const __half*>(p.v_pool_ptrs[p.layer_id]);
+    // host's copy of the pool addresses (tensor maps over the pools): used only if it agrees with the device table
+    const bool pool_maps = p.k_base != nullptr && kpool == p.k_base && vpool == p.v_base;
+    if (tid == 0 && pool_maps) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); prefetch_tmap(&p.tm_kg); prefetch_tmap(&p.tm_vg); }
 
     auto request_of = [&](uint32_t t) -> int {            // which request KV tile t (phase-local index) belongs to
         int b = 0;
@@ -183,17 +186,11 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
             const int rbeg = meta[b * 4 + 1], rend = meta[b * 4 + 2];
             const int i = (int)(t - tile0[b]);
             const int r = rbeg + i * ROWS512 + (lane & 15);
-            const bool valid = r < rend;
             const bool odd = (g / CONSUMER_WARPS) & 1u;
             const long long slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
             const int nvalid = min(ROWS512, rend - (rbeg + i * ROWS512));
-            if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
-            __syncwarp();
-            if (valid) {
-                const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
-                if (lane < 16) bulk_load_1d(d, kpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
-                else bulk_load_1d(d + STAGE_BYTES / 2, vpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
-            }
+            (void)r;
+            issue_kv_stage(p, pool_maps, false, dst, fb, head * HEAD_DIM, slot, nvalid, kpool, vpool, kv_cols, lane, pol);
         } else {
             if (lane == 0) {
                 const uint32_t i = g - n_qkv_tiles - n_kv_tiles;

@@ -14,11 +14,9 @@
  *               CTA publishes its row sums, every CTA reads all 768 back, adds the (at most two) parts in a fixed order
  *               and applies RoPE itself.
  *   exchange 2  softmax state: CTA r streams KV rows [r*chunk, ...) for all NQ query heads and publishes its
- *               NQ x [m, l, o[128]].  For the O projection CTA r owns ONE query head (r % NQ) and hidden*NQ/G output rows,
- *               so it needs the merged state of that head only: it gathers [m, l, o[128]] of its head from all G ranks
- *               (G x 130 words: 17 KB at G = 16, 68 KB at G = 64), merges them in a fixed order and normalises -- ONE
- *               hop.  (Round 1 split the O projection by output rows over all NQ*128 input columns, which needs the whole
- *               merged attention output in every CTA: reduce-scatter + all-gather, two hops, 4.9 us per layer.)
+ *               NQ x [m, l, o[128]]; CTA j merges dims [j*512/G, ...) over all G states in rank order and publishes the
+ *               normalised fp16-rounded result; every CTA reads the 512 merged values (reduce-scatter + all-gather: an
+ *               all-to-all of full states would be 67-270 KB per CTA through a ~64 GB/s SM port).
  *
  * Both exchanges use a flag-in-data protocol (what NCCL calls LL): every 64-bit word carries a float and the launch's
  * epoch, written with one st.relaxed.gpu.b64 and polled with ld.relaxed.gpu.b64 until the epoch matches.  No fence, no
@@ -28,8 +26,17 @@
  * CTA 0 once it has seen every group's output partial.  The TMA ring keeps landing the next phase's tiles while a CTA
  * waits.  The output partials of the groups are summed the same way (batch 1: ll_finalize_columns, deterministic; for
  * head-parallel shards the finalising CTAs also push / poll the peers' words over NVLink = the layer's all-reduce).
- * Attention over contiguous KV runs QK^T and PV on the tensor cores (mma.sync m16n8k16 on 128-byte-swizzled K/V tiles):
- * with 4 query heads per K/V row the CUDA-core loop is issue-bound.  Everything else -- the single 24 x 8 KB self-issuing
+ * Attention runs QK^T and PV on the tensor cores (mma.sync m16n8k16 on 128-byte-swizzled K/V tiles) whenever K/V arrive through
+ * tensor maps -- a contiguous cache, or a paged pool whose address the caller also passed on the host: full tiles of 16
+ * consecutive rows as tiled boxes, everything else (arbitrary page tables, a ragged last tile) through sm_100 tile::gather4
+ * requests of 4 rows x 128 B, whose swizzle pattern is a function of the shared-memory address and therefore composes into the
+ * same 8-row atoms (profiles/round2_gather4_probe.txt).  With 4 query heads per K/V row the CUDA-core loop is issue-bound;
+ * it remains for paged launches without the host-side pool address (linear 256-byte row copies cannot swizzle).
+ * Tried in round 2 and rejected on a same-box A/B (profiles/round2_gqa_onehop_vs_round1_same_box.txt, commit b31f9de):
+ * a ONE-hop softmax-state exchange (every CTA gathers the G states of one head and owns that head's 128 input columns in the
+ * O projection, tensor-core O GEMV over swizzled [32 x 64] boxes): exchange 2 + O phase 1.6 us shorter, but the 4x larger
+ * cross-CTA output reduction and the 128-byte row segments of the O tiles cost 3.8 us elsewhere (Llama-3-8B 24.2 / 27.8 us
+ * against 21.9 / 25.8).  Everything else -- the single 24 x 8 KB self-issuing
  * tile stream, fp32 reductions, fp16 rounding points of the eager model -- is as in the MHA kernel.
  * nn.Linear weight layout only (SGLANG / PAGED), NQ = 4 query heads per group; a KV head with 8 query heads (70B) gets
  * two groups.
@@ -49,7 +56,7 @@ namespace cfb {
 
 constexpr int G2_HIDDEN_MAX = 8192;
 constexpr int G2_RB_LOCAL_MAX = 8;        // 16-row blocks a CTA can touch in the QKV phase (48 / G whole + 1 partial, G >= 8)
-constexpr int G2_OROWS_MAX = 4096;        // output rows per CTA in the O phase: hidden * NQ / G (G >= 8, hidden <= 8192)
+constexpr int G2_OROWS_MAX = 1024;        // hidden / G
 constexpr int G2_GROUPS_MAX = 16;         // groups per request
 constexpr int G2_G_MAX = 64;              // CTAs per group
 constexpr int G2_SLOTS = 160;             // softmax-state slots per request (groups x G <= 148 whenever batch == 1)
@@ -63,22 +70,21 @@ struct SmemGqa2 {
     static constexpr int RING = 0;
     static constexpr int UNION = RING + NSTAGES * STAGE_BYTES;
     //   phase QKV : xs fp16[hidden <= 8192] | part fp32[12 warps][G2_RB_LOCAL_MAX][16]
-    //   phase ATTN: attn_part fp32[12][NQ][132] | ml fp32[G_MAX][2] | opart fp32[3][128]
-    //   phase O   : out_part fp32[G2_OROWS_MAX]
+    //   phase ATTN: attn_part fp32[12][NQ][132] | mg fp32[640]
+    //   phase O   : out_part fp32[NQ*128/256][G2_OROWS_MAX]
     static constexpr int XS = UNION;
     static constexpr int PART = UNION + G2_HIDDEN_MAX * 2;
     static constexpr int QKV_BYTES = G2_HIDDEN_MAX * 2 + CONSUMER_WARPS * G2_RB_LOCAL_MAX * ROWS512 * 4;
     static constexpr int ATTN_PART = UNION;                                // fp32 [12 warps][NQ][132]
-    static constexpr int ML = UNION + CONSUMER_WARPS * NQ * PAY * 4;       // fp32 [G2_G_MAX][2]: (m, l) of this CTA's head, per rank
-    static constexpr int OPART = ML + G2_G_MAX * 2 * 4;                    // fp32 [3][128]: partial merges of three rank ranges
-    static constexpr int ATTN_BYTES = CONSUMER_WARPS * NQ * PAY * 4 + G2_G_MAX * 2 * 4 + 3 * HEAD_DIM * 4;
+    static constexpr int MG = UNION + CONSUMER_WARPS * NQ * PAY * 4;       // fp32 [G][S2 + 2] <= 640 floats
+    static constexpr int ATTN_BYTES = CONSUMER_WARPS * NQ * PAY * 4 + 640 * 4;
     static constexpr int OUT_PART = UNION;
-    static constexpr int OUT_BYTES = G2_OROWS_MAX * 4;
+    static constexpr int OUT_BYTES = (NQ * HEAD_DIM / 256) * G2_OROWS_MAX * 4;
     static constexpr int UNION_SIZE = QKV_BYTES > ATTN_BYTES ? (QKV_BYTES > OUT_BYTES ? QKV_BYTES : OUT_BYTES)
                                                              : (ATTN_BYTES > OUT_BYTES ? ATTN_BYTES : OUT_BYTES);
     static constexpr int QKV_FIN = UNION + UNION_SIZE;                     // fp32[R] roped q*scale | k | v
-    static constexpr int ATTN_OUT = QKV_FIN + R * 4;                       // fp32[128] merged attention output of this CTA's head
-    static constexpr int RED = ATTN_OUT + HEAD_DIM * 4;                    // fp32[32]
+    static constexpr int AG2 = QKV_FIN + R * 4;                            // fp32[NQ*128] attention output
+    static constexpr int RED = AG2 + NQ * HEAD_DIM * 4;                    // fp32[32]
     static constexpr int BARS = RED + 32 * 4;                              // u64 full[NSTAGES]
     static constexpr int FLAGS = BARS + NSTAGES * 8;
     static constexpr int TOTAL = FLAGS + 16;
@@ -194,11 +200,9 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     using S = SmemGqa2<NQ>;
     static_assert(VARIANT != CHAT, "GQA uses the nn.Linear weight layout");
     constexpr bool kPaged = (VARIANT == PAGED);
-    // KV that arrives through tensor maps (tiled boxes over consecutive rows, tile::gather4 over arbitrary pool rows) is laid
-    // out 128-byte-swizzled, which makes ldmatrix conflict-free: QK^T and PV then run on the tensor cores (mma.sync
-    // m16n8k16).  That is every contiguous-cache launch, and every paged launch whose caller passed the pool addresses on
-    // the host (see `pool_maps`).  Paged launches without them gather linear 256-byte rows with bulk copies (which cannot
-    // swizzle) and keep the CUDA-core loop.
+    // contiguous KV arrives through TMA and can be laid out 128-byte-swizzled, which makes ldmatrix conflict-free: that
+    // variant runs QK^T and PV on the tensor cores (mma.sync m16n8k16).  Page-size-1 KV lands as linear 256-byte rows
+    // (bulk copies cannot swizzle) and keeps the CUDA-core loop.
     constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;      // 1/sqrt(128) * log2(e)
     const KParams& p = gp.k;
 
@@ -218,9 +222,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     const int kvh = gid / qsplit;
     const int qh0 = kvh * (Hq / Hkv) + (gid % qsplit) * NQ;     // first query head of this group
     const bool writes_kv = (gid % qsplit) == 0;
-    // O projection: CTA `rank` owns query head ho of the group and output rows [rq*OROWS, +OROWS)
-    const int ho = rank % NQ, rq = rank / NQ;
-    const int OROWS = hidden / (G / NQ);
+    const int OROWS = hidden / G;                        // this CTA's slice of the O output dim
     const int kv_cols = Hkv * HEAD_DIM;
     const int wins = hidden / 256;
 
@@ -242,7 +244,8 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     const uint32_t t_first = rank * n_qkv_tiles;                                 // group-level index of this CTA's first tile
     const int rb_first = t_first / wins;
     const uint32_t n_kv_tiles = (row_end - row_begin + ROWS512 - 1) / ROWS512;
-    const uint32_t n_o_tiles = OROWS / ROWS256;          // [32 output rows x this head's 128 input cols] per tile
+    constexpr int owins = NQ * HEAD_DIM / 256;
+    const uint32_t n_o_tiles = (OROWS / ROWS512) * owins;
 
     CF_MARK(0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -268,6 +271,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         if constexpr (kPaged) return p.indices[kv_base + r];
         else return r;
     };
+
     auto issue_tile = [&](uint32_t g) {
         if (g >= total_tiles) return;
         const uint32_t s = ring_stage(g);
@@ -335,11 +339,9 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         } else {
             if (lane == 0) {
                 const uint32_t i = g - n_qkv_tiles - n_kv_tiles;
-                // Wo [out][in]: 32 output rows x the 128 input cols of head qh0 + ho, as two swizzled [32 x 64] boxes
-                const int c0 = (qh0 + ho) * HEAD_DIM, r0 = rq * OROWS + (int)i * ROWS256;
+                const int rb = i / owins, win = i % owins;       // Wo [out][in]: 16 output rows x 256 of this group's input cols
                 dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                tma_load_2d(dst, &p.tm_wo, c0, r0, fb, pol);
-                tma_load_2d(dst + 4096, &p.tm_wo, c0 + 64, r0, fb, pol);
+                tma_load_2d(dst, &p.tm_wo, qh0 * HEAD_DIM + win * 256, rank * OROWS + rb * ROWS512, fb, pol);
             }
         }
         if constexpr (kPaged) {
@@ -369,11 +371,10 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     __half* xs = reinterpret_cast<__half*>(smem + S::XS);
     float* part = reinterpret_cast<float*>(smem + S::PART);
     float* attn_part = reinterpret_cast<float*>(smem + S::ATTN_PART);
-    float* ml = reinterpret_cast<float*>(smem + S::ML);
-    float* opart = reinterpret_cast<float*>(smem + S::OPART);
+    float* mg = reinterpret_cast<float*>(smem + S::MG);
     float* out_part = reinterpret_cast<float*>(smem + S::OUT_PART);
     float* qkv_fin = reinterpret_cast<float*>(smem + S::QKV_FIN);
-    float* attn_out = reinterpret_cast<float*>(smem + S::ATTN_OUT);
+    float* ag2 = reinterpret_cast<float*>(smem + S::AG2);
     float* red = reinterpret_cast<float*>(smem + S::RED);
     uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
 
@@ -383,6 +384,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
     const bool residual_inplace = (static_cast<const void*>(rout) == static_cast<const void*>(rg));
     unsigned long long* qkv_ll = gp.qkv_ll + ((size_t)batch * G2_GROUPS_MAX + gid) * (2 * S::R);
     unsigned long long* attn_ll = gp.attn_ll + ((size_t)batch * G2_SLOTS + (size_t)gid * G) * (NQ * S::PAY);
+    unsigned long long* ag_ll = gp.ag_ll + ((size_t)batch * G2_GROUPS_MAX + gid) * (NQ * HEAD_DIM);
     unsigned* gcnt = gp.gcounters + (size_t)batch * G2_COUNTERS;
 
     // zero this warp's accumulation slots (smem only: legal before griddepcontrol.wait)
@@ -422,7 +424,7 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 rr[it] = make_uint4(0, 0, 0, 0);
             }
         }
-        const int own_lo = rank * (hidden / G), own_hi = own_lo + hidden / G;       // residual_out slice written by group 0
+        const int own_lo = rank * OROWS, own_hi = own_lo + OROWS;       // residual_out slice written by group 0
 #pragma unroll
         for (int it = 0; it < P0_ITERS; ++it) {
             const int e = (it * CONSUMER_THREADS + tid) * 8;
@@ -795,97 +797,97 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             ll_store(st + 4 + d, O, flag);
             if (d == 0) { ll_store(st, M, flag); ll_store(st + 1, L, flag); }
         }
-        // ---- exchange 2, the ONE hop: this CTA needs the merged state of query head `ho` only (its O-projection tiles are
-        //      that head's 128 input columns).  Gather [m, l] and o[128] of head ho from all G ranks: thread (part, d) =
-        //      (tid / 128, tid % 128) probes dim d of ranks [part*R3, ...), R3 = ceil(G / 3), all probes of a thread back to
-        //      back (one L2 round trip for up to 22 words per thread); threads 0 .. 2G-1 also fetch the (m, l) words. ----
+        // this CTA owns merged dims [rank*S2, +S2) of the group's NQ*128: gather [m, l, o[S2]] of every rank ...
+        const int S2 = NQ * HEAD_DIM / G;                        // 64 / 32 / 16 / 8 for G = 8 / 16 / 32 / 64
+        const int hh = (rank * S2) >> 7, d0 = (rank * S2) & 127;
         {
-            constexpr int RMAX = (G2_G_MAX + 2) / 3;                   // 22
-            const int R3 = (G + 2) / 3;
-            const int part = tid >> 7, d = tid & 127;
-            const int rlo = part * R3, rhi = min(G, rlo + R3);
-            const unsigned long long* obase = attn_ll + ho * S::PAY + 4 + d;
-            unsigned long long w[RMAX];
+            const int nw = G * (S2 + 2);                         // <= 640 words: at most two per thread
+            const unsigned long long* src[2];
+            unsigned long long w[2];
 #pragma unroll
-            for (int j = 0; j < RMAX; ++j)
-                w[j] = (rlo + j < rhi) ? ll_load(obase + (size_t)(rlo + j) * (NQ * S::PAY)) : 0ull;
-            const unsigned long long* mlsrc = attn_ll + (size_t)(tid >> 1) * (NQ * S::PAY) + ho * S::PAY + (tid & 1);
-            unsigned long long wml = ((int)tid < 2 * G) ? ll_load(mlsrc) : 0ull;
-            if ((int)tid < 2 * G) ml[tid] = ll_resolve(mlsrc, wml, flag, p.header + 2);
-            float ov[RMAX];
-#pragma unroll
-            for (int j = 0; j < RMAX; ++j)
-                ov[j] = (rlo + j < rhi) ? ll_resolve(obase + (size_t)(rlo + j) * (NQ * S::PAY), w[j], flag, p.header + 2) : 0.f;
-            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-            // merge in a fixed order (deterministic): every thread derives the same M and L from shared memory
-            float M = -INFINITY;
-            for (int r = 0; r < G; ++r) M = fmaxf(M, ml[2 * r]);
-            float O = 0.f;
-#pragma unroll
-            for (int j = 0; j < RMAX; ++j)
-                if (rlo + j < rhi) O = fmaf(ov[j], dsm::exp2_diff(ml[2 * (rlo + j)], M), O);
-            opart[part * HEAD_DIM + d] = O;
-            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-            if (tid < HEAD_DIM) {
-                float L = 0.f;
-                for (int r = 0; r < G; ++r) L = fmaf(ml[2 * r + 1], dsm::exp2_diff(ml[2 * r], M), L);
-                const float Osum = (opart[d] + opart[HEAD_DIM + d]) + opart[2 * HEAD_DIM + d];
-                attn_out[d] = round_h(Osum / L);                       // attention output leaves as fp16 (eager model)
+            for (int u = 0; u < 2; ++u) {
+                const int i = tid + u * CONSUMER_THREADS;
+                const int r = i / (S2 + 2), j = i % (S2 + 2);
+                src[u] = attn_ll + (size_t)r * (NQ * S::PAY) + hh * S::PAY + (j < 2 ? j : 4 + d0 + (j - 2));
+                w[u] = i < nw ? ll_load(src[u]) : 0ull;
             }
-            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = tid + u * CONSUMER_THREADS;
+                if (i < nw) mg[i] = ll_resolve(src[u], w[u], flag, p.header + 2);
+            }
         }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        // ... merge them in rank order (deterministic) and publish the normalised, fp16-rounded slice (hop B)
+        if ((int)tid < S2) {
+            float M = -INFINITY;
+            for (int r = 0; r < G; ++r) M = fmaxf(M, mg[r * (S2 + 2)]);
+            float L = 0.f, O = 0.f;
+            for (int r = 0; r < G; ++r) {
+                const float w = dsm::exp2_diff(mg[r * (S2 + 2)], M);
+                L = fmaf(mg[r * (S2 + 2) + 1], w, L);
+                O = fmaf(mg[r * (S2 + 2) + 2 + tid], w, O);
+            }
+            ll_store(ag_ll + rank * S2 + tid, round_h(O / L), flag);   // attention output leaves as fp16 (eager model)
+        }
+        // every CTA reads the whole merged attention output of the group
+        {
+            constexpr int NA = NQ * HEAD_DIM;                    // 512 words: at most two per thread
+            unsigned long long w[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * CONSUMER_THREADS;
+                w[u] = e < NA ? ll_load(ag_ll + e) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * CONSUMER_THREADS;
+                if (e < NA) ag2[e] = ll_resolve(ag_ll + e, w[u], flag, p.header + 2);
+            }
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
     CF_MARK(6);
 
-    // ---- phase 3: O GEMV, output rows [rq*OROWS, +OROWS) x the 128 input columns of head qh0 + ho, on the tensor cores
-    //      (attention output on column 0 of N = 8; same loop as the MHA kernel's nn.Linear O phase) ----
+    // ---- phase 3: O GEMV for output rows [rank*OROWS, +OROWS) over this group's NQ*128 input columns --------
     {
-        const int g4 = lane >> 2, t4 = lane & 3;
-        uint32_t ab[8][2];
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) { ab[ks][0] = bfrag_col0(attn_out, ks * 16, lane); ab[ks][1] = bfrag_col0(attn_out, ks * 16 + 8, lane); }
         for (uint32_t i = first_tile(gbase, warp); i < n_o_tiles; i += CONSUMER_WARPS) {
-            const uint32_t g = gbase + i, s_ = ring_stage(g);
-            ring_wait_full(full_u32, g);
-            const uint32_t st = smem_base + S::RING + s_ * STAGE_BYTES;
-            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                    uint32_t af[4];
-                    ldsm_a_mrows(af, st + (ks >> 2) * 4096, mb * 16, (ks & 3) * 2, lane);
-                    mma16816(acc[mb], af, ab[ks][0], ab[ks][1]);
-                }
+            const uint32_t g = gbase + i, s = ring_stage(g);
+            const int rb = i / owins, win = i % owins;
+            float a8[8];
+            {
+                const float4 a = *reinterpret_cast<const float4*>(ag2 + win * 256 + lane * 8);
+                const float4 b = *reinterpret_cast<const float4*>(ag2 + win * 256 + lane * 8 + 4);
+                a8[0] = a.x; a8[1] = a.y; a8[2] = a.z; a8[3] = a.w; a8[4] = b.x; a8[5] = b.y; a8[6] = b.z; a8[7] = b.w;
             }
+            ring_wait_full(full_u32, g);
+            gemv_tile_16x256(reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES), a8,
+                             out_part + win * G2_OROWS_MAX + rb * ROWS512, lane);
             __syncwarp();
             issue_tile(g + NSTAGES);
-            if (t4 == 0) {
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                    out_part[i * ROWS256 + mb * 16 + g4] = acc[mb][0];
-                    out_part[i * ROWS256 + mb * 16 + g4 + 8] = acc[mb][2];
-                }
-            }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
     CF_MARK(7);
 
-    const int ncl = gp.n_groups * NQ;                    // partials per output column: one per (group, query head)
-    const int cid = gid * NQ + ho;                       // this CTA's index among the ncl CTAs that share row slice rq
     if (gridDim.y == 1 && p.out_ll != nullptr) {
-        // ---- cross-head reduction, batch == 1: publish the fp32 partial of this CTA's row slice as (value, epoch) words; the
-        //      ncl CTAs that share the slice (one per group and query head) each sum 1/ncl of its columns over all of them
-        //      in (group, head) order (deterministic; see ll_finalize_columns in llama_decoder_kernel.cuh) ----
-        unsigned long long* mine = p.out_ll + (size_t)cid * hidden + rq * OROWS;
+        // ---- cross-group reduction, batch == 1: publish the fp32 partial of this rank's output slice as (value, epoch)
+        //      words; the n_groups CTAs that share the slice each sum 1/n_groups of its columns over all groups in group
+        //      order (deterministic; see ll_finalize_columns in llama_decoder_kernel.cuh) ----
+        unsigned long long* mine = p.out_ll + (size_t)gid * hidden + rank * OROWS;
         for (int e = tid * 2; e < OROWS; e += CONSUMER_THREADS * 2) {
-            const float2 v = *reinterpret_cast<const float2*>(out_part + e);
+            float2 v = *reinterpret_cast<const float2*>(out_part + e);
+#pragma unroll
+            for (int w = 1; w < owins; ++w) {
+                const float2 u = *reinterpret_cast<const float2*>(out_part + w * G2_OROWS_MAX + e);
+                v.x += u.x; v.y += u.y;
+            }
             ll_store2(mine + e, v.x, v.y, flag);
         }
         CF_MARK(8);
-        const int lo = (int)((long long)cid * OROWS / ncl), hi = (int)((long long)(cid + 1) * OROWS / ncl);
-        ll_finalize_columns(p, p.out_ll, hidden, ncl, rq * OROWS, lo, hi, flag, tp_flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
+        const int ng = gp.n_groups;
+        const int lo = (int)((long long)gid * OROWS / ng), hi = (int)((long long)(gid + 1) * OROWS / ng);
+        ll_finalize_columns(p, p.out_ll, hidden, ng, rank * OROWS, lo, hi, flag, tp_flag, p.out, (p.flags & 1u) != 0, tid, CONSUMER_THREADS);
         // a CTA that got here has seen every group's partial of its slice, and a group only gets past its exchanges once
         // all of its CTAs are past phase 0: CTA 0 may bump the epoch and (in-place form) overwrite `residual`
         if (blockIdx.x == 0) {
@@ -909,14 +911,21 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         return;
     }
     // ---- cross-group reduction, batch > 1: fp32 red into scratch, last arriver of the slice finalises ----------------
-    float* scratch = p.scratch + (size_t)batch * hidden + rq * OROWS;
-    for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4)
-        red_add_v4(scratch + e, *reinterpret_cast<const float4*>(out_part + e));
+    float* scratch = p.scratch + (size_t)batch * hidden + rank * OROWS;
+    for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4) {
+        float4 v = *reinterpret_cast<const float4*>(out_part + e);
+#pragma unroll
+        for (int w = 1; w < owins; ++w) {
+            const float4 u = *reinterpret_cast<const float4*>(out_part + w * G2_OROWS_MAX + e);
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+        red_add_v4(scratch + e, v);
+    }
     __threadfence();
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     if (tid == 0) {
-        const unsigned prev = atomicAdd(&gcnt[rq], 1u);
-        sflags[0] = (prev == (unsigned)ncl - 1u);
+        const unsigned prev = atomicAdd(&gcnt[rank], 1u);
+        sflags[0] = (prev == (unsigned)gp.n_groups - 1u);
     }
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     CF_MARK(8);
@@ -926,13 +935,13 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             // a slice is finalised only after every group reached the end, so when the launch's last slice is, no CTA
             // will read another flag-in-data word: bump the workspace epoch for the next launch
             const unsigned prevf = atomicAdd(p.header + 1, 1u);
-            if (prevf == gridDim.y * (unsigned)(G / NQ) - 1u) { p.header[1] = 0u; p.header[0] = epoch + 1u; }
+            if (prevf == gridDim.y * (unsigned)G - 1u) { p.header[1] = 0u; p.header[0] = epoch + 1u; }
         }
         const bool fp32_out = p.flags & 1u;
         for (int e = tid * 4; e < OROWS; e += CONSUMER_THREADS * 4) {
             const float4 v = ld_cg_v4(scratch + e);
             *reinterpret_cast<float4*>(scratch + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-            const size_t off = (size_t)batch * hidden + rq * OROWS + e;
+            const size_t off = (size_t)batch * hidden + rank * OROWS + e;
             if (fp32_out) {
                 *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
             } else {
@@ -941,13 +950,13 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                 *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
             }
         }
-        if (tid == 0) gcnt[rq] = 0u;
+        if (tid == 0) gcnt[rank] = 0u;
         if (residual_inplace) {
             __threadfence();
             dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
             if (tid == 0) {
                 const unsigned prev = atomicAdd(&gcnt[64], 1u);
-                sflags[1] = (prev == (unsigned)(G / NQ) - 1u);
+                sflags[1] = (prev == (unsigned)G - 1u);
                 if (sflags[1]) gcnt[64] = 0u;
             }
             dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);

@@ -206,7 +206,9 @@ __device__ __forceinline__ float ll_resolve(const unsigned long long* p, unsigne
     return __uint_as_float((unsigned)w);
 }
 
-__device__ __forceinline__ unsigned ll_flag_of_epoch(unsigned epoch) { return epoch + 1u == 0u ? 1u : epoch + 1u; }
+// Flag of a launch epoch: never 0 (a zero-filled workspace must not match), different for any two CONSECUTIVE epochs including
+// across the 2^32 wrap of the counter (0xFFFFFFFF -> 0), and its low bit alternates strictly (the peer stage double-buffers on it).
+__device__ __forceinline__ unsigned ll_flag_of_epoch(unsigned epoch) { return 0x80000000u | (epoch & 0x7fffffffu); }
 
 // ---- the same words at SYSTEM scope: peer GPUs' memory over NVLink (an aligned 64-bit store is one transaction) ----
 __device__ __forceinline__ void ll_store_sys(unsigned long long* p, float v, unsigned flag) {
@@ -354,6 +356,51 @@ __device__ __forceinline__ void trace_mark(int slot, int launch_id) {
 #define CF_MARK(slot) ((void)0)
 #endif
 
+// Fill one KV stage of the MHA kernels -- 16 K rows (256 B each, head `col0 / 128`) in the first 4 KB, the 16 V rows in the
+// second -- from cache / pool rows `slot` (this lane's row is lane & 15; `nvalid` of the 16 rows exist).  Called warp-converged.
+// Three ways, all with the same shared-memory layout:
+//   tiled   one {128 x 16} TMA box per tensor -- 16 rows in consecutive slots (contiguous cache: always; paged: a sequence
+//           that grew without competition), 2 requests per stage;
+//   gather4 four arbitrary pool rows per request (sm_100 tile::gather4), 8 requests per stage;
+//   rows    one 256-byte bulk copy per row per tensor, 32 requests per stage -- the ragged last tile of a request, and paged
+//           launches whose caller did not pass the pool addresses on the host (`maps` false: no tensor map over the pool).
+__device__ __forceinline__ void issue_kv_stage(const KParams& p, bool maps, bool contiguous, uint32_t dst, uint32_t fb, int col0,
+                                               long long slot, int nvalid, const __half* kbase, const __half* vbase, int kv_cols,
+                                               uint32_t lane, uint64_t pol) {
+    bool tiled = maps && nvalid == ROWS512, gather = false;
+    if (tiled && !contiguous) {
+        const long long slot0 = __shfl_sync(0xffffffffu, slot, 0);
+        const bool run = __all_sync(0xffffffffu, slot == slot0 + (long long)(lane & 15));
+        gather = !run;
+        tiled = run;
+    }
+    if (tiled) {
+        if (lane == 0) {
+            dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+            tma_load_2d(dst, &p.tm_k, col0, (int)slot, fb, pol);
+            tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, col0, (int)slot, fb, pol);
+        }
+    } else if (gather) {
+        const int s1 = (int)__shfl_down_sync(0xffffffffu, slot, 1);
+        const int s2 = (int)__shfl_down_sync(0xffffffffu, slot, 2);
+        const int s3 = (int)__shfl_down_sync(0xffffffffu, slot, 3);
+        if (lane == 0) dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+        __syncwarp();
+        if ((lane & 3) == 0) {                          // lanes 0,4,8,12: K rows 4q..4q+3; lanes 16,..,28: V rows
+            const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2) + (lane < 16 ? 0 : STAGE_BYTES / 2);
+            tma_gather4_2d(d, lane < 16 ? &p.tm_kg : &p.tm_vg, col0, (int)slot, s1, s2, s3, fb, pol);
+        }
+    } else {
+        if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
+        __syncwarp();
+        if ((int)(lane & 15) < nvalid) {
+            const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
+            if (lane < 16) bulk_load_1d(d, kbase + slot * kv_cols + col0, HEAD_DIM * 2, fb, pol);
+            else bulk_load_1d(d + STAGE_BYTES / 2, vbase + slot * kv_cols + col0, HEAD_DIM * 2, fb, pol);
+        }
+    }
+}
+
 // ring bookkeeping: global tile index g -> (stage, parity)
 __device__ __forceinline__ uint32_t ring_stage(uint32_t g) { return g % NSTAGES; }
 __device__ __forceinline__ uint32_t ring_parity(uint32_t g) { return (g / NSTAGES) & 1u; }
@@ -481,48 +528,12 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             const uint32_t i = g - n_qkv_tiles;                 // 16 KV rows: K in the first 4 KB of the stage, V in the second
             const int r0 = row_begin + (int)i * ROWS512;
             const int nvalid = min(ROWS512, row_end - r0);
-            // Three ways to fill the stage, all with the same shared-memory layout:
-            //   tiled   one {128 x 16} TMA box per tensor -- 16 rows in consecutive slots (contiguous cache: always; paged: a
-            //           sequence that grew without competition), 2 requests per stage;
-            //   gather4 four arbitrary pool rows per request (sm_100 tile::gather4), 8 requests per stage;
-            //   rows    one 256-byte bulk copy per row per tensor, 32 requests per stage -- ragged last tile of a request,
-            //           and paged launches whose caller did not pass the pool addresses on the host (no tensor map).
             long long slot = r0 + (int)(lane & 15);             // contiguous cache: the row index itself
-            bool tiled = (nvalid == ROWS512), gather = false;
             if constexpr (kPaged) {
                 const bool odd = (g / CONSUMER_WARPS) & 1u;
                 slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
-                const long long slot0 = __shfl_sync(0xffffffffu, slot, 0);
-                const bool run = __all_sync(0xffffffffu, slot == slot0 + (long long)(lane & 15));
-                gather = pool_maps && tiled && !run;
-                tiled = pool_maps && tiled && run;
             }
-            if (tiled) {
-                if (lane == 0) {
-                    const int s0 = (int)slot;
-                    dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                    tma_load_2d(dst, &p.tm_k, head * HEAD_DIM, s0, fb, pol);
-                    tma_load_2d(dst + STAGE_BYTES / 2, &p.tm_v, head * HEAD_DIM, s0, fb, pol);
-                }
-            } else if (gather) {
-                const int s1 = (int)__shfl_down_sync(0xffffffffu, slot, 1);
-                const int s2 = (int)__shfl_down_sync(0xffffffffu, slot, 2);
-                const int s3 = (int)__shfl_down_sync(0xffffffffu, slot, 3);
-                if (lane == 0) dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                __syncwarp();
-                if ((lane & 3) == 0) {                          // lanes 0,4,8,12: K rows 4q..4q+3; lanes 16,..,28: V rows
-                    const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2) + (lane < 16 ? 0 : STAGE_BYTES / 2);
-                    tma_gather4_2d(d, lane < 16 ? &p.tm_kg : &p.tm_vg, head * HEAD_DIM, (int)slot, s1, s2, s3, fb, pol);
-                }
-            } else {
-                if (lane == 0) dsm::mbar_arrive_expect_tx(fb, nvalid * 2 * HEAD_DIM * 2);
-                __syncwarp();
-                if ((int)(lane & 15) < nvalid) {
-                    const uint32_t d = dst + (lane & 15) * (HEAD_DIM * 2);
-                    if (lane < 16) bulk_load_1d(d, kpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
-                    else bulk_load_1d(d + STAGE_BYTES / 2, vpool + slot * kv_cols + head * HEAD_DIM, HEAD_DIM * 2, fb, pol);
-                }
-            }
+            issue_kv_stage(p, pool_maps, !kPaged, dst, fb, head * HEAD_DIM, slot, nvalid, kpool, vpool, kv_cols, lane, pol);
         } else {
             if (lane == 0) {
                 const uint32_t i = g - n_qkv_tiles - n_kv_tiles;

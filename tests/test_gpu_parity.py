@@ -1008,3 +1008,27 @@ def test_workspace_status_word_round_trip():
     assert cabi.workspace_status(ws.data_ptr(), CT.stream_handle()) == 1
     cabi.workspace_clear_status(ws.data_ptr(), CT.stream_handle())
     assert cabi.workspace_status(ws.data_ptr(), CT.stream_handle()) == 0
+
+
+def test_flag_in_data_epoch_survives_the_32_bit_wrap():
+    """The launch epoch in the workspace header is a 32-bit counter bumped once per launch (10-100k launches/s in a serving
+    process: it wraps within hours).  Preset it to 0xFFFFFFFE and run launches across the wrap through both users of the
+    flag-in-data words -- the group kernel and the MHA kernel's CF_FLAG_LL_OUT path: every launch must still match the oracle
+    (consecutive flags distinct, never 0) and no poll may time out."""
+    import cabi_torch as ct
+    from clusterfusion_b200 import cabi
+    for shape, flags in ((S8, 0), (S7, cabi.CF_FLAG_LL_OUT)):
+        d = O.make_inputs(shape, 300, seed=9, layout="sglang")
+        want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"], d["rms_w"], 1e-5,
+                              d["cos"], d["sin"], n_heads=shape.n_heads, n_kv_heads=shape.n_kv_heads, mode="eager")
+        c = cuda(d)
+        ws = ct.workspace(shape.hidden, 1, c["x"].device)
+        torch.cuda.synchronize()
+        ws.view(torch.int32)[0] = -2                      # 0xFFFFFFFE
+        for it in range(5):
+            o, r, k, v = ct.sglang(c["x"], c["residual"], c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"], c["rms_w"], 1e-5,
+                                   c["cos"], c["sin"], n_heads=shape.n_heads, n_kv_heads=shape.n_kv_heads, flags=flags)
+            torch.cuda.synchronize()
+            assert close(o, want[0]), (shape, it)
+        hdr = ws[:16].view(torch.int32).cpu()
+        assert int(hdr[0]) == 3 and int(hdr[2]) == 0, hdr          # 0xFFFFFFFE + 5 launches = 3 (mod 2^32); no poll time-out

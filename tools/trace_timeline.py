@@ -87,9 +87,13 @@ for rep in range(3):          # back-to-back launches; the last repetition's mar
         launch(i, h); h = layers[i]["o"]
 torch.cuda.synchronize()
 t = trace.cpu().numpy().astype("int64")
+if os.environ.get("CF_TRACE_SAVE"):
+    import numpy as np
+    np.save(os.environ["CF_TRACE_SAVE"], t)
 print("variant", variant, "H", H, "heads", NH, NKV, "ctas", ncta)
 names = {0: "entry", 12: "first TMA issue", 1: "rms done", 2: "qkv tiles done", 3: "xchg1 done", 4: "rope done", 5: "kv tiles done",
-         6: "xchg2 done", 7: "o tiles done", 13: "prod last TMA", 8: "reds+counter", 9: "cta done"}
+         6: "xchg2 done", 7: "o tiles done", 13: "prod last TMA", 8: "reds+counter", 9: "cta done", 10: "state published",
+         11: "states read w0", 14: "states read all"}
 starts = [t[i][:, 0].min() for i in range(nl)]
 ends = [t[i][:, 9].max() for i in range(nl)]
 print("launch-to-launch (first CTA entry) us:", [round((starts[i + 1] - starts[i]) / 1e3, 2) for i in range(nl - 1)])
@@ -98,6 +102,8 @@ for li in (nl - 2,):
     T = t[li]
     t0 = T[:, 0].min()
     print(f"layer {li}: kernel span {(T[:, 9].max() - t0) / 1e3:.2f} us (kv={kv})")
-    for k in (0, 12, 1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for k in (0, 12, 1, 2, 3, 4, 5, 10, 11, 14, 6, 7, 8, 9):
+        if T[:, k].max() == 0:
+            continue
         v = (T[:, k] - t0) / 1e3
         print(f"  {names[k]:16s} min {v.min():7.2f}  med {sorted(v)[len(v)//2]:7.2f}  max {v.max():7.2f} us")
