@@ -266,6 +266,24 @@ def run_ours(args, rank, world, local_rank):
     x_dev = torch.randn(1, HIDDEN, device=dev).half()
     gr, keep = graph_of(layers, kv, x_dev)
 
+    # nn.Linear-layout copies of the same weights + paged-KV metadata for the 15-argument e2e leg (set-up, not timed)
+    def build_paged():
+        Lp = []
+        for lay in layers:
+            wq, wk, wv = lay["w_qkv"].view(3, HIDDEN, HIDDEN)                 # chat layout [W^T] -> nn.Linear layout
+            Lp.append(dict(w_qkv=torch.cat([wq.t(), wk.t(), wv.t()], 0).contiguous(), w_o=lay["w_o"].t().contiguous(),
+                           rms=lay["rms"], kpool=lay["k"], vpool=lay["v"]))
+        kptrs = torch.tensor([l["kpool"].data_ptr() for l in Lp], dtype=torch.uint64).to(dev)
+        vptrs = torch.tensor([l["vpool"].data_ptr() for l in Lp], dtype=torch.uint64).to(dev)
+        indptr = torch.tensor([0, kv + 1], dtype=torch.int32, device=dev)
+        indices = torch.arange(kv + 1, dtype=torch.int32, device=dev)
+        positions = torch.tensor([kv], dtype=torch.int64, device=dev)
+        inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2).float() / D))
+        ang = torch.outer(torch.arange(kv + 1).float(), inv)
+        cos_sin_tab = torch.cat([ang.cos(), ang.sin()], 1).contiguous().to(dev)
+        return Lp, kptrs, vptrs, indptr, indices, positions, cos_sin_tab
+    Lp, kptrs, vptrs, indptr, indices, positions, cos_sin_tab = build_paged()
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
@@ -335,22 +353,6 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- e2e, 15-argument paged form (the call the reference README shows, README.md:55-75): KV append, residual
     #      add and RoPE-table lookup are inside the kernel, so the step is 32 operator calls and nothing else
-    def build_paged():
-        Lp = []
-        for lay in layers:
-            wq, wk, wv = lay["w_qkv"].view(3, HIDDEN, HIDDEN)                 # chat layout [W^T] -> nn.Linear layout
-            Lp.append(dict(w_qkv=torch.cat([wq.t(), wk.t(), wv.t()], 0).contiguous(), w_o=lay["w_o"].t().contiguous(),
-                           rms=lay["rms"], kpool=lay["k"], vpool=lay["v"]))
-        kptrs = torch.tensor([l["kpool"].data_ptr() for l in Lp], dtype=torch.uint64).to(dev)
-        vptrs = torch.tensor([l["vpool"].data_ptr() for l in Lp], dtype=torch.uint64).to(dev)
-        indptr = torch.tensor([0, kv + 1], dtype=torch.int32, device=dev)
-        indices = torch.arange(kv + 1, dtype=torch.int32, device=dev)
-        positions = torch.tensor([kv], dtype=torch.int64, device=dev)
-        inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2).float() / D))
-        ang = torch.outer(torch.arange(kv + 1).float(), inv)
-        cos_sin_tab = torch.cat([ang.cos(), ang.sin()], 1).contiguous().to(dev)
-        return Lp, kptrs, vptrs, indptr, indices, positions, cos_sin_tab
-    Lp, kptrs, vptrs, indptr, indices, positions, cos_sin_tab = build_paged()
     bufs = [torch.empty(1, HIDDEN, dtype=torch.float16, device=dev) for _ in range(4)]
     zero_res = torch.zeros(1, HIDDEN, dtype=torch.float16, device=dev)
     x_host2 = x_host.view(1, HIDDEN)
@@ -883,6 +885,11 @@ def run_full_model(torch, dist, dev, world, peak, kv0=1024, n_tok=128, shape_nam
             out[mode]["h2d_d2h_bytes_per_token"] = 16
         del eng
         torch.cuda.empty_cache()
+    if shape_name == "llama2-7b" and "fused_attn_fused_ffn" in out:
+        # the one end-to-end figure the reference publishes (assets/example.gif, 1x H100, Llama-2-7B chat,
+        # max_seq_len 1024, wall clock incl. prefill / detokenisation / printing) -- other hardware, other timing: context only
+        out["reference_published_h100_chat_tokens_per_s"] = 127.46
+        out["ratio_to_reference_published_h100"] = round(out["fused_attn_fused_ffn"]["tokens_per_s_host_step"] / 127.46, 2)
     if "fused" in out and "eager" in out:
         out["speedup_fused_attention_vs_eager"] = round(out["fused"]["tokens_per_s"] / out["eager"]["tokens_per_s"], 3)
     if "fused_attn_fused_ffn" in out and "eager" in out:

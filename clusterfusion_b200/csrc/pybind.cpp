@@ -485,6 +485,24 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("set_check_status", [](bool on) { g_check_status.store(on); },
           "debug mode: after every launch read the workspace's sticky error word back (synchronises) and raise on an "
           "in-kernel exchange time-out");
+    m.def("workspace_status", []() {
+              // sticky error words of every workspace this module owns (synchronises their streams): 0 = all launches so far
+              // completed their in-kernel exchanges; non-zero = some launch timed out waiting for a peer CTA / rank
+              std::vector<std::pair<void*, void*>> ws;
+              {
+                  std::lock_guard<std::mutex> lk(g_ws_mu);
+                  for (auto& kv : g_ws_cache) ws.emplace_back(kv.second.buf.data_ptr(), std::get<1>(kv.first));
+              }
+              uint32_t worst = 0;
+              for (auto& w : ws) {
+                  uint32_t st = 0;
+                  const int rc = cf_workspace_status(w.first, w.second, &st);
+                  TORCH_CHECK(rc == 0, "clusterfusion_b200: cf_workspace_status failed (", rc, "): ", cf_last_error_string());
+                  worst |= st;
+              }
+              return worst;
+          },
+          "OR of the sticky error words of all workspaces owned by this module (0 = ok); synchronises their streams");
     m.def("tensor_map_encodes", []() { return cf_debug_tensor_map_encodes(); },
           "cuTensorMapEncodeTiled calls made by the library so far (0 per token in a steady-state decode loop)");
     // called from an atexit hook of the Python package: CUDA tensors must not be destroyed by static destructors after the

@@ -205,14 +205,24 @@ class LlamaDecodeEngine:
         else:
             self._step_body()
 
+    def check_status(self) -> None:
+        """Raise if an exchange poll inside one of the fused kernels ever timed out (CTAs of a group not co-resident because
+        another kernel held SMs, a stalled peer rank): the tokens produced since are invalid.  Synchronises."""
+        if self._cf.workspace_status() != 0:
+            raise RuntimeError("clusterfusion_b200: an in-kernel exchange timed out; decode results since the last check are invalid")
+
     @torch.no_grad()
-    def step_host(self, token_id: int) -> int:
-        """User-facing step: token id in from the host, next token id back to the host."""
+    def step_host(self, token_id: int, check_every: int = 64) -> int:
+        """User-facing step: token id in from the host, next token id back to the host.  Every `check_every` tokens the
+        workspaces' error words are read back as well (0 disables)."""
         self._host_in[0] = token_id
         self.token.copy_(self._host_in, non_blocking=True)
         self.step()
         self._host_out.copy_(self.token, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        self._host_steps = getattr(self, "_host_steps", 0) + 1
+        if check_every and self._host_steps % check_every == 0:
+            self.check_status()
         return int(self._host_out[0])
 
     def bytes_per_token(self, kv_len: int) -> int:

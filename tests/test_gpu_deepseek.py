@@ -139,3 +139,20 @@ def test_properties_at_long_cache():
     o1, _, _ = run(e, seq_len=1)
     torch.cuda.synchronize()
     assert close(o4, o1, 2e-3), float((o4.float() - o1.float()).abs().max())
+
+
+def test_deepseek_layer_vs_the_reference_kernels_race_free_output():
+    """CUDA path against the golden vector the reference's own kernel produced on B200 under compute-sanitizer memcheck
+    (tests/golden/deepseek_ref_kernel_seq4096.npz; see tests/test_oracle_deepseek.py for the tolerance)."""
+    import numpy as np
+    from conftest import GOLDEN
+    from oracle.gen_golden_deepseek_ref import inputs_digest
+    z = np.load(GOLDEN / "deepseek_ref_kernel_seq4096.npz")
+    d = D.make_inputs(int(z["seq_len"]), seed=int(z["seed"]), out_gain=float(z["out_gain"]))
+    assert inputs_digest(d) == str(z["inputs_sha256"])
+    c = {k: v.cuda() for k, v in d.items()}
+    o, _, _ = run(c)
+    torch.cuda.synchronize()
+    err = float((o.float().cpu().reshape(-1) - torch.from_numpy(z["out"]).float()).abs().max())
+    print(f"ours vs reference kernel: max |diff| {err:.4f}")
+    assert err <= 1e-2

@@ -1032,3 +1032,31 @@ def test_flag_in_data_epoch_survives_the_32_bit_wrap():
             assert close(o, want[0]), (shape, it)
         hdr = ws[:16].view(torch.int32).cpu()
         assert int(hdr[0]) == 3 and int(hdr[2]) == 0, hdr          # 0xFFFFFFFE + 5 launches = 3 (mod 2^32); no poll time-out
+
+
+def test_soak_10000_launches_as_the_reference_test_runs_them():
+    """/root/reference/tests/test_llama.py:17-22, :143-157 launches the 10-argument operator `test_run = 10000` times on the same
+    inputs (kv_len 4096, a fresh residual clone per launch) and asserts nothing.  Same loop here, with the asserts: every 500th
+    output is kept and all of them must match the oracle, agree with the first to 1 fp16 ulp (the cross-head fp32 sum is the
+    only order-dependent step), the in-place residual must be right on the last launch, and no workspace word may be left set."""
+    import clusterfusion
+    d = O.make_inputs(S7, 4096, seed=4242, layout="sglang")
+    want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"], d["rms_w"], 1e-6,
+                          d["cos"], d["sin"], n_heads=32, mode="eager")
+    c = cuda(d)
+    kept = []
+    for i in range(10000):
+        tmp_residual = c["residual"].clone()
+        o, r, k, v = clusterfusion.llama_decoder_layer_sglang(c["x"], tmp_residual, c["weight_qkv"], c["weight_o"], c["k_cache"],
+                                                              c["v_cache"], c["rms_w"], 1e-6, c["cos"], c["sin"])
+        if i % 500 == 0 or i == 9999:
+            kept.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(r.cpu(), want[1])
+    ref = kept[0].float()
+    ulp = torch.maximum(ref.abs() * 2 ** -10, torch.full_like(ref, 2 ** -24))
+    for o in kept:
+        assert close(o, want[0])
+        assert bool(((o.float() - ref).abs() <= ulp).all())
+    assert close(v, want[3]) and close_k(k, want[2])
+    assert clusterfusion.workspace_status() == 0
