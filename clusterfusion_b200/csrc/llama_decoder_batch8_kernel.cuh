@@ -99,24 +99,33 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
     uint32_t* tile0 = reinterpret_cast<uint32_t*>(smem + S::META) + BC * 4;   // [9]
     uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
 
-    // ---- per-request KV ranges -> shared memory (8 requests x 5 words would not stay in registers) ----------------
-    if (tid == 0) {
-        uint32_t acc = 0;
-        tile0[0] = 0;
-        for (int b = 0; b < BC; ++b) {
-            int len = 0, kb = 0, ns = 0;
-            if (b < nb) {
-                kb = p.indptr[b0 + b];
-                const int end = p.indptr[b0 + b + 1] - 1;
-                len = end - kb;
-                ns = p.indices[end];
-            }
-            const int chunk = (((len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);
-            const int rb = min((int)rank * chunk, len), re = min(rb + chunk, len);
+    // ---- per-request KV ranges -> shared memory (8 requests x 5 words would not stay in registers).  Lane b of warp 0 handles
+    //      request b (the eight index loads go out together), the tile offsets are a warp prefix sum: no single-thread loop
+    //      in front of the block barrier (compute-sanitizer synccheck flagged the warp as divergent at that barrier when
+    //      thread 0 alone walked the requests -- second chunk of a batch of 9, profiles/round2_sanitizer.txt). ----
+    if (warp == 0) {
+        const int b = (int)lane;
+        int len = 0, kb = 0, ns = 0;
+        if (b < nb) {
+            kb = p.indptr[b0 + b];
+            const int end = p.indptr[b0 + b + 1] - 1;
+            len = end - kb;
+            ns = p.indices[end];
+        }
+        const int chunk = (((len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);
+        const int rb = min((int)rank * chunk, len), re = min(rb + chunk, len);
+        uint32_t acc = (b < BC) ? (uint32_t)((re - rb + ROWS512 - 1) / ROWS512) : 0u;
+#pragma unroll
+        for (int o = 1; o < BC; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, acc, o);
+            if ((int)lane >= o) acc += v;
+        }
+        if (b < BC) {
             meta[b * 4 + 0] = kb; meta[b * 4 + 1] = rb; meta[b * 4 + 2] = re; meta[b * 4 + 3] = ns;
-            acc += (re - rb + ROWS512 - 1) / ROWS512;
             tile0[b + 1] = acc;
         }
+        if (lane == 0) tile0[0] = 0;
+        __syncwarp();
     }
     if (lane == 0) {
         dsm::mbar_init(full_u32 + 8 * warp, 1);

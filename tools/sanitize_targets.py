@@ -1,7 +1,8 @@
 """One launch of every kernel at small kv_len, for compute-sanitizer (memcheck / racecheck / synccheck):
     compute-sanitizer --tool memcheck python tools/sanitize_targets.py"""
-import sys, torch
+import os, sys, torch
 sys.path.insert(0, ".")
+ONLY = os.environ.get("CF_SANITIZE_ONLY_BATCH")      # e.g. "9": run only the paged launch with that batch (bisecting a report)
 import clusterfusion
 from oracle import llama_oracle as O
 dev = "cuda"
@@ -14,6 +15,8 @@ g = {k: v.to(dev) for k, v in O.make_inputs(S8, 77, seed=3, layout="sglang").ite
 clusterfusion.llama_decoder_layer_sglang(g["x"], g["residual"].clone(), g["weight_qkv"], g["weight_o"], g["k_cache"], g["v_cache"], g["rms_w"], 1e-5, g["cos"], g["sin"])
 for shape, dd, bs in ((S7, d, 1), (S7, d, 3), (S7, d, 5), (S7, d, 9), (S8, g, 2)):   # bs 3: chunks-of-4 kernel; bs 5: chunks-of-8 kernel;
                                                                                   # bs 9: two chunks = 256 CTAs = two waves of clusters
+    if ONLY and int(ONLY) != bs:
+        continue
     lens = [33, 0, 17, 40, 5, 16, 1, 31, 8][:bs]
     n = sum(lens) + bs + 3
     kvd = shape.n_kv_heads * 128
