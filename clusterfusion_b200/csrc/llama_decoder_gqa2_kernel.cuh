@@ -302,8 +302,12 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             }
             if (use_mma) {
                 // stage = K dims 0-63 | K dims 64-127 | V dims 0-63 | V dims 64-127, each [16 rows][128 B] 128-byte swizzled
-                const int slot0 = __shfl_sync(0xffffffffu, slot, 0);
-                const bool run = nvalid == ROWS512 && __all_sync(0xffffffffu, slot == slot0 + (int)(lane & 15));
+                int slot0 = r0;
+                bool run = nvalid == ROWS512;                // contiguous cache: every full tile is a run, no vote needed
+                if constexpr (kPaged) {
+                    slot0 = __shfl_sync(0xffffffffu, slot, 0);
+                    run = run && __all_sync(0xffffffffu, slot == slot0 + (int)(lane & 15));
+                }
                 if (run) {                                  // 16 consecutive rows: one tiled box per quarter
                     if (lane == 0) {
                         dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
