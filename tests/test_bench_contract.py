@@ -35,3 +35,13 @@ def test_ours_arm_fails_loudly_without_a_gpu():
                        timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert not [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+
+
+def test_reference_arm_under_torchrun_only_rank_0_prints():
+    """N > 1: rank 0 alone runs and prints the reference arm; the other ranks exit 0 without work (and nothing on stdout)."""
+    import os
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert not [l for l in r.stdout.splitlines() if l.strip()]
