@@ -333,7 +333,7 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, 3 * H, H, 64, cfb::ROWS256, true))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, qd, H, 64, cfb::ROWS256, true))) return rc;
     } else if (!gqa) {
-        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, cfb::ROWS512, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, cfb::ROWS256, true))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, cfb::ROWS256, true))) return rc;
     } else {
         // group kernel: CUDA-core GEMVs over unswizzled [16 x 256] tiles (512-byte row segments)

@@ -110,7 +110,7 @@ struct Smem {
     static constexpr int ATTN_PAYLOAD = HEAD_DIM + 4;            // [m, l, -, -, o[128]]
     static constexpr int RING = 0;
     static constexpr int UNION = RING + NSTAGES * STAGE_BYTES;
-    //   phase QKV : xs fp32[KS_MAX] | qkv_part  (chat: fp32[12 warps][128]; sglang: fp32[KS/256][384])
+    //   phase QKV : xs fp32[KS_MAX] | qkv_part  (chat only: fp32[12 warps][128]; nn.Linear layout keeps its sums in registers)
     //   phase ATTN: attn_part fp32[24][132]
     //   phase O   : out_part  (chat: fp32[4][KS <= 1024]; sglang: fp32[KS])
     static constexpr int UNION_BYTES = KS_MAX * 4 + 8 * QKV_OUT * 4;   // 20480 >= 2*KS_MAX*4
@@ -460,7 +460,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     const int chunk = (((kv_len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);   // KV rows per CTA, tile aligned
     const int row_begin = min((int)rank * chunk, kv_len);
     const int row_end = min(row_begin + chunk, kv_len);
-    const uint32_t n_qkv_tiles = kChat ? 3u * (KS / ROWS256) : (uint32_t)(S::QKV_OUT / ROWS512) * (KS / 256);
+    const uint32_t n_qkv_tiles = kChat ? 3u * (KS / ROWS256) : (uint32_t)(S::QKV_OUT / ROWS256) * (KS / 128);
     const uint32_t n_kv_tiles = (row_end - row_begin + ROWS512 - 1) / ROWS512;
     const uint32_t n_o_tiles = kChat ? (uint32_t)(HEAD_DIM / ROWS256) * (KS / 128) : (uint32_t)(KS / ROWS256);
 
@@ -505,24 +505,18 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
                     const int j = i % 3, t = i / 3;
                     c0 = head * HEAD_DIM;
                     c1 = j * hidden + rank * KS + t * ROWS256;
-                } else {                         // tile i: 16 output rows x 256 input cols
-                    const int wins = KS / 256;
-                    const int rb = i / wins, win = i % wins;          // rb in [0,24): matrix j = rb / 8
-                    const int j = rb / (HEAD_DIM / ROWS512), sub = rb % (HEAD_DIM / ROWS512);
+                } else {                         // tile i: 32 output rows (block rb = i % 12 of the head's 384 q|k|v rows) x 128
+                    const int rb = i % CONSUMER_WARPS, win = i / CONSUMER_WARPS;     // input cols (window win): window-major, so
+                    const int j = rb / (HEAD_DIM / ROWS256), sub = rb % (HEAD_DIM / ROWS256);   // warp w only ever sees block w
                     const int row0 = (j == 0) ? head * HEAD_DIM
                                    : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
                                               : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
-                    c0 = rank * KS + win * 256;
-                    c1 = row0 + sub * ROWS512;
+                    c0 = rank * KS + win * 128;
+                    c1 = row0 + sub * ROWS256;
                 }
-                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                if constexpr (kChat) {           // two [32 rows x 64 cols] swizzled boxes
-                    tma_load_2d(dst, &p.tm_wqkv, c0, c1, fb, pol);
-                    tma_load_2d(dst + 4096, &p.tm_wqkv, c0 + 64, c1, fb, pol);
-                } else {                         // four [16 rows x 64 cols] swizzled boxes
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * 2048, &p.tm_wqkv, c0 + q * 64, c1, fb, pol);
-                }
+                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);           // two [32 rows x 64 cols] swizzled boxes, either layout
+                tma_load_2d(dst, &p.tm_wqkv, c0, c1, fb, pol);
+                tma_load_2d(dst + 4096, &p.tm_wqkv, c0 + 64, c1, fb, pol);
             }
         } else if (g < n_qkv_tiles + n_kv_tiles) {
             const uint32_t i = g - n_qkv_tiles;                 // 16 KV rows: K in the first 4 KB of the stage, V in the second
@@ -723,48 +717,52 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             }
         }
     } else {
-        // tile = 16 output rows x 256 input cols as four swizzled [16 x 64] boxes.  Tensor cores: D[16 rows][8] =
-        // tile[16 x 256] * x[256 x 8] (x on column 0): one m-block x 16 k-steps per tile.
-        const int wins = KS / 256;
+        // tile = 32 output rows x 128 input cols as two swizzled [32 x 64] boxes (half the TMA requests of round 1's four
+        // [16 x 64] boxes per stage).  The tiles are dealt window-major and 12 row blocks = 12 warps, so warp w only ever sees
+        // row block w of the head's 384 q|k|v rows: its 32 row sums stay in registers for the whole phase and go straight
+        // to the exchange buffer -- no per-window partial slots, no fold pass.  Tensor cores: D[32 rows][8] += tile[32 x 128]
+        // * x[128 x 8] (x on column 0): two m-blocks x 8 k-steps per tile.
+        static_assert(S::QKV_OUT / ROWS256 == CONSUMER_WARPS, "one 32-row block of q|k|v per warp");
         const int g4 = lane >> 2, t4 = lane & 3;
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         for (uint32_t i = first_tile(gbase, warp); i < n_qkv_tiles; i += CONSUMER_WARPS) {
             const uint32_t g = gbase + i, s = ring_stage(g);
-            const int rb = i / wins, win = i % wins;
-            const float* xw = xs + win * 256;
-            uint32_t xb[16][2];
+            const float* xw = xs + (i / CONSUMER_WARPS) * 128;
+            uint32_t xb[8][2];
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks) { xb[ks][0] = bfrag_col0(xw, ks * 16, lane); xb[ks][1] = bfrag_col0(xw, ks * 16 + 8, lane); }
+            for (int ks = 0; ks < 8; ++ks) { xb[ks][0] = bfrag_col0(xw, ks * 16, lane); xb[ks][1] = bfrag_col0(xw, ks * 16 + 8, lane); }
             ring_wait_full(full_u32, g);
             const uint32_t st = smem_base + S::RING + s * STAGE_BYTES;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks) {
-                uint32_t af[4];
-                ldsm_a_mrows(af, st + (ks >> 2) * 2048, 0, (ks & 3) * 2, lane);
-                mma16816(acc, af, xb[ks][0], xb[ks][1]);
-            }
-            if (t4 == 0) {                                       // write-once slots
-                qkv_part[win * S::QKV_OUT + rb * ROWS512 + g4] = acc[0];
-                qkv_part[win * S::QKV_OUT + rb * ROWS512 + g4 + 8] = acc[2];
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    uint32_t af[4];
+                    ldsm_a_mrows(af, st + (ks >> 2) * 4096, mb * 16, (ks & 3) * 2, lane);
+                    mma16816(acc[mb], af, xb[ks][0], xb[ks][1]);
+                }
             }
             __syncwarp();
             issue_tile(g + NSTAGES);          // stage is free again: request the tile that will live in it next
+        }
+        if (t4 == 0) {                        // C fragment column 0: rows g4 and g4 + 8 of each 16-row block
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                qkv_src[warp * ROWS256 + mb * 16 + g4] = acc[mb][0];
+                qkv_src[warp * ROWS256 + mb * 16 + g4 + 8] = acc[mb][2];
+            }
         }
     }
     gbase += n_qkv_tiles;
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     CF_MARK(2);   // QKV tiles consumed (this warp)
 
-    // fold the write-once slots in a fixed order -> this CTA's partial q|k|v
-    {
+    // chat layout: fold the four write-once slots of a matrix in a fixed order -> this CTA's partial q|k|v
+    // (nn.Linear layout: every warp already wrote its 32 complete row sums to qkv_src)
+    if constexpr (kChat) {
         for (int o = tid; o < S::QKV_OUT; o += CONSUMER_THREADS) {
             float a = 0.f;
-            if constexpr (kChat) {      // matrix j = o / 128 was accumulated by warps j, j+3, j+6, j+9
-                for (int w = o >> 7; w < CONSUMER_WARPS; w += 3) a += qkv_part[w * HEAD_DIM + (o & 127)];
-            } else {
-                const int nslots = KS / 256;
-                for (int sl = 0; sl < nslots; ++sl) a += qkv_part[sl * S::QKV_OUT + o];
-            }
+            for (int w = o >> 7; w < CONSUMER_WARPS; w += 3) a += qkv_part[w * HEAD_DIM + (o & 127)];   // warps j, j+3, j+6, j+9
             qkv_src[o] = a;
         }
     }
