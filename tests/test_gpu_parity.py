@@ -1027,3 +1027,59 @@ def test_soak_10000_launches_as_the_reference_test_runs_them():
         assert bool(((o.float() - ref).abs() <= ulp).all())
     assert close(v, want[3]) and close_k(k, want[2])
     assert clusterfusion.workspace_status() == 0
+
+
+def test_first_call_inside_stream_capture_and_debug_status_mode():
+    """The public operators keep one workspace per (device, stream, hidden).  If the FIRST call on a stream happens inside a
+    CUDA-graph capture, the workspace must be allocated and zeroed OUTSIDE the graph (relaxed capture mode, private non-blocking
+    stream): a memset recorded into the graph would re-zero the workspace on every replay and the buffer would die with the
+    graph's pool.  Replays must match the oracle, the epoch must advance once per replayed launch, and the debug mode
+    set_check_status(True) (read the error word back after every launch) must stay silent."""
+    import clusterfusion
+    d = O.make_inputs(S8, 500, seed=77, layout="sglang", theta=500000.0)
+    want = O.sglang_layer(d["x"], d["residual"], d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"], d["rms_w"], 1e-5,
+                          d["cos"], d["sin"], n_heads=32, n_kv_heads=8, mode="eager")
+    c = cuda(d)
+    res = c["residual"].clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):          # first use of stream `s` by the module: workspace created during capture
+        o, r, k, v = clusterfusion.llama_decoder_layer_sglang(c["x"], res, c["weight_qkv"], c["weight_o"], c["k_cache"], c["v_cache"],
+                                                              c["rms_w"], 1e-5, c["cos"], c["sin"])
+    for _ in range(3):
+        res.copy_(c["residual"])
+        g.replay()
+        torch.cuda.synchronize()
+        assert close(o, want[0]) and close(v, want[3]) and close_k(k, want[2]) and torch.equal(res.cpu(), want[1])
+    assert clusterfusion.workspace_status() == 0
+    clusterfusion.set_check_status(True)
+    try:
+        o2, _, _, _ = clusterfusion.llama_decoder_layer_sglang(c["x"], c["residual"].clone(), c["weight_qkv"], c["weight_o"], c["k_cache"],
+                                                               c["v_cache"], c["rms_w"], 1e-5, c["cos"], c["sin"])
+        assert close(o2, want[0])
+    finally:
+        clusterfusion.set_check_status(False)
+
+
+def test_aliasing_outputs_are_rejected():
+    """output / residual_output overlapping input / residual (other than residual_output IS residual) would be silently corrupted
+    by the in-place epilogues: the operator must raise instead."""
+    import clusterfusion
+    d = O.make_inputs(S7, 10, seed=3, layout="sglang", bs=2)
+    c = cuda(d)
+    pool = torch.zeros(32, 4096, dtype=torch.float16, device="cuda")
+    kp = torch.tensor([pool.data_ptr()], dtype=torch.uint64).cuda()
+    indptr = torch.tensor([0, 3, 6], dtype=torch.int32).cuda(); indices = torch.arange(6, dtype=torch.int32).cuda()
+    pos = torch.tensor([2, 2], dtype=torch.int64).cuda(); cs = torch.rand(8, 128).cuda()
+    out = torch.empty_like(c["x"]); rout = torch.empty_like(c["x"])
+    args = lambda o_, ro_, x_, r_: (o_, ro_, x_, r_, c["weight_qkv"], c["weight_o"], indptr, indices, kp, kp, 0, c["rms_w"], 1e-5, pos, cs)
+    with pytest.raises(RuntimeError):
+        clusterfusion.llama_decoder_layer_batch_decode_sglang(*args(c["x"], rout, c["x"], c["residual"]))          # output is input
+    with pytest.raises(RuntimeError):
+        clusterfusion.llama_decoder_layer_batch_decode_sglang(*args(out, c["x"], c["x"], c["residual"]))           # residual_output is input
+    both = torch.empty(3, 4096, dtype=torch.float16, device="cuda")
+    with pytest.raises(RuntimeError):
+        clusterfusion.llama_decoder_layer_batch_decode_sglang(*args(both[:2], both[1:], c["x"], c["residual"]))    # outputs overlap each other
+    clusterfusion.llama_decoder_layer_batch_decode_sglang(*args(out, c["residual"].clone(), c["x"], c["residual"]))
+    torch.cuda.synchronize()
