@@ -89,3 +89,61 @@ def test_70b_head_parallel_nccl(world, fused):
     from parity_helpers import close_k
     assert close_k(k, want[2])
     assert torch.allclose(v.view(-1).float(), want[3].view(-1).float(), rtol=1e-3, atol=1e-3)
+
+
+def _stall_worker(rank, world, port, q):
+    try:
+        import torch.distributed as dist
+        from clusterfusion_b200 import sharded
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        H, nq, nkv, kv = 8192, 32, 4, 64
+        g = torch.Generator(device="cuda").manual_seed(5)
+        r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device="cuda") * sc).half()
+        lay = sharded.ShardedDecoderLayer(r((nq + 2 * nkv) * 128, H, sc=0.02), r(H, nq * 128, sc=0.02), (1 + 0.1 * r(H).float()).half(),
+                                          nq, nkv, H, 1e-5, None, world, rank=rank, fused_allreduce=True)
+        x, res, kc, vc = r(1, H), r(1, H), r(kv, nkv * 128), r(kv, nkv * 128)
+        cos, sin = torch.rand(64, device="cuda"), torch.rand(64, device="cuda")
+        o, _, _, _ = lay.forward(x, res, kc, vc, cos, sin)           # both ranks: a healthy launch
+        torch.cuda.synchronize()
+        ok0 = lay.status() == 0 and bool(torch.isfinite(o).all())
+        dist.barrier()
+        if rank == 0:                                                 # rank 1 "stalls": it never issues the second launch
+            o, _, _, _ = lay.forward(x, res, kc, vc, cos, sin)
+            torch.cuda.synchronize()
+            raised = False
+            try:
+                lay.check()
+            except RuntimeError:
+                raised = True
+            q.put(("ok", ok0, lay.status(), bool(torch.isnan(o.float()).any()), raised))
+        dist.barrier()
+        dist.destroy_process_group()
+    except BaseException as e:
+        import traceback
+        q.put(("error", f"rank {rank}: {e!r}\n{traceback.format_exc()}"))
+        raise
+
+
+def test_fused_allreduce_stalled_peer_is_reported_not_silent():
+    """ADVICE (round 1): a peer rank that never launches must not produce a silently wrong output.  Rank 1 skips a launch;
+    rank 0's kernel polls its exchange buffer for about a second, then writes NaN and sets the workspace's sticky error word:
+    ShardedDecoderLayer.status() is non-zero and .check() raises."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stall_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+    if got[0] == "error":
+        pytest.fail(got[1])
+    _, healthy, status, has_nan, raised = got
+    assert healthy, "the first (matched) launch must be clean"
+    assert status != 0 and has_nan and raised
