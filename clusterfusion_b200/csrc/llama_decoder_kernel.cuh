@@ -447,6 +447,63 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     const uint32_t full_u32 = smem_base + S::BARS;          // u64 full[NSTAGES]
     const uint32_t xbar_u32 = full_u32 + NSTAGES * 8;        // u64 xbar[2]
 
+    const uint32_t n_qkv_tiles = kChat ? 3u * (KS / ROWS256) : (uint32_t)(S::QKV_OUT / ROWS256) * (KS / 128);     // >= 24
+    const uint32_t n_o_tiles = kChat ? (uint32_t)(HEAD_DIM / ROWS256) * (KS / 128) : (uint32_t)(KS / ROWS256);
+
+    CF_MARK(0);   // kernel entry
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // no-op unless the NEXT launch opted into PDL
+
+    // ---- tile stream ----------------------------------------------------------------------------------
+    const uint64_t pol = policy_evict_first();
+    // QKV weight tile g (< n_qkv_tiles) into its stage; elected lane only.  Needs nothing but the CTA's coordinates.
+    auto issue_qkv_tile = [&](uint32_t g) {
+        if (lane != 0) return;
+        const uint32_t s = ring_stage(g);
+        const uint32_t fb = full_u32 + 8 * s;
+        const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
+        const uint32_t i = g;
+        int c0, c1;
+        if constexpr (kChat) {           // tile i: matrix j = i % 3, rows t = i / 3 (32 input rows x 128 output cols)
+            const int j = i % 3, t = i / 3;
+            c0 = head * HEAD_DIM;
+            c1 = j * hidden + rank * KS + t * ROWS256;
+        } else {                         // tile i: 32 output rows (block rb = i % 12 of the head's 384 q|k|v rows) x 128
+            const int rb = i % CONSUMER_WARPS, win = i / CONSUMER_WARPS;     // input cols (window win): window-major, so
+            const int j = rb / (HEAD_DIM / ROWS256), sub = rb % (HEAD_DIM / ROWS256);   // warp w only ever sees block w
+            const int row0 = (j == 0) ? head * HEAD_DIM
+                           : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
+                                      : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
+            c0 = rank * KS + win * 128;
+            c1 = row0 + sub * ROWS256;
+        }
+        dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);           // two [32 rows x 64 cols] swizzled boxes, either layout
+        tma_load_2d(dst, &p.tm_wqkv, c0, c1, fb, pol);
+        tma_load_2d(dst + 4096, &p.tm_wqkv, c0 + 64, c1, fb, pol);
+    };
+
+    // ---- barrier init + first two tiles of every warp ---------------------------------------------------
+    // Each warp initialises the full barriers of its own two stages and requests its first two tiles at once (always QKV
+    // weight tiles: n_qkv_tiles >= 24): nothing here depends on the other warps, on the peer CTAs, on the previous kernel in
+    // the stream (programmatic dependent launch) or -- paged form -- on the request's page table, whose two dependent index
+    // loads would otherwise sit in front of the first TMA request of every layer (round 2: they now overlap it).
+    // The exchange barriers are armed by thread 0 before the cluster-wide arrive.
+    if (lane == 0) {
+        dsm::mbar_init(full_u32 + 8 * warp, 1);
+        dsm::mbar_init(full_u32 + 8 * (warp + CONSUMER_WARPS), 1);
+        if (tid == 0) {
+            prefetch_tmap(&p.tm_wqkv);
+            prefetch_tmap(&p.tm_wo);
+            cluster_reduce_arm<CLUSTER>(xbar_u32, S::QKV_OUT * 4);
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::ATTN_PAYLOAD * 4);
+        }
+        dsm::mbar_fence_init();
+    }
+    __syncwarp();
+    CF_MARK(12);  // first TMA issue
+    issue_qkv_tile(warp);
+    issue_qkv_tile(warp + CONSUMER_WARPS);
+    dsm::cluster_arrive();     // peers may push into this CTA's smem only after every CTA armed its barriers
+
     // ---- per-request KV range -----------------------------------------------------------------
     int kv_len, kv_base = 0, new_slot = 0;
     if constexpr (kPaged) {
@@ -460,15 +517,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     const int chunk = (((kv_len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);   // KV rows per CTA, tile aligned
     const int row_begin = min((int)rank * chunk, kv_len);
     const int row_end = min(row_begin + chunk, kv_len);
-    const uint32_t n_qkv_tiles = kChat ? 3u * (KS / ROWS256) : (uint32_t)(S::QKV_OUT / ROWS256) * (KS / 128);
     const uint32_t n_kv_tiles = (row_end - row_begin + ROWS512 - 1) / ROWS512;
-    const uint32_t n_o_tiles = kChat ? (uint32_t)(HEAD_DIM / ROWS256) * (KS / 128) : (uint32_t)(KS / ROWS256);
-
-    CF_MARK(0);   // kernel entry
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // no-op unless the NEXT launch opted into PDL
-
-    // ---- tile stream ----------------------------------------------------------------------------------
-    const uint64_t pol = policy_evict_first();
     const uint32_t total_tiles = n_qkv_tiles + n_kv_tiles + n_o_tiles;
     const __half* kpool = p.k_base;      // contiguous forms: the cache itself
     const __half* vpool = p.v_base;
@@ -498,26 +547,7 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         const uint32_t fb = full_u32 + 8 * s;
         const uint32_t dst = smem_base + S::RING + s * STAGE_BYTES;
         if (g < n_qkv_tiles) {
-            if (lane == 0) {
-                const uint32_t i = g;
-                int c0, c1;
-                if constexpr (kChat) {           // tile i: matrix j = i % 3, rows t = i / 3 (32 input rows x 128 output cols)
-                    const int j = i % 3, t = i / 3;
-                    c0 = head * HEAD_DIM;
-                    c1 = j * hidden + rank * KS + t * ROWS256;
-                } else {                         // tile i: 32 output rows (block rb = i % 12 of the head's 384 q|k|v rows) x 128
-                    const int rb = i % CONSUMER_WARPS, win = i / CONSUMER_WARPS;     // input cols (window win): window-major, so
-                    const int j = rb / (HEAD_DIM / ROWS256), sub = rb % (HEAD_DIM / ROWS256);   // warp w only ever sees block w
-                    const int row0 = (j == 0) ? head * HEAD_DIM
-                                   : (j == 1) ? p.n_heads * HEAD_DIM + head * HEAD_DIM
-                                              : (p.n_heads + p.n_kv_heads) * HEAD_DIM + head * HEAD_DIM;
-                    c0 = rank * KS + win * 128;
-                    c1 = row0 + sub * ROWS256;
-                }
-                dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);           // two [32 rows x 64 cols] swizzled boxes, either layout
-                tma_load_2d(dst, &p.tm_wqkv, c0, c1, fb, pol);
-                tma_load_2d(dst + 4096, &p.tm_wqkv, c0 + 64, c1, fb, pol);
-            }
+            issue_qkv_tile(g);
         } else if (g < n_qkv_tiles + n_kv_tiles) {
             const uint32_t i = g - n_qkv_tiles;                 // 16 KV rows: K in the first 4 KB of the stage, V in the second
             const int r0 = row_begin + (int)i * ROWS512;
@@ -553,30 +583,10 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
         }
     };
 
-    // ---- barrier init + first two tiles of every warp ---------------------------------------------------
-    // Each warp initialises the full barriers of its own two stages and requests its first two tiles at once:
-    // nothing here depends on the other warps, on the peer CTAs or (under programmatic dependent launch) on the
-    // previous kernel in the stream.  The exchange barriers are armed by thread 0 before the cluster-wide arrive.
-    if (lane == 0) {
-        dsm::mbar_init(full_u32 + 8 * warp, 1);
-        dsm::mbar_init(full_u32 + 8 * (warp + CONSUMER_WARPS), 1);
-        if (tid == 0) {
-            prefetch_tmap(&p.tm_wqkv);
-            prefetch_tmap(&p.tm_wo);
-            if (pool_maps) {
-                prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v);
-                if constexpr (kPaged) { prefetch_tmap(&p.tm_kg); prefetch_tmap(&p.tm_vg); }
-            }
-            cluster_reduce_arm<CLUSTER>(xbar_u32, S::QKV_OUT * 4);
-            cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::ATTN_PAYLOAD * 4);
-        }
-        dsm::mbar_fence_init();
+    if (tid == 0 && pool_maps) {
+        prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v);
+        if constexpr (kPaged) { prefetch_tmap(&p.tm_kg); prefetch_tmap(&p.tm_vg); }
     }
-    __syncwarp();
-    CF_MARK(12);  // first TMA issue
-    issue_tile(warp);
-    issue_tile(warp + CONSUMER_WARPS);
-    dsm::cluster_arrive();     // peers may push into this CTA's smem only after every CTA armed its barriers
 
     // =============================================================================================
     // ALL WARPS
