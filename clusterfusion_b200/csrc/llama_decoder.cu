@@ -361,10 +361,10 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         kp.v_base = static_cast<const __half*>(vc);
     } else if (gqa && a->k_cache && a->v_cache) {
         // paged group kernel with the pool addresses known on the host: swizzled maps over the pools, tensor-core attention
-        if ((rc = get_tensor_map(&kp.tm_k, a->k_cache, 1ull << 24, kvd, 64, cfb::ROWS512, true))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_v, a->v_cache, 1ull << 24, kvd, 64, cfb::ROWS512, true))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_kg, a->k_cache, 1ull << 24, kvd, 64, 1, true))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_vg, a->v_cache, 1ull << 24, kvd, 64, 1, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_k, a->k_cache, (uint64_t)cfb::POOL_MAP_ROWS, kvd, 64, cfb::ROWS512, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_v, a->v_cache, (uint64_t)cfb::POOL_MAP_ROWS, kvd, 64, cfb::ROWS512, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_kg, a->k_cache, (uint64_t)cfb::POOL_MAP_ROWS, kvd, 64, 1, true))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_vg, a->v_cache, (uint64_t)cfb::POOL_MAP_ROWS, kvd, 64, 1, true))) return rc;
         kp.k_base = static_cast<const __half*>(a->k_cache);
         kp.v_base = static_cast<const __half*>(a->v_cache);
     } else if (!gqa && a->k_cache && a->v_cache) {
@@ -372,10 +372,10 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
         // v_cache = its copy of k_pool_ptrs[layer_id] / v_pool_ptrs[layer_id]).  Tiles whose 16 rows sit in consecutive
         // slots are fetched with one tiled TMA load per tensor, all other full tiles with tile::gather4 requests (four
         // arbitrary rows each).  The pool's slot count is not part of the interface: the maps cover 2^24 slots.
-        if ((rc = get_tensor_map(&kp.tm_k, a->k_cache, 1ull << 24, kvd, 128, cfb::ROWS512))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_v, a->v_cache, 1ull << 24, kvd, 128, cfb::ROWS512))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_kg, a->k_cache, 1ull << 24, kvd, 128, 1))) return rc;
-        if ((rc = get_tensor_map(&kp.tm_vg, a->v_cache, 1ull << 24, kvd, 128, 1))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_k, a->k_cache, (uint64_t)cfb::POOL_MAP_ROWS, kvd, 128, cfb::ROWS512))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_v, a->v_cache, (uint64_t)cfb::POOL_MAP_ROWS, kvd, 128, cfb::ROWS512))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_kg, a->k_cache, (uint64_t)cfb::POOL_MAP_ROWS, kvd, 128, 1))) return rc;
+        if ((rc = get_tensor_map(&kp.tm_vg, a->v_cache, (uint64_t)cfb::POOL_MAP_ROWS, kvd, 128, 1))) return rc;
         kp.k_base = static_cast<const __half*>(a->k_cache);
         kp.v_base = static_cast<const __half*>(a->v_cache);
     }

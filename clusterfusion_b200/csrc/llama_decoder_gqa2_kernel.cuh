@@ -308,6 +308,8 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
                     slot0 = __shfl_sync(0xffffffffu, slot, 0);
                     run = run && __all_sync(0xffffffffu, slot == slot0 + (int)(lane & 15));
                 }
+                // (the pool maps cover POOL_MAP_ROWS = 2^24 slots -- 34 GB of K per layer at 8 KV heads; the limit is part of the
+                //  contract of passing the host-side pool address, include/clusterfusion_b200.h)
                 if (run) {                                  // 16 consecutive rows: one tiled box per quarter
                     if (lane == 0) {
                         dsm::mbar_arrive_expect_tx(fb, STAGE_BYTES);

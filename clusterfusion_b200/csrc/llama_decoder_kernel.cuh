@@ -54,6 +54,7 @@ constexpr int ROWS256 = STAGE_BYTES / 256;              // rows of a {128 halves
 constexpr int ROWS512 = STAGE_BYTES / 512;              // rows of a {256 halves wide} tile / KV rows per stage (16)
 constexpr int KS_MAX = 2048;                            // max hidden / CLUSTER
 constexpr int CONSUMER_BAR = 1;                         // named barrier id for the consumer threads
+constexpr long long POOL_MAP_ROWS = 1ll << 24;          // row extent of the tensor maps the host builds over a paged KV pool
 
 enum Variant : int { CHAT = 0, SGLANG = 1, PAGED = 2 };
 static_assert(CONSUMER_WARPS % 3 == 0 && CONSUMER_THREADS >= 3 * HEAD_DIM, "chat QKV mapping needs warps % 3 == 0");
@@ -369,10 +370,13 @@ __device__ __forceinline__ void issue_kv_stage(const KParams& p, bool maps, bool
                                                uint32_t lane, uint64_t pol) {
     bool tiled = maps && nvalid == ROWS512, gather = false;
     if (tiled && !contiguous) {
+        // the pool maps cover POOL_MAP_ROWS slots (the pool's real size is not part of the interface): a tile that names a
+        // slot beyond them -- a > 100 GB pool -- takes the row-copy path, which addresses the pool directly
         const long long slot0 = __shfl_sync(0xffffffffu, slot, 0);
         const bool run = __all_sync(0xffffffffu, slot == slot0 + (long long)(lane & 15));
-        gather = !run;
-        tiled = run;
+        const bool in_map = __all_sync(0xffffffffu, slot < (long long)POOL_MAP_ROWS);
+        gather = in_map && !run;
+        tiled = in_map && run;
     }
     if (tiled) {
         if (lane == 0) {
