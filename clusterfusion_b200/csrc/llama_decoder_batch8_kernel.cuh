@@ -224,6 +224,8 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
 
     // ---- phase 0: fused residual add + RMSNorm for the 8 requests ---------------------------------------------------
     {
+        BatchSlice<BC> slice;
+        batch_slice_load<BC>(slice, p, b0, nb, hidden, KS, rank, tid);      // in flight across the reduction below
         float ss[BC];
 #pragma unroll
         for (int b = 0; b < BC; ++b) {
@@ -247,36 +249,7 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
             if (lane == 0) red[warp * BC + b] = ss[b];
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-#pragma unroll
-        for (int b = 0; b < BC; ++b) {
-            float tot = 0.f;
-#pragma unroll
-            for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w * BC + b];
-            const float rstd = rsqrtf(tot / (float)hidden + p.eps);
-            for (int e = tid * 8; e < KS; e += CONSUMER_THREADS * 8) {
-                __align__(16) __half xn[8];
-                if (b < nb) {
-                    const int ge = rank * KS + e;
-                    const __half* xg = p.x + (size_t)(b0 + b) * hidden;
-                    const __half* rg = p.residual_in + (size_t)(b0 + b) * hidden;
-                    float f[8], w8[8], r8[8];
-                    unpack8(*reinterpret_cast<const uint4*>(xg + ge), f);
-                    unpack8(*reinterpret_cast<const uint4*>(p.rms_w + ge), w8);
-                    unpack8(*reinterpret_cast<const uint4*>(rg + ge), r8);
-                    __align__(16) __half hs[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { hs[k] = __float2half_rn(f[k] + r8[k]); f[k] = __half2float(hs[k]); }
-                    if (head == 0)
-                        *reinterpret_cast<uint4*>(p.residual_out + (size_t)(b0 + b) * hidden + ge) = *reinterpret_cast<const uint4*>(hs);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(round_h(f[k] * rstd) * w8[k]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(0.f);
-                }
-                *reinterpret_cast<uint4*>(xs + b * BK_XS_STRIDE + e) = *reinterpret_cast<const uint4*>(xn);
-            }
-        }
+        batch_slice_store<BC>(slice, p, b0, nb, hidden, KS, rank, head, tid, red, xs);
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
     CF_MARK(1);

@@ -70,6 +70,67 @@ struct SmemB {
     static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
 };
 
+// Second half of the batched kernels' phase 0: the normalised activations of this CTA's K-slice for all BC requests.  The
+// (request, 8-element chunk) items are dealt over ALL threads and their x / residual / rms_w loads are issued by
+// batch_slice_load() BEFORE the block barrier of the sum-of-squares reduction, so the slice costs no second L2 round trip
+// (round 1 walked the requests one after the other behind that barrier, 128 threads busy, each request's loads stuck behind the
+// previous request's residual_out store: ~6.5 us from the previous layer's last CTA to "RMSNorm done" at batch 4).
+template <int BC>
+struct BatchSlice {
+    static constexpr int ITEMS = (BC * (BK_KS_MAX / 8) + CONSUMER_THREADS - 1) / CONSUMER_THREADS;
+    uint4 x[ITEMS], r[ITEMS], w[ITEMS];
+};
+template <int BC>
+__device__ __forceinline__ void batch_slice_load(BatchSlice<BC>& sl, const KParams& p, int b0, int nb, int hidden, int KS, uint32_t rank,
+                                                 uint32_t tid) {
+    const int cpk = KS / 8;
+#pragma unroll
+    for (int it = 0; it < BatchSlice<BC>::ITEMS; ++it) {
+        const int item = (int)tid + it * CONSUMER_THREADS;
+        const int b = item / cpk, ge = (int)rank * KS + (item % cpk) * 8;
+        sl.x[it] = sl.r[it] = sl.w[it] = make_uint4(0, 0, 0, 0);
+        if (item < BC * cpk && b < nb) {
+            sl.x[it] = *reinterpret_cast<const uint4*>(p.x + (size_t)(b0 + b) * hidden + ge);
+            sl.r[it] = *reinterpret_cast<const uint4*>(p.residual_in + (size_t)(b0 + b) * hidden + ge);
+            sl.w[it] = *reinterpret_cast<const uint4*>(p.rms_w + ge);
+        }
+    }
+}
+// red[w * BC + b] holds the per-warp sums of squares of request b (written before the barrier the caller just passed)
+template <int BC>
+__device__ __forceinline__ void batch_slice_store(const BatchSlice<BC>& sl, const KParams& p, int b0, int nb, int hidden, int KS,
+                                                  uint32_t rank, uint32_t head, uint32_t tid, const float* red, __half* xs) {
+    const int cpk = KS / 8;
+#pragma unroll
+    for (int it = 0; it < BatchSlice<BC>::ITEMS; ++it) {
+        const int item = (int)tid + it * CONSUMER_THREADS;
+        if (item >= BC * cpk) continue;
+        const int b = item / cpk, e = (item % cpk) * 8;
+        __align__(16) __half xn[8];
+        if (b < nb) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w * BC + b];
+            const float rstd = rsqrtf(tot / (float)hidden + p.eps);
+            float f[8], w8[8], r8[8];
+            unpack8(sl.x[it], f);
+            unpack8(sl.w[it], w8);
+            unpack8(sl.r[it], r8);
+            __align__(16) __half hs[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { hs[k] = __float2half_rn(f[k] + r8[k]); f[k] = __half2float(hs[k]); }
+            if (head == 0)
+                *reinterpret_cast<uint4*>(p.residual_out + (size_t)(b0 + b) * hidden + rank * KS + e) = *reinterpret_cast<const uint4*>(hs);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(round_h(f[k] * rstd) * w8[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(0.f);
+        }
+        *reinterpret_cast<uint4*>(xs + b * BK_XS_STRIDE + e) = *reinterpret_cast<const uint4*>(xn);
+    }
+}
+
 template <int BC>
 __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
@@ -231,6 +292,8 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
 
     // ---- phase 0: fused residual add + RMSNorm for the BC requests of the chunk ---------------------------
     {
+        BatchSlice<BC> slice;
+        batch_slice_load<BC>(slice, p, b0, nb, hidden, KS, rank, tid);      // in flight across the reduction below
         float ss[BC];
 #pragma unroll
         for (int b = 0; b < BC; ++b) {                       // loads of all requests first: no barrier or shuffle between them
@@ -254,36 +317,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
             if (lane == 0) red[warp * BC + b] = ss[b];
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-#pragma unroll
-        for (int b = 0; b < BC; ++b) {
-            float tot = 0.f;
-#pragma unroll
-            for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w * BC + b];
-            const float rstd = rsqrtf(tot / (float)hidden + p.eps);
-            for (int e = tid * 8; e < KS; e += CONSUMER_THREADS * 8) {
-                __align__(16) __half xn[8];
-                if (b < nb) {
-                    const int ge = rank * KS + e;
-                    const __half* xg = p.x + (size_t)(b0 + b) * hidden;
-                    const __half* rg = p.residual_in + (size_t)(b0 + b) * hidden;
-                    float f[8], w8[8], r8[8];
-                    unpack8(*reinterpret_cast<const uint4*>(xg + ge), f);
-                    unpack8(*reinterpret_cast<const uint4*>(p.rms_w + ge), w8);
-                    unpack8(*reinterpret_cast<const uint4*>(rg + ge), r8);
-                    __align__(16) __half hs[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { hs[k] = __float2half_rn(f[k] + r8[k]); f[k] = __half2float(hs[k]); }
-                    if (head == 0)
-                        *reinterpret_cast<uint4*>(p.residual_out + (size_t)(b0 + b) * hidden + ge) = *reinterpret_cast<const uint4*>(hs);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(round_h(f[k] * rstd) * w8[k]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) xn[k] = __float2half_rn(0.f);
-                }
-                *reinterpret_cast<uint4*>(xs + b * BK_XS_STRIDE + e) = *reinterpret_cast<const uint4*>(xn);
-            }
-        }
+        batch_slice_store<BC>(slice, p, b0, nb, hidden, KS, rank, head, tid, red, xs);
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
 
