@@ -227,21 +227,7 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
         BatchSlice<BC> slice;
         batch_slice_load<BC>(slice, p, b0, nb, hidden, KS, rank, tid);      // in flight across the reduction below
         float ss[BC];
-#pragma unroll
-        for (int b = 0; b < BC; ++b) {
-            ss[b] = 0.f;
-            if (b < nb) {
-                const __half* xg = p.x + (size_t)(b0 + b) * hidden;
-                const __half* rg = p.residual_in + (size_t)(b0 + b) * hidden;
-                for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
-                    float f[8], r8[8];
-                    unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
-                    unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { const float h = round_h(f[k] + r8[k]); ss[b] = fmaf(h, h, ss[b]); }
-                }
-            }
-        }
+        batch_sum_squares<BC>(ss, p, b0, nb, hidden, tid);
 #pragma unroll
         for (int b = 0; b < BC; ++b) {
 #pragma unroll

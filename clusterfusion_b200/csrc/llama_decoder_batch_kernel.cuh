@@ -70,6 +70,44 @@ struct SmemB {
     static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
 };
 
+// First half of phase 0: sum of squares of fp16(x + residual) over the whole row, for the BC requests of the chunk.  All loads
+// of a group of up to four requests go out before anything is consumed (hidden <= 4 * BK_KS_MAX = 4096: at most two 8-element
+// chunks per thread and request), so the pass costs one L2 round trip per group instead of one per request and chunk.
+template <int BC>
+__device__ __forceinline__ void batch_sum_squares(float (&ss)[BC], const KParams& p, int b0, int nb, int hidden, uint32_t tid) {
+    constexpr int ITERS = (4 * BK_KS_MAX / 8 + CONSUMER_THREADS - 1) / CONSUMER_THREADS;      // 2
+    constexpr int GROUP = BC < 4 ? BC : 4;
+#pragma unroll
+    for (int g0 = 0; g0 < BC; g0 += GROUP) {
+        uint4 xr[GROUP][ITERS], rr[GROUP][ITERS];
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const int e = ((int)tid + it * CONSUMER_THREADS) * 8;
+                xr[j][it] = rr[j][it] = make_uint4(0, 0, 0, 0);
+                if (g0 + j < nb && e < hidden) {
+                    xr[j][it] = *reinterpret_cast<const uint4*>(p.x + (size_t)(b0 + g0 + j) * hidden + e);
+                    rr[j][it] = *reinterpret_cast<const uint4*>(p.residual_in + (size_t)(b0 + g0 + j) * hidden + e);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                float f[8], r8[8];
+                unpack8(xr[j][it], f);
+                unpack8(rr[j][it], r8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float h = round_h(f[k] + r8[k]); acc = fmaf(h, h, acc); }     // zeros past the end
+            }
+            ss[g0 + j] = acc;
+        }
+    }
+}
+
 // Second half of the batched kernels' phase 0: the normalised activations of this CTA's K-slice for all BC requests.  The
 // (request, 8-element chunk) items are dealt over ALL threads and their x / residual / rms_w loads are issued by
 // batch_slice_load() BEFORE the block barrier of the sum-of-squares reduction, so the slice costs no second L2 round trip
@@ -295,21 +333,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
         BatchSlice<BC> slice;
         batch_slice_load<BC>(slice, p, b0, nb, hidden, KS, rank, tid);      // in flight across the reduction below
         float ss[BC];
-#pragma unroll
-        for (int b = 0; b < BC; ++b) {                       // loads of all requests first: no barrier or shuffle between them
-            ss[b] = 0.f;
-            if (b < nb) {
-                const __half* xg = p.x + (size_t)(b0 + b) * hidden;
-                const __half* rg = p.residual_in + (size_t)(b0 + b) * hidden;
-                for (int e = tid * 8; e < hidden; e += CONSUMER_THREADS * 8) {
-                    float f[8], r8[8];
-                    unpack8(*reinterpret_cast<const uint4*>(xg + e), f);
-                    unpack8(*reinterpret_cast<const uint4*>(rg + e), r8);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { const float h = round_h(f[k] + r8[k]); ss[b] = fmaf(h, h, ss[b]); }
-                }
-            }
-        }
+        batch_sum_squares<BC>(ss, p, b0, nb, hidden, tid);
 #pragma unroll
         for (int b = 0; b < BC; ++b) {
 #pragma unroll

@@ -49,7 +49,7 @@ if variant == 2:
     positions = torch.full((BS,), kv, dtype=torch.int64, device=dev)
     cos_sin = torch.rand(kv + 1, D, device=dev)
 if variant == 2 and NH == NKV:
-    ncta = NH * 4 * (((BS + 3) // 4) if (BS >= 2 and not (flags & 16)) else BS)
+    ncta = NH * 4 * ((((BS + 7) // 8) if BS >= 5 else ((BS + 3) // 4)) if (BS >= 2 and not (flags & 16)) else BS)
 elif NH == NKV:
     ncta = NH * 4
 else:
@@ -68,7 +68,9 @@ def launch(i, h):
                              residual_in=res.data_ptr(), residual_out=lay["ro"].data_ptr(), x=h.data_ptr(), w_qkv=lay["w_qkv"].data_ptr(),
                              w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(), out=lay["o"].data_ptr(), indptr=indptr.data_ptr(),
                              indices=indices.data_ptr(), k_pool_ptrs=kptrs.data_ptr(), v_pool_ptrs=vptrs.data_ptr(),
-                             positions=positions.data_ptr(), cos=cos_sin.data_ptr(), workspace=ws.data_ptr())
+                             positions=positions.data_ptr(), cos=cos_sin.data_ptr(), workspace=ws.data_ptr(),
+                             k_cache=(0 if os.environ.get('CF_NO_POOL_PTRS') else lay['k'].data_ptr()),
+                             v_cache=(0 if os.environ.get('CF_NO_POOL_PTRS') else lay['v'].data_ptr()))   # host copy of the pool addresses
         rc = lib.cf_llama_decoder_layer_launch(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0, rc
         return
