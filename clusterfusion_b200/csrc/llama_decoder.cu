@@ -15,6 +15,7 @@
 #include "llama_decoder_gqa2_kernel.cuh"
 #include "llama_decoder_batch_kernel.cuh"
 #include "llama_decoder_batch8_kernel.cuh"
+#include "llama_decoder_gqa_batch_kernel.cuh"
 #include "llama_ffn_kernel.cuh"
 #include "rmsnorm_kernel.cuh"
 #include "deepseek_mla_kernel.cuh"
@@ -206,9 +207,27 @@ size_t ws_off_gcounters(int hidden, int batch) {
 size_t ws_off_out_ll_b1(int hidden, int batch) {
     return ws_off_gcounters(hidden, batch) + (size_t)batch * cfb::G2_COUNTERS * sizeof(uint32_t);
 }
-size_t ws_total(int hidden, int batch) {
+// grouped-query batched kernel (llama_decoder_gqa_batch_kernel.cuh): per chunk of 8 requests, all (value, epoch) words
+size_t ws_off_gb(int hidden, int batch) {
     // batch == 1 launches reduce the O projection across clusters through (value, epoch) words [hidden/128][hidden]
     return ws_off_out_ll_b1(hidden, batch) + (size_t)(hidden / 128) * hidden * sizeof(uint64_t);
+}
+int gb_chunks(int batch) { return batch >= 2 ? (batch + cfb::GB_BC - 1) / cfb::GB_BC : 0; }
+size_t ws_off_gb_qkvp(int hidden, int batch) { return ws_off_gb(hidden, batch) + (size_t)gb_chunks(batch) * cfb::GB_CTAS_MAX * cfb::GB_BC * sizeof(uint64_t); }
+size_t ws_off_gb_qkvf(int hidden, int batch) {
+    return ws_off_gb_qkvp(hidden, batch) + (size_t)gb_chunks(batch) * cfb::GB_CTAS_MAX * cfb::SmemGqaB::R * cfb::GB_BC * sizeof(uint64_t);
+}
+size_t ws_off_gb_attn(int hidden, int batch) {
+    return ws_off_gb_qkvf(hidden, batch) + (size_t)gb_chunks(batch) * cfb::G2_GROUPS_MAX * cfb::GB_BC * cfb::GB_QKVF_WORDS * sizeof(uint64_t);
+}
+size_t ws_off_gb_ag(int hidden, int batch) {
+    return ws_off_gb_attn(hidden, batch) + (size_t)gb_chunks(batch) * cfb::GB_CTAS_MAX * cfb::GB_BC * cfb::GB_STATE_WORDS * sizeof(uint64_t);
+}
+size_t ws_off_gb_out(int hidden, int batch) {
+    return ws_off_gb_ag(hidden, batch) + (size_t)gb_chunks(batch) * cfb::G2_GROUPS_MAX * cfb::GB_BC * cfb::GB_AG_WORDS * sizeof(uint64_t);
+}
+size_t ws_total(int hidden, int batch) {
+    return ws_off_gb_out(hidden, batch) + (size_t)gb_chunks(batch) * cfb::G2_GROUPS_MAX * hidden * cfb::GB_BC * sizeof(uint64_t);
 }
 
 bool device_is_sm100() {
@@ -324,7 +343,13 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     // batched paged decode: one cluster per head serves chunks of 4 requests, weights streamed once per chunk
     const bool batched = paged && !gqa && a->batch >= 2 && a->hidden / CL <= cfb::BK_KS_MAX &&
                          a->residual_out != a->residual_in && !(a->flags & CF_FLAG_PER_REQUEST);
-    if (batched) {
+    // grouped-query shapes, batch >= 2: weights streamed once per chunk of 8 requests
+    // (two requests whose groups are co-resident with 8 CTAs each are faster through the group kernel: 27.9 vs 31.2 us for
+    //  Llama-3-8B shapes, profiles/round2_gqa_batch_probe_8b.txt)
+    const bool two_coresident = a->batch == 2 && gqa &&
+                                a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4) * 8 * 2 <= sm_count_of_current_device();
+    const bool gqa_batched = paged && gqa && a->batch >= 2 && a->tp_world <= 1 && !(a->flags & CF_FLAG_PER_REQUEST) && !two_coresident;
+    if (batched || gqa_batched) {
         // tensor-core GEMVs: [32 rows x 64 cols] boxes, 128-byte swizzled (two per 8 KB tile)
         if ((rc = get_tensor_map(&kp.tm_wqkv, a->w_qkv, qd + 2 * kvd, H, 64, 32, true))) return rc;
         if ((rc = get_tensor_map(&kp.tm_wo, a->w_o, H, qd, 64, 32, true))) return rc;
@@ -424,6 +449,43 @@ int cf_llama_decoder_layer_launch(const CfLlamaArgs* a, void* stream_) {
     }
 
     const bool pdl = (a->flags & CF_FLAG_PDL) != 0;
+    if (gqa_batched) {
+        const int n_groups = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);
+        if (n_groups > cfb::G2_GROUPS_MAX)
+            return fail(CF_ERR_BAD_SHAPE, "GQA: at most %d (KV head, 4 query heads) groups per call (got %d)", cfb::G2_GROUPS_MAX, n_groups);
+        // the CTAs of a chunk spin on each other through L2: one chunk (groups x G CTAs) must fit the device; later chunks are
+        // dispatched as earlier ones drain (chunks are the slow grid dimension, see llama_decoder_gqa2_kernel.cuh)
+        static int capacity[16] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (capacity[dev & 15] == 0) {
+            int occ = 0;
+            cudaFuncSetAttribute(cfb::llama_decoder_layer_gqa_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cfb::SmemGqaB::TOTAL);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cfb::llama_decoder_layer_gqa_batch_kernel, cfb::BLOCK_THREADS,
+                                                              cfb::SmemGqaB::TOTAL) != cudaSuccess || occ < 1)
+                occ = 1;
+            capacity[dev & 15] = occ * sm_count_of_current_device();
+        }
+        const int n_sm = capacity[dev & 15] < cfb::GB_CTAS_MAX ? capacity[dev & 15] : cfb::GB_CTAS_MAX;
+        int G = cfb::G2_G_MAX;
+        while (G > 8 && (n_groups * G > n_sm || a->hidden / G < 128)) G >>= 1;
+        if (n_groups * G > n_sm || a->hidden / G > cfb::BK_KS_MAX || a->hidden % (G * 128) != 0)
+            return fail(CF_ERR_BAD_SHAPE, "GQA batched: %d groups x %d CTAs (hidden %d) do not fit this device (%d CTAs)", n_groups, G, a->hidden, n_sm);
+        cfb::GBParams gp;
+        memset(&gp, 0, sizeof gp);
+        gp.k = kp;
+        char* ws = static_cast<char*>(a->workspace);
+        gp.ss_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_gb(a->hidden, wsb));
+        gp.qkvp_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_gb_qkvp(a->hidden, wsb));
+        gp.qkvf_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_gb_qkvf(a->hidden, wsb));
+        gp.attn_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_gb_attn(a->hidden, wsb));
+        gp.ag_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_gb_ag(a->hidden, wsb));
+        gp.out_ll = reinterpret_cast<unsigned long long*>(ws + ws_off_gb_out(a->hidden, wsb));
+        gp.G = G;
+        gp.n_groups = n_groups;
+        return launch_kernel<1>(cfb::llama_decoder_layer_gqa_batch_kernel, cfb::SmemGqaB::TOTAL, 7, gp, n_groups * G,
+                                (a->batch + cfb::GB_BC - 1) / cfb::GB_BC, pdl, stream);
+    }
     if (gqa) {
         // group kernel: G CTAs per group, G = largest power of two in [8, 64] with groups * G * batch <= #SMs
         const int n_groups = a->n_kv_heads * ((a->n_q_heads / a->n_kv_heads) / 4);

@@ -398,6 +398,7 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
                     issue_tile(g + NSTAGES);
                 }
             }
+            if (h == 0) { CF_MARK(5); } else { CF_MARK(10); }   // KV tiles of this half consumed (warp 0)
             // merge the two half-warps in registers, then block merge one request per round through [12][132]
 #pragma unroll
             for (int bb = 0; bb < HB; ++bb) {
@@ -459,6 +460,7 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
                 }
                 dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
             }
+            if (h == 0) { CF_MARK(3); } else { CF_MARK(11); }   // block merges of this half done
             uint32_t ph_a = 0;
             cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
                 HB * S::PAY * 4, tid, HB * S::PAY, rank, smem_base + S::ATTN_SRC, smem_base + S::ATTN_RECV,

@@ -809,7 +809,7 @@ def _paged_case(lens, seed, table="random", nslots_extra=37, shape=None):
     return d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r
 
 
-def _run_paged_cabi(d, indptr, indices, positions, cos_sin, flags=0, host_pool_copy="right", shape=None):
+def _run_paged_cabi(d, indptr, indices, positions, cos_sin, flags=0, host_pool_copy="right", shape=None, inplace=False):
     """One 15-argument launch through the C ABI.  host_pool_copy: right = pass the host's copy of the pool addresses
     (tiled / gather4 KV fast paths), none = NULL (row-by-row gather), stale = a WRONG copy (the kernel must notice)."""
     import cabi_torch as CT
@@ -823,7 +823,7 @@ def _run_paged_cabi(d, indptr, indices, positions, cos_sin, flags=0, host_pool_c
     kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
     vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
     out = torch.full((bs, H), float("nan"), dtype=torch.float16, device="cuda")
-    rout = torch.full((bs, H), float("nan"), dtype=torch.float16, device="cuda")
+    rout = c["residual"] if inplace else torch.full((bs, H), float("nan"), dtype=torch.float16, device="cuda")
     dev_t = (indptr.cuda(), indices.cuda(), positions.cuda(), cos_sin.cuda())
     hk = {"right": kpool, "stale": decoy_k, "none": None}[host_pool_copy]
     hv = {"right": vpool, "stale": decoy_v, "none": None}[host_pool_copy]
@@ -867,6 +867,54 @@ def test_gqa_paged_kv_fetch_paths_agree_with_oracle(table, host_pool_copy, lens)
     assert torch.equal(rout.cpu(), want_r)
     assert close(out, want_o)
     assert close_k(kpool, kp) and close(vpool, vp)
+
+
+GQA_BATCH_CASES = {
+    "8b_bs8_kv1k": (S8, [1024] * 8, "random"),
+    "8b_bs8_ragged": (S8, [700, 0, 33, 2100, 1, 16, 640, 5], "runs"),
+    "8b_bs9_two_chunks": (S8, [100, 257, 0, 31, 1000, 48, 16, 15, 300], "random"),
+    "8b_bs16": (S8, [64 + 37 * i for i in range(16)], "sequential"),
+    "8b_bs3_all_empty": (S8, [0, 0, 0], "random"),
+    "8b_bs3_long": (S8, [16384, 5, 3000], "random"),
+    "70b_bs5": (S70, [300, 64, 0, 1000, 17], "random"),
+    "70b_shard4_bs3": (O.LayerShape(8192, 16, 2), [500, 0, 129], "runs"),
+    "70b_shard8_bs4": (O.LayerShape(8192, 8, 1), [77, 1024, 0, 3], "random"),
+}
+
+
+@pytest.mark.parametrize("case", sorted(GQA_BATCH_CASES))
+def test_gqa_batched_weights_once_kernel_vs_oracle(case):
+    """Grouped-query shapes at batch >= 2 run llama_decoder_gqa_batch_kernel.cuh: weights streamed once per chunk of 8 requests,
+    requests on the N dimension of the MMA, KV rows of the chunk cut into equal segments over the group's CTAs.  Against the
+    oracle: full and ragged chunks, two chunks, empty requests (new token only), a long request next to short ones, Llama-2-70B
+    shapes (hidden 8192: G = 8, 1024 columns per CTA) and its 4- / 8-way shards (G = 32 / 64: one RoPE pair per CTA and slot)."""
+    shape, lens, table = GQA_BATCH_CASES[case]
+    d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r = _paged_case(lens, seed=len(lens) * 7 + shape.hidden, table=table, shape=shape)
+    out, rout, kpool, vpool = _run_paged_cabi(d, indptr, indices, positions, cos_sin, shape=shape)
+    assert torch.equal(rout.cpu(), want_r)
+    assert close(out, want_o)
+    assert close_k(kpool, kp) and close(vpool, vp)
+
+
+def test_gqa_batched_weights_once_kernel_matches_per_request_launch_inplace_and_repeatable():
+    """Same call three ways: weights-once kernel, weights-once kernel with residual_out == residual_in (the chunk's CTA 0 rewrites
+    the residual once every CTA is past phase 0), and the group kernel launched per request (CF_FLAG_PER_REQUEST).  The
+    weights-once kernel has no atomics: 20 launches on the same workspace give bit-identical outputs and a clean status word."""
+    import cabi_torch as CT
+    from clusterfusion_b200 import cabi
+    lens = [333, 0, 2100, 64, 1, 900]
+    d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r = _paged_case(lens, seed=606, table="random", shape=S8)
+    out, rout, kpool, vpool = _run_paged_cabi(d, indptr, indices, positions, cos_sin, shape=S8)
+    out_i, rout_i, kpool_i, vpool_i = _run_paged_cabi(d, indptr, indices, positions, cos_sin, shape=S8, inplace=True)
+    out_p, rout_p, kpool_p, vpool_p = _run_paged_cabi(d, indptr, indices, positions, cos_sin, shape=S8, flags=cabi.CF_FLAG_PER_REQUEST)
+    assert torch.equal(rout.cpu(), want_r) and torch.equal(rout_i.cpu(), want_r) and torch.equal(rout_p.cpu(), want_r)
+    assert torch.equal(out, out_i) and torch.equal(kpool, kpool_i) and torch.equal(vpool, vpool_i)
+    assert close(out, want_o) and close(out_p, want_o)
+    assert close(vpool, vpool_p) and close_k(kpool, kpool_p)     # (different fp32 summation orders: K-split vs row-split)
+    for _ in range(20):
+        o2, _, k2, _ = _run_paged_cabi(d, indptr, indices, positions, cos_sin, shape=S8)
+        assert torch.equal(o2, out) and torch.equal(k2, kpool)
+    assert cabi.workspace_status(CT.workspace(4096, len(lens), out.device).data_ptr()) == 0
 
 
 @pytest.mark.parametrize("table", ["random", "sequential"])

@@ -1,17 +1,16 @@
-"""GPU probe (not product code): grouped-query paged form at batch > 1 (Llama-3-8B shapes), CUDA graph of 8 distinct layers through
-the C ABI.  The two columns were an A/B of the L2 policy of the weight tiles at batch > 1 (evict-last vs evict-first, switch 0x40 of
-an experimental build); evict-last was 2-5 % slower and is not in the product, where both columns are the same code
-(profiles/round2_gqa_batch_probe.txt holds the measured A/B)."""
+"""GPU probe (not product code): grouped-query paged form at batch > 1, CUDA graph of 8 distinct layers through the C ABI.
+Columns: the weights-once kernel (llama_decoder_gqa_batch_kernel.cuh, default) against the group kernel launched with requests as
+the slow grid dimension (CF_FLAG_PER_REQUEST).  `python tools/gqa_batch_probe.py [8b|70b]`."""
 import json, sys, torch
 sys.path.insert(0, ".")
 from clusterfusion_b200 import cabi
 dev = torch.device("cuda", 0)
 cabi.load()
-H, HQ, HKV, D, nl = 4096, 32, 8, 128, 8
+H, HQ, HKV, D, nl = (8192, 64, 8, 128, 4) if (len(sys.argv) > 1 and sys.argv[1] == "70b") else (4096, 32, 8, 128, 8)
 r = lambda *s, sc=1.0: (torch.randn(*s, device=dev) * sc).half()
 L = [dict(w_qkv=r((HQ + 2 * HKV) * D, H, sc=0.02), w_o=r(H, HQ * D, sc=0.02), rms=(1 + 0.1 * r(H).float()).half()) for _ in range(nl)]
 for kv in (1024, 8192):
-    for bs in (1, 2, 4, 8):
+    for bs in (2, 3, 4, 6, 8, 16):
         nslots = bs * (kv + 1)
         pools = [(r(nslots, HKV * D), r(nslots, HKV * D)) for _ in range(nl)]
         kptrs = torch.tensor([a.data_ptr() for a, _ in pools], dtype=torch.uint64).to(dev)
@@ -25,7 +24,7 @@ for kv in (1024, 8192):
         bufs = [(torch.empty(bs, H, dtype=torch.float16, device=dev), torch.empty(bs, H, dtype=torch.float16, device=dev)) for _ in range(nl)]
         row = {"kv_len": kv, "batch": bs}
         outs = {}
-        for name, fl in (("weights_evict_last", 0), ("weights_evict_first", 0x40)):
+        for name, fl in (("weights_once", 0), ("per_request", cabi.CF_FLAG_PER_REQUEST)):
             def launch(h, rr, li, st):
                 a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=fl | cabi.CF_FLAG_PDL, hidden=H, n_q_heads=HQ, n_kv_heads=HKV, head_dim=D,
                                      batch=bs, layer_id=li, eps=1e-5, x=h.data_ptr(), residual_in=rr.data_ptr(), residual_out=bufs[li][1].data_ptr(),
@@ -56,7 +55,7 @@ for kv in (1024, 8192):
             row[name + "_us_per_layer"] = round(best, 2)
             outs[name] = bufs[-1][0].float().clone()
             del g
-        row["max_abs_diff"] = float((outs["weights_evict_last"] - outs["weights_evict_first"]).abs().max())
+        row["max_abs_diff"] = float((outs["weights_once"] - outs["per_request"]).abs().max())
         row["status"] = cabi.workspace_status(ws.data_ptr())
         print(json.dumps(row), flush=True)
         del pools, ws

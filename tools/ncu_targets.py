@@ -3,6 +3,7 @@
     python tools/ncu_targets.py ffn          # fused FFN half-layer, Llama-2-7B shapes
     python tools/ncu_targets.py deepseek 4096  # DeepSeek-MLA half-layer (3 kernels per call), through the C ABI
     python tools/ncu_targets.py paged 16384 random   # 15-argument paged-KV form, Llama-2-7B, batch 1 (random | sequential page table)
+    python tools/ncu_targets.py paged 1024 random 8  # ... batch 8 (the weights-once batched kernels)
 8 distinct layer sets, 3 passes (24 launches); capture with  ncu --set full -k regex:<kernel> -s 8 -c 3 ..."""
 import sys, torch
 sys.path.insert(0, ".")
@@ -32,20 +33,21 @@ if what == "gqa":
 elif what == "paged":
     kv = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
     table = sys.argv[3] if len(sys.argv) > 3 else "random"
+    bs = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     H, HQ = 4096, 32
-    ws = torch.zeros(cabi.workspace_bytes(H, 1), dtype=torch.uint8, device=dev)
-    L = [dict(w_qkv=r(3 * H, H, sc=0.02), w_o=r(H, H, sc=0.02), k=r(kv + 1, H), v=r(kv + 1, H), rms=(1 + 0.1 * r(H).float()).half(),
-              o=torch.empty(1, H, dtype=torch.float16, device=dev), ro=torch.empty(1, H, dtype=torch.float16, device=dev)) for _ in range(8)]
+    ws = torch.zeros(cabi.workspace_bytes(H, bs), dtype=torch.uint8, device=dev)
+    L = [dict(w_qkv=r(3 * H, H, sc=0.02), w_o=r(H, H, sc=0.02), k=r(bs * (kv + 1), H), v=r(bs * (kv + 1), H), rms=(1 + 0.1 * r(H).float()).half(),
+              o=torch.empty(bs, H, dtype=torch.float16, device=dev), ro=torch.empty(bs, H, dtype=torch.float16, device=dev)) for _ in range(8)]
     kp = torch.tensor([l["k"].data_ptr() for l in L], dtype=torch.uint64).to(dev)
     vp = torch.tensor([l["v"].data_ptr() for l in L], dtype=torch.uint64).to(dev)
-    indptr = torch.tensor([0, kv + 1], dtype=torch.int32, device=dev)
-    idx = (torch.arange(kv + 1) if table == "sequential" else torch.randperm(kv + 1)).int().to(dev)
-    pos = torch.tensor([kv], dtype=torch.int64, device=dev)
+    indptr = (torch.arange(0, bs + 1, dtype=torch.int32) * (kv + 1)).to(dev)
+    idx = (torch.arange(bs * (kv + 1)) if table == "sequential" else torch.randperm(bs * (kv + 1))).int().to(dev)
+    pos = torch.full((bs,), kv, dtype=torch.int64, device=dev)
     tab = torch.rand(kv + 1, 128, device=dev)
-    x = r(1, H); res = r(1, H)
+    x = r(bs, H); res = r(bs, H)
     for _ in range(3):
         for li, lay in enumerate(L):
-            a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=0, hidden=H, n_q_heads=HQ, n_kv_heads=HQ, head_dim=128, batch=1,
+            a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=0, hidden=H, n_q_heads=HQ, n_kv_heads=HQ, head_dim=128, batch=bs,
                                  layer_id=li, eps=1e-5, x=x.data_ptr(), residual_in=res.data_ptr(), residual_out=lay["ro"].data_ptr(),
                                  w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(), out=lay["o"].data_ptr(),
                                  indptr=indptr.data_ptr(), indices=idx.data_ptr(), k_pool_ptrs=kp.data_ptr(), v_pool_ptrs=vp.data_ptr(),

@@ -13,8 +13,8 @@ d = {k: v.to(dev) for k, v in O.make_inputs(S7, 77, seed=2, layout="sglang").ite
 clusterfusion.llama_decoder_layer_sglang(d["x"], d["residual"].clone(), d["weight_qkv"], d["weight_o"], d["k_cache"], d["v_cache"], d["rms_w"], 1e-5, d["cos"], d["sin"])
 g = {k: v.to(dev) for k, v in O.make_inputs(S8, 77, seed=3, layout="sglang").items()}
 clusterfusion.llama_decoder_layer_sglang(g["x"], g["residual"].clone(), g["weight_qkv"], g["weight_o"], g["k_cache"], g["v_cache"], g["rms_w"], 1e-5, g["cos"], g["sin"])
-for shape, dd, bs in ((S7, d, 1), (S7, d, 3), (S7, d, 5), (S7, d, 9), (S8, g, 2)):   # bs 3: chunks-of-4 kernel; bs 5: chunks-of-8 kernel;
-                                                                                  # bs 9: two chunks = 256 CTAs = two waves of clusters
+for shape, dd, bs in ((S7, d, 1), (S7, d, 3), (S7, d, 5), (S7, d, 9), (S8, g, 2), (S8, g, 4), (S8, g, 9)):   # bs 3: chunks-of-4 kernel; bs 5: chunks-of-8 kernel;
+                                                                                  # bs 9: two chunks = 256 CTAs = two waves of clusters; S8 bs 2: group kernel per request, bs 4 / 9: weights-once GQA kernel
     if ONLY and int(ONLY) != bs:
         continue
     lens = [33, 0, 17, 40, 5, 16, 1, 31, 8][:bs]

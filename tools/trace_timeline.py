@@ -45,7 +45,7 @@ if variant == 2:
     kptrs = torch.tensor([l["k"].data_ptr() for l in layers], dtype=torch.uint64).to(dev)
     vptrs = torch.tensor([l["v"].data_ptr() for l in layers], dtype=torch.uint64).to(dev)
     indptr = (torch.arange(0, BS + 1, dtype=torch.int32) * (kv + 1)).to(dev)
-    indices = torch.randperm(BS * (kv + 1)).int().to(dev)
+    indices = (torch.arange(BS * (kv + 1)) if os.environ.get('CF_SEQ_PAGES') == '1' else torch.randperm(BS * (kv + 1))).int().to(dev)
     positions = torch.full((BS,), kv, dtype=torch.int64, device=dev)
     cos_sin = torch.rand(kv + 1, D, device=dev)
 if variant == 2 and NH == NKV:
@@ -94,8 +94,8 @@ if os.environ.get("CF_TRACE_SAVE"):
     np.save(os.environ["CF_TRACE_SAVE"], t)
 print("variant", variant, "H", H, "heads", NH, NKV, "ctas", ncta)
 names = {0: "entry", 12: "first TMA issue", 1: "rms done", 2: "qkv tiles done", 3: "xchg1 done", 4: "rope done", 5: "kv tiles done",
-         6: "xchg2 done", 7: "o tiles done", 13: "prod last TMA", 8: "reds+counter", 9: "cta done", 10: "state published",
-         11: "states read w0", 14: "states read all"}
+         6: "xchg2 done", 7: "o tiles done", 13: "prod last TMA", 8: "reds+counter", 9: "cta done", 10: "state published / 2nd-half kv done (batch8)",
+         11: "states read w0 / 2nd-half merges done (batch8)", 14: "states read all"}
 starts = [t[i][:, 0].min() for i in range(nl)]
 ends = [t[i][:, 9].max() for i in range(nl)]
 print("launch-to-launch (first CTA entry) us:", [round((starts[i + 1] - starts[i]) / 1e3, 2) for i in range(nl - 1)])
