@@ -492,12 +492,16 @@ def run_ours(args, rank, world, local_rank):
     def gqa_legs():
         return run_gqa_8b(torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl, kvs=(1024, 8192))
 
-    gqa = ffn_res = batched = deepseek = None
+    gqa = ffn_res = batched = batched_gqa = deepseek = None
     if not args.no_sweep:
         deepseek = guarded(run_deepseek, torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
         gqa = guarded(gqa_legs)
         ffn_res = guarded(run_ffn, torch, cabi, dev, timed_replays, peak, pdl=not args.no_pdl)
         batched = guarded(run_batched_paged, torch, cabi, dev, timed_replays, peak)
+        batched_gqa = {"llama3_8b": guarded(run_batched_paged, torch, cabi, dev, timed_replays, peak, batches=(4, 8), HEADS=32, KV_HEADS=8),
+                       "llama3_8b_kv8k": guarded(run_batched_paged, torch, cabi, dev, timed_replays, peak, kv=8192, batches=(8,), HEADS=32, KV_HEADS=8),
+                       "llama2_70b_layer": guarded(run_batched_paged, torch, cabi, dev, timed_replays, peak, nl=4, batches=(8,),
+                                                   HIDDEN=8192, HEADS=64, KV_HEADS=8)}
     # ------------------------------------------------------------------ whole-model decode
     full = full8b = None
     if not args.no_sweep and not args.no_full_model:
@@ -622,6 +626,8 @@ def run_ours(args, rank, world, local_rank):
         line["fused_ffn_half_layer"] = ffn_res
     if batched is not None:
         line["batched_paged_decode"] = batched
+    if batched_gqa is not None:
+        line["batched_paged_decode_gqa"] = batched_gqa
     if gqa is not None:
         line["llama3_8b_gqa"] = gqa
     if deepseek is not None:
@@ -692,18 +698,20 @@ def run_ref_gpu_kernel(torch, dev, kvs=(1024, 16384), nsets=8):
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
-def run_batched_paged(torch, cabi, dev, timed_replays, peak, kv=1024, nl=8, batches=(1, 4, 8)):
-    """Row f3: 15-argument paged form at batch > 1, Llama-2-7B shapes, kv rows per request = `kv`.  The batched kernel
-    streams every weight tile once per chunk of 4 requests; CF_FLAG_PER_REQUEST launches one cluster per (request, head)
-    like the reference (grid 32*4*bs, llama_kernel_batch_sglang_dispatch.cu:89)."""
+def run_batched_paged(torch, cabi, dev, timed_replays, peak, kv=1024, nl=8, batches=(1, 4, 8), HIDDEN=HIDDEN, HEADS=HEADS, KV_HEADS=HEADS):
+    """Row f3: 15-argument paged form at batch > 1 (default: Llama-2-7B shapes), kv rows per request = `kv`.  The batched kernels
+    stream every weight tile once per chunk of 4 / 8 requests (MHA: llama_decoder_batch*_kernel.cuh; grouped-query shapes:
+    llama_decoder_gqa_batch_kernel.cuh); CF_FLAG_PER_REQUEST launches one cluster / group set per (request, head) like the
+    reference (grid 32*4*bs, llama_kernel_batch_sglang_dispatch.cu:89)."""
     g = torch.Generator(device=dev).manual_seed(31)
     r = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * sc).half()
     out = []
-    L = [dict(w_qkv=r(3 * HIDDEN, HIDDEN, sc=0.02), w_o=r(HIDDEN, HIDDEN, sc=0.02), rms=(1 + 0.1 * r(HIDDEN).float()).half())
+    QD, KVD = HEADS * D, KV_HEADS * D
+    L = [dict(w_qkv=r(QD + 2 * KVD, HIDDEN, sc=0.02), w_o=r(HIDDEN, QD, sc=0.02), rms=(1 + 0.1 * r(HIDDEN).float()).half())
          for _ in range(nl)]
     for bs in batches:
         nslots = bs * (kv + 1)
-        pools = [(r(nslots, HIDDEN), r(nslots, HIDDEN)) for _ in range(nl)]
+        pools = [(r(nslots, KVD), r(nslots, KVD)) for _ in range(nl)]
         kptrs = torch.tensor([pk.data_ptr() for pk, _ in pools], dtype=torch.uint64).to(dev)
         vptrs = torch.tensor([pv.data_ptr() for _, pv in pools], dtype=torch.uint64).to(dev)
         indptr = torch.arange(0, bs + 1, dtype=torch.int32, device=dev) * (kv + 1)
@@ -723,7 +731,7 @@ def run_batched_paged(torch, cabi, dev, timed_replays, peak, kv=1024, nl=8, batc
 
             def launch(h, rr, li, st):
                 a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=fl | cabi.CF_FLAG_PDL, hidden=HIDDEN, n_q_heads=HEADS,
-                                     n_kv_heads=HEADS, head_dim=D, batch=bs, layer_id=li, eps=1e-5, x=h.data_ptr(), residual_in=rr.data_ptr(),
+                                     n_kv_heads=KV_HEADS, head_dim=D, batch=bs, layer_id=li, eps=1e-5, x=h.data_ptr(), residual_in=rr.data_ptr(),
                                      residual_out=bufs[li][1].data_ptr(), w_qkv=L[li]["w_qkv"].data_ptr(), w_o=L[li]["w_o"].data_ptr(),
                                      rms_w=L[li]["rms"].data_ptr(), out=bufs[li][0].data_ptr(), indptr=indptr.data_ptr(),
                                      indices=indices.data_ptr(), k_pool_ptrs=kptrs.data_ptr(), v_pool_ptrs=vptrs.data_ptr(),
@@ -745,9 +753,10 @@ def run_batched_paged(torch, cabi, dev, timed_replays, peak, kv=1024, nl=8, batc
                     h, rr = bufs[li]
             ms = timed_replays(gr, 30, 5)
             us = ms * 1e3 / (30 * nl)
-            B = 2 * 4 * HIDDEN * HIDDEN + bs * 4 * kv * HIDDEN          # weights once + every request's K and V
+            B = 2 * (2 * QD + 2 * KVD) * HIDDEN + bs * 4 * kv * KVD     # weights once + every request's K and V
             row[name] = {"us_per_layer": round(us, 2), "tokens_per_s_32_layers": round(bs * 1e6 / (us * LAYERS), 1),
-                         "achieved_gbs_weights_once": round(B / (us * 1e-6) / 1e9, 1)}
+                         "achieved_gbs_weights_once": round(B / (us * 1e-6) / 1e9, 1),
+                         "frac_of_measured_peak": round(B / (us * 1e-6) / 1e9 / peak, 4)}
             del gr
         if "per_request" in row:
             row["speedup_vs_per_request"] = round(row["per_request"]["us_per_layer"] / row["batched"]["us_per_layer"], 2)

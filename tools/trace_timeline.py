@@ -56,10 +56,14 @@ else:
     ncl = NKV * ((NH // NKV) // 4)
     if flags & 4:                       # CF_FLAG_GQA_CLUSTER: first-generation cluster kernel
         ncta = ncl * (16 if ncl <= 4 else 8)
-    else:                               # group kernel: G CTAs per group
+    elif variant == 2 and BS >= 2 and not (flags & 16) and not (BS == 2 and ncl * 16 <= 148):   # weights-once GQA kernel
         G = 64
-        while G > 8 and ncl * G > 148: G //= 2
-        ncta = ncl * G
+        while G > 8 and (ncl * G > 148 or H // G < 128): G //= 2
+        ncta = ncl * G * ((BS + 7) // 8)
+    else:                               # group kernel: G CTAs per group, requests as the slow grid dimension
+        G = 64
+        while G > 8 and ncl * G * BS > 148: G //= 2
+        ncta = ncl * G * BS
 trace = torch.zeros(nl, ncta, 16, dtype=torch.int64, device=dev)
 def launch(i, h):
     lay = layers[i]
@@ -94,7 +98,7 @@ if os.environ.get("CF_TRACE_SAVE"):
     np.save(os.environ["CF_TRACE_SAVE"], t)
 print("variant", variant, "H", H, "heads", NH, NKV, "ctas", ncta)
 names = {0: "entry", 12: "first TMA issue", 1: "rms done", 2: "qkv tiles done", 3: "xchg1 done", 4: "rope done", 5: "kv tiles done",
-         6: "xchg2 done", 7: "o tiles done", 13: "prod last TMA", 8: "reds+counter", 9: "cta done", 10: "state published / 2nd-half kv done (batch8)",
+         6: "xchg2 done", 7: "o tiles done", 13: "prod last TMA", 8: "reds+counter", 9: "cta done", 10: "state published / 2nd-half kv done (batch8) / ag published (gqa batch)",
          11: "states read w0 / 2nd-half merges done (batch8)", 14: "states read all"}
 starts = [t[i][:, 0].min() for i in range(nl)]
 ends = [t[i][:, 9].max() for i in range(nl)]
