@@ -66,9 +66,9 @@ enum {
                                last-arriver finalize.  Costs ~2.5 us per layer in a PDL chain: every CTA then lives until the
                                slowest cluster has published, so the next layer's CTAs start later (measured). */
 
-#define CF_FLAG_PER_REQUEST 0x10u /* PAGED, batch >= 2, MHA: launch one cluster per (request, head) as the reference does
-                                     (weights re-streamed per request) instead of the batched kernel that streams every
-                                     weight tile once per chunk of 4 requests (measurement / A-B)                          */
+#define CF_FLAG_PER_REQUEST 0x10u /* PAGED, batch >= 2: launch one cluster (MHA) / one set of groups (grouped-query shapes) per
+                                     request as the reference does (weights re-streamed per request) instead of the batched
+                                     kernels that stream every weight tile once per chunk of 4 / 8 requests (measurement / A-B) */
 
 /* 0x20u was CF_FLAG_BATCH4 (chunks of 4 requests at batch >= 5, removed in ABI 3) */
 
@@ -135,7 +135,8 @@ typedef struct CfLlamaArgs {
     void* tp_peer[8];
 } CfLlamaArgs;
 
-/* Bytes of zero-initialised device workspace needed for a call with this hidden / batch. */
+/* Bytes of zero-initialised device workspace needed for a call with this hidden / batch (about 1 MB per request + 1-4 MB, and
+ * for batch >= 2 another 18-22 MB per chunk of 8 requests: the exchange words of the grouped-query batched kernel). */
 size_t cf_llama_workspace_bytes(int32_t hidden, int32_t batch);
 
 /* Validate, encode (cached) TMA descriptors, launch the fused kernel on `stream`. */
