@@ -51,8 +51,9 @@ struct SmemB8 {
     static constexpr int QKV_FIN = X + X_BYTES;                           // fp16 [8][384]  roped q (unscaled) | k | v
     static constexpr int ATTN_OUT = QKV_FIN + BC * QKV_OUT * 2;           // fp16 [8][128]
     static constexpr int RED = ATTN_OUT + BC * HEAD_DIM * 2;              // fp32 [12][8] + [8]
-    static constexpr int META = RED + (CONSUMER_WARPS + 1) * BC * 4;      // int [8][4]: kv_base, row_begin, row_end, new_slot; u32 [9] tile0
-    static constexpr int BARS = META + (BC * 4 + BC + 1 + 3) / 4 * 16;    // u64 full[NSTAGES], xbar[6]
+    static constexpr int META = RED + (CONSUMER_WARPS + 1) * BC * 4;      // int [8][4] requests: kv_base, len, new_slot, -; int [8][4] segments:
+                                                                          // request | owner << 8, row begin, row end, -; u32 [9] tile0; [1] n_seg
+    static constexpr int BARS = META + 76 * 4;                            // u64 full[NSTAGES], xbar[6]
     static constexpr int FLAGS = BARS + (NSTAGES + 6) * 8;                // u32 [8]
     static constexpr int TOTAL = FLAGS + BC * 4;
     static_assert(BARS % 8 == 0, "mbarrier alignment");
@@ -96,13 +97,18 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
     float* ostage = reinterpret_cast<float*>(smem + S::OSTAGE);
     float* red = reinterpret_cast<float*>(smem + S::RED);
     int* meta = reinterpret_cast<int*>(smem + S::META);                       // [b][4]
-    uint32_t* tile0 = reinterpret_cast<uint32_t*>(smem + S::META) + BC * 4;   // [9]
+    int* mseg = meta + BC * 4;                                                // [s][4]
+    uint32_t* tile0 = reinterpret_cast<uint32_t*>(mseg + BC * 4);             // [9]: first KV tile of segment s (entries >= n_seg: total)
+    int* mmisc = reinterpret_cast<int*>(tile0 + BC + 1);                      // [0] n_seg
     uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
 
-    // ---- per-request KV ranges -> shared memory (8 requests x 5 words would not stay in registers).  Lane b of warp 0 handles
-    //      request b (the eight index loads go out together), the tile offsets are a warp prefix sum: no single-thread loop
-    //      in front of the block barrier (compute-sanitizer synccheck flagged the warp as divergent at that barrier when
-    //      thread 0 alone walked the requests -- second chunk of a batch of 9, profiles/round2_sanitizer.txt). ----
+    // ---- segments: the chunk's KV rows (this head), concatenated request after request, are cut into CLUSTER equal ranges
+    //      (multiples of 16 rows), so a CTA streams one or two SEGMENTS (request, row range) however ragged the batch is and all
+    //      12 warps work on the same request at a time: one copy of the KV loop and one block merge per segment instead of
+    //      per-request register states in eight unrolled copies (207 KB of code, 64 % instruction-cache hit rate, 16 us per
+    //      half chunk against 9.5 us for the same rows in the chunks-of-4 kernel).  A request's new token is folded in by the rank
+    //      that holds its last row ("owner"; an empty request: the rank its offset falls into).  Lane b of warp 0 handles
+    //      request b, offsets are warp prefix sums (no single-thread loop in front of the block barrier). ----
     if (warp == 0) {
         const int b = (int)lane;
         int len = 0, kb = 0, ns = 0;
@@ -112,19 +118,42 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
             len = end - kb;
             ns = p.indices[end];
         }
-        const int chunk = (((len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);
-        const int rb = min((int)rank * chunk, len), re = min(rb + chunk, len);
-        uint32_t acc = (b < BC) ? (uint32_t)((re - rb + ROWS512 - 1) / ROWS512) : 0u;
+        int incl = len;
 #pragma unroll
         for (int o = 1; o < BC; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, acc, o);
-            if ((int)lane >= o) acc += v;
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
         }
-        if (b < BC) {
-            meta[b * 4 + 0] = kb; meta[b * 4 + 1] = rb; meta[b * 4 + 2] = re; meta[b * 4 + 3] = ns;
-            tile0[b + 1] = acc;
+        const int T = __shfl_sync(0xffffffffu, incl, BC - 1);
+        const int off = incl - len;
+        const int per = (((T + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);
+        const int c0 = min((int)rank * per, T), c1 = min(c0 + per, T);
+        int s0 = max(c0, off) - off, s1 = min(c1, off + len) - off;
+        const bool nonempty = b < nb && s1 > s0;
+        const int owner = len > 0 ? (off + len - 1) / per : (per > 0 ? min(off / per, CLUSTER - 1) : b % CLUSTER);
+        const bool has = b < nb && (nonempty || owner == (int)rank);
+        if (!nonempty) { s0 = 0; s1 = 0; }
+        const uint32_t nt = has ? (uint32_t)((s1 - s0 + ROWS512 - 1) / ROWS512) : 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        const int idx = __popc(bal & ((1u << lane) - 1u));
+        uint32_t tincl = nt;
+#pragma unroll
+        for (int o = 1; o < BC; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, tincl, o);
+            if ((int)lane >= o) tincl += v;
         }
-        if (lane == 0) tile0[0] = 0;
+        const uint32_t total = __shfl_sync(0xffffffffu, tincl, BC - 1);
+        const int nseg = __popc(bal);
+        if (b < BC) { meta[b * 4 + 0] = kb; meta[b * 4 + 1] = len; meta[b * 4 + 2] = ns; meta[b * 4 + 3] = owner; }
+        if ((int)lane >= nseg && lane <= BC) tile0[lane] = total;
+        __syncwarp();
+        if (has) {
+            mseg[idx * 4 + 0] = b | ((owner == (int)rank) ? 256 : 0);
+            mseg[idx * 4 + 1] = s0;
+            mseg[idx * 4 + 2] = s1;
+            tile0[idx] = tincl - nt;
+        }
+        if (lane == 0) mmisc[0] = nseg;
         __syncwarp();
     }
     if (lane == 0) {
@@ -159,19 +188,20 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
     const bool pool_maps = p.k_base != nullptr && kpool == p.k_base && vpool == p.v_base;
     if (tid == 0 && pool_maps) { prefetch_tmap(&p.tm_k); prefetch_tmap(&p.tm_v); prefetch_tmap(&p.tm_kg); prefetch_tmap(&p.tm_vg); }
 
-    auto request_of = [&](uint32_t t) -> int {            // which request KV tile t (phase-local index) belongs to
-        int b = 0;
+    const int n_seg = mmisc[0];
+    auto seg_of = [&](uint32_t t) -> int {                // which segment KV tile t (phase-local index) belongs to
+        int sgi = 0;
 #pragma unroll
-        for (int q = 1; q < BC; ++q) b += (t >= tile0[q]) ? 1 : 0;
-        return b;
+        for (int q = 1; q < BC; ++q) sgi += (t >= tile0[q]) ? 1 : 0;
+        return sgi;
     };
     int pre_slot0 = 0, pre_slot1 = 0;
     uint32_t pre_g0 = 0xffffffffu, pre_g1 = 0xffffffffu;
     auto page_of = [&](uint32_t g) -> int {               // page index of this lane's row of KV tile g
         const uint32_t t = g - n_qkv_tiles;
-        const int b = request_of(t);
-        const int r = meta[b * 4 + 1] + (int)(t - tile0[b]) * ROWS512 + (int)(lane & 15);
-        return (r < meta[b * 4 + 2]) ? p.indices[meta[b * 4 + 0] + r] : 0;
+        const int sgi = seg_of(t);
+        const int r = mseg[sgi * 4 + 1] + (int)(t - tile0[sgi]) * ROWS512 + (int)(lane & 15);
+        return (r < mseg[sgi * 4 + 2]) ? p.indices[meta[(mseg[sgi * 4] & 255) * 4] + r] : 0;
     };
     auto issue_tile = [&](uint32_t g) {
         if (g >= total_tiles) return;
@@ -191,14 +221,12 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
             }
         } else if (g < n_qkv_tiles + n_kv_tiles) {
             const uint32_t t = g - n_qkv_tiles;
-            const int b = request_of(t);
-            const int rbeg = meta[b * 4 + 1], rend = meta[b * 4 + 2];
-            const int i = (int)(t - tile0[b]);
-            const int r = rbeg + i * ROWS512 + (lane & 15);
+            const int sgi = seg_of(t);
+            const int rbeg = mseg[sgi * 4 + 1], rend = mseg[sgi * 4 + 2];
+            const int i = (int)(t - tile0[sgi]);
             const bool odd = (g / CONSUMER_WARPS) & 1u;
             const long long slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
             const int nvalid = min(ROWS512, rend - (rbeg + i * ROWS512));
-            (void)r;
             issue_kv_stage(p, pool_maps, false, dst, fb, head * HEAD_DIM, slot, nvalid, kpool, vpool, kv_cols, lane, pol);
         } else {
             if (lane == 0) {
@@ -318,11 +346,11 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
                     outv = __float2half_rn(rot);
                     if (which == 1 && rank == 0) {
                         __half* kp = reinterpret_cast<__half*>(p.k_pool_ptrs[p.layer_id]);
-                        kp[(size_t)meta[b * 4 + 3] * kv_cols + head * HEAD_DIM + d] = outv;
+                        kp[(size_t)meta[b * 4 + 2] * kv_cols + head * HEAD_DIM + d] = outv;
                     }
                 } else if (rank == 0) {
                     __half* vp = reinterpret_cast<__half*>(p.v_pool_ptrs[p.layer_id]);
-                    vp[(size_t)meta[b * 4 + 3] * kv_cols + head * HEAD_DIM + d] = outv;
+                    vp[(size_t)meta[b * 4 + 2] * kv_cols + head * HEAD_DIM + d] = outv;
                 }
             }
             qkv_fin[b * S::QKV_OUT + e] = outv;
@@ -332,135 +360,145 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
     CF_MARK(4);
     dsm::cluster_arrive();                                      // B2: done reading ag_recv (X changes role again)
 
-    // ---- phase 2: flash-decode + softmax-state exchange, one half chunk at a time -------------------------------------
+    // ---- phase 2: flash-decode over this CTA's segments (all 12 warps on one request at a time), then the softmax-state
+    //      exchange, one half chunk at a time ------------------------------------------------------------------------------
     {
         const int sub = lane >> 4, c = lane & 15;
+        // block-merged state of request b on this CTA: thread tid < 128 keeps o[dim tid] in registers, (m, l) sit in red[2b], red[2b+1]
+        // (the RMSNorm partials there are dead); requests without a segment here stay (-inf, 0, 0)
+        float Ov[BC];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float m[HB], l[HB], o8[HB][8];
+        for (int b = 0; b < BC; ++b) Ov[b] = 0.f;
+        if (tid < (uint32_t)BC) { red[2 * tid] = -INFINITY; red[2 * tid + 1] = 0.f; }
+        for (int sg = 0; sg < n_seg; ++sg) {
+            const int b = mseg[sg * 4] & 255;
+            const bool owner = (mseg[sg * 4] & 256) != 0;
+            const int rbeg = mseg[sg * 4 + 1], rend = mseg[sg * 4 + 2];
+            const uint32_t nt = tile0[sg + 1] - tile0[sg];
+            const uint32_t gb = gbase + tile0[sg];
+            float m = -INFINITY, l = 0.f, o8[8];
 #pragma unroll
-            for (int bb = 0; bb < HB; ++bb) {
-                const int b = h * HB + bb;
-                m[bb] = -INFINITY; l[bb] = 0.f;
+            for (int k = 0; k < 8; ++k) o8[k] = 0.f;
+            float q8[8];
+            unpack8(*reinterpret_cast<const uint4*>(qkv_fin + b * S::QKV_OUT + c * 8), q8);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o8[bb][k] = 0.f;
-                float q8[8];
-                unpack8(*reinterpret_cast<const uint4*>(qkv_fin + b * S::QKV_OUT + c * 8), q8);
+            for (int k = 0; k < 8; ++k) q8[k] *= kScaleLog2;
+            for (uint32_t i = first_tile(gb, warp); i < nt; i += CONSUMER_WARPS) {
+                const uint32_t g = gb + i, s = ring_stage(g);
+                ring_wait_full(full_u32, g);
+                const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
+                const uint4* vt = kt + STAGE_BYTES / 32;
+                const int rows_left = rend - (rbeg + (int)i * ROWS512);
+                float sc[ROWS512 / 2];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) q8[k] *= kScaleLog2;
-                const uint32_t nt = tile0[b + 1] - tile0[b];
-                const uint32_t gb = gbase + tile0[b];
-                const int rbeg = meta[b * 4 + 1], rend = meta[b * 4 + 2];
-                for (uint32_t i = first_tile(gb, warp); i < nt; i += CONSUMER_WARPS) {
-                    const uint32_t g = gb + i, s = ring_stage(g);
-                    ring_wait_full(full_u32, g);
-                    const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
-                    const uint4* vt = kt + STAGE_BYTES / 32;
-                    const int rows_left = rend - (rbeg + (int)i * ROWS512);
-                    float sc[ROWS512 / 2];
-#pragma unroll
-                    for (int jj = 0; jj < ROWS512 / 2; ++jj) {
-                        const int row = 2 * jj + sub;
-                        float k8[8];
-                        unpack8(kt[row * 16 + c], k8);
-                        float a = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) a = fmaf(q8[k], k8[k], a);
-                        a += __shfl_xor_sync(0xffffffffu, a, 1);
-                        a += __shfl_xor_sync(0xffffffffu, a, 2);
-                        a += __shfl_xor_sync(0xffffffffu, a, 4);
-                        a += __shfl_xor_sync(0xffffffffu, a, 8);
-                        sc[jj] = (row < rows_left) ? a : -INFINITY;
-                    }
-                    float mx = sc[0];
-#pragma unroll
-                    for (int jj = 1; jj < ROWS512 / 2; ++jj) mx = fmaxf(mx, sc[jj]);
-                    const float m_new = fmaxf(m[bb], mx);
-                    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-                    const float corr = dsm::exp2_diff(m[bb], m_use);
-                    l[bb] *= corr;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) o8[bb][k] *= corr;
-#pragma unroll
-                    for (int jj = 0; jj < ROWS512 / 2; ++jj) {
-                        const int row = 2 * jj + sub;
-                        const float pr = dsm::fast_exp2(sc[jj] - m_use);
-                        l[bb] += pr;
-                        uint4 raw = vt[row * 16 + c];
-                        if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
-                        float v8[8];
-                        unpack8(raw, v8);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) o8[bb][k] = fmaf(pr, v8[k], o8[bb][k]);
-                    }
-                    m[bb] = m_new;
-                    __syncwarp();
-                    issue_tile(g + NSTAGES);
-                }
-            }
-            if (h == 0) { CF_MARK(5); } else { CF_MARK(10); }   // KV tiles of this half consumed (warp 0)
-            // merge the two half-warps in registers, then block merge one request per round through [12][132]
-#pragma unroll
-            for (int bb = 0; bb < HB; ++bb) {
-                const float m2 = __shfl_xor_sync(0xffffffffu, m[bb], 16);
-                const float l2 = __shfl_xor_sync(0xffffffffu, l[bb], 16);
-                const float M = fmaxf(m[bb], m2);
-                const float w1 = dsm::exp2_diff(m[bb], M), w2 = dsm::exp2_diff(m2, M);
-                l[bb] = l[bb] * w1 + l2 * w2;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float o2 = __shfl_xor_sync(0xffffffffu, o8[bb][k], 16);
-                    o8[bb][k] = o8[bb][k] * w1 + o2 * w2;
-                }
-                m[bb] = M;
-            }
-            if (h == 0) dsm::cluster_wait();                    // B2: every peer is past its RoPE, X may take exchange-2 data
-            else dsm::cluster_wait();                           // B3: every peer has merged the first half out of attn_recv
-#pragma unroll
-            for (int bb = 0; bb < HB; ++bb) {
-                const int b = h * HB + bb;
-                if (sub == 0) {
-                    float* slot = attn_part + warp * S::PAY;
-                    if (c == 0) { slot[0] = m[bb]; slot[1] = l[bb]; }
-                    *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[bb][0], o8[bb][1], o8[bb][2], o8[bb][3]);
-                    *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[bb][4], o8[bb][5], o8[bb][6], o8[bb][7]);
-                }
-                if (warp == 0) {
+                for (int jj = 0; jj < ROWS512 / 2; ++jj) {
+                    const int row = 2 * jj + sub;
+                    float k8[8];
+                    unpack8(kt[row * 16 + c], k8);
                     float a = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        a = fmaf(__half2float(qkv_fin[b * S::QKV_OUT + lane * 4 + k]),
-                                 __half2float(qkv_fin[b * S::QKV_OUT + HEAD_DIM + lane * 4 + k]), a);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                    if (lane == 0) red[CONSUMER_WARPS * BC + b] = a * kScaleLog2;
+                    for (int k = 0; k < 8; ++k) a = fmaf(q8[k], k8[k], a);
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    sc[jj] = (row < rows_left) ? a : -INFINITY;
                 }
-                dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-                if (tid < HEAD_DIM) {
-                    const bool with_new = (rank == 0);
-                    const float s_new = red[CONSUMER_WARPS * BC + b];
-                    float M = with_new ? s_new : -INFINITY;
+                float mx = sc[0];
 #pragma unroll
-                    for (int gI = 0; gI < CONSUMER_WARPS; ++gI) M = fmaxf(M, attn_part[gI * S::PAY]);
-                    float L = 0.f, Ov = 0.f;
+                for (int jj = 1; jj < ROWS512 / 2; ++jj) mx = fmaxf(mx, sc[jj]);
+                const float m_new = fmaxf(m, mx);
+                const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                const float corr = dsm::exp2_diff(m, m_use);
+                l *= corr;
 #pragma unroll
-                    for (int gI = 0; gI < CONSUMER_WARPS; ++gI) {
-                        const float w = dsm::exp2_diff(attn_part[gI * S::PAY], M);
-                        L = fmaf(attn_part[gI * S::PAY + 1], w, L);
-                        Ov = fmaf(attn_part[gI * S::PAY + 4 + tid], w, Ov);
-                    }
-                    if (with_new) {
-                        const float w = dsm::exp2_diff(s_new, M);
-                        L += w;
-                        Ov = fmaf(__half2float(qkv_fin[b * S::QKV_OUT + 2 * HEAD_DIM + tid]), w, Ov);
-                    }
-                    float* stp = attn_src + bb * S::PAY;
-                    stp[4 + tid] = Ov;
-                    if (tid == 0) { stp[0] = M; stp[1] = L; stp[2] = 0.f; stp[3] = 0.f; }
+                for (int k = 0; k < 8; ++k) o8[k] *= corr;
+#pragma unroll
+                for (int jj = 0; jj < ROWS512 / 2; ++jj) {
+                    const int row = 2 * jj + sub;
+                    const float pr = dsm::fast_exp2(sc[jj] - m_use);
+                    l += pr;
+                    uint4 raw = vt[row * 16 + c];
+                    if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);
+                    float v8[8];
+                    unpack8(raw, v8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o8[k] = fmaf(pr, v8[k], o8[k]);
                 }
-                dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+                m = m_new;
+                __syncwarp();
+                issue_tile(g + NSTAGES);
             }
-            if (h == 0) { CF_MARK(3); } else { CF_MARK(11); }   // block merges of this half done
+            // merge the two half-warps in registers, then the block merge through [12][132]
+            {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m, 16);
+                const float l2 = __shfl_xor_sync(0xffffffffu, l, 16);
+                const float M = fmaxf(m, m2);
+                const float w1 = dsm::exp2_diff(m, M), w2 = dsm::exp2_diff(m2, M);
+                l = l * w1 + l2 * w2;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float o2 = __shfl_xor_sync(0xffffffffu, o8[k], 16);
+                    o8[k] = o8[k] * w1 + o2 * w2;
+                }
+                m = M;
+            }
+            if (sub == 0) {
+                float* slot = attn_part + warp * S::PAY;
+                if (c == 0) { slot[0] = m; slot[1] = l; }
+                *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+                *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+            }
+            if (owner && warp == 0) {                           // score of the request's new token
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    a = fmaf(__half2float(qkv_fin[b * S::QKV_OUT + lane * 4 + k]),
+                             __half2float(qkv_fin[b * S::QKV_OUT + HEAD_DIM + lane * 4 + k]), a);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) red[CONSUMER_WARPS * BC + b] = a * kScaleLog2;
+            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            if (tid < HEAD_DIM) {
+                const float s_new = red[CONSUMER_WARPS * BC + b];
+                float M = owner ? s_new : -INFINITY;
+#pragma unroll
+                for (int gI = 0; gI < CONSUMER_WARPS; ++gI) M = fmaxf(M, attn_part[gI * S::PAY]);
+                float L = 0.f, Ovv = 0.f;
+#pragma unroll
+                for (int gI = 0; gI < CONSUMER_WARPS; ++gI) {
+                    const float w = dsm::exp2_diff(attn_part[gI * S::PAY], M);
+                    L = fmaf(attn_part[gI * S::PAY + 1], w, L);
+                    Ovv = fmaf(attn_part[gI * S::PAY + 4 + tid], w, Ovv);
+                }
+                if (owner) {
+                    const float w = dsm::exp2_diff(s_new, M);
+                    L += w;
+                    Ovv = fmaf(__half2float(qkv_fin[b * S::QKV_OUT + 2 * HEAD_DIM + tid]), w, Ovv);
+                }
+#pragma unroll
+                for (int q = 0; q < BC; ++q) Ov[q] = (q == b) ? Ovv : Ov[q];
+                if (tid == 0) { red[2 * b] = M; red[2 * b + 1] = L; }
+            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        }
+        gbase += n_kv_tiles;
+        CF_MARK(5);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            dsm::cluster_wait();                                // h == 0: B2, every peer is past its RoPE (X may take exchange-2 data);
+                                                                // h == 1: B3, every peer has merged the first half out of attn_recv
+            if (tid < HEAD_DIM) {
+#pragma unroll
+                for (int bb = 0; bb < HB; ++bb) {
+                    float* stp = attn_src + bb * S::PAY;
+                    stp[4 + tid] = Ov[h * HB + bb];
+                    if (tid == 0) { stp[0] = red[2 * (h * HB + bb)]; stp[1] = red[2 * (h * HB + bb) + 1]; stp[2] = 0.f; stp[3] = 0.f; }
+                }
+            }
+            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+            if (h == 0) { CF_MARK(3); } else { CF_MARK(11); }
             uint32_t ph_a = 0;
             cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
                 HB * S::PAY * 4, tid, HB * S::PAY, rank, smem_base + S::ATTN_SRC, smem_base + S::ATTN_RECV,
@@ -470,20 +508,19 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
                 float M = -INFINITY;
 #pragma unroll
                 for (int r = 0; r < CLUSTER; ++r) M = fmaxf(M, attn_recv[(r * HB + bb) * S::PAY]);
-                float L = 0.f, Ov = 0.f;
+                float L = 0.f, Ovv = 0.f;
 #pragma unroll
                 for (int r = 0; r < CLUSTER; ++r) {
                     const float* stp = attn_recv + (r * HB + bb) * S::PAY;
                     const float w = dsm::exp2_diff(stp[0], M);
                     L = fmaf(stp[1], w, L);
-                    Ov = fmaf(stp[4 + d], w, Ov);
+                    Ovv = fmaf(stp[4 + d], w, Ovv);
                 }
-                attn_out[b * HEAD_DIM + d] = __float2half_rn((b < nb) ? Ov / L : 0.f);   // fp16, as the eager model
+                attn_out[b * HEAD_DIM + d] = __float2half_rn((b < nb) ? Ovv / L : 0.f);   // fp16, as the eager model
             }
             dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
             if (h == 0) dsm::cluster_arrive();                  // B3: done reading attn_recv of the first half
         }
-        gbase += n_kv_tiles;
     }
     CF_MARK(6);
 
