@@ -369,7 +369,10 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
         float Ov[BC];
 #pragma unroll
         for (int b = 0; b < BC; ++b) Ov[b] = 0.f;
-        if (tid < (uint32_t)BC) { red[2 * tid] = -INFINITY; red[2 * tid + 1] = 0.f; }
+        if (tid == 0) {                                         // (written and read by thread 0 only: no barrier needed when n_seg == 0)
+#pragma unroll
+            for (int b = 0; b < BC; ++b) { red[2 * b] = -INFINITY; red[2 * b + 1] = 0.f; }
+        }
         for (int sg = 0; sg < n_seg; ++sg) {
             const int b = mseg[sg * 4] & 255;
             const bool owner = (mseg[sg * 4] & 256) != 0;
