@@ -4,6 +4,7 @@
     python tools/ncu_targets.py deepseek 4096  # DeepSeek-MLA half-layer (3 kernels per call), through the C ABI
     python tools/ncu_targets.py paged 16384 random   # 15-argument paged-KV form, Llama-2-7B, batch 1 (random | sequential page table)
     python tools/ncu_targets.py paged 1024 random 8  # ... batch 8 (the weights-once batched kernels)
+    python tools/ncu_targets.py paged 1024 random 8 8  # ... batch 8, 8 KV heads (Llama-3-8B: the grouped-query weights-once kernel)
 8 distinct layer sets, 3 passes (24 launches); capture with  ncu --set full -k regex:<kernel> -s 8 -c 3 ..."""
 import sys, torch
 sys.path.insert(0, ".")
@@ -34,9 +35,10 @@ elif what == "paged":
     kv = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
     table = sys.argv[3] if len(sys.argv) > 3 else "random"
     bs = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    HKV = int(sys.argv[5]) if len(sys.argv) > 5 else 32       # 8: Llama-3-8B shapes (grouped-query kernels)
     H, HQ = 4096, 32
     ws = torch.zeros(cabi.workspace_bytes(H, bs), dtype=torch.uint8, device=dev)
-    L = [dict(w_qkv=r(3 * H, H, sc=0.02), w_o=r(H, H, sc=0.02), k=r(bs * (kv + 1), H), v=r(bs * (kv + 1), H), rms=(1 + 0.1 * r(H).float()).half(),
+    L = [dict(w_qkv=r((HQ + 2 * HKV) * 128, H, sc=0.02), w_o=r(H, H, sc=0.02), k=r(bs * (kv + 1), HKV * 128), v=r(bs * (kv + 1), HKV * 128), rms=(1 + 0.1 * r(H).float()).half(),
               o=torch.empty(bs, H, dtype=torch.float16, device=dev), ro=torch.empty(bs, H, dtype=torch.float16, device=dev)) for _ in range(8)]
     kp = torch.tensor([l["k"].data_ptr() for l in L], dtype=torch.uint64).to(dev)
     vp = torch.tensor([l["v"].data_ptr() for l in L], dtype=torch.uint64).to(dev)
@@ -47,7 +49,7 @@ elif what == "paged":
     x = r(bs, H); res = r(bs, H)
     for _ in range(3):
         for li, lay in enumerate(L):
-            a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=0, hidden=H, n_q_heads=HQ, n_kv_heads=HQ, head_dim=128, batch=bs,
+            a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_PAGED, flags=0, hidden=H, n_q_heads=HQ, n_kv_heads=HKV, head_dim=128, batch=bs,
                                  layer_id=li, eps=1e-5, x=x.data_ptr(), residual_in=res.data_ptr(), residual_out=lay["ro"].data_ptr(),
                                  w_qkv=lay["w_qkv"].data_ptr(), w_o=lay["w_o"].data_ptr(), rms_w=lay["rms"].data_ptr(), out=lay["o"].data_ptr(),
                                  indptr=indptr.data_ptr(), indices=idx.data_ptr(), k_pool_ptrs=kp.data_ptr(), v_pool_ptrs=vp.data_ptr(),
