@@ -53,8 +53,8 @@ struct SmemB8 {
     static constexpr int RED = ATTN_OUT + BC * HEAD_DIM * 2;              // fp32 [12][8] + [8]
     static constexpr int META = RED + (CONSUMER_WARPS + 1) * BC * 4;      // int [8][4] requests: kv_base, len, new_slot, -; int [8][4] segments:
                                                                           // request | owner << 8, row begin, row end, -; u32 [9] tile0; [1] n_seg
-    static constexpr int BARS = META + 76 * 4;                            // u64 full[NSTAGES], xbar[6]
-    static constexpr int FLAGS = BARS + (NSTAGES + 6) * 8;                // u32 [8]
+    static constexpr int BARS = META + 76 * 4;                            // u64 full[NSTAGES], xbar[7]
+    static constexpr int FLAGS = BARS + (NSTAGES + 7) * 8;                // u32 [8]
     static constexpr int TOTAL = FLAGS + BC * 4;
     static_assert(BARS % 8 == 0, "mbarrier alignment");
     static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
@@ -168,6 +168,7 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 24, S::SLICE1 * 4);       // gather, half 1
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 32, HB * S::PAY * 4);     // softmax states, half 0
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 40, HB * S::PAY * 4);     // softmax states, half 1
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 48, BC * 4);              // sums of squares
         }
         dsm::mbar_fence_init();
     }
@@ -250,22 +251,9 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
 
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // ---- phase 0: fused residual add + RMSNorm for the 8 requests ---------------------------------------------------
-    {
-        BatchSlice<BC> slice;
-        batch_slice_load<BC>(slice, p, b0, nb, hidden, KS, rank, tid);      // in flight across the reduction below
-        float ss[BC];
-        batch_sum_squares<BC>(ss, p, b0, nb, hidden, tid);
-#pragma unroll
-        for (int b = 0; b < BC; ++b) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
-            if (lane == 0) red[warp * BC + b] = ss[b];
-        }
-        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-        batch_slice_store<BC>(slice, p, b0, nb, hidden, KS, rank, head, tid, red, xs);
-        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-    }
+    // ---- phase 0: fused residual add + RMSNorm for the 8 requests, K-split over the cluster -----------------------------
+    dsm::cluster_wait();                                                      // B0: every peer has armed its exchange barriers
+    batch_rmsnorm_slice<BC, CLUSTER>(p, b0, nb, hidden, KS, rank, head, tid, red, smem_base + S::RED, xbar_u32 + 48, xs);
     CF_MARK(1);
 
     uint32_t gbase = 0;
@@ -299,7 +287,6 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
     gbase += n_qkv_tiles;
     dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);       // every warp is done reading xs
     CF_MARK(2);
-    dsm::cluster_wait();                                        // B0
     dsm::cluster_arrive();                                      // B1: this CTA no longer reads xs (X changes role)
     dsm::cluster_wait();
 

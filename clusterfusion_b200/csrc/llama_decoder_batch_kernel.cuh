@@ -63,56 +63,17 @@ struct SmemB {
     static_assert(BC * BK_KS_MAX * 4 <= X1_BYTES + CL * SLICE1 * 4, "out_part must fit");
     static constexpr int ATTN_OUT = RS_RECV + CL * SLICE1 * 4;            // fp32 [BC][128]
     static constexpr int RED = ATTN_OUT + BC * HEAD_DIM * 4;              // fp32 [12 warps][BC] + [BC] new-token scores
-    static constexpr int BARS = RED + (CONSUMER_WARPS + 1) * BC * 4;      // u64 full[NSTAGES], xbar[3]
-    static constexpr int FLAGS = BARS + (NSTAGES + 3) * 8;                // u32 [BC]
+    static constexpr int BARS = RED + (CONSUMER_WARPS + 1) * BC * 4;      // u64 full[NSTAGES], xbar[4]
+    static constexpr int FLAGS = BARS + (NSTAGES + 4) * 8;                // u32 [BC]
     static constexpr int TOTAL = FLAGS + ((BC * 4 + 15) & ~15);
     static_assert(BARS % 8 == 0, "mbarrier alignment");
     static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
 };
 
-// First half of phase 0: sum of squares of fp16(x + residual) over the whole row, for the BC requests of the chunk.  All loads
-// of a group of up to four requests go out before anything is consumed (hidden <= 4 * BK_KS_MAX = 4096: at most two 8-element
-// chunks per thread and request), so the pass costs one L2 round trip per group instead of one per request and chunk.
-template <int BC>
-__device__ __forceinline__ void batch_sum_squares(float (&ss)[BC], const KParams& p, int b0, int nb, int hidden, uint32_t tid) {
-    constexpr int ITERS = (4 * BK_KS_MAX / 8 + CONSUMER_THREADS - 1) / CONSUMER_THREADS;      // 2
-    constexpr int GROUP = BC < 4 ? BC : 4;
-#pragma unroll
-    for (int g0 = 0; g0 < BC; g0 += GROUP) {
-        uint4 xr[GROUP][ITERS], rr[GROUP][ITERS];
-#pragma unroll
-        for (int j = 0; j < GROUP; ++j) {
-#pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                const int e = ((int)tid + it * CONSUMER_THREADS) * 8;
-                xr[j][it] = rr[j][it] = make_uint4(0, 0, 0, 0);
-                if (g0 + j < nb && e < hidden) {
-                    xr[j][it] = *reinterpret_cast<const uint4*>(p.x + (size_t)(b0 + g0 + j) * hidden + e);
-                    rr[j][it] = *reinterpret_cast<const uint4*>(p.residual_in + (size_t)(b0 + g0 + j) * hidden + e);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < GROUP; ++j) {
-            float acc = 0.f;
-#pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                float f[8], r8[8];
-                unpack8(xr[j][it], f);
-                unpack8(rr[j][it], r8);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { const float h = round_h(f[k] + r8[k]); acc = fmaf(h, h, acc); }     // zeros past the end
-            }
-            ss[g0 + j] = acc;
-        }
-    }
-}
-
-// Second half of the batched kernels' phase 0: the normalised activations of this CTA's K-slice for all BC requests.  The
-// (request, 8-element chunk) items are dealt over ALL threads and their x / residual / rms_w loads are issued by
-// batch_slice_load() BEFORE the block barrier of the sum-of-squares reduction, so the slice costs no second L2 round trip
-// (round 1 walked the requests one after the other behind that barrier, 128 threads busy, each request's loads stuck behind the
-// previous request's residual_out store: ~6.5 us from the previous layer's last CTA to "RMSNorm done" at batch 4).
+// Phase 0 of the batched kernels: the normalised activations of this CTA's K-slice for all BC requests.  The (request, 8-element
+// chunk) items are dealt over ALL threads; a CTA only ever loads its own slice -- the sums of squares over the whole row are
+// completed by a cluster all-gather of the BC slice sums (batch_rmsnorm_slice below; until late in round 2 every CTA re-read the
+// whole rows of all BC requests for them: 128 KB of L2 reads per CTA at batch 8).
 template <int BC>
 struct BatchSlice {
     static constexpr int ITEMS = (BC * (BK_KS_MAX / 8) + CONSUMER_THREADS - 1) / CONSUMER_THREADS;
@@ -134,8 +95,8 @@ __device__ __forceinline__ void batch_slice_load(BatchSlice<BC>& sl, const KPara
         }
     }
 }
-// red[w * BC + b] holds the per-warp sums of squares of request b (written before the barrier the caller just passed)
-template <int BC>
+// red[w * BC + b], w < NPARTS, holds the partial sums of squares of request b (written before the barrier the caller just passed)
+template <int BC, int NPARTS = CONSUMER_WARPS>
 __device__ __forceinline__ void batch_slice_store(const BatchSlice<BC>& sl, const KParams& p, int b0, int nb, int hidden, int KS,
                                                   uint32_t rank, uint32_t head, uint32_t tid, const float* red, __half* xs) {
     const int cpk = KS / 8;
@@ -148,7 +109,7 @@ __device__ __forceinline__ void batch_slice_store(const BatchSlice<BC>& sl, cons
         if (b < nb) {
             float tot = 0.f;
 #pragma unroll
-            for (int w = 0; w < CONSUMER_WARPS; ++w) tot += red[w * BC + b];
+            for (int w = 0; w < NPARTS; ++w) tot += red[w * BC + b];
             const float rstd = rsqrtf(tot / (float)hidden + p.eps);
             float f[8], w8[8], r8[8];
             unpack8(sl.x[it], f);
@@ -167,6 +128,48 @@ __device__ __forceinline__ void batch_slice_store(const BatchSlice<BC>& sl, cons
         }
         *reinterpret_cast<uint4*>(xs + b * BK_XS_STRIDE + e) = *reinterpret_cast<const uint4*>(xn);
     }
+}
+
+// Fused residual add + RMSNorm of the batched MHA kernels, K-split over the CLUSTER CTAs of a head.  `red` (16-byte aligned,
+// >= 9 * BC floats; `red_u32` its shared-memory address) is scratch: [0, 4*BC) per-warp sums, [4*BC, 5*BC) this CTA's BC slice
+// sums, [5*BC, 9*BC) the gathered sums of the CLUSTER ranks.  `bar_u32`: an exchange barrier armed with
+// cluster_reduce_arm<CLUSTER>(bar, BC * 4); every peer must be known to have armed it (cluster barrier) before the call.
+// The CLUSTER slice sums are added in rank order by everybody: all CTAs (and all heads) compute the same rstd.
+template <int BC, int CLUSTER>
+__device__ __forceinline__ void batch_rmsnorm_slice(const KParams& p, int b0, int nb, int hidden, int KS, uint32_t rank, uint32_t head,
+                                                    uint32_t tid, float* red, uint32_t red_u32, uint32_t bar_u32, __half* xs) {
+    static_assert(BC * 4 % 16 == 0, "the slice sums travel as 16-byte vectors");
+    BatchSlice<BC> slice;
+    batch_slice_load<BC>(slice, p, b0, nb, hidden, KS, rank, tid);
+    const int cpk = KS / 8;                                   // items per request: a multiple of 32 (KS is a multiple of 256)
+    float* sseg = red;
+    float* ss_src = red + 4 * BC;
+    float* ss_recv = red + 5 * BC;
+#pragma unroll
+    for (int it = 0; it < BatchSlice<BC>::ITEMS; ++it) {
+        const int item = (int)tid + it * CONSUMER_THREADS;
+        float f[8], r8[8];
+        unpack8(slice.x[it], f);
+        unpack8(slice.r[it], r8);
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float h = round_h(f[k] + r8[k]); v = fmaf(h, h, v); }     // zeros past the end
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0 && item < BC * cpk) sseg[item >> 5] = v;       // a warp's 32 items belong to one request
+    }
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+    if (tid < (uint32_t)BC) {
+        const int nw = cpk / 32;                              // <= 4
+        float a = 0.f;
+        for (int k = 0; k < nw; ++k) a += sseg[tid * nw + k];
+        ss_src[tid] = a;
+    }
+    uint32_t ph = 0;
+    cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
+        BC * 4, tid, BC, rank, red_u32 + 4 * BC * 4, red_u32 + 5 * BC * 4, bar_u32, ph, ss_src, ss_recv);
+    batch_slice_store<BC, CLUSTER>(slice, p, b0, nb, hidden, KS, rank, head, tid, ss_recv, xs);
+    dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
 }
 
 template <int BC>
@@ -303,6 +306,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
             cluster_reduce_arm<CLUSTER>(xbar_u32, S::SLICE1 * 4);
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::SLICE1 * 4);
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 16, BC * S::PAY * 4);
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 24, BC * 4);              // sums of squares
         }
         dsm::mbar_fence_init();
     }
@@ -328,22 +332,9 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
 
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // ---- phase 0: fused residual add + RMSNorm for the BC requests of the chunk ---------------------------
-    {
-        BatchSlice<BC> slice;
-        batch_slice_load<BC>(slice, p, b0, nb, hidden, KS, rank, tid);      // in flight across the reduction below
-        float ss[BC];
-        batch_sum_squares<BC>(ss, p, b0, nb, hidden, tid);
-#pragma unroll
-        for (int b = 0; b < BC; ++b) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
-            if (lane == 0) red[warp * BC + b] = ss[b];
-        }
-        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-        batch_slice_store<BC>(slice, p, b0, nb, hidden, KS, rank, head, tid, red, xs);
-        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-    }
+    // ---- phase 0: fused residual add + RMSNorm for the BC requests of the chunk, K-split over the cluster --------
+    dsm::cluster_wait();                 // every peer has armed its exchange barriers (it arrived before its dependency wait)
+    batch_rmsnorm_slice<BC, CLUSTER>(p, b0, nb, hidden, KS, rank, head, tid, red, smem_base + S::RED, xbar_u32 + 24, xs);
 
     CF_MARK(1);
     uint32_t gbase = 0;
@@ -401,7 +392,6 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     CF_MARK(2);
 
     // ---- exchange 1: reduce-scatter (sum, rank order) + all-gather of BC x (q|k|v) ---------------------------
-    dsm::cluster_wait();
     uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
     cluster_scatter<CLUSTER, CONSUMER_THREADS, CONSUMER_BAR>(S::SLICE1 * 4, tid, rank, smem_base + S::RS_RECV, xbar_u32, ph0,
                                                              qkv_src, rs_recv);
