@@ -102,60 +102,11 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
     int* mmisc = reinterpret_cast<int*>(tile0 + BC + 1);                      // [0] n_seg
     uint32_t* sflags = reinterpret_cast<uint32_t*>(smem + S::FLAGS);
 
-    // ---- segments: the chunk's KV rows (this head), concatenated request after request, are cut into CLUSTER equal ranges
-    //      (multiples of 16 rows), so a CTA streams one or two SEGMENTS (request, row range) however ragged the batch is and all
-    //      12 warps work on the same request at a time: one copy of the KV loop and one block merge per segment instead of
-    //      per-request register states in eight unrolled copies (207 KB of code, 64 % instruction-cache hit rate, 16 us per
-    //      half chunk against 9.5 us for the same rows in the chunks-of-4 kernel).  A request's new token is folded in by the rank
-    //      that holds its last row ("owner"; an empty request: the rank its offset falls into).  Lane b of warp 0 handles
-    //      request b, offsets are warp prefix sums (no single-thread loop in front of the block barrier). ----
-    if (warp == 0) {
-        const int b = (int)lane;
-        int len = 0, kb = 0, ns = 0;
-        if (b < nb) {
-            kb = p.indptr[b0 + b];
-            const int end = p.indptr[b0 + b + 1] - 1;
-            len = end - kb;
-            ns = p.indices[end];
-        }
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < BC; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += v;
-        }
-        const int T = __shfl_sync(0xffffffffu, incl, BC - 1);
-        const int off = incl - len;
-        const int per = (((T + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);
-        const int c0 = min((int)rank * per, T), c1 = min(c0 + per, T);
-        int s0 = max(c0, off) - off, s1 = min(c1, off + len) - off;
-        const bool nonempty = b < nb && s1 > s0;
-        const int owner = len > 0 ? (off + len - 1) / per : (per > 0 ? min(off / per, CLUSTER - 1) : b % CLUSTER);
-        const bool has = b < nb && (nonempty || owner == (int)rank);
-        if (!nonempty) { s0 = 0; s1 = 0; }
-        const uint32_t nt = has ? (uint32_t)((s1 - s0 + ROWS512 - 1) / ROWS512) : 0u;
-        const unsigned bal = __ballot_sync(0xffffffffu, has);
-        const int idx = __popc(bal & ((1u << lane) - 1u));
-        uint32_t tincl = nt;
-#pragma unroll
-        for (int o = 1; o < BC; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, tincl, o);
-            if ((int)lane >= o) tincl += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, tincl, BC - 1);
-        const int nseg = __popc(bal);
-        if (b < BC) { meta[b * 4 + 0] = kb; meta[b * 4 + 1] = len; meta[b * 4 + 2] = ns; meta[b * 4 + 3] = owner; }
-        if ((int)lane >= nseg && lane <= BC) tile0[lane] = total;
-        __syncwarp();
-        if (has) {
-            mseg[idx * 4 + 0] = b | ((owner == (int)rank) ? 256 : 0);
-            mseg[idx * 4 + 1] = s0;
-            mseg[idx * 4 + 2] = s1;
-            tile0[idx] = tincl - nt;
-        }
-        if (lane == 0) mmisc[0] = nseg;
-        __syncwarp();
-    }
+    // ---- KV segments of this CTA (batch_build_segments, llama_decoder_batch_kernel.cuh): all 12 warps work on the same request at a
+    //      time -- one copy of the KV loop and one block merge per segment instead of per-request register states in eight
+    //      unrolled copies (207 KB of code, 64 % instruction-cache hit rate, 16 us per half chunk against 9.5 us for the same rows in
+    //      the chunks-of-4 kernel of that time) ----
+    if (warp == 0) batch_build_segments<BC>(p, b0, nb, (int)rank, CLUSTER, lane, meta, mseg, tile0, mmisc);
     if (lane == 0) {
         dsm::mbar_init(full_u32 + 8 * warp, 1);
         dsm::mbar_init(full_u32 + 8 * (warp + CONSUMER_WARPS), 1);

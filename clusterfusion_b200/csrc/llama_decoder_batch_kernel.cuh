@@ -63,7 +63,8 @@ struct SmemB {
     static_assert(BC * BK_KS_MAX * 4 <= X1_BYTES + CL * SLICE1 * 4, "out_part must fit");
     static constexpr int ATTN_OUT = RS_RECV + CL * SLICE1 * 4;            // fp32 [BC][128]
     static constexpr int RED = ATTN_OUT + BC * HEAD_DIM * 4;              // fp32 [12 warps][BC] + [BC] new-token scores
-    static constexpr int BARS = RED + (CONSUMER_WARPS + 1) * BC * 4;      // u64 full[NSTAGES], xbar[4]
+    static constexpr int META = RED + (CONSUMER_WARPS + 1) * BC * 4;      // int [BC][4] requests, [BC][4] segments, u32 [BC+1] tile0, [1] n_seg
+    static constexpr int BARS = META + (9 * BC + 2 + 3) / 4 * 16;         // u64 full[NSTAGES], xbar[4]
     static constexpr int FLAGS = BARS + (NSTAGES + 4) * 8;                // u32 [BC]
     static constexpr int TOTAL = FLAGS + ((BC * 4 + 15) & ~15);
     static_assert(BARS % 8 == 0, "mbarrier alignment");
@@ -128,6 +129,63 @@ __device__ __forceinline__ void batch_slice_store(const BatchSlice<BC>& sl, cons
         }
         *reinterpret_cast<uint4*>(xs + b * BK_XS_STRIDE + e) = *reinterpret_cast<const uint4*>(xn);
     }
+}
+
+// KV segments of a chunk (warp 0 of every CTA; result in shared memory, made visible by the caller's block barrier).  The chunk's
+// KV rows of this head, concatenated request after request, are cut into `nranks` equal ranges (multiples of 16 rows), so a CTA
+// streams one or two SEGMENTS (request, row range) however ragged the batch is.  A request's new token is folded in by the rank
+// that holds its last row ("owner"; an empty request: the rank its offset falls into).  Lane b handles request b, offsets are
+// warp prefix sums (no single-thread loop in front of a block barrier).
+//   meta [BC][4]  kv_base, len, new_slot, owner          mseg [BC][4]  request | owner-is-me << 8, row begin, row end, -
+//   tile0 [BC+1]  first KV tile (phase-local) of segment s; entries >= n_seg hold the total          mmisc [0] n_seg
+template <int BC>
+__device__ __forceinline__ void batch_build_segments(const KParams& p, int b0, int nb, int rank, int nranks, uint32_t lane,
+                                                     int* meta, int* mseg, uint32_t* tile0, int* mmisc) {
+    const int b = (int)lane;
+    int len = 0, kb = 0, ns = 0;
+    if (b < nb) {
+        kb = p.indptr[b0 + b];
+        const int end = p.indptr[b0 + b + 1] - 1;
+        len = end - kb;
+        ns = p.indices[end];
+    }
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < BC; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += v;
+    }
+    const int T = __shfl_sync(0xffffffffu, incl, BC - 1);
+    const int off = incl - len;
+    const int per = (((T + nranks - 1) / nranks) + ROWS512 - 1) & ~(ROWS512 - 1);
+    const int c0 = min(rank * per, T), c1 = min(c0 + per, T);
+    int s0 = max(c0, off) - off, s1 = min(c1, off + len) - off;
+    const bool nonempty = b < nb && s1 > s0;
+    const int owner = len > 0 ? (off + len - 1) / per : (per > 0 ? min(off / per, nranks - 1) : b % nranks);
+    const bool has = b < nb && (nonempty || owner == rank);
+    if (!nonempty) { s0 = 0; s1 = 0; }
+    const uint32_t nt = has ? (uint32_t)((s1 - s0 + ROWS512 - 1) / ROWS512) : 0u;
+    const unsigned bal = __ballot_sync(0xffffffffu, has);
+    const int idx = __popc(bal & ((1u << lane) - 1u));
+    uint32_t tincl = nt;
+#pragma unroll
+    for (int o = 1; o < BC; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, tincl, o);
+        if ((int)lane >= o) tincl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, tincl, BC - 1);
+    const int nseg = __popc(bal);
+    if (b < BC) { meta[b * 4 + 0] = kb; meta[b * 4 + 1] = len; meta[b * 4 + 2] = ns; meta[b * 4 + 3] = owner; }
+    if ((int)lane >= nseg && (int)lane <= BC) tile0[lane] = total;
+    __syncwarp();
+    if (has) {
+        mseg[idx * 4 + 0] = b | ((owner == rank) ? 256 : 0);
+        mseg[idx * 4 + 1] = s0;
+        mseg[idx * 4 + 2] = s1;
+        tile0[idx] = tincl - nt;
+    }
+    if (lane == 0) mmisc[0] = nseg;
+    __syncwarp();
 }
 
 // Fused residual add + RMSNorm of the batched MHA kernels, K-split over the CLUSTER CTAs of a head.  `red` (16-byte aligned,
@@ -196,25 +254,14 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     const uint32_t full_u32 = smem_base + S::BARS;
     const uint32_t xbar_u32 = full_u32 + NSTAGES * 8;
 
-    // ---- per-request KV ranges ---------------------------------------------------------------------------
-    int kv_base[BC], row_begin[BC], row_end[BC], new_slot[BC];
-    uint32_t kv_tile0[BC + 1];                             // first KV tile (phase-local index) of request b
-    kv_tile0[0] = 0;
-#pragma unroll
-    for (int b = 0; b < BC; ++b) {
-        int len = 0;
-        kv_base[b] = 0; new_slot[b] = 0;
-        if (b < nb) {
-            kv_base[b] = p.indptr[b0 + b];
-            const int end = p.indptr[b0 + b + 1] - 1;
-            len = end - kv_base[b];
-            new_slot[b] = p.indices[end];
-        }
-        const int chunk = (((len + CLUSTER - 1) / CLUSTER) + ROWS512 - 1) & ~(ROWS512 - 1);
-        row_begin[b] = min((int)rank * chunk, len);
-        row_end[b] = min(row_begin[b] + chunk, len);
-        kv_tile0[b + 1] = kv_tile0[b] + (row_end[b] - row_begin[b] + ROWS512 - 1) / ROWS512;
-    }
+    // ---- KV segments of this CTA (batch_build_segments): all 12 warps work on the same request at a time ----------------
+    int* meta = reinterpret_cast<int*>(smem + S::META);                       // [b][4]
+    int* mseg = meta + BC * 4;                                                // [s][4]
+    uint32_t* kv_tile0 = reinterpret_cast<uint32_t*>(mseg + BC * 4);          // [BC + 1]
+    int* mmisc = reinterpret_cast<int*>(kv_tile0 + BC + 1);
+    if (warp == 0) batch_build_segments<BC>(p, b0, nb, (int)rank, CLUSTER, lane, meta, mseg, kv_tile0, mmisc);
+    __syncthreads();                                                          // segments visible to every warp
+    const int n_seg = mmisc[0];
     const uint32_t n_qkv_tiles = (uint32_t)CONSUMER_WARPS * (KS / 128);          // 12 row blocks of 32 x KS/128 column tiles
     const uint32_t n_kv_tiles = kv_tile0[BC];
     const uint32_t n_o_tiles = (uint32_t)(KS / ROWS256);
@@ -232,18 +279,17 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     // page index of this lane's row of KV tile g (phase-global index), fetched one ring cycle ahead of the tile
     int pre_slot0 = 0, pre_slot1 = 0;
     uint32_t pre_g0 = 0xffffffffu, pre_g1 = 0xffffffffu;
+    auto seg_of = [&](uint32_t t) -> int {                // which segment KV tile t (phase-local index) belongs to
+        int sgi = 0;
+#pragma unroll
+        for (int q = 1; q < BC; ++q) sgi += (t >= kv_tile0[q]) ? 1 : 0;
+        return sgi;
+    };
     auto page_of = [&](uint32_t g) -> int {
         const uint32_t t = g - n_qkv_tiles;
-        int b = 0;
-#pragma unroll
-        for (int q = 1; q < BC; ++q) b += (t >= kv_tile0[q]) ? 1 : 0;
-        int rbeg = row_begin[0], rend = row_end[0], kb = kv_base[0];
-        uint32_t t0 = kv_tile0[0];
-#pragma unroll
-        for (int q = 1; q < BC; ++q)
-            if (b == q) { rbeg = row_begin[q]; rend = row_end[q]; kb = kv_base[q]; t0 = kv_tile0[q]; }
-        const int r = rbeg + (int)(t - t0) * ROWS512 + (int)(lane & 15);
-        return (r < rend) ? p.indices[kb + r] : 0;
+        const int sgi = seg_of(t);
+        const int r = mseg[sgi * 4 + 1] + (int)(t - kv_tile0[sgi]) * ROWS512 + (int)(lane & 15);
+        return (r < mseg[sgi * 4 + 2]) ? p.indices[meta[(mseg[sgi * 4] & 255) * 4] + r] : 0;
     };
     auto issue_tile = [&](uint32_t g) {
         if (g >= total_tiles) return;
@@ -265,21 +311,12 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
             }
         } else if (g < n_qkv_tiles + n_kv_tiles) {
             const uint32_t t = g - n_qkv_tiles;
-            int b = 0;
-#pragma unroll
-            for (int q = 1; q < BC; ++q) b += (t >= kv_tile0[q]) ? 1 : 0;
-            int rbeg = row_begin[0], rend = row_end[0], kb = kv_base[0];
-            uint32_t t0 = kv_tile0[0];
-#pragma unroll
-            for (int q = 1; q < BC; ++q)
-                if (b == q) { rbeg = row_begin[q]; rend = row_end[q]; kb = kv_base[q]; t0 = kv_tile0[q]; }
-            const int i = (int)(t - t0);
-            // paged KV, page size 1: one 256-byte bulk copy per row per tensor; lanes 0-15 fetch K rows, 16-31 V rows
-            const int r = rbeg + i * ROWS512 + (lane & 15);
+            const int sgi = seg_of(t);
+            const int rbeg = mseg[sgi * 4 + 1], rend = mseg[sgi * 4 + 2];
+            const int i = (int)(t - kv_tile0[sgi]);
             const bool odd = (g / CONSUMER_WARPS) & 1u;
             const long long slot = (odd ? pre_g1 : pre_g0) == g ? (long long)(odd ? pre_slot1 : pre_slot0) : (long long)page_of(g);
             const int nvalid = min(ROWS512, rend - (rbeg + i * ROWS512));
-            (void)r;
             issue_kv_stage(p, pool_maps, false, dst, fb, head * HEAD_DIM, slot, nvalid, kpool, vpool, kv_cols, lane, pol);
         } else {
             if (lane == 0) {
@@ -424,17 +461,11 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
                     outv = which == 0 ? __half2float(rh) * kScaleLog2 : __half2float(rh);
                     if (which == 1 && rank == 0) {
                         __half* kp = reinterpret_cast<__half*>(p.k_pool_ptrs[p.layer_id]);
-                        int ns = new_slot[0];
-#pragma unroll
-                        for (int q = 1; q < BC; ++q) if (b == q) ns = new_slot[q];
-                        kp[(size_t)ns * kv_cols + head * HEAD_DIM + d] = rh;
+                        kp[(size_t)meta[b * 4 + 2] * kv_cols + head * HEAD_DIM + d] = rh;
                     }
                 } else if (rank == 0) {
                     __half* vp = reinterpret_cast<__half*>(p.v_pool_ptrs[p.layer_id]);
-                    int ns = new_slot[0];
-#pragma unroll
-                    for (int q = 1; q < BC; ++q) if (b == q) ns = new_slot[q];
-                    vp[(size_t)ns * kv_cols + head * HEAD_DIM + d] = __float2half_rn(a);
+                    vp[(size_t)meta[b * 4 + 2] * kv_cols + head * HEAD_DIM + d] = __float2half_rn(a);
                 }
             }
             qkv_fin[f] = outv;        // aliases rs_recv: every thread finished folding it before the all-gather barrier
@@ -445,26 +476,36 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
     dsm::cluster_arrive();
 
     CF_MARK(4);
-    // ---- phase 2: flash-decode, request after request through the same tile stream -----------------------------
+    // ---- phase 2: flash-decode over this CTA's segments, all 12 warps on one request at a time -------------------------
     {
         const int sub = lane >> 4, c = lane & 15;
-        float m[BC], l[BC], o8[BC][8];
+        // block-merged state of request b on this CTA: thread tid < 128 keeps o[dim tid] in registers, (m, l) in red[2b], red[2b+1]
+        // (written and read by thread 0 only); requests without a segment here stay (-inf, 0, 0)
+        float Ov[BC];
 #pragma unroll
-        for (int b = 0; b < BC; ++b) {
-            m[b] = -INFINITY; l[b] = 0.f;
+        for (int b = 0; b < BC; ++b) Ov[b] = 0.f;
+        if (tid == 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o8[b][k] = 0.f;
+            for (int b = 0; b < BC; ++b) { red[2 * b] = -INFINITY; red[2 * b + 1] = 0.f; }
+        }
+        for (int sg = 0; sg < n_seg; ++sg) {
+            const int b = mseg[sg * 4] & 255;
+            const bool owner = (mseg[sg * 4] & 256) != 0;
+            const int rbeg = mseg[sg * 4 + 1], rend = mseg[sg * 4 + 2];
+            const uint32_t nt = kv_tile0[sg + 1] - kv_tile0[sg];
+            const uint32_t gb = gbase + kv_tile0[sg];
+            float m = -INFINITY, l = 0.f, o8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o8[k] = 0.f;
             float q8[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) q8[k] = qkv_fin[b * S::QKV_OUT + c * 8 + k];
-            const uint32_t nt = kv_tile0[b + 1] - kv_tile0[b];
-            const uint32_t gb = gbase + kv_tile0[b];
             for (uint32_t i = first_tile(gb, warp); i < nt; i += CONSUMER_WARPS) {
                 const uint32_t g = gb + i, s = ring_stage(g);
                 ring_wait_full(full_u32, g);
                 const uint4* kt = reinterpret_cast<const uint4*>(smem + S::RING + s * STAGE_BYTES);
                 const uint4* vt = kt + STAGE_BYTES / 32;
-                const int rows_left = row_end[b] - (row_begin[b] + (int)i * ROWS512);     // >= 1
+                const int rows_left = rend - (rbeg + (int)i * ROWS512);     // >= 1
                 float sc[ROWS512 / 2];
 #pragma unroll
                 for (int jj = 0; jj < ROWS512 / 2; ++jj) {
@@ -483,42 +524,37 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
                 float mx = sc[0];
 #pragma unroll
                 for (int jj = 1; jj < ROWS512 / 2; ++jj) mx = fmaxf(mx, sc[jj]);
-                const float m_new = fmaxf(m[b], mx);
+                const float m_new = fmaxf(m, mx);
                 const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-                const float corr = dsm::exp2_diff(m[b], m_use);
-                l[b] *= corr;
+                const float corr = dsm::exp2_diff(m, m_use);
+                l *= corr;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o8[b][k] *= corr;
+                for (int k = 0; k < 8; ++k) o8[k] *= corr;
 #pragma unroll
                 for (int jj = 0; jj < ROWS512 / 2; ++jj) {
                     const int row = 2 * jj + sub;
                     const float pr = dsm::fast_exp2(sc[jj] - m_use);       // -inf -> 0
-                    l[b] += pr;
+                    l += pr;
                     uint4 raw = vt[row * 16 + c];
                     if (row >= rows_left) raw = make_uint4(0, 0, 0, 0);    // rows past the end were never copied
                     float v8[8];
                     unpack8(raw, v8);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) o8[b][k] = fmaf(pr, v8[k], o8[b][k]);
+                    for (int k = 0; k < 8; ++k) o8[k] = fmaf(pr, v8[k], o8[k]);
                 }
-                m[b] = m_new;
+                m = m_new;
                 __syncwarp();
                 issue_tile(g + NSTAGES);
             }
-        }
-        gbase += n_kv_tiles;
-        CF_MARK(5);
-        // block merge, one request per round through the 24 x 132 buffer; rank 0 folds in the request's current token
-#pragma unroll
-        for (int b = 0; b < BC; ++b) {
+            // block merge through the 24 x 132 buffer (two half-warp states per warp); the owner folds in the request's new token
             {
                 const int grp = warp * 2 + sub;
                 float* slot = attn_part + grp * S::PAY;
-                if (c == 0) { slot[0] = m[b]; slot[1] = l[b]; }
-                *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[b][0], o8[b][1], o8[b][2], o8[b][3]);
-                *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[b][4], o8[b][5], o8[b][6], o8[b][7]);
+                if (c == 0) { slot[0] = m; slot[1] = l; }
+                *reinterpret_cast<float4*>(slot + 4 + c * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+                *reinterpret_cast<float4*>(slot + 4 + c * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
             }
-            if (warp == 0) {
+            if (owner && warp == 0) {
                 float a = 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -529,28 +565,37 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
             }
             dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
             if (tid < HEAD_DIM) {
-                const bool with_new = (rank == 0);
                 const float s_new = red[CONSUMER_WARPS * BC + b];
-                float M = with_new ? s_new : -INFINITY;
+                float M = owner ? s_new : -INFINITY;
 #pragma unroll
                 for (int gI = 0; gI < 2 * CONSUMER_WARPS; ++gI) M = fmaxf(M, attn_part[gI * S::PAY]);
-                float L = 0.f, Ov = 0.f;
+                float L = 0.f, Ovv = 0.f;
 #pragma unroll
                 for (int gI = 0; gI < 2 * CONSUMER_WARPS; ++gI) {
                     const float w = dsm::exp2_diff(attn_part[gI * S::PAY], M);
                     L = fmaf(attn_part[gI * S::PAY + 1], w, L);
-                    Ov = fmaf(attn_part[gI * S::PAY + 4 + tid], w, Ov);
+                    Ovv = fmaf(attn_part[gI * S::PAY + 4 + tid], w, Ovv);
                 }
-                if (with_new) {
+                if (owner) {
                     const float w = dsm::exp2_diff(s_new, M);
                     L += w;
-                    Ov = fmaf(qkv_fin[b * S::QKV_OUT + 2 * HEAD_DIM + tid], w, Ov);
+                    Ovv = fmaf(qkv_fin[b * S::QKV_OUT + 2 * HEAD_DIM + tid], w, Ovv);
                 }
-                float* st = attn_src + b * S::PAY;       // aliases qkv_src / red1: dead since the all-gather
-                st[4 + tid] = Ov;
-                if (tid == 0) { st[0] = M; st[1] = L; st[2] = 0.f; st[3] = 0.f; }
+#pragma unroll
+                for (int q = 0; q < BC; ++q) Ov[q] = (q == b) ? Ovv : Ov[q];
+                if (tid == 0) { red[2 * b] = M; red[2 * b + 1] = L; }
             }
             dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        }
+        gbase += n_kv_tiles;
+        CF_MARK(5);
+        if (tid < HEAD_DIM) {
+#pragma unroll
+            for (int b = 0; b < BC; ++b) {
+                float* st = attn_src + b * S::PAY;       // aliases qkv_src / red1: dead since the all-gather
+                st[4 + tid] = Ov[b];
+                if (tid == 0) { st[0] = red[2 * b]; st[1] = red[2 * b + 1]; st[2] = 0.f; st[3] = 0.f; }
+            }
         }
         // ---- exchange 2: all-gather of the BC softmax states, merged in rank order -------------------------------
         dsm::cluster_wait();          // every peer is past RoPE: its exchange-1 buffers may now be overwritten
