@@ -7,8 +7,9 @@
  * next to the 192 KB tile ring is time-sharing one 19.5 KB region X:
  *
  *   QKV phase      X = the 8 activation vectors, fp16 [8][1024 + 8]
- *   exchange 1     X = reduce-scatter / all-gather buffers for FOUR requests; run twice (requests 0-3, then 4-7: the
- *                  accumulators of the second half wait in registers), result kept as fp16 q|k|v [8][384] outside X
+ *   exchange 1     X = reduce-scatter slots (fp32 partials written by the peers straight from their MMA accumulators with 8-byte
+ *                  st.async, no staging copy) + all-gather buffers in fp16 (the folded values are fp16-exact): all 8 requests in
+ *                  one pass (two passes of four until late in round 2), result kept as fp16 q|k|v [8][384] outside X
  *   attention      two passes of four requests (softmax states in registers), each followed by its own state exchange
  *                  through X
  *   O phase        X = a 1 KB staging tile per warp: the [32 rows x 8 requests] C fragments are transposed through it
@@ -27,19 +28,18 @@ namespace cfb {
 struct SmemB8 {
     static constexpr int BC = 8, HB = 4, CL = 4;                          // chunk, half chunk, cluster
     static constexpr int QKV_OUT = 3 * HEAD_DIM;                          // 384
-    static constexpr int SLICE1 = HB * QKV_OUT / CL;                      // 384 floats per CTA slice in exchange 1
     static constexpr int PAY = HEAD_DIM + 4;
     static constexpr int RING = 0;
     static constexpr int ATTN_PART = RING + NSTAGES * STAGE_BYTES;        // fp32 [12 warps][132]
     static constexpr int X = ATTN_PART + CONSUMER_WARPS * PAY * 4;
     // role 1: activations
     static constexpr int XS = X;                                          // fp16 [8][BK_XS_STRIDE]
-    // role 2: exchange 1 of one half chunk
-    static constexpr int QKV_SRC = X;                                     // fp32 [4][384]
-    static constexpr int RED1 = QKV_SRC + HB * QKV_OUT * 4;               // fp32 [384]
-    static constexpr int AG_RECV = RED1 + SLICE1 * 4;                     // fp32 [4][384]
-    static constexpr int RS_RECV = AG_RECV + CL * SLICE1 * 4;             // fp32 [4][384]
-    static constexpr int X_BYTES = RS_RECV + CL * SLICE1 * 4 - X;         // 19968
+    // role 2: exchange 1, all 8 requests in one pass: rank r reduces requests 2r and 2r + 1
+    static constexpr int SLICE1 = 2 * QKV_OUT;                            // 768 values per rank
+    static constexpr int RS_RECV = X;                                     // fp32 [4 source ranks][384 rows][2 requests]
+    static constexpr int RED1 = RS_RECV + CL * SLICE1 * 4;                // fp16 [2][384]   my two folded requests
+    static constexpr int AG_RECV = RED1 + SLICE1 * 2;                     // fp16 [4 ranks][2][384] = [8][384]
+    static constexpr int X_BYTES = AG_RECV + CL * SLICE1 * 2 - X;         // 19968
     static_assert(BC * BK_XS_STRIDE * 2 <= X_BYTES, "activations must fit into X");
     // role 3: exchange 2 of one half chunk
     static constexpr int ATTN_SRC = X;                                    // fp32 [4][132]
@@ -86,10 +86,9 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
 
     __half* xs = reinterpret_cast<__half*>(smem + S::XS);
     float* attn_part = reinterpret_cast<float*>(smem + S::ATTN_PART);
-    float* qkv_src = reinterpret_cast<float*>(smem + S::QKV_SRC);
     float* rs_recv = reinterpret_cast<float*>(smem + S::RS_RECV);
-    float* red1 = reinterpret_cast<float*>(smem + S::RED1);
-    float* ag_recv = reinterpret_cast<float*>(smem + S::AG_RECV);
+    __half* red1 = reinterpret_cast<__half*>(smem + S::RED1);
+    __half* ag_recv = reinterpret_cast<__half*>(smem + S::AG_RECV);
     __half* qkv_fin = reinterpret_cast<__half*>(smem + S::QKV_FIN);
     float* attn_src = reinterpret_cast<float*>(smem + S::ATTN_SRC);
     float* attn_recv = reinterpret_cast<float*>(smem + S::ATTN_RECV);
@@ -113,10 +112,8 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
         if (tid == 0) {
             prefetch_tmap(&p.tm_wqkv);
             prefetch_tmap(&p.tm_wo);
-            cluster_reduce_arm<CLUSTER>(xbar_u32, S::SLICE1 * 4);            // scatter, half 0
-            cluster_reduce_arm<CLUSTER>(xbar_u32 + 8, S::SLICE1 * 4);        // scatter, half 1
-            cluster_reduce_arm<CLUSTER>(xbar_u32 + 16, S::SLICE1 * 4);       // gather, half 0
-            cluster_reduce_arm<CLUSTER>(xbar_u32 + 24, S::SLICE1 * 4);       // gather, half 1
+            cluster_reduce_arm<CLUSTER>(xbar_u32, S::SLICE1 * 4);            // scatter: 768 fp32 partials from every peer
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 16, S::SLICE1 * 2);       // gather: 768 fp16 results from every peer
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 32, HB * S::PAY * 4);     // softmax states, half 0
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 40, HB * S::PAY * 4);     // softmax states, half 1
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 48, BC * 4);              // sums of squares
@@ -241,44 +238,47 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
     dsm::cluster_arrive();                                      // B1: this CTA no longer reads xs (X changes role)
     dsm::cluster_wait();
 
-    // ---- exchange 1 + RoPE, one half chunk at a time --------------------------------------------------------------
+    // ---- exchange 1 + RoPE, all 8 requests in one pass.  A lane's C fragments hold requests 2*t4 and 2*t4 + 1 of rows g4 / g4 + 8:
+    //      both belong to rank t4, so the fragments go straight from registers into that rank's receive slots as 8-byte
+    //      st.async (no staging copy: the fp32 staging of 8 requests would not fit next to the receive buffers) ----------------
+    {
+        const uint32_t dst_rank = (uint32_t)t4;
+        const uint32_t slot_u32 = smem_base + S::RS_RECV + rank * (S::SLICE1 * 4);      // my slot in the destination's buffer
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        // this half's accumulators -> qkv_src [4][384]: C fragment = rows g4 / g4 + 8, requests 2*t4 and 2*t4 + 1
-        if ((t4 >> 1) == h) {
-            const int n0 = (2 * t4) & 3;
+        for (int mb = 0; mb < 2; ++mb) {
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
-                const int row = (int)warp * 32 + mb * 16 + g4;
-                qkv_src[n0 * S::QKV_OUT + row] = acc[mb][0];
-                qkv_src[(n0 + 1) * S::QKV_OUT + row] = acc[mb][1];
-                qkv_src[n0 * S::QKV_OUT + row + 8] = acc[mb][2];
-                qkv_src[(n0 + 1) * S::QKV_OUT + row + 8] = acc[mb][3];
+            for (int hh = 0; hh < 2; ++hh) {
+                const int row = (int)warp * 32 + mb * 16 + g4 + hh * 8;
+                const float2 v = make_float2(acc[mb][2 * hh], acc[mb][2 * hh + 1]);
+                if (dst_rank == rank) *reinterpret_cast<float2*>(rs_recv + rank * S::SLICE1 + row * 2) = v;
+                else dsm::st_async_v2(dsm::mapa(slot_u32 + row * 8, dst_rank), v, dsm::mapa(xbar_u32, dst_rank));
             }
         }
-        uint32_t ph_s = 0, ph_g = 0;
-        cluster_scatter<CLUSTER, CONSUMER_THREADS, CONSUMER_BAR>(S::SLICE1 * 4, tid, rank, smem_base + S::RS_RECV,
-                                                                 xbar_u32 + 8 * h, ph_s, qkv_src, rs_recv);
+        dsm::mbar_wait_cluster(xbar_u32, 0);
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
+        // fold my two requests in rank order; q / k / v leave the projection as fp16 (eager model)
         for (int e = tid; e < S::SLICE1; e += CONSUMER_THREADS) {
+            const int rl = e / S::QKV_OUT, row = e % S::QKV_OUT;
             float a = 0.f;
 #pragma unroll
-            for (int r = 0; r < CLUSTER; ++r) a += rs_recv[r * S::SLICE1 + e];
-            red1[e] = round_h(a);                                // q / k / v leave the projection as fp16 (eager model)
+            for (int r = 0; r < CLUSTER; ++r) a += rs_recv[r * S::SLICE1 + row * 2 + rl];
+            red1[e] = __float2half_rn(a);
         }
+        uint32_t ph_g = 0;
         cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
-            S::SLICE1 * 4, tid, S::SLICE1, rank, smem_base + S::RED1, smem_base + S::AG_RECV, xbar_u32 + 16 + 8 * h, ph_g,
-            red1, ag_recv);
-        // RoPE (NeoX) for the half's 4 requests; new K / V rows into the pool; q stays unscaled fp16
-        for (int f = tid; f < HB * S::QKV_OUT; f += CONSUMER_THREADS) {
-            const int bb = f / S::QKV_OUT, e = f % S::QKV_OUT, b = h * HB + bb;
+            S::SLICE1 * 2, tid, S::SLICE1, rank, smem_base + S::RED1, smem_base + S::AG_RECV, xbar_u32 + 16, ph_g,
+            reinterpret_cast<float*>(red1), reinterpret_cast<float*>(ag_recv));
+        // RoPE (NeoX) for the 8 requests (ag_recv = [8][384]); new K / V rows into the pool; q stays unscaled fp16
+        for (int f = tid; f < BC * S::QKV_OUT; f += CONSUMER_THREADS) {
+            const int b = f / S::QKV_OUT, e = f % S::QKV_OUT;
             const int which = e >> 7, d = e & 127;
-            const float a = ag_recv[f];
-            __half outv = __float2half_rn(a);
+            __half outv = ag_recv[f];
             if (b < nb) {
                 if (which < 2) {
+                    const float a = __half2float(outv);
                     const float* cosp = p.cos + p.positions[b0 + b] * HEAD_DIM;
                     const float* sinp = cosp + HEAD_DIM / 2;
-                    const float bbv = ag_recv[f ^ 64];
+                    const float bbv = __half2float(ag_recv[f ^ 64]);
                     const int i = d & 63;
                     const float rot = (d & 64) ? fmaf(a, cosp[i], bbv * sinp[i]) : fmaf(a, cosp[i], -bbv * sinp[i]);
                     outv = __float2half_rn(rot);

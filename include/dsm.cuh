@@ -125,6 +125,12 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint
         "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
         ::"r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar) : "memory");
 }
+// 8-byte variant (two floats that belong together, e.g. the two columns a lane holds of an MMA C fragment row)
+__device__ __forceinline__ void st_async_v2(uint32_t remote_addr, float2 v, uint32_t remote_bar) {
+    asm volatile(
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+        ::"r"(remote_addr), "f"(v.x), "f"(v.y), "r"(remote_bar) : "memory");
+}
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
