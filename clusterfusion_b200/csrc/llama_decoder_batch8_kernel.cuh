@@ -10,14 +10,14 @@
  *   exchange 1     X = reduce-scatter slots (fp32 partials written by the peers straight from their MMA accumulators with 8-byte
  *                  st.async, no staging copy) + all-gather buffers in fp16 (the folded values are fp16-exact): all 8 requests in
  *                  one pass (two passes of four until late in round 2), result kept as fp16 q|k|v [8][384] outside X
- *   attention      two passes of four requests (softmax states in registers), each followed by its own state exchange
- *                  through X
+ *   attention      over this CTA's KV segments (batch_build_segments), then ONE all-gather of the 8 block-merged states through X
  *   O phase        X = a 1 KB staging tile per warp: the [32 rows x 8 requests] C fragments are transposed through it
  *                  and leave as red.global.add.v4 straight away (no 32 KB out_part; the reds overlap the stream)
  *
  * X is written by peer CTAs (st.async) in the exchange phases, so every change of its role is fenced by a cluster barrier
- * (arrive as soon as this CTA is done with the old role, wait right before the first remote write of the new one): B1
- * after the QKV loop, B2 after the second RoPE, B3 after the first softmax merge.  PAGED variant, MHA, hidden <= 4096.
+ * (arrive as soon as this CTA is done with the old role, wait right before the first remote write of the new one): B0
+ * at the start (peers have armed their exchange barriers; waited on before the sums-of-squares exchange), B1 after the QKV
+ * loop, B2 after RoPE.  PAGED variant, MHA, hidden <= 4096.
  */
 #pragma once
 
@@ -41,10 +41,9 @@ struct SmemB8 {
     static constexpr int AG_RECV = RED1 + SLICE1 * 2;                     // fp16 [4 ranks][2][384] = [8][384]
     static constexpr int X_BYTES = AG_RECV + CL * SLICE1 * 2 - X;         // 19968
     static_assert(BC * BK_XS_STRIDE * 2 <= X_BYTES, "activations must fit into X");
-    // role 3: exchange 2 of one half chunk
-    static constexpr int ATTN_SRC = X;                                    // fp32 [4][132]
-    static constexpr int ATTN_RECV = ATTN_SRC + HB * PAY * 4;             // fp32 [4 ranks][4][132]
-    static_assert((1 + CL) * HB * PAY * 4 <= X_BYTES, "exchange-2 buffers must fit into X");
+    // role 3: exchange 2, all 8 requests in one pass: slot [rank] of ATTN_RECV is also the source of this CTA's contribution
+    static constexpr int ATTN_RECV = X;                                   // fp32 [4 ranks][8][132]
+    static_assert(CL * BC * PAY * 4 <= X_BYTES, "exchange-2 buffers must fit into X");
     // role 4: O-phase staging
     static constexpr int OSTAGE = X;                                      // fp32 [12 warps][8][32]
     static_assert(CONSUMER_WARPS * BC * 32 * 4 <= X_BYTES, "staging must fit into X");
@@ -90,7 +89,6 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
     __half* red1 = reinterpret_cast<__half*>(smem + S::RED1);
     __half* ag_recv = reinterpret_cast<__half*>(smem + S::AG_RECV);
     __half* qkv_fin = reinterpret_cast<__half*>(smem + S::QKV_FIN);
-    float* attn_src = reinterpret_cast<float*>(smem + S::ATTN_SRC);
     float* attn_recv = reinterpret_cast<float*>(smem + S::ATTN_RECV);
     __half* attn_out = reinterpret_cast<__half*>(smem + S::ATTN_OUT);
     float* ostage = reinterpret_cast<float*>(smem + S::OSTAGE);
@@ -114,8 +112,7 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
             prefetch_tmap(&p.tm_wo);
             cluster_reduce_arm<CLUSTER>(xbar_u32, S::SLICE1 * 4);            // scatter: 768 fp32 partials from every peer
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 16, S::SLICE1 * 2);       // gather: 768 fp16 results from every peer
-            cluster_reduce_arm<CLUSTER>(xbar_u32 + 32, HB * S::PAY * 4);     // softmax states, half 0
-            cluster_reduce_arm<CLUSTER>(xbar_u32 + 40, HB * S::PAY * 4);     // softmax states, half 1
+            cluster_reduce_arm<CLUSTER>(xbar_u32 + 32, BC * S::PAY * 4);     // softmax states of the 8 requests
             cluster_reduce_arm<CLUSTER>(xbar_u32 + 48, BC * 4);              // sums of squares
         }
         dsm::mbar_fence_init();
@@ -426,42 +423,39 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
         }
         gbase += n_kv_tiles;
         CF_MARK(5);
+        // ---- exchange 2: all-gather of the 8 block-merged states (this CTA's go into its own slot of the receive buffer, which
+        //      is also the source of the pushes), merged in rank order ----
+        dsm::cluster_wait();                                    // B2: every peer is past its RoPE, X may take exchange-2 data
+        float* mine = attn_recv + rank * (BC * S::PAY);
+        if (tid < HEAD_DIM) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            dsm::cluster_wait();                                // h == 0: B2, every peer is past its RoPE (X may take exchange-2 data);
-                                                                // h == 1: B3, every peer has merged the first half out of attn_recv
-            if (tid < HEAD_DIM) {
-#pragma unroll
-                for (int bb = 0; bb < HB; ++bb) {
-                    float* stp = attn_src + bb * S::PAY;
-                    stp[4 + tid] = Ov[h * HB + bb];
-                    if (tid == 0) { stp[0] = red[2 * (h * HB + bb)]; stp[1] = red[2 * (h * HB + bb) + 1]; stp[2] = 0.f; stp[3] = 0.f; }
-                }
+            for (int b = 0; b < BC; ++b) {
+                float* stp = mine + b * S::PAY;
+                stp[4 + tid] = Ov[b];
+                if (tid == 0) { stp[0] = red[2 * b]; stp[1] = red[2 * b + 1]; stp[2] = 0.f; stp[3] = 0.f; }
             }
-            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-            if (h == 0) { CF_MARK(3); } else { CF_MARK(11); }
-            uint32_t ph_a = 0;
-            cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
-                HB * S::PAY * 4, tid, HB * S::PAY, rank, smem_base + S::ATTN_SRC, smem_base + S::ATTN_RECV,
-                xbar_u32 + 32 + 8 * h, ph_a, attn_src, attn_recv);
-            for (int f = tid; f < HB * HEAD_DIM; f += CONSUMER_THREADS) {
-                const int bb = f >> 7, d = f & 127, b = h * HB + bb;
-                float M = -INFINITY;
-#pragma unroll
-                for (int r = 0; r < CLUSTER; ++r) M = fmaxf(M, attn_recv[(r * HB + bb) * S::PAY]);
-                float L = 0.f, Ovv = 0.f;
-#pragma unroll
-                for (int r = 0; r < CLUSTER; ++r) {
-                    const float* stp = attn_recv + (r * HB + bb) * S::PAY;
-                    const float w = dsm::exp2_diff(stp[0], M);
-                    L = fmaf(stp[1], w, L);
-                    Ovv = fmaf(stp[4 + d], w, Ovv);
-                }
-                attn_out[b * HEAD_DIM + d] = __float2half_rn((b < nb) ? Ovv / L : 0.f);   // fp16, as the eager model
-            }
-            dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-            if (h == 0) dsm::cluster_arrive();                  // B3: done reading attn_recv of the first half
         }
+        CF_MARK(3);
+        uint32_t ph_a = 0;
+        cluster_reduce<CLUSTER, Stage::QUK_DEEPSEEK, CONSUMER_THREADS, CONSUMER_BAR>(
+            BC * S::PAY * 4, tid, BC * S::PAY, rank, smem_base + S::ATTN_RECV + rank * (BC * S::PAY * 4), smem_base + S::ATTN_RECV,
+            xbar_u32 + 32, ph_a, mine, attn_recv);
+        for (int f = tid; f < BC * HEAD_DIM; f += CONSUMER_THREADS) {
+            const int b = f >> 7, d = f & 127;
+            float M = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < CLUSTER; ++r) M = fmaxf(M, attn_recv[(r * BC + b) * S::PAY]);
+            float L = 0.f, Ovv = 0.f;
+#pragma unroll
+            for (int r = 0; r < CLUSTER; ++r) {
+                const float* stp = attn_recv + (r * BC + b) * S::PAY;
+                const float w = dsm::exp2_diff(stp[0], M);
+                L = fmaf(stp[1], w, L);
+                Ovv = fmaf(stp[4 + d], w, Ovv);
+            }
+            attn_out[b * HEAD_DIM + d] = __float2half_rn((b < nb) ? Ovv / L : 0.f);   // fp16, as the eager model
+        }
+        dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
     }
     CF_MARK(6);
 
