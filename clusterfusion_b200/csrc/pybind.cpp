@@ -20,6 +20,7 @@
  * with the C ABI's message on failure.
  */
 #include <torch/extension.h>
+#include <ATen/cuda/EmptyTensor.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 
@@ -96,6 +97,13 @@ std::atomic<bool> g_pdl{false};
 // exchange poll timed out -- see cf_workspace_status in the C ABI header
 std::atomic<bool> g_check_status{false};
 
+// Output tensors of the forms that allocate (8- and 10-argument): straight from the caching allocator, without a trip through
+// the dispatcher -- three torch::empty calls were ~3.6 us of the 8-argument form's 10.9 us host cost per call
+// (tools/host_overhead_probe.py), in a chat loop that is host-bound.
+inline Tensor empty_half_like(const Tensor& like, at::IntArrayRef sizes) {
+    return at::detail::empty_cuda(sizes, at::kHalf, like.device(), std::nullopt);
+}
+
 // [a, a+na) and [b, b+nb) overlap?
 bool overlaps(const Tensor& a, const Tensor& b) {
     const char* pa = static_cast<const char*>(a.data_ptr());
@@ -162,10 +170,9 @@ std::tuple<Tensor, Tensor, Tensor> llama_decoder_layer(
 
     const c10::cuda::CUDAGuard guard(input.device());
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
-    auto opt = input.options();
-    Tensor o = torch::empty({1, hidden}, opt);
-    Tensor k = torch::empty({1, n_heads, 128}, opt);
-    Tensor v = torch::empty({1, n_heads, 128}, opt);
+    Tensor o = empty_half_like(input, {1, hidden});
+    Tensor k = empty_half_like(input, {1, n_heads, 128});
+    Tensor v = empty_half_like(input, {1, n_heads, 128});
     Workspace ws = workspace_for(input, (int)hidden, 1, stream);
 
     CfLlamaArgs a{};
@@ -213,10 +220,9 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> llama_decoder_layer_sglang(
 
     const c10::cuda::CUDAGuard guard(input.device());
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
-    auto opt = input.options();
-    Tensor o = torch::empty({1, hidden}, opt);
-    Tensor k = torch::empty({1, kvd / 128, 128}, opt);
-    Tensor v = torch::empty({1, kvd / 128, 128}, opt);
+    Tensor o = empty_half_like(input, {1, hidden});
+    Tensor k = empty_half_like(input, {1, kvd / 128, 128});
+    Tensor v = empty_half_like(input, {1, kvd / 128, 128});
     Workspace ws = workspace_for(input, (int)hidden, 1, stream);
 
     CfLlamaArgs a{};
