@@ -917,6 +917,45 @@ def test_gqa_batched_weights_once_kernel_matches_per_request_launch_inplace_and_
     assert cabi.workspace_status(CT.workspace(4096, len(lens), out.device).data_ptr()) == 0
 
 
+@pytest.mark.parametrize("shape_name", ["llama2_7b", "llama3_8b"])
+def test_batched_kernels_random_ragged_batches_vs_oracle(shape_name):
+    """The batched kernels cut the chunk's concatenated KV rows into equal segments over the CTAs of a head / group.  Random ragged
+    batches (2..9 requests, lengths 0..400 with many empty and one-row requests, so that segment boundaries fall everywhere:
+    inside tiles, on request boundaries, ranks with no rows at all) against the oracle, MHA (chunks of 4 / 8) and grouped-query."""
+    shape = S7 if shape_name == "llama2_7b" else S8
+    g = torch.Generator().manual_seed(20260)
+    for case in range(10):
+        bs = int(torch.randint(2, 10, (1,), generator=g))
+        kinds = torch.randint(0, 4, (bs,), generator=g)
+        lens = [0 if k == 0 else 1 if k == 1 else int(torch.randint(2, 400, (1,), generator=g)) for k in kinds.tolist()]
+        d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r = _paged_case(lens, seed=7000 + case, table="random", shape=shape)
+        out, rout, kpool, vpool = _run_paged_cabi(d, indptr, indices, positions, cos_sin, shape=shape)
+        assert torch.equal(rout.cpu(), want_r), (case, lens)
+        assert close(out, want_o), (case, lens)
+        assert close_k(kpool, kp) and close(vpool, vp), (case, lens)
+
+
+def test_gqa_batched_kernel_on_a_workspace_sized_for_a_larger_batch():
+    """The public operator keeps one workspace per (device, stream, hidden) sized for the largest batch seen: a batch of 9 first
+    (two chunks), then a batch of 3 on the same, larger workspace (CfLlamaArgs.workspace_batch > batch) -- both against the oracle."""
+    import clusterfusion
+    for lens, seed in (([40, 0, 300, 17, 64, 1, 128, 33, 250], 91), ([200, 31, 0], 92)):
+        d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r = _paged_case(lens, seed=seed, table="random", shape=S8)
+        c = cuda(d)
+        kpool, vpool = c["k_cache"].clone(), c["v_cache"].clone()
+        kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
+        vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
+        out = torch.full((len(lens), 4096), float("nan"), dtype=torch.float16, device="cuda"); rout = torch.empty_like(out)
+        clusterfusion.llama_decoder_layer_batch_decode_sglang(out, rout, c["x"], c["residual"], c["weight_qkv"], c["weight_o"],
+                                                              indptr.cuda(), indices.cuda(), kptrs, vptrs, 0, c["rms_w"], 1e-5,
+                                                              positions.cuda(), cos_sin.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(rout.cpu(), want_r)
+        assert close(out, want_o)
+        assert close_k(kpool, kp) and close(vpool, vp)
+    assert clusterfusion.workspace_status() == 0
+
+
 @pytest.mark.parametrize("table", ["random", "sequential"])
 def test_paged_form_kv16384_bs1_vs_oracle(table):
     """north_star's form at north_star's size: 15-argument paged call, batch 1, kv_len 16384 (Llama-2-7B), through the public
