@@ -62,6 +62,12 @@ struct SmemFfn {
     static_assert(TOTAL <= 227 * 1024, "shared-memory layout exceeds the 227 KB opt-in limit");
 };
 
+#ifdef CF_TRACE
+#define FFN_MARK(slot) trace_mark(slot, (int)(p.flags >> 16))      /* tools/trace_ffn.py passes the launch index in the high flag bits */
+#else
+#define FFN_MARK(slot) ((void)0)
+#endif
+
 __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
 {
@@ -80,6 +86,7 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
     const uint32_t n_dn_tiles = nb * wins;
     const uint32_t total_tiles = n_gu_tiles + n_dn_tiles;
 
+    FFN_MARK(0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint64_t pol = policy_evict_first();
     auto issue_tile = [&](uint32_t g) {
@@ -182,6 +189,7 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
         __syncthreads();
     }
 
+    FFN_MARK(1);
     // ---- phase 1: gate / up rows of this CTA's blocks ------------------------------------------------------
     for (uint32_t g = warp; g < n_gu_tiles; g += CONSUMER_WARPS) {
         const uint32_t s = ring_stage(g);
@@ -238,6 +246,7 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
         issue_tile(g + NSTAGES);
     }
     __syncthreads();
+    FFN_MARK(2);
 
     // ---- SwiGLU on this CTA's nb * 16 intermediate values (fp16 rounding points of the eager model) ---------
     for (int e = tid; e < nb * FFN_BLOCK; e += CONSUMER_THREADS) {
@@ -250,6 +259,7 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
     for (int e = tid; e < hidden; e += CONSUMER_THREADS) out_acc[e] = 0.f;
     __syncthreads();
 
+    FFN_MARK(4);
     // ---- phase 2: down projection, rows of W2^T for this CTA's blocks ---------------------------------------
     for (uint32_t i = first_tile(n_gu_tiles, warp); i < n_dn_tiles; i += CONSUMER_WARPS) {
         const uint32_t g = n_gu_tiles + i, s = ring_stage(g);
@@ -273,6 +283,7 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
         for (int kk = 0; kk < 8; ++kk) atomicAdd(dst + kk, acc[kk]);
     }
     __syncthreads();
+    FFN_MARK(5);
 
     // ---- cross-CTA reduction: fp32 red into scratch, the last CTA finalises ------------------------------------
     for (int e = tid * 4; e < hidden; e += CONSUMER_THREADS * 4)
@@ -284,6 +295,7 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
         sflags[0] = (prev == (unsigned)grid - 1u);
     }
     __syncthreads();
+    FFN_MARK(8);
     if (sflags[0]) {
         __threadfence();
         const bool fp32_out = p.flags & 1u;
@@ -312,6 +324,7 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
             }
         }
     }
+    FFN_MARK(9);
 }
 
 }  // namespace cfb
