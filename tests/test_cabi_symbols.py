@@ -30,6 +30,12 @@ def test_workspace_and_bytes_model():
     from clusterfusion_b200 import cabi
     assert cabi.workspace_bytes(4096, 1) >= 4096 * 4 + 5 * 4
     assert cabi.workspace_bytes(4096, 3) >= 3 * (4096 * 4 + 5 * 4)
+    # batch >= 2 adds the exchange words of the grouped-query batched kernel, one set per chunk of 8 requests
+    # (llama_decoder_gqa_batch_kernel.cuh: per-CTA QKV partials [160][768][8], states [160][8][528], per-group O partials [16][hidden][8])
+    per_chunk = 8 * (160 * 768 * 8 + 160 * 8 * 528 + 16 * 4096 * 8)
+    b1, b2, b8, b9 = (cabi.workspace_bytes(4096, b) for b in (1, 2, 8, 9))
+    assert b2 - b1 >= per_chunk and b9 - b8 >= per_chunk and b8 - b2 < per_chunk
+    assert cabi.workspace_bytes(8192, 8) > b8
     a = cabi.CfLlamaArgs(variant=cabi.CF_VARIANT_CHAT, hidden=4096, n_q_heads=32, n_kv_heads=32, head_dim=128, batch=1)
     # Llama-2-7B, kv 1K -> 151 036 928 B; kv 16K -> 402 695 168 B
     assert cabi.algorithmic_bytes(a, 1024) == 151_036_928 - 41_984 + (2 * 4096 * 3 + 2 * 2 * 4096 + 2 * 4 * 128)
