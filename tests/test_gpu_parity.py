@@ -809,7 +809,7 @@ def _paged_case(lens, seed, table="random", nslots_extra=37, shape=None):
     return d, indptr, indices, positions, cos_sin, kp, vp, want_o, want_r
 
 
-def _run_paged_cabi(d, indptr, indices, positions, cos_sin, flags=0, host_pool_copy="right", shape=None, inplace=False):
+def _run_paged_cabi(d, indptr, indices, positions, cos_sin, flags=0, host_pool_copy="right", shape=None, inplace=False, fp32_out=False):
     """One 15-argument launch through the C ABI.  host_pool_copy: right = pass the host's copy of the pool addresses
     (tiled / gather4 KV fast paths), none = NULL (row-by-row gather), stale = a WRONG copy (the kernel must notice)."""
     import cabi_torch as CT
@@ -822,7 +822,7 @@ def _run_paged_cabi(d, indptr, indices, positions, cos_sin, flags=0, host_pool_c
     decoy_k, decoy_v = torch.zeros_like(kpool), torch.zeros_like(vpool)
     kptrs = torch.tensor([kpool.data_ptr()], dtype=torch.uint64).cuda()
     vptrs = torch.tensor([vpool.data_ptr()], dtype=torch.uint64).cuda()
-    out = torch.full((bs, H), float("nan"), dtype=torch.float16, device="cuda")
+    out = torch.full((bs, H), float("nan"), dtype=torch.float32 if fp32_out else torch.float16, device="cuda")
     rout = c["residual"] if inplace else torch.full((bs, H), float("nan"), dtype=torch.float16, device="cuda")
     dev_t = (indptr.cuda(), indices.cuda(), positions.cuda(), cos_sin.cuda())
     hk = {"right": kpool, "stale": decoy_k, "none": None}[host_pool_copy]
@@ -911,6 +911,9 @@ def test_gqa_batched_weights_once_kernel_matches_per_request_launch_inplace_and_
     assert torch.equal(out, out_i) and torch.equal(kpool, kpool_i) and torch.equal(vpool, vpool_i)
     assert close(out, want_o) and close(out_p, want_o)
     assert close(vpool, vpool_p) and close_k(kpool, kpool_p)     # (different fp32 summation orders: K-split vs row-split)
+    # fp32 output (CF_FLAG_OUT_FP32_PARTIAL): the same sums before the final rounding
+    out_f, _, _, _ = _run_paged_cabi(d, indptr, indices, positions, cos_sin, shape=S8, flags=cabi.CF_FLAG_OUT_FP32_PARTIAL, fp32_out=True)
+    assert out_f.dtype == torch.float32 and torch.equal(out_f.half(), out)
     for _ in range(20):
         o2, _, k2, _ = _run_paged_cabi(d, indptr, indices, positions, cos_sin, shape=S8)
         assert torch.equal(o2, out) and torch.equal(k2, kpool)
