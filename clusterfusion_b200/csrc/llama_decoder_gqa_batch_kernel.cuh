@@ -460,21 +460,27 @@ llama_decoder_layer_gqa_batch_kernel(const __grid_constant__ GBParams gp)
         const int PR = 64 / G;                                   // pairs per slot (8 .. 1)
         const int NR = 12 * PR;                                  // rows of this CTA = 768 / G, local row lr = (slot*2 + half)*PR + u
         const int n_out = NR * BC;                               // sums this CTA owns (6144 / G)
-        // all G * n_out = 6144 partial words: 16 per thread, probed back to back, then resolved
+        // all G * n_out = 6144 partial words as 3072 pairs of adjacent requests (16-byte loads: half the L2 requests), 8 per
+        // thread, probed back to back, then resolved
         {
-            unsigned long long w[16];
-            const unsigned long long* src[16];
+            unsigned long long w[8][2];
+            const unsigned long long* src[8];
+            const int n_pairs = n_out / 2;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
+            for (int k = 0; k < 8; ++k) {
                 const int i = (int)tid + k * CONSUMER_THREADS;
-                const int part = i / n_out, o = i % n_out, lr = o / BC, rq = o % BC;
+                const int part = i / n_pairs, o2 = i % n_pairs, lr = o2 / (BC / 2), rqp = o2 % (BC / 2);
                 const int sl2 = lr / PR, u = lr % PR;            // sl2 = slot * 2 + half
                 const int row = (sl2 >> 1) * HEAD_DIM + (sl2 & 1) * 64 + (int)rank * PR + u;
-                src[k] = qkvp_ll + (((size_t)gid * G + part) * S::R + row) * BC + rq;
-                w[k] = ll_load(src[k]);
+                src[k] = qkvp_ll + (((size_t)gid * G + part) * S::R + row) * BC + 2 * rqp;
+                ll_load2(src[k], w[k][0], w[k][1]);
             }
 #pragma unroll
-            for (int k = 0; k < 16; ++k) stage1[(int)tid + k * CONSUMER_THREADS] = ll_resolve(src[k], w[k], flag, p.header + 2);
+            for (int k = 0; k < 8; ++k) {
+                const int i = (int)tid + k * CONSUMER_THREADS;
+                stage1[2 * i] = ll_resolve(src[k], w[k][0], flag, p.header + 2);
+                stage1[2 * i + 1] = ll_resolve(src[k] + 1, w[k][1], flag, p.header + 2);
+            }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
         for (int o = tid; o < n_out; o += CONSUMER_THREADS) {
@@ -693,20 +699,24 @@ llama_decoder_layer_gqa_batch_kernel(const __grid_constant__ GBParams gp)
             ll_store(ag_ll + (size_t)b * GB_AG_WORDS + d / 2, __uint_as_float(*reinterpret_cast<const uint32_t*>(&h2)), flag);
         }
         CF_MARK(10);
-        for (int i0 = tid; i0 < BC * GB_AG_WORDS; i0 += CONSUMER_THREADS * 4) {
-            unsigned long long w[4];
+        for (int i0 = tid; i0 < BC * GB_AG_WORDS / 2; i0 += CONSUMER_THREADS * 3) {     // pairs of words, 16-byte loads
+            unsigned long long w[3][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * CONSUMER_THREADS;
-                w[u] = (i < nb * GB_AG_WORDS) ? ll_load(ag_ll + i) : 0ull;
+            for (int u = 0; u < 3; ++u) {
+                const int i = 2 * (i0 + u * CONSUMER_THREADS);
+                w[u][0] = 0ull; w[u][1] = 0ull;
+                if (i < nb * GB_AG_WORDS) ll_load2(ag_ll + i, w[u][0], w[u][1]);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * CONSUMER_THREADS;
+            for (int u = 0; u < 3; ++u) {
+                const int i = 2 * (i0 + u * CONSUMER_THREADS);
                 if (i >= BC * GB_AG_WORDS) continue;
-                uint32_t bits = 0u;
-                if (i < nb * GB_AG_WORDS) bits = __float_as_uint(ll_resolve(ag_ll + i, w[u], flag, p.header + 2));
-                *reinterpret_cast<uint32_t*>(ag16 + (i / GB_AG_WORDS) * S::AG_STRIDE + (i % GB_AG_WORDS) * 2) = bits;
+                uint2 bits = make_uint2(0u, 0u);
+                if (i < nb * GB_AG_WORDS) {
+                    bits.x = __float_as_uint(ll_resolve(ag_ll + i, w[u][0], flag, p.header + 2));
+                    bits.y = __float_as_uint(ll_resolve(ag_ll + i + 1, w[u][1], flag, p.header + 2));
+                }
+                *reinterpret_cast<uint2*>(ag16 + (i / GB_AG_WORDS) * S::AG_STRIDE + (i % GB_AG_WORDS) * 2) = bits;
             }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
