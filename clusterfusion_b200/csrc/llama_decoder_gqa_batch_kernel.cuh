@@ -96,10 +96,6 @@ struct GBParams {
     int n_groups;                   // groups per request
 };
 
-__device__ __forceinline__ void ll_load2(const unsigned long long* p, unsigned long long& w0, unsigned long long& w1) {   // p 16-byte aligned
-    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
-}
-
 __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 llama_decoder_layer_gqa_batch_kernel(const __grid_constant__ GBParams gp)
 {

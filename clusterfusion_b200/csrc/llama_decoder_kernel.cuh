@@ -194,6 +194,10 @@ __device__ __forceinline__ unsigned long long ll_load(const unsigned long long* 
     asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return w;
 }
+// two adjacent words with one 16-byte request (p 16-byte aligned); each word still carries and is validated by its own epoch
+__device__ __forceinline__ void ll_load2(const unsigned long long* p, unsigned long long& w0, unsigned long long& w1) {
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
 // spin until the word carries this launch's epoch (the first probe `w` was issued by the caller, batched with others).
 // The spin is bounded (~1 s of dependent L2 round trips): a publisher that never arrives -- CTAs of a group not
 // co-resident, a workspace shared by two streams -- turns into an error word in the workspace header (`err`, header[2])
