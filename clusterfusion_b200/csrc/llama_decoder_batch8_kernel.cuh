@@ -520,30 +520,24 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
         __threadfence();
         const bool fp32_out = p.flags & 1u;
         const int e = tid * 4;                                // KS <= 1024: one float4 per thread
+        float4 v[BC];                                         // all eight loads go out before anything is stored: one L2 round trip
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float4 v[HB];
+        for (int b = 0; b < BC; ++b)
+            if (b < nb && sflags[b] && e < KS) v[b] = ld_cg_v4(p.scratch + (size_t)(b0 + b) * hidden + rank * KS + e);
 #pragma unroll
-            for (int bb = 0; bb < HB; ++bb) {
-                const int b = half * HB + bb;
-                if (b < nb && sflags[b] && e < KS) v[bb] = ld_cg_v4(p.scratch + (size_t)(b0 + b) * hidden + rank * KS + e);
-            }
-#pragma unroll
-            for (int bb = 0; bb < HB; ++bb) {
-                const int b = half * HB + bb;
-                if (b < nb && sflags[b] && e < KS) {
-                    const size_t off = (size_t)(b0 + b) * hidden + rank * KS + e;
-                    *reinterpret_cast<float4*>(p.scratch + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (fp32_out) {
-                        *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v[bb];
-                    } else {
-                        __align__(8) __half h4[4] = {__float2half_rn(v[bb].x), __float2half_rn(v[bb].y),
-                                                     __float2half_rn(v[bb].z), __float2half_rn(v[bb].w)};
-                        *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
-                    }
+        for (int b = 0; b < BC; ++b) {
+            if (b < nb && sflags[b] && e < KS) {
+                const size_t off = (size_t)(b0 + b) * hidden + rank * KS + e;
+                *reinterpret_cast<float4*>(p.scratch + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fp32_out) {
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v[b];
+                } else {
+                    __align__(8) __half h4[4] = {__float2half_rn(v[b].x), __float2half_rn(v[b].y),
+                                                 __float2half_rn(v[b].z), __float2half_rn(v[b].w)};
+                    *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + off) = *reinterpret_cast<const uint2*>(h4);
                 }
-                if (b < nb && sflags[b] && tid == 0) p.counters[(size_t)(b0 + b) * (CLUSTER + 1) + rank] = 0u;
             }
+            if (b < nb && sflags[b] && tid == 0) p.counters[(size_t)(b0 + b) * (CLUSTER + 1) + rank] = 0u;
         }
     }
     CF_MARK(9);
