@@ -299,15 +299,26 @@ llama_ffn_layer_kernel(const __grid_constant__ FfnParams p)
     if (sflags[0]) {
         __threadfence();
         const bool fp32_out = p.flags & 1u;
-        for (int e = tid * 4; e < hidden; e += CONSUMER_THREADS * 4) {
-            const float4 v = ld_cg_v4(p.scratch + e);
-            *reinterpret_cast<float4*>(p.scratch + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (fp32_out) {
-                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + e) = v;
-            } else {
-                __align__(8) __half h4[4] = {__float2half_rn(v.x), __float2half_rn(v.y),
-                                             __float2half_rn(v.z), __float2half_rn(v.w)};
-                *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + e) = *reinterpret_cast<const uint2*>(h4);
+        // the last CTA is the critical path of the next kernel: all scratch loads go out first (one L2 round trip, not three)
+        constexpr int FIN_ITERS = (FFN_HIDDEN_MAX / 4 + CONSUMER_THREADS - 1) / CONSUMER_THREADS;      // 6
+        float4 v[FIN_ITERS];
+#pragma unroll
+        for (int it = 0; it < FIN_ITERS; ++it) {
+            const int e = (it * CONSUMER_THREADS + tid) * 4;
+            if (e < hidden) v[it] = ld_cg_v4(p.scratch + e);
+        }
+#pragma unroll
+        for (int it = 0; it < FIN_ITERS; ++it) {
+            const int e = (it * CONSUMER_THREADS + tid) * 4;
+            if (e < hidden) {
+                *reinterpret_cast<float4*>(p.scratch + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fp32_out) {
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.out) + e) = v[it];
+                } else {
+                    __align__(8) __half h4[4] = {__float2half_rn(v[it].x), __float2half_rn(v[it].y),
+                                                 __float2half_rn(v[it].z), __float2half_rn(v[it].w)};
+                    *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + e) = *reinterpret_cast<const uint2*>(h4);
+                }
             }
         }
         if (tid == 0) p.counters[0] = 0u;
