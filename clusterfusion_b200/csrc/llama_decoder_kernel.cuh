@@ -622,6 +622,20 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     const int nchunks = hidden / 8;
     uint4 wraw = make_uint4(0, 0, 0, 0);
     if ((int)tid < cpk) wraw = *reinterpret_cast<const uint4*>(p.rms_w + rank * KS + tid * 8);
+    // Neither do the RoPE factors of this thread's q / k element (nor `positions`, by the PDL contract): fetched here they cost
+    // nothing later, fetched in the RoPE step they put one (paged form: two dependent) L2 round trips right behind exchange 1.
+    float rope_c = 0.f, rope_s = 0.f;
+    if (tid < 2u * HEAD_DIM) {
+        const int d = tid & 127;
+        if constexpr (kChat) {
+            rope_c = p.cos[d]; rope_s = p.sin[d];
+        } else if constexpr (kPaged) {
+            const float* cs = p.cos + p.positions[batch] * HEAD_DIM;
+            rope_c = cs[d & 63]; rope_s = cs[HEAD_DIM / 2 + (d & 63)];
+        } else {
+            rope_c = p.cos[d & 63]; rope_s = p.sin[d & 63];
+        }
+    }
 
     // Programmatic dependent launch: everything above (and the whole producer warp) may run while the previous
     // kernel in the stream is still finishing; activations, outputs and the workspace may only be touched after it.
@@ -795,12 +809,6 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
     // ---- RoPE (fp16 rounding points of the eager model), new K/V out -------------------------------
     {
         constexpr float kScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;   // 1/sqrt(128) * log2(e)
-        const float* cosp = p.cos;
-        const float* sinp = p.sin;
-        if constexpr (kPaged) {
-            cosp = p.cos + p.positions[batch] * HEAD_DIM;
-            sinp = cosp + HEAD_DIM / 2;
-        }
         if (tid < 2 * HEAD_DIM) {
             const int which = tid >> 7, d = tid & 127;          // 0: q, 1: k
             const float* v = qkv_src + which * HEAD_DIM;
@@ -808,11 +816,10 @@ llama_decoder_layer_kernel(const __grid_constant__ KParams p)
             float rot;
             if constexpr (kChat) {                              // GPT-J pairs (2i, 2i+1), cos/sin pair-repeated
                 const float b = round_h(v[d ^ 1]);
-                rot = (d & 1) ? fmaf(a, cosp[d], b * sinp[d]) : fmaf(a, cosp[d], -b * sinp[d]);
+                rot = (d & 1) ? fmaf(a, rope_c, b * rope_s) : fmaf(a, rope_c, -b * rope_s);
             } else {                                            // NeoX pairs (i, i+64), cos/sin [64]
                 const float b = round_h(v[d ^ 64]);
-                const int i = d & 63;
-                rot = (d & 64) ? fmaf(a, cosp[i], b * sinp[i]) : fmaf(a, cosp[i], -b * sinp[i]);
+                rot = (d & 64) ? fmaf(a, rope_c, b * rope_s) : fmaf(a, rope_c, -b * rope_s);
             }
             const __half rh = __float2half_rn(rot);
             qkv_fin[tid] = which == 0 ? __half2float(rh) * kScaleLog2 : __half2float(rh);
