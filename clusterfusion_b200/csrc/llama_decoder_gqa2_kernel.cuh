@@ -405,6 +405,23 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
         wraw[it] = e < hidden ? *reinterpret_cast<const uint4*>(p.rms_w + e) : make_uint4(0, 0, 0, 0);
     }
 
+    // the RoPE factors of this thread's two projected rows (rows tid and tid + 384; not needed for v) do not depend on the previous
+    // kernel either (nor does `positions`, by the PDL contract): fetched here, not right behind exchange 1
+    float rope_c[2] = {0.f, 0.f}, rope_s[2] = {0.f, 0.f};
+    {
+        const float* cosp = p.cos;
+        const float* sinp = p.sin;
+        if constexpr (kPaged) {
+            cosp = p.cos + p.positions[batch] * HEAD_DIM;
+            sinp = cosp + HEAD_DIM / 2;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = (int)tid + u * CONSUMER_THREADS;
+            if ((e >> 7) <= NQ) { rope_c[u] = cosp[e & 63]; rope_s[u] = sinp[e & 63]; }
+        }
+    }
+
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // this launch's epoch: every flag-in-data word written below carries it (header zeroed once by the caller,
@@ -506,12 +523,6 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
 
     // ---- RoPE (NeoX), new K/V out ---------------------------------------------------------------------
     {
-        const float* cosp = p.cos;
-        const float* sinp = p.sin;
-        if constexpr (kPaged) {
-            cosp = p.cos + p.positions[batch] * HEAD_DIM;
-            sinp = cosp + HEAD_DIM / 2;
-        }
         // read a projected row: sum of its 1 or 2 published parts, each validated by its own epoch
         auto n_parts = [&](int e) {
             const int rb = e / ROWS512;
@@ -540,14 +551,15 @@ llama_decoder_layer_gqa2_kernel(const __grid_constant__ G2Params gp)
             }
         }
         dsm::named_bar_sync(CONSUMER_BAR, CONSUMER_THREADS);
-        for (int e = tid; e < S::R; e += CONSUMER_THREADS) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = (int)tid + u * CONSUMER_THREADS;
             const int hd = e >> 7, d = e & 127;                  // hd < NQ: query head; NQ: k; NQ+1: v
             const float a = qkv_raw[e];
             const float bv = qkv_raw[e ^ 64];
             if (hd <= NQ) {
                 const float b = bv;
-                const int i = d & 63;
-                const float rot = (d & 64) ? fmaf(a, cosp[i], b * sinp[i]) : fmaf(a, cosp[i], -b * sinp[i]);
+                const float rot = (d & 64) ? fmaf(a, rope_c[u], b * rope_s[u]) : fmaf(a, rope_c[u], -b * rope_s[u]);
                 const __half rh = __float2half_rn(rot);
                 // CUDA-core loop: q pre-scaled in fp32; mma loop: q must stay an exact fp16 value, the scale goes onto S
                 qkv_fin[e] = (hd < NQ && !use_mma) ? __half2float(rh) * kScaleLog2 : __half2float(rh);
