@@ -50,7 +50,7 @@ struct SmemB8 {
     static constexpr int QKV_FIN = X + X_BYTES;                           // fp16 [8][384]  roped q (unscaled) | k | v
     static constexpr int ATTN_OUT = QKV_FIN + BC * QKV_OUT * 2;           // fp16 [8][128]
     static constexpr int RED = ATTN_OUT + BC * HEAD_DIM * 2;              // fp32 [12][8] + [8]
-    static constexpr int META = RED + (CONSUMER_WARPS + 1) * BC * 4;      // int [8][4] requests: kv_base, len, new_slot, -; int [8][4] segments:
+    static constexpr int META = RED + (CONSUMER_WARPS + 1) * BC * 4;      // int [8][4] requests: kv_base, position, new_slot, owner; int [8][4] segments:
                                                                           // request | owner << 8, row begin, row end, -; u32 [9] tile0; [1] n_seg
     static constexpr int BARS = META + 76 * 4;                            // u64 full[NSTAGES], xbar[7]
     static constexpr int FLAGS = BARS + (NSTAGES + 7) * 8;                // u32 [8]
@@ -273,7 +273,7 @@ llama_decoder_layer_batch8_kernel(const __grid_constant__ KParams p)
             if (b < nb) {
                 if (which < 2) {
                     const float a = __half2float(outv);
-                    const float* cosp = p.cos + p.positions[b0 + b] * HEAD_DIM;
+                    const float* cosp = p.cos + (size_t)meta[b * 4 + 1] * HEAD_DIM;
                     const float* sinp = cosp + HEAD_DIM / 2;
                     const float bbv = __half2float(ag_recv[f ^ 64]);
                     const int i = d & 63;

@@ -136,18 +136,19 @@ __device__ __forceinline__ void batch_slice_store(const BatchSlice<BC>& sl, cons
 // streams one or two SEGMENTS (request, row range) however ragged the batch is.  A request's new token is folded in by the rank
 // that holds its last row ("owner"; an empty request: the rank its offset falls into).  Lane b handles request b, offsets are
 // warp prefix sums (no single-thread loop in front of a block barrier).
-//   meta [BC][4]  kv_base, len, new_slot, owner          mseg [BC][4]  request | owner-is-me << 8, row begin, row end, -
+//   meta [BC][4]  kv_base, position, new_slot, owner          mseg [BC][4]  request | owner-is-me << 8, row begin, row end, -
 //   tile0 [BC+1]  first KV tile (phase-local) of segment s; entries >= n_seg hold the total          mmisc [0] n_seg
 template <int BC>
 __device__ __forceinline__ void batch_build_segments(const KParams& p, int b0, int nb, int rank, int nranks, uint32_t lane,
                                                      int* meta, int* mseg, uint32_t* tile0, int* mmisc) {
     const int b = (int)lane;
-    int len = 0, kb = 0, ns = 0;
+    int len = 0, kb = 0, ns = 0, pos = 0;
     if (b < nb) {
         kb = p.indptr[b0 + b];
         const int end = p.indptr[b0 + b + 1] - 1;
         len = end - kb;
         ns = p.indices[end];
+        pos = (int)p.positions[b0 + b];                  // row of the RoPE table: read here, not behind exchange 1
     }
     int incl = len;
 #pragma unroll
@@ -175,7 +176,7 @@ __device__ __forceinline__ void batch_build_segments(const KParams& p, int b0, i
     }
     const uint32_t total = __shfl_sync(0xffffffffu, tincl, BC - 1);
     const int nseg = __popc(bal);
-    if (b < BC) { meta[b * 4 + 0] = kb; meta[b * 4 + 1] = len; meta[b * 4 + 2] = ns; meta[b * 4 + 3] = owner; }
+    if (b < BC) { meta[b * 4 + 0] = kb; meta[b * 4 + 1] = pos; meta[b * 4 + 2] = ns; meta[b * 4 + 3] = owner; }
     if ((int)lane >= nseg && (int)lane <= BC) tile0[lane] = total;
     __syncwarp();
     if (has) {
@@ -452,7 +453,7 @@ llama_decoder_layer_batch_kernel(const __grid_constant__ KParams p)
             float outv = a;
             if (b < nb) {
                 if (which < 2) {
-                    const float* cosp = p.cos + p.positions[b0 + b] * HEAD_DIM;
+                    const float* cosp = p.cos + (size_t)meta[b * 4 + 1] * HEAD_DIM;
                     const float* sinp = cosp + HEAD_DIM / 2;
                     const float bb = ag_recv[f ^ 64];
                     const int i = d & 63;

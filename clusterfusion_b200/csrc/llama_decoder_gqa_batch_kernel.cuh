@@ -137,7 +137,7 @@ llama_decoder_layer_gqa_batch_kernel(const __grid_constant__ GBParams gp)
     float* attn_part = reinterpret_cast<float*>(smem + S::ATTN_PART);
     __half* ag16 = reinterpret_cast<__half*>(smem + S::AG16);
     __half* qseg = reinterpret_cast<__half*>(smem + S::QSEG);
-    int* mreq = reinterpret_cast<int*>(smem + S::META);                       // [b][4]: kv_base, len, new_slot, first rank | owner << 16
+    int* mreq = reinterpret_cast<int*>(smem + S::META);                       // [b][4]: kv_base, position, new_slot, first rank | owner << 16
     int* mseg = mreq + 32;                                                    // [s][4]: request | owner << 8, row begin, row end, -
     uint32_t* stile0 = reinterpret_cast<uint32_t*>(mseg + 32);                // [9]: first KV tile of segment s (entries >= n_seg: total)
     int* mmisc = reinterpret_cast<int*>(stile0 + 9);                          // [0] n_seg
@@ -156,12 +156,13 @@ llama_decoder_layer_gqa_batch_kernel(const __grid_constant__ GBParams gp)
     //      that holds its last row ("owner"; for an empty request: the rank its offset falls into). ----
     if (warp == 0) {
         const int b = (int)lane;
-        int len = 0, kb = 0, ns = 0;
+        int len = 0, kb = 0, ns = 0, pos = 0;
         if (b < nb) {
             kb = p.indptr[b0 + b];
             const int end = p.indptr[b0 + b + 1] - 1;
             len = end - kb;
             ns = p.indices[end];
+            pos = (int)p.positions[b0 + b];              // row of the RoPE table: read here, not behind exchange 1
         }
         int incl = len;
 #pragma unroll
@@ -190,7 +191,7 @@ llama_decoder_layer_gqa_batch_kernel(const __grid_constant__ GBParams gp)
         }
         const uint32_t total = __shfl_sync(0xffffffffu, tincl, BC - 1);
         const int nseg = __popc(bal);
-        if (b < BC) { mreq[b * 4 + 0] = kb; mreq[b * 4 + 1] = len; mreq[b * 4 + 2] = ns; mreq[b * 4 + 3] = rf | (owner << 16); }
+        if (b < BC) { mreq[b * 4 + 0] = kb; mreq[b * 4 + 1] = pos; mreq[b * 4 + 2] = ns; mreq[b * 4 + 3] = rf | (owner << 16); }
         if ((int)lane >= nseg && lane <= BC) stile0[lane] = total;
         __syncwarp();
         if (has) {
@@ -495,7 +496,7 @@ llama_decoder_layer_gqa_batch_kernel(const __grid_constant__ GBParams gp)
             __half lo = __float2half_rn(a), hi = __float2half_rn(bv);
             if (rq < nb) {
                 if (sl < 5) {
-                    const float* cosp = p.cos + p.positions[b0 + rq] * HEAD_DIM;
+                    const float* cosp = p.cos + (size_t)mreq[rq * 4 + 1] * HEAD_DIM;
                     const float c = cosp[i], sn = cosp[HEAD_DIM / 2 + i];
                     lo = __float2half_rn(fmaf(a, c, -bv * sn));
                     hi = __float2half_rn(fmaf(bv, c, a * sn));
