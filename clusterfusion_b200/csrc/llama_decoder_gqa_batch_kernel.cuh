@@ -33,7 +33,11 @@
  * completes with a plain arrive, nothing is loaded) -- the ring parity stays a pure function of g.
  *
  * PAGED variant only, page size 1, batch >= 2 (batch 1 uses the group kernel).  K/V arrive through tensor maps over the pools when
- * the caller passed the pool addresses on the host (tiled boxes / tile::gather4, 128-byte swizzled), else as linear row pieces.  hidden / G must be a multiple of 128 and <= 1024.
+ * the caller passed the pool addresses on the host (tiled boxes / tile::gather4, 128-byte swizzled), else as linear 128-byte row
+ * pieces read without the swizzle.  hidden / G must be a multiple of 128 and <= 1024.
+ * Hops that read many words per thread (the reduce-scatter, the gather of the merged outputs, the cross-group sum) use 16-byte
+ * flag-in-data loads -- two adjacent words per request, each still validated by its own epoch (8- and 32-byte loads, a one-hop state
+ * exchange, L2 prefetches at the stall points: measured and rejected, profiles/round2_gqa_rejected_variants.txt).
  *
  * Reference: /root/reference/include/H100/llama/llama_kernel_batch_sglang_dispatch.cu:89 (the reference launches one cluster
  * per (head, request) and re-reads the weights for every request; grouped-query shapes are a new capability).
